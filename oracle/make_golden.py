@@ -1,0 +1,186 @@
+"""Generate tests/golden/*.npz by EXECUTING the unmodified reference (test infrastructure).
+
+Run here (the container that has /root/reference):  python -m oracle.make_golden
+The fixtures travel to the GPU box; the reference does not.  Every array named ``ref_*`` is an
+output of a reference function; the rest are the seeded inputs it was run on.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from litehandnet_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _ann(K, image_size, heatmap_size):
+    return dict(num_joints=K, image_size=np.array(image_size), heatmap_size=np.array(heatmap_size),
+                joint_weights=None, use_different_joint_weights=False)
+
+
+def decode_case(ref, name, N, K, H, W, seed, image_size):
+    T = ref.top_down_eval
+    hm, cen = synth.blob_heatmaps(N, K, H, W, seed=seed, zero_frac=0.08, tie_frac=0.08)
+    # hand-made edge planes: negative-only plane, NaN plane, border maxima, flat plateau
+    hm[0, 0] = -hm[0, 0].abs() - 0.1
+    hm[0, 1, 5, 7] = float("nan")
+    hm[0, 2] = 0.0; hm[0, 2, 0, 0] = 1.0
+    hm[0, 3] = 0.0; hm[0, 3, H - 1, W - 1] = 1.0
+    hm[0, 4] = 0.0; hm[0, 4, 10:13, 20:23] = 0.7
+    n1 = N - 1
+    hm[n1, 5] = 0.0; hm[n1, 5, 2, 2] = 0.9; hm[n1, 5, 2, 3] = 0.5; hm[n1, 5, 3, 2] = 0.4
+    hm[n1, 4 if N > 1 else 6] = 0.0; hm[n1, 4 if N > 1 else 6, 1, W - 2] = 0.9
+    hmn = hm.numpy()
+    center, scale = [t.numpy() for t in synth.bbox_center_scale(N, seed=seed + 1)]
+    d = dict(hm=hmn, center=center, scale=scale, image_size=np.array(image_size))
+    with np.errstate(all="ignore"):
+        for pp, tag in (("default", "default"), ("unbiased", "unbiased"), (None, "none")):
+            a = T.keypoints_from_heatmaps(hmn.copy(), center, scale, post_process=pp, kernel=11)
+            d[f"ref_g2_{tag}_hm_preds"], d[f"ref_g2_{tag}_preds"], d[f"ref_g2_{tag}_maxvals"] = a
+        d["ref_argmax_idx"] = np.argmax(hmn.reshape(N, K, -1), 2)
+        a = ref.evaluation.get_coordinates_from_heatmap(torch.from_numpy(hmn.copy()))
+        d["ref_a1_preds"], d["ref_a1_maxvals"] = a[0].numpy(), a[1].numpy()
+        a = ref.transforms.get_max_preds(hmn.copy())
+        d["ref_a3_preds"], d["ref_a3_maxvals"] = a
+        stride = (image_size[0] // W, image_size[1] // H)
+        for dark in (False, True):
+            rp = ref_loader.make_result_parser(ref, image_size=image_size, hm_size=(W, H), dark=dark)
+            for resized in (False, True):
+                k = rp.get_pred_kpt(torch.from_numpy(hmn.copy()), resized=resized)
+                d[f"ref_legacy_{'dark' if dark else 'offset'}_{'img' if resized else 'hm'}"] = \
+                    np.asarray(k, dtype=np.float32)
+        k, bb = ref.SPheatmapParser.HeatmapParser_SH().parse(torch.from_numpy(hmn.copy()),
+                                                            image_size=image_size)
+        assert bb is None
+        d["ref_parse_sh"] = k.numpy()
+        d["ref_final_preds"] = ref.transforms.get_final_preds(torch.from_numpy(hmn.copy()),
+                                                              center, scale)
+        pairs = synth.MPII_FLIP_PAIRS if K >= 16 else ((0, 1), (2, 3))
+        d["flip_pairs"] = np.array(pairs)
+        d["ref_flip_back"] = ref.transforms.flip_back(hmn.copy(), pairs)
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    return hm, cen, center, scale
+
+
+def render_loss_case(ref, name, N, K, H, W, seed, image_size, hm):
+    G = ref.generateTarget.TopDownGenerateTarget
+    L = ref.loss
+    j, v = synth.hand_joints(N, K, image_size=image_size, seed=seed, outside_frac=0.12, vis_prob=0.8)
+    v[0, 0, 0] = 0.3                       # fractional visibility: weight kept, target zero
+    jn, vn = j.numpy(), v.numpy()
+    d = dict(joints_3d=jn, joints_3d_visible=vn, image_size=np.array(image_size),
+             heatmap_size=np.array([W, H]))
+    for unb, tag in ((True, "unbiased"), (False, "int")):
+        g = G(sigma=2, unbiased_encoding=unb)
+        tg, tw = [], []
+        for b in range(N):
+            out = g(dict(joints_3d=jn[b], joints_3d_visible=vn[b], ann_info=_ann(K, image_size, (W, H))))
+            tg.append(out["target"]); tw.append(out["target_weight"])
+        tg, tw = np.stack(tg), np.stack(tw)
+        d[f"ref_target_{tag}"] = tg; d[f"ref_weight_{tag}"] = tw
+        o = hm.clone()
+        for bal in (True, False):
+            d[f"ref_distance_loss_{tag}_{'bal' if bal else 'nobal'}"] = np.float32(
+                L.DistanceLoss("L2", "mean", bal)(o.clone(), torch.from_numpy(tg), torch.from_numpy(tw)).item())
+        d[f"ref_joints_mse_{tag}"] = np.float32(
+            L.JointsDistanceLoss()(o.clone(), torch.from_numpy(tg), torch.from_numpy(tw)).item())
+    # 5-D hourglass shape [N,S,K,H,W] with a sigma list (generateTarget.py:252-268)
+    g = G(sigma=[2, 2], unbiased_encoding=True)
+    tg, tw = [], []
+    for b in range(N):
+        out = g(dict(joints_3d=jn[b], joints_3d_visible=vn[b], ann_info=_ann(K, image_size, (W, H))))
+        tg.append(out["target"]); tw.append(out["target_weight"])
+    tg, tw = np.stack(tg), np.stack(tw)
+    o5 = torch.stack([hm, hm * 0.5], 1)
+    d["ref_distance_loss_5d_bal"] = np.float32(
+        L.DistanceLoss("L2", "mean", True)(o5.clone(), torch.from_numpy(tg), torch.from_numpy(tw)).item())
+    # SimDR render + KLDiscretLoss + decode
+    k = 2
+    S = ref.generate_simder.GenerateSimDR(sigma=2, k=k)
+    sx, sy = [], []
+    for b in range(N):
+        out = S(dict(joints_3d=jn[b], joints_3d_visible=vn[b], ann_info=dict(image_size=np.array(image_size))))
+        sx.append(out["simdr_x"]); sy.append(out["simdr_y"])
+    sx, sy = np.stack(sx), np.stack(sy)
+    # stored as the argmax/max summary + a few full rows (the full vectors are regenerated by the oracle)
+    d["ref_simdr_x_row0"] = sx[:, 0]; d["ref_simdr_y_row0"] = sy[:, 0]
+    d["ref_simdr_x_sum"] = sx.sum(-1); d["ref_simdr_y_sum"] = sy.sum(-1)
+    xv, yv = synth.simdr_vectors(N, K, sx.shape[-1], seed=seed + 3, k=k)
+    d["simdr_xv"], d["simdr_yv"] = xv.numpy(), yv.numpy()
+    d["ref_kld_loss"] = np.float32(L.KLDiscretLoss()(
+        xv, yv, torch.from_numpy(sx), torch.from_numpy(sy), torch.from_numpy(d["ref_weight_unbiased"])).item())
+    center, scale = [t.numpy() for t in synth.bbox_center_scale(N, seed=seed + 1)]
+    d["center"], d["scale"] = center, scale
+    d["ref_simdr_decode"] = ref.top_down_eval.keypoints_from_simdr(xv.numpy(), yv.numpy(), center, scale, k)
+    np.savez_compressed(os.path.join(OUT, name), **d)
+
+
+def metrics_case(ref, name, N, K, seed):
+    T = ref.top_down_eval
+    H = W = 64
+    hm, cen = synth.blob_heatmaps(N, K, H, W, seed=seed)
+    center, scale = [t.numpy() for t in synth.bbox_center_scale(N, fixed=True)]
+    _, preds, _ = T.keypoints_from_heatmaps(hm.numpy().copy(), center, scale, post_process="default")
+    gt, mask, wh = synth.pck_inputs(cen, seed=seed + 1)
+    mask[3] = False                                   # a sample with no visible joint
+    mask[:, 2] = False                                # a joint never visible -> acc = -1
+    wh[5] = 0.0                                       # normalize == 0 -> sample masked out
+    gtn, m, whn = gt.numpy(), mask.numpy(), wh.numpy()
+    pred64 = preds.astype(np.float64)                 # as after the JSON round trip
+    t = np.max(whn, axis=1).astype(np.float64)
+    thr_bbox = np.stack([t, t], 1)
+    d = dict(preds=preds, gt=gtn, mask=m, bbox_wh=whn)
+    acc, avg, cnt = T.keypoint_pck_accuracy(pred64, gtn, m, 0.2, thr_bbox.copy())
+    d["ref_pck_acc"], d["ref_pck_avg"], d["ref_pck_cnt"] = acc, np.float64(avg), np.int64(cnt)
+    head = (t * 0.3)
+    acc, avg, cnt = T.keypoint_pck_accuracy(pred64, gtn, m, 0.5, np.stack([head, head], 1))
+    d["head_size"] = head
+    d["ref_pckh_acc"], d["ref_pckh_avg"] = acc, np.float64(avg)
+    d["ref_auc"] = np.float64(T.keypoint_auc(pred64, gtn, m, 30))
+    d["ref_epe"] = np.float64(T.keypoint_epe(pred64, gtn, m))
+    # all-f32 call (numpy promotion keeps f32 arithmetic)
+    acc, avg, cnt = T.keypoint_pck_accuracy(preds, gtn, m, 0.2, thr_bbox.astype(np.float32))
+    d["ref_pck_f32_acc"], d["ref_pck_f32_avg"] = acc, np.float64(avg)
+    # legacy evaluate_pck on heatmap pairs (small: first 6 samples, first 8 joints)
+    n2, k2 = 6, 8
+    ghm, _ = synth.blob_heatmaps(n2, k2, H, W, seed=seed + 2,
+                                 centers=cen[:n2, :k2] + torch.randn(n2, k2, 2) * 2)
+    phm = hm[:n2, :k2].contiguous()
+    bbox = torch.cat([torch.full((n2, 1, 2), 128.), torch.rand(n2, 1, 2) * 140 + 60], -1)
+    tw = mask[:n2, :k2].float()[..., None]
+    tw[0, 0, 0] = 0.5
+    d["pck_pred_hm"], d["pck_gt_hm"], d["pck_bbox"], d["pck_tw"] = \
+        phm.numpy(), ghm.numpy(), bbox.numpy(), tw.numpy()
+    with np.errstate(all="ignore"):
+        d["ref_evaluate_pck_w"] = np.float64(ref.evaluation.evaluate_pck(phm, ghm, bbox, 256, tw, 0.2))
+        d["ref_evaluate_pck_now"] = np.float64(ref.evaluation.evaluate_pck(phm, ghm, bbox, 256, None, 0.02))
+    np.savez_compressed(os.path.join(OUT, name), **d)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    ref = ref_loader.load()
+    hm, _, _, _ = decode_case(ref, "decode_64.npz", N=2, K=8, H=64, W=64, seed=11, image_size=(256, 256))
+    decode_case(ref, "decode_56.npz", N=2, K=6, H=56, W=56, seed=12, image_size=(224, 224))
+    decode_case(ref, "decode_mpii16.npz", N=1, K=16, H=64, W=64, seed=13, image_size=(256, 256))
+    render_loss_case(ref, "render_loss_64.npz", N=2, K=8, H=64, W=64, seed=21, image_size=(256, 256), hm=hm)
+    hm56, _ = synth.blob_heatmaps(2, 6, 56, 56, seed=12)
+    render_loss_case(ref, "render_loss_56.npz", N=2, K=6, H=56, W=56, seed=22, image_size=(224, 224), hm=hm56)
+    metrics_case(ref, "metrics_16.npz", N=48, K=16, seed=31)
+    # the reference's only hand-derivable known answer (utils/SPheatmapParser.py:221-233)
+    kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
+    k, _ = ref.SPheatmapParser.HeatmapParser_SH().parse(kpt_hm.clone(), image_size=(256, 256))
+    np.savez_compressed(os.path.join(OUT, "sp_parser_main.npz"), ref_kpt=k.numpy())
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
