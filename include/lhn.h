@@ -1,0 +1,255 @@
+/*
+ * lhn.h — C ABI of liblhn.so: the B200-native heatmap encode/decode hot path of
+ * Runki2018/litehandnet (render + target-weight MSE loss + heatmap/SimDR decode + PCK/EPE/AUC).
+ *
+ * The reference has no FFI: its boundary is plain Python callables.  Each entry
+ * point below names the reference function(s) whose arithmetic it replaces (file:line relative to
+ * the reference root); the Python mirror in litehandnet_b200/ keeps the reference's names and
+ * signatures and calls these through ctypes with raw device pointers.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless its comment says "host";
+ *   - returns 0 on success, a negative LHN_E* code on a rejected call; never throws, never
+ *     allocates, never synchronises the stream, keeps no global state; re-entrant and thread-safe
+ *     for distinct streams/workspaces;
+ *   - the caller owns every buffer, including the workspace whose size lhn_*_workspace_bytes gives;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream);
+ *   - a "plane" is one H x W slice; heatmap tensors are [B, C, H, W] with the plane contiguous,
+ *     batch stride `stride_b` and channel stride `stride_c` in ELEMENTS (so channel-sliced views
+ *     such as model_output[:, :num_joints] need no copy).  C = S*K for the stacked hourglass shape
+ *     [B, S, K, H, W]; joint k of stack s is channel s*K + k.
+ */
+#ifndef LHN_H_
+#define LHN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LHN_API __attribute__((visibility("default")))
+
+typedef void* lhn_stream_t; /* cudaStream_t */
+
+/* error codes */
+#define LHN_OK 0
+#define LHN_EINVAL (-1)      /* bad shape / null pointer / bad enum */
+#define LHN_EDTYPE (-2)      /* unsupported dtype */
+#define LHN_EALIGN (-3)      /* pointer not aligned as required */
+#define LHN_EWORKSPACE (-4)  /* workspace too small */
+#define LHN_ECUDA (-5)       /* launch failed; see lhn_last_cuda_error() */
+
+/* element types of heatmaps / vectors */
+#define LHN_F32 0
+#define LHN_BF16 1
+#define LHN_F16 2
+#define LHN_F64 3 /* metrics inputs only */
+
+/* argmax masking convention */
+#define LHN_MASK_NONE 0 /* A4: result_parser.py:76-90, SPheatmapParser.py:44-56 (topk k=1) */
+#define LHN_MASK_ZERO 1 /* A1/A3: evaluation.py:62-89, transforms.py:47-75 (coords*0 if max<=0) */
+#define LHN_MASK_NEG1 2 /* A2: top_down_eval.py:199-231 (coords=-1 if max<=0) */
+
+/* sub-pixel refinement */
+#define LHN_REFINE_NONE 0
+#define LHN_REFINE_OFFSET_HALF 1 /* D1: heatmap_post_processing.py:6-33 (+-0.25 clamped, then +0.5) */
+#define LHN_REFINE_OFFSET 2      /* D2: SPheatmapParser.py:140-167, HeatmapParser.py:197-223 */
+#define LHN_REFINE_SIGN 3        /* D3: top_down_eval.py:440-452 (guarded, sign(0)=0) */
+#define LHN_REFINE_SIGN_ROUND 4  /* D4: transforms.py:18-44 (px=floor(x+0.5)) */
+#define LHN_REFINE_DARK 5        /* D5: top_down_eval.py:233-272,338-372,433-439 (f32 blur) */
+#define LHN_REFINE_DARK_LEGACY 6 /* D6: heatmap_post_processing.py:35-91 (f64 blur, +1e-6) */
+
+/* heatmap -> image coordinates */
+#define LHN_XFORM_NONE 0
+#define LHN_XFORM_CENTER_SCALE 1 /* T1: post_transforms.py:6-48 transform_preds */
+#define LHN_XFORM_SCALE 2        /* T2: coords * (scale_x, scale_y) — SPheatmapParser.py:203,
+                                    result_parser.py:248, evaluation.py:34-36 */
+
+/* loss reductions */
+#define LHN_LOSS_NONE 0
+#define LHN_LOSS_DISTANCE 1         /* L1: DistanceLoss L2 balance=False, heatmapLoss.py:242-265 */
+#define LHN_LOSS_DISTANCE_BALANCE 2 /* L2: DistanceLoss L2 balance=True */
+#define LHN_LOSS_JOINTS_MSE 3       /* L3: JointsDistanceLoss mse, heatmapLoss.py:195-225 */
+
+#define LHN_MAX_TAPS 31
+#define LHN_MAX_STACKS 8
+
+/* Decode parameters. */
+typedef struct {
+  int32_t mask_mode;  /* LHN_MASK_* */
+  int32_t refine;     /* LHN_REFINE_* */
+  int32_t transform;  /* LHN_XFORM_* */
+  int32_t use_udp;    /* T1: divide by (W-1),(H-1) instead of W,H (post_transforms.py:37-39) */
+  int32_t blur_ksize; /* DARK Gaussian kernel size (odd, 3..31): 11 for D5, 19 for D6 */
+  int32_t reserved;
+  float scale_x, scale_y;         /* LHN_XFORM_SCALE factors */
+  double taps[LHN_MAX_TAPS];      /* cv2.getGaussianKernel(blur_ksize, 0) in double; host fills it
+                                     with lhn_gaussian_taps() */
+} lhn_decode_params;
+
+/* Render + loss parameters (fused op and lhn_render_targets). */
+typedef struct {
+  int32_t loss_mode;    /* LHN_LOSS_* (LHN_LOSS_NONE = decode only) */
+  int32_t unbiased;     /* 1: R1 sub-pixel full-plane Gaussian, generateTarget.py:100-123;
+                           0: R2 integer-centre (2*3*sigma+1)^2 patch, generateTarget.py:124-154 */
+  int32_t num_stacks;   /* S >= 1 (R3: sigma list -> [B,S,K,H,W], generateTarget.py:252-268) */
+  int32_t reserved;
+  float image_w, image_h;        /* cfg image_size; feat_stride = image_size / [W, H] */
+  float pos_value;               /* DistanceLoss `value` (0.5): positives are target > value */
+  float sigma[LHN_MAX_STACKS];   /* per stack */
+} lhn_render_params;
+
+/* ---- host helpers ------------------------------------------------------------------------- */
+
+/* Library/ABI version (major*100 + minor). */
+LHN_API int lhn_version(void);
+/* Text of the last CUDA error seen by this thread's failed launch (host pointer, static storage). */
+LHN_API const char* lhn_last_cuda_error(void);
+/* Fill taps[0..ksize) with cv2.getGaussianKernel(ksize, sigma<=0, CV_64F) (host pointer). */
+LHN_API int lhn_gaussian_taps(int ksize, double* taps);
+
+/* ---- K1: heatmap decode, optionally fused with target render + masked MSE partial sums -------
+ *
+ * Replaces, in ONE pass over each heatmap plane:
+ *   decode : _get_max_preds / get_coordinates_from_heatmap / get_max_preds / topk(k=1) (A1-A4),
+ *            the +-0.25 rules and DARK (D1-D6), flip_back + averaging (F1/F2: transforms.py:78-92),
+ *            transform_preds (T1) or the plain scale (T2);
+ *   render : TopDownGenerateTarget._msra_generate_target (R1/R2/R3) evaluated in registers;
+ *   loss   : the per-plane sums of DistanceLoss / JointsDistanceLoss (L1-L3) against that target.
+ *
+ * hm            [B, C, H, W] dtype (C = S*K), strides in elements.
+ * hm_flip       same layout or NULL; when given the kernel decodes
+ *               (hm[b,c] + hm_flip[b, s*K+flip_index[k], :, ::-1]) * 0.5 (f32).
+ * flip_index    int32 [K] or NULL (identity).
+ * center, scale f32 [B,2] (T1) or NULL.
+ * out_hm        f32 [B*C, 3] (x, y, maxval) in heatmap space, or NULL.
+ * out_kpts      f32 [B*C, 3] (X, Y, maxval) after the transform, or NULL.
+ * out_idx       int32 [B*C] first-maximal flat index (NaN counts as maximal), or NULL.
+ * Render/loss inputs (ignored when rp == NULL or rp->loss_mode == LHN_LOSS_NONE):
+ * joints        f32 [B, K, joints_stride] (x, y in image pixels in columns 0,1).
+ * vis           f32 [B, K, vis_stride] (column 0 = visibility / weight).
+ * out_weight    f32 [B*C] target_weight after the visibility rule, or NULL.
+ * partials      f64 [B*C, 4] per-plane (w^p*S_pos, w^p*S_neg, N_pos, H*W); reduce with
+ *               lhn_loss_reduce + lhn_loss_finalize.  The loss is taken on `hm` (not the flip
+ *               average), as the training loss is.
+ */
+LHN_API int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int32_t* flip_index,
+                               int dtype, int64_t B, int K, int H, int W,
+                               int64_t stride_b, int64_t stride_c,
+                               int64_t flip_stride_b, int64_t flip_stride_c,
+                               const float* center, const float* scale,
+                               const lhn_decode_params* dp,
+                               float* out_hm, float* out_kpts, int32_t* out_idx,
+                               const lhn_render_params* rp,
+                               const float* joints, int joints_stride,
+                               const float* vis, int vis_stride,
+                               float* out_weight, double* partials,
+                               lhn_stream_t stream);
+
+/* ---- loss against an explicit target tensor (the un-fused drop-in) ----------------------------
+ * DistanceLoss.forward(output, target, target_weight) / JointsDistanceLoss.forward
+ * (heatmapLoss.py:242-265, :195-225).  output/target [P, HW] contiguous planes (any leading
+ * dims flattened), weight f32 [P].  Writes partials f64 [P,4] as above (pos = target > pos_value).
+ */
+LHN_API int lhn_loss_partials(const void* output, const void* target, const float* weight,
+                              int dtype, int64_t n_planes, int64_t plane_elems, int loss_mode,
+                              float pos_value, double* partials, lhn_stream_t stream);
+
+/* Deterministic fixed-order reduction of partials[P,4] to sums[4] = (S_pos, S_neg, N_pos, numel)
+ * in f64.  `accumulate` != 0 adds into sums (multi-tensor losses), else overwrites. */
+LHN_API int lhn_loss_reduce(const double* partials, int64_t n_planes, double* sums, int accumulate,
+                            lhn_stream_t stream);
+
+/* loss[0] (f32) = scale * f(sums):
+ *   LHN_LOSS_DISTANCE          (S_pos+S_neg)/numel                       (reduction='mean')
+ *   LHN_LOSS_DISTANCE_BALANCE  0.1*S_pos/(N_pos+1) + S_neg/(N_neg+1)
+ *   LHN_LOSS_JOINTS_MSE        0.5*(S_pos+S_neg)/numel
+ * sum_reduction != 0 multiplies by numel (reduction='sum').  `accumulate` adds into loss[0]. */
+LHN_API int lhn_loss_finalize(const double* sums, int loss_mode, int sum_reduction, float scale,
+                              float* loss, int accumulate, lhn_stream_t stream);
+
+/* ---- render (the un-fused drop-in; write-bound) -----------------------------------------------
+ * TopDownGenerateTarget (generateTarget.py:100-154,245-300) for a batch: target f32
+ * [B, S, K, H, W] contiguous, target_weight f32 [B, S, K]. */
+LHN_API int lhn_render_targets(const float* joints, int joints_stride, const float* vis,
+                               int vis_stride, int64_t B, int K, int H, int W,
+                               const lhn_render_params* rp, float* target, float* target_weight,
+                               lhn_stream_t stream);
+
+/* GenerateSimDR._generate_sa_simdr (generate_simder.py:9-31): simdr_x f32 [B,K,Lx],
+ * simdr_y f32 [B,K,Ly]; Lx = int(image_w*k), Ly = int(image_h*k). */
+LHN_API int lhn_render_simdr(const float* joints, int joints_stride, const float* vis,
+                             int vis_stride, int64_t B, int K, int Lx, int Ly, float split_ratio,
+                             float sigma, float* simdr_x, float* simdr_y, lhn_stream_t stream);
+
+/* ---- K2: SimDR --------------------------------------------------------------------------------
+ * keypoints_from_simdr (top_down_eval.py:466-500): x = argmax(x_vec)/k, y = argmax(y_vec)/k,
+ * score = (max_x+max_y)/2, transform_preds with output_size [Lx//k, Ly//k] (center==NULL: none).
+ * With `nms` != 0 applies ResultParser.vector_nms (result_parser.py:61-74) first and, when
+ * `ranges` (int32 [B,4] = x1,x2,y1,y2 bins) is given, the bbox mask of
+ * get_coordinates_from_vectors (result_parser.py:92-129) — without mutating the inputs.
+ * out f32 [B*K,3]; out_idx int32 [B*K,2] or NULL. */
+LHN_API int lhn_decode_simdr(const void* x_vec, const void* y_vec, int dtype, int64_t B, int K,
+                             int Lx, int Ly, int split_ratio, const float* center,
+                             const float* scale, int nms, const int32_t* ranges, float* out,
+                             int32_t* out_idx, lhn_stream_t stream);
+
+/* KLDiscretLoss.forward (centernet_simdr_loss.py:27-39): per-joint SmoothL1(beta=1) sums.
+ * out/target [B,K,L*]; weight f32 [B,K]; joint_sums f64 [K,3] = (sum_x, sum_y, sum_w) must be
+ * zeroed by the caller (the kernel adds per-(b,k) partials in a fixed order per joint).
+ * loss[0] = (1/K) sum_j (sum_x/(B*Lx) + sum_y/(B*Ly)) * (sum_w/B). */
+LHN_API int64_t lhn_simdr_loss_workspace_bytes(int64_t B, int K);
+LHN_API int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const void* tgt_x,
+                               const void* tgt_y, const float* weight, int dtype, int64_t B, int K,
+                               int Lx, int Ly, void* workspace, int64_t workspace_bytes, float* loss,
+                               lhn_stream_t stream);
+
+/* ---- K3: metrics ------------------------------------------------------------------------------
+ * _calc_distances + _distance_acc (top_down_eval.py:12-62) as shardable counters.
+ * pred [N,K,pred_stride] / gt [N,K,gt_stride] (x,y in columns 0,1), dtype f32 or f64 each;
+ * mask uint8 [N,K]; normalize [N,2] (norm_dtype) or NULL -> the constant `norm_const` on both
+ * axes.  The distance is computed in f64 unless pred, gt and normalize are all f32 (numpy
+ * promotion), rounded to f32 and compared with (float)thr[t].
+ * counters int64 [(T+2)*K]: hits[t][k] (t<T), valid[k], dist_fix[k] = sum of valid distances
+ * in 2^-20 fixed point.  ADDS into counters (zero them first; all-reduce them across ranks
+ * with ncclSum for the sharded evaluation — SURVEY §8e). */
+LHN_API int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_stride, const void* gt,
+                               int gt_dtype, int gt_stride, const uint8_t* mask,
+                               const void* normalize, int norm_dtype, double norm_const, int64_t N,
+                               int K, const float* thr /* host, T floats */, int T,
+                               int64_t* counters, lhn_stream_t stream);
+
+/* Fused decode + metrics counters for the sharded evaluation (BASELINE config 4): as
+ * lhn_decode_heatmap (decode only) and, per plane, the three _report_metric accumulations
+ * (base_dataset.py:193-261): PCK@pck_thr / max(bbox w,h), AUC thresholds i/auc_steps / auc_nor,
+ * EPE.  gt f32 [B,K,2], mask uint8 [B,K], bbox_wh f32 [B,2].
+ * counters int64 [(1 + auc_steps + 4) * K] laid out as
+ *   pck_hits[K], pck_valid[K], auc_hits[auc_steps][K], auc_valid[K], epe_valid[K], epe_fix[K]. */
+LHN_API int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, int H, int W,
+                                   int64_t stride_b, int64_t stride_c, const float* center,
+                                   const float* scale, const lhn_decode_params* dp, float* out_hm,
+                                   float* out_kpts, int32_t* out_idx, const float* gt,
+                                   const uint8_t* mask, const float* bbox_wh, float pck_thr,
+                                   float auc_nor, int auc_steps, int64_t* counters,
+                                   lhn_stream_t stream);
+
+/* evaluate_pck (evaluation.py:10-59): argmax (A1) on pred and gt heatmap batches [B,K,H,W],
+ * * image_size/[W,H], distance / max(bbox[:,0,2:]), per-image hits/(2*sum w)*2 in f32.
+ * bbox_wh f32 [B,2]; weight f32 [B,K] or NULL (ones).  pck_per_image f32 [B]; mean_out f64 [1]
+ * = mean over images (np.mean), NaN if an image has no weight, as the reference. */
+LHN_API int64_t lhn_evaluate_pck_workspace_bytes(int64_t B, int K);
+LHN_API int lhn_evaluate_pck(const void* pred_hm, const void* gt_hm, int dtype, int64_t B, int K,
+                             int H, int W, const float* bbox_wh, const float* weight,
+                             float image_w, float image_h, float thr, void* workspace,
+                             int64_t workspace_bytes, float* pck_per_image, double* mean_out,
+                             lhn_stream_t stream);
+
+/* flip_back (transforms.py:78-92) materialised: out[b,k,y,x] = in[b,flip_index[k],y,W-1-x]. */
+LHN_API int lhn_flip_back(const void* in, void* out, int dtype, int64_t B, int K, int H, int W,
+                          const int32_t* flip_index, lhn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LHN_H_ */

@@ -1,0 +1,326 @@
+// Un-fused drop-ins: masked MSE against an explicit target tensor, the deterministic loss
+// reduction/finalisation, batched Gaussian target rendering (2-D and SimDR 1-D) and flip_back.
+// All are single-pass, 128-bit vectorised streaming kernels; grids are sized as multiples of the
+// SM count with grid-stride loops.
+#include <math_constants.h>
+
+#include "lhn_common.cuh"
+
+namespace lhn {
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms = n > 0 ? n : 148;
+  }
+  return g_num_sms;
+}
+
+// ---- loss partials against an explicit target (heatmapLoss.py:242-265, :195-225) -------------
+// one warp per plane: 2 streams of 128-bit loads, no shared memory needed
+template <typename T>
+__global__ void __launch_bounds__(256) loss_partials_kernel(const T* __restrict__ out,
+                                                            const T* __restrict__ tgt,
+                                                            const float* __restrict__ weight,
+                                                            int64_t n_planes, int64_t HW,
+                                                            int loss_mode, float pos_value,
+                                                            double* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (HW & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tgt)) % (4 * sizeof(T)) == 0);
+  for (int64_t p = warp_global; p < n_planes; p += nwarps) {
+    const T* o = out + p * HW;
+    const T* t = tgt + p * HW;
+    float sp0 = 0.f, sp1 = 0.f, sn0 = 0.f, sn1 = 0.f;
+    int npos = 0;
+    if (vec) {
+      const int64_t nq = HW >> 2;
+#pragma unroll 4
+      for (int64_t q = lane; q < nq; q += 32) {
+        const float4 a = ldg_stream4<T>(o + 4 * q);
+        const float4 g = ldg_stream4<T>(t + 4 * q);
+        const float d0 = a.x - g.x, d1 = a.y - g.y, d2 = a.z - g.z, d3 = a.w - g.w;
+        const float l0 = d0 * d0, l1 = d1 * d1, l2 = d2 * d2, l3 = d3 * d3;
+        const bool p0 = g.x > pos_value, p1 = g.y > pos_value, p2 = g.z > pos_value, p3 = g.w > pos_value;
+        sp0 += p0 ? l0 : 0.f; sn0 += p0 ? 0.f : l0;
+        sp1 += p1 ? l1 : 0.f; sn1 += p1 ? 0.f : l1;
+        sp0 += p2 ? l2 : 0.f; sn0 += p2 ? 0.f : l2;
+        sp1 += p3 ? l3 : 0.f; sn1 += p3 ? 0.f : l3;
+        npos += (int)p0 + (int)p1 + (int)p2 + (int)p3;
+      }
+    } else {
+      for (int64_t e = lane; e < HW; e += 32) {
+        const float a = Elem<T>::to_f32(o[e]), g = Elem<T>::to_f32(t[e]);
+        const float d = a - g, l = d * d;
+        const bool pp = g > pos_value;
+        sp0 += pp ? l : 0.f; sn0 += pp ? 0.f : l; npos += (int)pp;
+      }
+    }
+    double sp = warp_sum((double)sp0 + (double)sp1);
+    double sn = warp_sum((double)sn0 + (double)sn1);
+    npos = __reduce_add_sync(0xffffffffu, npos);
+    if (lane == 0) {
+      const float w = weight[p];
+      const double wp = (loss_mode == LHN_LOSS_JOINTS_MSE) ? (double)(w * w) : (double)w;
+      double* dst = partials + 4 * p;
+      if (loss_mode == LHN_LOSS_DISTANCE_BALANCE) { dst[0] = sp * wp; dst[1] = sn * wp; dst[2] = (double)npos; }
+      else { dst[0] = 0.0; dst[1] = (sp + sn) * wp; dst[2] = 0.0; }
+      dst[3] = (double)HW;
+    }
+  }
+}
+
+// ---- deterministic reduction: one block, fixed strided order, f64 ------------------------------
+__global__ void __launch_bounds__(1024) loss_reduce_kernel(const double* __restrict__ partials,
+                                                           int64_t n_planes, double* __restrict__ sums,
+                                                           int accumulate) {
+  __shared__ double red[4][32];
+  double acc[4] = {0, 0, 0, 0};
+  for (int64_t p = threadIdx.x; p < n_planes; p += blockDim.x) {
+    const double4 v = *reinterpret_cast<const double4*>(partials + 4 * p);
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double v = warp_sum(acc[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double v = lane < (blockDim.x >> 5) ? red[i][lane] : 0.0;
+      v = warp_sum(v);
+      if (lane == 0) sums[i] = accumulate ? sums[i] + v : v;
+    }
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, int loss_mode, int sum_reduction,
+                                     float scale, float* __restrict__ loss, int accumulate) {
+  const double sp = sums[0], sn = sums[1], npos = sums[2], numel = sums[3];
+  double v;
+  if (loss_mode == LHN_LOSS_DISTANCE_BALANCE) v = 0.1 * sp / (npos + 1.0) + sn / (numel - npos + 1.0);
+  else if (loss_mode == LHN_LOSS_JOINTS_MSE) v = 0.5 * (sp + sn) / numel;
+  else v = (sp + sn) / numel;
+  if (sum_reduction) v *= numel;
+  const float r = (float)(v * (double)scale);
+  loss[0] = accumulate ? loss[0] + r : r;
+}
+
+// ---- batched target rendering (generateTarget.py:100-154) --------------------------------------
+// One CTA per plane: the separable factors are evaluated in f64 (as NumPy>=2 does for the
+// unbiased branch), the plane is written with 128-bit stores.
+struct RenderArgs {
+  const float* joints; int joints_stride;
+  const float* vis; int vis_stride;
+  int64_t n_planes;
+  int S, K, H, W;
+  int unbiased;
+  double feat_x, feat_y;
+  float sigma[LHN_MAX_STACKS];
+  float* target; float* target_weight;
+};
+
+__global__ void __launch_bounds__(128) render_targets_kernel(const __grid_constant__ RenderArgs a) {
+  extern __shared__ float tab[];   // ex[W], ey[H]
+  const int W = a.W, H = a.H;
+  float* ex = tab; float* ey = tab + W;
+  const int64_t p = blockIdx.x;
+  const int C = a.S * a.K;
+  const int64_t b = p / C;
+  const int c = (int)(p - b * C);
+  const int s = c / a.K, k = c - s * a.K;
+  const float* jp = a.joints + (b * a.K + k) * (int64_t)a.joints_stride;
+  float w = a.vis[(b * a.K + k) * (int64_t)a.vis_stride];
+  const double sig = (double)a.sigma[s], tmp = sig * 3.0;
+  double mux = (double)jp[0] / a.feat_x, muy = (double)jp[1] / a.feat_y;
+  double x0p = 0, ulx, uly, brx, bry;
+  if (a.unbiased) { ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1; }
+  else {
+    mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);
+    ulx = trunc(mux - tmp); uly = trunc(muy - tmp); brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
+    x0p = floor((2 * tmp + 1) * 0.5);
+  }
+  if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
+  const bool on = w > 0.5f;
+  const double inv2s2 = 1.0 / (2.0 * sig * sig);
+  for (int i = threadIdx.x; i < W + H; i += blockDim.x) {
+    const bool isx = i < W;
+    const int pos = isx ? i : i - W;
+    float v = 0.f;
+    if (on) {
+      if (a.unbiased) { double d = (double)pos - (isx ? mux : muy); v = (float)exp(-(d * d) * inv2s2); }
+      else {
+        double ul = isx ? ulx : uly, br = isx ? brx : bry;
+        if ((double)pos >= ul && (double)pos < br) { double d = ((double)pos - ul) - x0p; v = (float)exp(-(d * d) * inv2s2); }
+      }
+    }
+    tab[i] = v;
+  }
+  __syncthreads();
+  float* dst = a.target + p * (int64_t)H * W;
+  if ((W & 3) == 0) {
+    const int QR = W >> 2, nq = (H * W) >> 2;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+      const int row = q / QR, cq = q - row * QR;
+      const float4 gx = *reinterpret_cast<const float4*>(ex + 4 * cq);
+      const float gy = ey[row];
+      *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(gx.x * gy, gx.y * gy, gx.z * gy, gx.w * gy);
+    }
+  } else {
+    for (int e = threadIdx.x; e < H * W; e += blockDim.x) dst[e] = ex[e % W] * ey[e / W];
+  }
+  if (threadIdx.x == 0) a.target_weight[p] = w;
+}
+
+// ---- SimDR target (generate_simder.py:9-31): f32 arithmetic throughout ---------------------------
+__global__ void __launch_bounds__(128) render_simdr_kernel(const float* __restrict__ joints, int js,
+                                                           const float* __restrict__ vis, int vs,
+                                                           int64_t n_bk, int Lx, int Ly, float kf,
+                                                           float sigma, float* __restrict__ sx,
+                                                           float* __restrict__ sy) {
+  const int64_t bk = blockIdx.x;
+  if (bk >= n_bk) return;
+  const bool on = vis[bk * vs] > 0.f;
+  const float mux = __fmul_rn(joints[bk * js], kf), muy = __fmul_rn(joints[bk * js + 1], kf);
+  const float den = 2.f * sigma * sigma;
+  float* dx = sx + bk * Lx; float* dy = sy + bk * Ly;
+  for (int i = threadIdx.x; i < Lx + Ly; i += blockDim.x) {
+    const bool isx = i < Lx;
+    const int pos = isx ? i : i - Lx;
+    float v = 0.f;
+    if (on) {
+      const float d = __fsub_rn((float)pos, isx ? mux : muy);
+      v = (float)exp((double)__fdiv_rn(-__fmul_rn(d, d), den));   // f32 argument, exp rounded once
+    }
+    if (isx) dx[pos] = v; else dy[pos] = v;
+  }
+}
+
+// ---- flip_back (transforms.py:78-92) --------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) flip_back_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                        int64_t n_planes, int K, int H, int W,
+                                                        const int32_t* __restrict__ flip_index) {
+  const int64_t total = n_planes * H * W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(e % W);
+    const int64_t r = e / W;
+    const int y = (int)(r % H);
+    const int64_t p = r / H;
+    const int k = (int)(p % K);
+    const int64_t b = p / K;
+    const int ks = flip_index ? flip_index[k] : k;
+    out[e] = in[((b * K + ks) * H + y) * (int64_t)W + (W - 1 - x)];
+  }
+}
+
+}  // namespace lhn
+
+using namespace lhn;
+
+extern "C" int lhn_loss_partials(const void* output, const void* target, const float* weight,
+                                 int dtype, int64_t n_planes, int64_t plane_elems, int loss_mode,
+                                 float pos_value, double* partials, lhn_stream_t stream) {
+  if (!output || !target || !weight || !partials || n_planes < 0 || plane_elems <= 0 ||
+      loss_mode < 1 || loss_mode > 3)
+    return LHN_EINVAL;
+  if (n_planes == 0) return LHN_OK;
+  const int threads = 256;
+  int64_t blocks_needed = (n_planes * 32 + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * 8;
+  int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case LHN_F32:
+      loss_partials_kernel<float><<<blocks, threads, 0, st>>>((const float*)output, (const float*)target,
+          weight, n_planes, plane_elems, loss_mode, pos_value, partials);
+      break;
+    case LHN_BF16:
+      loss_partials_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)output,
+          (const __nv_bfloat16*)target, weight, n_planes, plane_elems, loss_mode, pos_value, partials);
+      break;
+    case LHN_F16:
+      loss_partials_kernel<__half><<<blocks, threads, 0, st>>>((const __half*)output, (const __half*)target,
+          weight, n_planes, plane_elems, loss_mode, pos_value, partials);
+      break;
+    default: return LHN_EDTYPE;
+  }
+  return check_launch();
+}
+
+extern "C" int lhn_loss_reduce(const double* partials, int64_t n_planes, double* sums, int accumulate,
+                               lhn_stream_t stream) {
+  if (!partials || !sums || n_planes < 0) return LHN_EINVAL;
+  if ((uintptr_t)partials % 32) return LHN_EALIGN;
+  loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_planes, sums, accumulate);
+  return check_launch();
+}
+
+extern "C" int lhn_loss_finalize(const double* sums, int loss_mode, int sum_reduction, float scale,
+                                 float* loss, int accumulate, lhn_stream_t stream) {
+  if (!sums || !loss || loss_mode < 1 || loss_mode > 3) return LHN_EINVAL;
+  loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, loss_mode, sum_reduction, scale, loss, accumulate);
+  return check_launch();
+}
+
+extern "C" int lhn_render_targets(const float* joints, int joints_stride, const float* vis,
+                                  int vis_stride, int64_t B, int K, int H, int W,
+                                  const lhn_render_params* rp, float* target, float* target_weight,
+                                  lhn_stream_t stream) {
+  if (!joints || !vis || !rp || !target || !target_weight || B < 0 || K <= 0 || H <= 0 || W <= 0 ||
+      joints_stride < 2 || vis_stride < 1 || rp->image_w <= 0 || rp->image_h <= 0)
+    return LHN_EINVAL;
+  const int S = rp->num_stacks > 0 ? rp->num_stacks : 1;
+  if (S > LHN_MAX_STACKS) return LHN_EINVAL;
+  if ((uintptr_t)target % 16) return LHN_EALIGN;
+  RenderArgs a{};
+  a.joints = joints; a.joints_stride = joints_stride; a.vis = vis; a.vis_stride = vis_stride;
+  a.S = S; a.K = K; a.H = H; a.W = W; a.unbiased = rp->unbiased;
+  a.n_planes = B * S * K;
+  a.feat_x = (double)rp->image_w / W; a.feat_y = (double)rp->image_h / H;
+  for (int i = 0; i < S; ++i) { if (!(rp->sigma[i] > 0.f)) return LHN_EINVAL; a.sigma[i] = rp->sigma[i]; }
+  a.target = target; a.target_weight = target_weight;
+  if (a.n_planes == 0) return LHN_OK;
+  if (a.n_planes > 0x7fffffffLL) return LHN_EINVAL;
+  size_t smem = (size_t)(W + H) * sizeof(float);
+  render_targets_kernel<<<(unsigned)a.n_planes, 128, smem, (cudaStream_t)stream>>>(a);
+  return check_launch();
+}
+
+extern "C" int lhn_render_simdr(const float* joints, int joints_stride, const float* vis,
+                                int vis_stride, int64_t B, int K, int Lx, int Ly, float split_ratio,
+                                float sigma, float* simdr_x, float* simdr_y, lhn_stream_t stream) {
+  if (!joints || !vis || !simdr_x || !simdr_y || B < 0 || K <= 0 || Lx <= 0 || Ly <= 0 ||
+      joints_stride < 2 || vis_stride < 1 || !(sigma > 0.f))
+    return LHN_EINVAL;
+  const int64_t n = B * K;
+  if (n == 0) return LHN_OK;
+  if (n > 0x7fffffffLL) return LHN_EINVAL;
+  render_simdr_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(joints, joints_stride, vis, vis_stride,
+      n, Lx, Ly, split_ratio, sigma, simdr_x, simdr_y);
+  return check_launch();
+}
+
+extern "C" int lhn_flip_back(const void* in, void* out, int dtype, int64_t B, int K, int H, int W,
+                             const int32_t* flip_index, lhn_stream_t stream) {
+  if (!in || !out || B < 0 || K <= 0 || H <= 0 || W <= 0) return LHN_EINVAL;
+  const int64_t n_planes = B * K, total = n_planes * H * W;
+  if (total == 0) return LHN_OK;
+  int64_t need = (total + 255) / 256, cap = (int64_t)num_sms() * 16;
+  int blocks = (int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LHN_F32)
+    flip_back_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, (float*)out, n_planes, K, H, W, flip_index);
+  else if (dtype == LHN_BF16 || dtype == LHN_F16)
+    flip_back_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, n_planes, K, H, W, flip_index);
+  else return LHN_EDTYPE;
+  return check_launch();
+}

@@ -1,0 +1,186 @@
+// K3 — PCK / AUC / EPE accumulation as shardable integer counters, and the legacy evaluate_pck.
+// The arithmetic of _calc_distances is reproduced in the dtype numpy would promote to (f64 unless
+// every input is f32), rounded to f32 and compared with the f32 threshold, so hit counts are
+// bit-exact; counters are int64 and order-independent, hence identical for any sharding.
+#include <math_constants.h>
+
+#include "lhn_common.cuh"
+
+namespace lhn {
+int num_sms();
+
+constexpr int kMaxThr = 64;
+
+struct PckArgs {
+  const void* pred; int pred_dtype, pred_stride;
+  const void* gt; int gt_dtype, gt_stride;
+  const uint8_t* mask;
+  const void* normalize; int norm_dtype;
+  double norm_const;
+  int64_t N; int K, T;
+  float thr[kMaxThr];
+  int all_f32;
+  unsigned long long* counters;
+};
+
+__device__ __forceinline__ double ld_as_f64(const void* p, int dtype, int64_t i) {
+  return dtype == LHN_F64 ? reinterpret_cast<const double*>(p)[i] : (double)reinterpret_cast<const float*>(p)[i];
+}
+
+// block-local counters in shared memory, flushed once per block
+__global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_constant__ PckArgs a) {
+  extern __shared__ unsigned long long sc[];   // (T+2)*K
+  const int K = a.K, T = a.T;
+  const int ncnt = (T + 2) * K;
+  for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sc[i] = 0ull;
+  __syncthreads();
+  const int64_t total = a.N * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = e / K;
+    const int k = (int)(e - n * K);
+    if (!a.mask[e]) continue;
+    double nx = a.norm_const, ny = a.norm_const;
+    if (a.normalize) { nx = ld_as_f64(a.normalize, a.norm_dtype, 2 * n); ny = ld_as_f64(a.normalize, a.norm_dtype, 2 * n + 1); }
+    if (nx == 0.0 || ny == 0.0) continue;              // _mask[normalize==0 rows] = False
+    if (nx < 0.0) nx = 1e6;                            // normalize[normalize<=0] = 1e6
+    if (ny < 0.0) ny = 1e6;
+    const double px = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride);
+    const double py = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride + 1);
+    const double gx = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride);
+    const double gy = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride + 1);
+    float d;
+    if (a.all_f32) {
+      const float qx = __fdiv_rn(__fsub_rn((float)px, (float)gx), (float)nx);
+      const float qy = __fdiv_rn(__fsub_rn((float)py, (float)gy), (float)ny);
+      d = __fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)));
+    } else {
+      const double qx = __ddiv_rn(__dsub_rn(px, gx), nx), qy = __ddiv_rn(__dsub_rn(py, gy), ny);
+      d = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
+    }
+    atomicAdd(&sc[T * K + k], 1ull);
+    if (d == d) atomicAdd(&sc[(T + 1) * K + k], (unsigned long long)llrint((double)d * 1048576.0));
+    for (int t = 0; t < T; ++t)
+      if (d < a.thr[t]) atomicAdd(&sc[t * K + k], 1ull);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncnt; i += blockDim.x)
+    if (sc[i]) atomicAdd(a.counters + i, sc[i]);
+}
+
+// ---- legacy evaluate_pck (evaluation.py:10-59): per-image reduction over the decoded joints -----
+// pk/gk: [B*K,3] (x*fx, y*fy, maxval) already scaled (A1 + T2 from the heatmap kernel).
+__global__ void __launch_bounds__(128) evaluate_pck_image_kernel(const float* __restrict__ pk,
+                                                                 const float* __restrict__ gk,
+                                                                 const float* __restrict__ bbox_wh,
+                                                                 const float* __restrict__ weight,
+                                                                 int64_t B, int K, float thr,
+                                                                 float* __restrict__ pck) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const float max_wh = fmaxf(bbox_wh[2 * b], bbox_wh[2 * b + 1]);
+  int hits = 0;
+  float wsum = 0.f;   // sum over the doubled [K,2] weight, f32 like torch
+  for (int k = lane; k < K; k += 32) {
+    const float w = weight ? weight[b * K + k] : 1.f;
+    wsum += w;
+    if (w == 1.f) {
+      const float* p = pk + 3 * (b * K + k);
+      const float* g = gk + 3 * (b * K + k);
+      const float dx = __fsub_rn(p[0], g[0]), dy = __fsub_rn(p[1], g[1]);
+      // torch.norm accumulates in double on CPU; coordinates are small integers * stride
+      const float dist = (float)sqrt((double)dx * dx + (double)dy * dy);
+      if (__fdiv_rn(dist, max_wh) < thr) hits += 1;
+    }
+  }
+  hits = __reduce_add_sync(0xffffffffu, hits);
+  wsum = warp_sum(wsum);
+  if (lane == 0) pck[b] = __fmul_rn(__fdiv_rn((float)hits, __fmul_rn(wsum, 2.f)), 2.f);
+}
+
+__global__ void __launch_bounds__(1024) mean_f32_to_f64_kernel(const float* __restrict__ v, int64_t n,
+                                                               double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t / (double)n;
+  }
+}
+
+}  // namespace lhn
+
+using namespace lhn;
+
+extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_stride, const void* gt,
+                                  int gt_dtype, int gt_stride, const uint8_t* mask,
+                                  const void* normalize, int norm_dtype, double norm_const, int64_t N,
+                                  int K, const float* thr, int T, int64_t* counters,
+                                  lhn_stream_t stream) {
+  if (!pred || !gt || !mask || !counters || N < 0 || K <= 0 || T < 0 || T > kMaxThr ||
+      pred_stride < 2 || gt_stride < 2 || (T > 0 && !thr))
+    return LHN_EINVAL;
+  auto okdt = [](int d) { return d == LHN_F32 || d == LHN_F64; };
+  if (!okdt(pred_dtype) || !okdt(gt_dtype) || (normalize && !okdt(norm_dtype))) return LHN_EDTYPE;
+  if (N == 0) return LHN_OK;
+  PckArgs a{};
+  a.pred = pred; a.pred_dtype = pred_dtype; a.pred_stride = pred_stride;
+  a.gt = gt; a.gt_dtype = gt_dtype; a.gt_stride = gt_stride;
+  a.mask = mask; a.normalize = normalize; a.norm_dtype = norm_dtype; a.norm_const = norm_const;
+  a.N = N; a.K = K; a.T = T;
+  for (int i = 0; i < T; ++i) a.thr[i] = thr[i];
+  // numpy promotion: f32 only if every array operand is f32 (a python-float constant is f64)
+  a.all_f32 = pred_dtype == LHN_F32 && gt_dtype == LHN_F32 && normalize && norm_dtype == LHN_F32;
+  a.counters = reinterpret_cast<unsigned long long*>(counters);
+  const int threads = 256;
+  int64_t need = (N * K + threads - 1) / threads, cap = (int64_t)num_sms() * 4;
+  int blocks = (int)(need < cap ? need : cap);
+  size_t smem = (size_t)(T + 2) * K * sizeof(unsigned long long);
+  if (smem > 48 * 1024) return LHN_EINVAL;
+  pck_accumulate_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  return check_launch();
+}
+
+extern "C" int64_t lhn_evaluate_pck_workspace_bytes(int64_t B, int K) {
+  if (B < 0 || K <= 0) return LHN_EINVAL;
+  return 2 * B * K * 3 * (int64_t)sizeof(float);
+}
+
+extern "C" int lhn_evaluate_pck(const void* pred_hm, const void* gt_hm, int dtype, int64_t B, int K,
+                                int H, int W, const float* bbox_wh, const float* weight,
+                                float image_w, float image_h, float thr, void* workspace,
+                                int64_t workspace_bytes, float* pck_per_image, double* mean_out,
+                                lhn_stream_t stream) {
+  if (!pred_hm || !gt_hm || !bbox_wh || !workspace || !pck_per_image || !mean_out || B <= 0 || K <= 0)
+    return LHN_EINVAL;
+  if (workspace_bytes < lhn_evaluate_pck_workspace_bytes(B, K)) return LHN_EWORKSPACE;
+  if ((uintptr_t)workspace % 4) return LHN_EALIGN;
+  float* pk = (float*)workspace;
+  float* gk = pk + B * K * 3;
+  lhn_decode_params dp{};
+  dp.mask_mode = LHN_MASK_ZERO; dp.refine = LHN_REFINE_NONE; dp.transform = LHN_XFORM_SCALE;
+  dp.scale_x = image_w / (float)W; dp.scale_y = image_h / (float)H;   // tensor(image_size)/tensor([w,h])
+  const int64_t HW = (int64_t)H * W;
+  int rc = lhn_decode_heatmap(pred_hm, nullptr, nullptr, dtype, B, K, H, W, K * HW, HW, 0, 0, nullptr,
+                              nullptr, &dp, nullptr, pk, nullptr, nullptr, nullptr, 0, nullptr, 0,
+                              nullptr, nullptr, stream);
+  if (rc) return rc;
+  rc = lhn_decode_heatmap(gt_hm, nullptr, nullptr, dtype, B, K, H, W, K * HW, HW, 0, 0, nullptr,
+                          nullptr, &dp, nullptr, gk, nullptr, nullptr, nullptr, 0, nullptr, 0,
+                          nullptr, nullptr, stream);
+  if (rc) return rc;
+  const int threads = 128;
+  int64_t blocks = (B * 32 + threads - 1) / threads;
+  evaluate_pck_image_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(pk, gk, bbox_wh, weight,
+                                                                                   B, K, thr, pck_per_image);
+  rc = check_launch();
+  if (rc) return rc;
+  mean_f32_to_f64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pck_per_image, B, mean_out);
+  return check_launch();
+}

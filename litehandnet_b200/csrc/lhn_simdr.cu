@@ -1,0 +1,242 @@
+// K2 — SimDR 1-D vector decode (+ optional vector_nms / bbox mask) and the KLDiscretLoss
+// (SmoothL1) sums.  One warp owns one (b, k) pair: the x- and y-vector are streamed with 128-bit
+// coalesced loads, reduced with redux/shuffles; nothing is staged in shared memory because every
+// element is used exactly once (the 3-tap NMS neighbourhood comes from warp shuffles).
+#include <math_constants.h>
+
+#include "lhn_common.cuh"
+
+namespace lhn {
+int num_sms();
+
+// first-max argmax of one vector by one warp; NaN is maximal.
+// NMS: value kept iff it equals max(v[i-1], v[i], v[i+1]) (max_pool1d k=3,s=1,p=1 with -inf
+// padding) else 0; then multiplied by the [lo, hi) mask (result_parser.py:61-74,113-121).
+template <typename T, bool NMS>
+__device__ __forceinline__ void warp_vec_argmax(const T* __restrict__ v, int L, int lo, int hi,
+                                                int lane, uint32_t& out_idx, float& out_val) {
+  uint32_t bkey = 0u, bidx = 0xffffffffu;
+  const bool vec = ((L & 3) == 0) && (reinterpret_cast<uintptr_t>(v) % (4 * sizeof(T)) == 0);
+  if (vec && !NMS) {
+    const int nq = L >> 2;
+    float best = -CUDART_INF_F; bool has_nan = false; uint32_t nan_idx = 0xffffffffu;
+#pragma unroll 4
+    for (int q = lane; q < nq; q += 32) {
+      const float4 a = ldg_stream4<T>(v + 4 * q);
+      const uint32_t e = 4u * q;
+      if (a.x > best) { best = a.x; bidx = e; }
+      if (a.y > best) { best = a.y; bidx = e + 1; }
+      if (a.z > best) { best = a.z; bidx = e + 2; }
+      if (a.w > best) { best = a.w; bidx = e + 3; }
+      if (!has_nan) {
+        if (a.x != a.x) { has_nan = true; nan_idx = e; }
+        else if (a.y != a.y) { has_nan = true; nan_idx = e + 1; }
+        else if (a.z != a.z) { has_nan = true; nan_idx = e + 2; }
+        else if (a.w != a.w) { has_nan = true; nan_idx = e + 3; }
+      }
+    }
+    if (has_nan) { bkey = 0xffffffffu; bidx = nan_idx; }
+    else bkey = order_key(best);
+  } else {
+    // scalar path (also the NMS path: neighbours via an overlapping read)
+    for (int i = lane; i < L; i += 32) {
+      float x = Elem<T>::to_f32(v[i]);
+      if (NMS) {
+        const float l = i > 0 ? Elem<T>::to_f32(v[i - 1]) : -CUDART_INF_F;
+        const float r = i + 1 < L ? Elem<T>::to_f32(v[i + 1]) : -CUDART_INF_F;
+        // torch max_pool1d propagates NaN; eq(NaN, .) is false -> mask 0 -> NaN*0 = NaN
+        float m = fmaxf(fmaxf(l, x), r);
+        if (l != l || x != x || r != r) m = CUDART_NAN_F;
+        x = x * ((m == x) ? 1.f : 0.f);
+        x = x * ((i >= lo && i < hi) ? 1.f : 0.f);
+      }
+      const uint32_t kx = order_key(x);
+      if (bidx == 0xffffffffu || kx > bkey) { bkey = kx; bidx = (uint32_t)i; }
+    }
+    if (bidx == 0xffffffffu) bkey = 0u;
+  }
+  if (bidx == 0xffffffffu && bkey != 0xffffffffu) { /* lane saw nothing or only -inf */ }
+  warp_argmax(bkey, bidx);
+  if (bidx == 0xffffffffu) bidx = 0;
+  out_idx = bidx;
+  out_val = key_to_float(bkey);
+}
+
+template <typename T, bool NMS>
+__global__ void __launch_bounds__(256) decode_simdr_kernel(const T* __restrict__ xv, const T* __restrict__ yv,
+                                                           int64_t n_bk, int K, int Lx, int Ly, int k,
+                                                           const float* __restrict__ center,
+                                                           const float* __restrict__ scale,
+                                                           const int32_t* __restrict__ ranges,
+                                                           float* __restrict__ out,
+                                                           int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t bk = wg; bk < n_bk; bk += nw) {
+    const int64_t b = bk / K;
+    int x1 = 0, x2 = Lx, y1 = 0, y2 = Ly;
+    if (NMS && ranges) { x1 = ranges[4 * b]; x2 = ranges[4 * b + 1]; y1 = ranges[4 * b + 2]; y2 = ranges[4 * b + 3]; }
+    uint32_t ix, iy; float mx, my;
+    warp_vec_argmax<T, NMS>(xv + bk * Lx, Lx, x1, x2, lane, ix, mx);
+    warp_vec_argmax<T, NMS>(yv + bk * Ly, Ly, y1, y2, lane, iy, my);
+    if (lane == 0) {
+      // preds = idx / k (int64 / int -> f64 -> f32), score = (max_x + max_y) / 2
+      float px = (float)((double)ix / (double)k), py = (float)((double)iy / (double)k);
+      const float score = __fdiv_rn(__fadd_rn(mx, my), 2.f);
+      if (center) {
+        const float s0 = __fmul_rn(scale[2 * b], 200.f), s1 = __fmul_rn(scale[2 * b + 1], 200.f);
+        const float fx = __fdiv_rn(s0, (float)(Lx / k)), fy = __fdiv_rn(s1, (float)(Ly / k));
+        px = __fsub_rn(__fadd_rn(__fmul_rn(px, fx), center[2 * b]), __fmul_rn(s0, 0.5f));
+        py = __fsub_rn(__fadd_rn(__fmul_rn(py, fy), center[2 * b + 1]), __fmul_rn(s1, 0.5f));
+      }
+      float* o = out + 3 * bk;
+      o[0] = px; o[1] = py; o[2] = score;
+      if (out_idx) { out_idx[2 * bk] = (int32_t)ix; out_idx[2 * bk + 1] = (int32_t)iy; }
+    }
+  }
+}
+
+// ---- KLDiscretLoss: SmoothL1(beta=1) sums per (b,k), then a fixed-order per-joint reduction -----
+__device__ __forceinline__ float smooth_l1(float d) {
+  const float a = fabsf(d);
+  return a < 1.f ? 0.5f * d * d : a - 0.5f;
+}
+
+template <typename T>
+__device__ __forceinline__ double warp_sl1_sum(const T* __restrict__ o, const T* __restrict__ t, int L, int lane) {
+  float s0 = 0.f, s1 = 0.f;
+  const bool vec = ((L & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(t)) % (4 * sizeof(T)) == 0);
+  if (vec) {
+    const int nq = L >> 2;
+#pragma unroll 4
+    for (int q = lane; q < nq; q += 32) {
+      const float4 a = ldg_stream4<T>(o + 4 * q), g = ldg_stream4<T>(t + 4 * q);
+      s0 += smooth_l1(a.x - g.x); s1 += smooth_l1(a.y - g.y);
+      s0 += smooth_l1(a.z - g.z); s1 += smooth_l1(a.w - g.w);
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) s0 += smooth_l1(Elem<T>::to_f32(o[i]) - Elem<T>::to_f32(t[i]));
+  }
+  return warp_sum((double)s0 + (double)s1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) simdr_sl1_kernel(const T* __restrict__ ox, const T* __restrict__ oy,
+                                                        const T* __restrict__ tx, const T* __restrict__ ty,
+                                                        int64_t n_bk, int Lx, int Ly,
+                                                        double* __restrict__ per_bk /* [n_bk,2] */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t bk = wg; bk < n_bk; bk += nw) {
+    const double sx = warp_sl1_sum<T>(ox + bk * Lx, tx + bk * Lx, Lx, lane);
+    const double sy = warp_sl1_sum<T>(oy + bk * Ly, ty + bk * Ly, Ly, lane);
+    if (lane == 0) { per_bk[2 * bk] = sx; per_bk[2 * bk + 1] = sy; }
+  }
+}
+
+// one block: joint j handled by warp j%nwarps in fixed batch order -> deterministic
+__global__ void __launch_bounds__(1024) simdr_loss_finalize_kernel(const double* __restrict__ per_bk,
+                                                                   const float* __restrict__ weight,
+                                                                   int64_t B, int K, int Lx, int Ly,
+                                                                   float* __restrict__ loss) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double acc = 0.0;
+  for (int j = warp; j < K; j += nwarps) {
+    double sx = 0, sy = 0, sw = 0;
+    for (int64_t b = lane; b < B; b += 32) {
+      sx += per_bk[2 * (b * K + j)]; sy += per_bk[2 * (b * K + j) + 1]; sw += (double)weight[b * K + j];
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sw = warp_sum(sw);
+    acc += (sx / ((double)B * Lx) + sy / ((double)B * Ly)) * (sw / (double)B);
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nwarps; ++i) t += red[i];
+    loss[0] = (float)(t / (double)K);
+  }
+}
+
+template <typename T>
+static int launch_simdr(const void* xv, const void* yv, int64_t n_bk, int K, int Lx, int Ly, int k,
+                        const float* center, const float* scale, int nms, const int32_t* ranges,
+                        float* out, int32_t* out_idx, cudaStream_t st) {
+  const int threads = 256;
+  int64_t need = (n_bk * 32 + threads - 1) / threads, cap = (int64_t)num_sms() * 8;
+  int blocks = (int)(need < cap ? need : cap);
+  if (nms)
+    decode_simdr_kernel<T, true><<<blocks, threads, 0, st>>>((const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k,
+                                                             center, scale, ranges, out, out_idx);
+  else
+    decode_simdr_kernel<T, false><<<blocks, threads, 0, st>>>((const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k,
+                                                              center, scale, ranges, out, out_idx);
+  return check_launch();
+}
+
+}  // namespace lhn
+
+using namespace lhn;
+
+extern "C" int lhn_decode_simdr(const void* x_vec, const void* y_vec, int dtype, int64_t B, int K,
+                                int Lx, int Ly, int split_ratio, const float* center,
+                                const float* scale, int nms, const int32_t* ranges, float* out,
+                                int32_t* out_idx, lhn_stream_t stream) {
+  if (!x_vec || !y_vec || !out || B < 0 || K <= 0 || Lx <= 0 || Ly <= 0 || split_ratio <= 0 ||
+      ((center == nullptr) != (scale == nullptr)))
+    return LHN_EINVAL;
+  const int64_t n = B * K;
+  if (n == 0) return LHN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case LHN_F32: return launch_simdr<float>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, st);
+    case LHN_BF16: return launch_simdr<__nv_bfloat16>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, st);
+    case LHN_F16: return launch_simdr<__half>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, st);
+    default: return LHN_EDTYPE;
+  }
+}
+
+extern "C" int64_t lhn_simdr_loss_workspace_bytes(int64_t B, int K) {
+  if (B < 0 || K <= 0) return LHN_EINVAL;
+  return B * K * 2 * (int64_t)sizeof(double);
+}
+
+extern "C" int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const void* tgt_x,
+                                  const void* tgt_y, const float* weight, int dtype, int64_t B, int K,
+                                  int Lx, int Ly, void* workspace, int64_t workspace_bytes, float* loss,
+                                  lhn_stream_t stream) {
+  if (!out_x || !out_y || !tgt_x || !tgt_y || !weight || !workspace || !loss || B <= 0 || K <= 0 ||
+      Lx <= 0 || Ly <= 0)
+    return LHN_EINVAL;
+  if (workspace_bytes < lhn_simdr_loss_workspace_bytes(B, K)) return LHN_EWORKSPACE;
+  if ((uintptr_t)workspace % 8) return LHN_EALIGN;
+  const int64_t n = B * K;
+  const int threads = 256;
+  int64_t need = (n * 32 + threads - 1) / threads, cap = (int64_t)num_sms() * 8;
+  int blocks = (int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* per_bk = (double*)workspace;
+  switch (dtype) {
+    case LHN_F32:
+      simdr_sl1_kernel<float><<<blocks, threads, 0, st>>>((const float*)out_x, (const float*)out_y,
+          (const float*)tgt_x, (const float*)tgt_y, n, Lx, Ly, per_bk);
+      break;
+    case LHN_BF16:
+      simdr_sl1_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)out_x,
+          (const __nv_bfloat16*)out_y, (const __nv_bfloat16*)tgt_x, (const __nv_bfloat16*)tgt_y, n, Lx, Ly, per_bk);
+      break;
+    case LHN_F16:
+      simdr_sl1_kernel<__half><<<blocks, threads, 0, st>>>((const __half*)out_x, (const __half*)out_y,
+          (const __half*)tgt_x, (const __half*)tgt_y, n, Lx, Ly, per_bk);
+      break;
+    default: return LHN_EDTYPE;
+  }
+  int rc = check_launch();
+  if (rc) return rc;
+  simdr_loss_finalize_kernel<<<1, 1024, 0, st>>>(per_bk, weight, B, K, Lx, Ly, loss);
+  return check_launch();
+}

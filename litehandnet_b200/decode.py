@@ -1,0 +1,385 @@
+"""Drop-in mirrors of the reference's decode entry points — same names, arguments and return
+structure; the per-plane work (argmax, refinement, flip average, back-transform) runs in one CUDA
+kernel on the device-resident heatmaps.
+
+Mirrored (file:line relative to the reference root):
+  utils/post_processing/evaluation/top_down_eval.py:199  _get_max_preds
+  utils/post_processing/evaluation/top_down_eval.py:375  keypoints_from_heatmaps
+  utils/post_processing/evaluation/top_down_eval.py:466  keypoints_from_simdr
+  utils/post_processing/decoder.py:9                     TopDownDecoder (.decode / .decode_simdr)
+  utils/heatmap_post_processing.py:6,35                  adjust_keypoints_by_offset / _by_DARK
+  utils/result_parser.py:14                              ResultParser (.get_coordinates_from_heatmaps,
+                                                         .get_pred_kpt, .vector_nms, .get_coordinates_from_vectors)
+  utils/SPheatmapParser.py:12                            HeatmapParser_SH (.get_coordinates, .adjust_keypoints, .parse)
+  utils/HeatmapParser.py:197                             HeatmapParser.adjust_keypoints (list-of-lists form)
+  utils/transforms.py:18,47,78                           get_final_preds, get_max_preds, flip_back
+  utils/evaluation.py:62                                 get_coordinates_from_heatmap
+
+Array convention: the reference takes/returns NumPy for the Gen-2 functions and torch tensors for the
+legacy ones.  Here every function accepts CUDA tensors (preferred: no copies) and also NumPy arrays /
+CPU tensors, which are uploaded; the result comes back in the kind the reference returns when the
+input was NumPy/CPU, and as CUDA tensors when the input was a CUDA tensor.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .fused import flip_index_from_pairs
+
+_DEV = None
+
+
+def _device():
+    global _DEV
+    if _DEV is None:
+        if not torch.cuda.is_available():
+            raise L.LhnError("no CUDA device: the B200 hot path has no CPU fallback")
+        _DEV = torch.device("cuda", torch.cuda.current_device())
+    return _DEV
+
+
+def _up(x, dtype=None):
+    """-> (cuda tensor, was_cuda)."""
+    if isinstance(x, torch.Tensor):
+        was = x.is_cuda
+        t = x.detach() if was else x.detach().to(_device())
+    else:
+        was = False
+        t = torch.as_tensor(np.ascontiguousarray(x)).to(_device())
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t, was
+
+
+def _hm(x):
+    t, was = _up(x)
+    if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        t = t.float()
+    return t, was
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ---- Gen-2 (mmpose-style) ---------------------------------------------------------------------------
+def _get_max_preds(heatmaps):
+    """top_down_eval.py:199-231 -> (preds [N,K,2], maxvals [N,K,1]); coords = -1 where max <= 0."""
+    if not isinstance(heatmaps, (np.ndarray, torch.Tensor)):
+        raise AssertionError('heatmaps should be numpy.ndarray')
+    assert heatmaps.ndim == 4, 'batch_images should be 4-ndim'
+    t, was = _hm(heatmaps)
+    r = ops.decode_heatmap(t, L.MASK_NEG1, L.REFINE_NONE, want_idx=False)
+    preds, maxvals = r["hm_kpts"][..., :2], r["hm_kpts"][..., 2:]
+    return (preds, maxvals) if was else (_np(preds), _np(maxvals))
+
+
+def keypoints_from_heatmaps(heatmaps, center, scale, post_process='default', kernel=11, use_udp=False,
+                            target_type='GaussianHeatmap', only_original_preds=False,
+                            heatmaps_flipped=None, flip_pairs=()):
+    """top_down_eval.py:375-463.  Returns (hm_preds [N,K,2], preds [N,K,2], maxvals [N,K,1]) or
+    (preds, maxvals) with only_original_preds.  The input heatmaps are never modified.
+
+    Additive: ``heatmaps_flipped`` (+ ``flip_pairs``) fuses the flip-test average
+    (heatmaps + flip_back(heatmaps_flipped, flip_pairs)) * 0.5 into the same pass."""
+    if use_udp:
+        raise NotImplementedError("UDP decoding (post_dark_udp) is SURVEY §8f 'next' (rank 3)")
+    if post_process == 'unbiased':
+        assert kernel > 0
+    if post_process == 'megvii':
+        raise NotImplementedError("'megvii' post-processing is not in the reference either")
+    t, was = _hm(heatmaps)
+    c, _ = _up(center, torch.float32)
+    s, _ = _up(scale, torch.float32)
+    refine = L.REFINE_DARK if post_process == 'unbiased' else (L.REFINE_SIGN if post_process is not None else L.REFINE_NONE)
+    hf = fi = None
+    if heatmaps_flipped is not None:
+        hf, _ = _hm(heatmaps_flipped)
+        hf = hf.to(t.dtype)
+        if flip_pairs:
+            fi = flip_index_from_pairs(t.shape[1], flip_pairs, t.device)
+    r = ops.decode_heatmap(t, L.MASK_NEG1, refine, L.XFORM_CENTER_SCALE, c, s, hm_flip=hf, flip_index=fi,
+                           blur_ksize=kernel, want_idx=False)
+    hm_preds, preds, maxvals = r["hm_kpts"][..., :2], r["kpts"][..., :2], r["kpts"][..., 2:]
+    if not was:
+        hm_preds, preds, maxvals = _np(hm_preds), _np(preds), _np(maxvals)
+    if only_original_preds:
+        return preds, maxvals
+    return hm_preds, preds, maxvals
+
+
+def keypoints_from_simdr(x_vectors, y_vectors, center, scale, k=2):
+    """top_down_eval.py:466-500 -> [B,K,3] (x, y, score)."""
+    assert k > 0, f"Error: {k=}"
+    xv, was = _hm(x_vectors)
+    yv, _ = _hm(y_vectors)
+    c, _ = _up(center, torch.float32)
+    s, _ = _up(scale, torch.float32)
+    out = ops.decode_simdr(xv, yv, int(k), c, s)
+    return out if was else _np(out)
+
+
+class TopDownDecoder:
+    """utils/post_processing/decoder.py:9-107."""
+
+    def __init__(self, cfg):
+        self.image_size = np.array(cfg.DATASET.image_size)
+        self.heatmap_size = np.array(cfg.DATASET.heatmap_size)
+        self.num_joints = cfg.DATASET.num_joints
+        self.post_process = 'unbiased' if cfg.PIPELINE.unbiased_encoding else 'default'
+        self.kernel = cfg.PIPELINE.kernel[0]
+        self.use_udp = cfg.PIPELINE.use_udp
+        self.k = cfg.PIPELINE.get('simdr_split_ratio', 0)
+
+    @staticmethod
+    def _boxes(center, scale, score):
+        n = center.shape[0]
+        all_boxes = np.zeros((n, 6), dtype=np.float32)
+        all_boxes[:, 0:2] = center[:, 0:2]
+        all_boxes[:, 2:4] = scale[:, 0:2]
+        all_boxes[:, 4] = np.prod(scale * 200.0, axis=1)
+        all_boxes[:, 5] = score
+        return all_boxes
+
+    def decode(self, meta, model_output, model_output_flipped=None, flip_pairs=()):
+        """-> dict(preds [N,K,3], hm_preds [N,K,3], boxes [N,6], image_paths, bbox_ids,
+        output_heatmap).  ``model_output`` stays on the GPU; only the [N,K,3] results (and the
+        heatmap copy the reference's dict carries) cross to the host."""
+        score = _np(torch.as_tensor(meta['bbox_score']))
+        bbox_ids = _np(torch.as_tensor(meta['bbox_id']))
+        center_t = torch.as_tensor(meta['center'])
+        scale_t = torch.as_tensor(meta['scale'])
+        hm = model_output[:, :self.num_joints]                     # a view: no copy (strided planes)
+        hf = None if model_output_flipped is None else model_output_flipped[:, :self.num_joints]
+        hm_preds, preds, maxvals = keypoints_from_heatmaps(
+            hm if hm.is_cuda else hm.to(_device()), center_t, scale_t, post_process=self.post_process,
+            kernel=self.kernel, use_udp=self.use_udp, heatmaps_flipped=hf, flip_pairs=flip_pairs)
+        hm_preds, preds, maxvals = _np(hm_preds), _np(preds), _np(maxvals)
+        center, scale = _np(center_t).astype(np.float32), _np(scale_t).astype(np.float32)
+        batch_size = model_output.shape[0]
+        all_preds = np.zeros((batch_size, self.num_joints, 3), dtype=np.float32)
+        all_preds[:, :, 0:2] = preds[:, :, 0:2]
+        all_preds[:, :, 2:3] = maxvals
+        result = {}
+        result['preds'] = all_preds
+        result['hm_preds'] = np.concatenate([hm_preds[:, :, 0:2] * 4, maxvals], axis=2)   # hard-coded x4 (decoder.py:65)
+        result['boxes'] = self._boxes(center, scale, score)
+        result['image_paths'] = meta['image_file']
+        result['bbox_ids'] = bbox_ids.tolist()
+        result['output_heatmap'] = _np(hm.float())
+        return result
+
+    def decode_simdr(self, meta, model_output):
+        score = _np(torch.as_tensor(meta['bbox_score']))
+        bbox_ids = _np(torch.as_tensor(meta['bbox_id']))
+        center_t = torch.as_tensor(meta['center'])
+        scale_t = torch.as_tensor(meta['scale'])
+        sx, sy = torch.as_tensor(meta['simdr_x']), torch.as_tensor(meta['simdr_y'])
+        all_preds = _np(torch.as_tensor(keypoints_from_simdr(sx.to(_device()), sy.to(_device()),
+                                                             center_t, scale_t, self.k)))
+        center, scale = _np(center_t).astype(np.float32), _np(scale_t).astype(np.float32)
+        result = {}
+        result['preds'] = all_preds
+        result['boxes'] = self._boxes(center, scale, score)
+        result['image_paths'] = meta['image_file']
+        result['bbox_ids'] = bbox_ids.tolist()
+        result['output_heatmap'] = _np(model_output[:, :self.num_joints].float())
+        return result
+
+
+# ---- legacy (Gen-1) ---------------------------------------------------------------------------------
+def adjust_keypoints_by_offset(keypoints, heatmaps):
+    """utils/heatmap_post_processing.py:6-33: keypoints [B,K,3] (x,y,conf) from the argmax ->
+    +-0.25 towards the higher clamped neighbour, then +0.5.  Returns a new tensor (callers pass
+    .clone() to the reference); the confidence column is preserved."""
+    kp, was = _up(keypoints, torch.float32)
+    t, _ = _hm(heatmaps)
+    r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_OFFSET_HALF, want_idx=False)
+    out = kp.clone()
+    out[..., :2] = _refine_from(kp, r["hm_kpts"], t)
+    return out if (was or isinstance(keypoints, torch.Tensor) and was) else (out.cpu() if isinstance(keypoints, torch.Tensor) else _np(out))
+
+
+def _refine_from(kp, decoded, hm):
+    """The reference refines around int(keypoints[..., :2]); every caller passes the plane argmax, for
+    which the kernel's own argmax is identical.  Reject anything else loudly instead of guessing."""
+    r0 = ops.decode_heatmap(hm, L.MASK_NONE, L.REFINE_NONE, want_idx=False)["hm_kpts"][..., :2]
+    same = torch.equal(kp[..., :2].to(torch.float32), r0)
+    if not same:
+        raise L.LhnError("adjust_keypoints_*: keypoints are not the per-plane argmax of `heatmaps`; "
+                         "only the reference's call pattern (argmax -> adjust) is supported")
+    return decoded[..., :2]
+
+
+def adjust_keypoints_by_DARK(keypoints, heatmaps):
+    """utils/heatmap_post_processing.py:35-54: blur k=pcfg['blue_kernel']=19 (f64), log, Taylor.
+    Returns a NumPy array like the reference; the input heatmap is left untouched (the reference's CUDA
+    semantics — on CPU inputs the reference blurs the caller's array in place)."""
+    kp, _ = _up(keypoints, torch.float32)
+    t, _ = _hm(heatmaps)
+    r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_DARK_LEGACY, want_idx=False)
+    out = kp.clone()
+    out[..., :2] = _refine_from(kp, r["hm_kpts"], t)
+    return _np(out)
+
+
+class ResultParser:
+    """utils/result_parser.py:14 — keypoint branch only (get_coordinates_from_heatmaps, get_pred_kpt,
+    vector_nms, get_coordinates_from_vectors).  The bbox/NMS/cycle-detection branch is out of scope."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.max_num_bbox = 1                                        # pcfg["max_num_bbox"]
+        self.image_size = torch.tensor(cfg['image_size'])
+        if cfg['model'] == 'srhandnet':
+            self.heatmap_size = torch.tensor([cfg['hm_size'][-1], cfg['hm_size'][-1]])
+        else:
+            self.heatmap_size = torch.tensor(cfg['hm_size'])
+        self.feature_stride = torch.div(self.image_size, self.heatmap_size, rounding_mode='trunc')
+        self.simdr_split_ratio = cfg['simdr_split_ratio']
+
+    def get_coordinates_from_heatmaps(self, heatmaps):
+        """topk(k=1) -> kpts [B,K,3] (x, y, score), no mask (result_parser.py:76-90)."""
+        t, _ = _hm(heatmaps)
+        return ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_NONE, want_idx=False)["hm_kpts"]
+
+    def get_pred_kpt(self, heatmap, resized=False):
+        """result_parser.py:231-249 -> Tensor [B,K,3] on the heatmap's device."""
+        t, was = _hm(heatmap)
+        refine = L.REFINE_DARK_LEGACY if self.cfg['DARK'] else L.REFINE_OFFSET_HALF
+        fs = self.feature_stride.tolist()
+        r = ops.decode_heatmap(t, L.MASK_NONE, refine, L.XFORM_SCALE if resized else L.XFORM_NONE,
+                               scale_xy=(float(fs[0]), float(fs[1])), want_idx=False)
+        out = r["kpts"] if resized else r["hm_kpts"]
+        return out if was else out.cpu()
+
+    def vector_nms(self, vector):
+        """result_parser.py:61-74 (returns a new tensor; the reference masks its argument in place)."""
+        v, was = _up(vector, torch.float32)
+        vmax = torch.max_pool1d(v, 3, 1, 1)
+        out = v * torch.eq(vmax, v).float()
+        return out if was else out.cpu()
+
+    def get_coordinates_from_vectors(self, x_vectors, y_vectors, pred_bboxes):
+        """result_parser.py:92-129 with max_num_bbox = 1: vector_nms, bbox-masked first-max argmax, /k,
+        mean score -> [B, 1, K, 3].  Samples whose bbox list is None stay zero."""
+        xv, was = _hm(x_vectors)
+        yv, _ = _hm(y_vectors)
+        B, K, w = xv.shape
+        h = yv.shape[2]
+        ranges = np.zeros((B, 4), np.int32)
+        valid = np.zeros(B, bool)
+        for i in range(B):
+            if pred_bboxes[i] is not None and len(pred_bboxes[i]) > 0:
+                bbox = np.round(np.array(pred_bboxes[i][0]) * self.simdr_split_ratio)
+                x1, y1 = bbox[:2] - bbox[2:4] / 2
+                x2, y2 = bbox[:2] + bbox[2:4] / 2
+                ranges[i] = (max(int(x1), 0), min(int(x2), w), max(int(y1), 0), min(int(y2), h))
+                valid[i] = True
+        out = ops.decode_simdr(xv, yv, int(self.simdr_split_ratio), nms=True,
+                               ranges=torch.from_numpy(ranges).to(xv.device))
+        out = out * torch.from_numpy(valid).to(xv.device)[:, None, None]
+        out = out.unsqueeze(1)
+        return out if was else out.cpu()
+
+
+class HeatmapParser_SH:
+    """utils/SPheatmapParser.py:12 — keypoint branch (get_coordinates, adjust_keypoints, parse with
+    center_maps=None)."""
+
+    @staticmethod
+    def get_coordinates(heatmaps):
+        t, _ = _hm(heatmaps)
+        return ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_NONE, want_idx=False)["hm_kpts"].cpu()   # reference allocates on CPU (:50)
+
+    @staticmethod
+    def adjust_keypoints(keypoints, heatmaps):
+        kp, _ = _up(keypoints, torch.float32)
+        t, _ = _hm(heatmaps)
+        r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_OFFSET, want_idx=False)
+        out = kp.clone()
+        out[..., :2] = _refine_from(kp, r["hm_kpts"], t)
+        return out.cpu() if not (isinstance(keypoints, torch.Tensor) and keypoints.is_cuda) else out
+
+    def parse(self, heatmaps, center_maps=None, size_maps=None, image_size=(256, 256), scale_factor=1):
+        """SPheatmapParser.py:169-206 -> (kpt [B,K,3] on CPU, pred_bboxes).  With center/size maps the
+        bbox branch would run — out of scope: raises."""
+        if center_maps is not None and size_maps is not None:
+            raise NotImplementedError("bbox decoding from centre/size maps is SURVEY §8f 'next' (rank 4)")
+        t, _ = _hm(heatmaps)
+        H, W = t.shape[2:]
+        isz = torch.tensor(image_size, dtype=torch.float32)
+        f = (isz / torch.tensor([W, H], dtype=torch.float32)).tolist()
+        r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_OFFSET, L.XFORM_SCALE, scale_xy=(f[0], f[1]), want_idx=False)
+        return r["kpts"].cpu(), None
+
+
+class HeatmapParser:
+    """utils/HeatmapParser.py:197-223 — only adjust_keypoints (list-of-lists form).  The reference
+    indexes ``heatmaps[batch, joint_id]`` on an (n_joints+1)-channel tensor whose channel 0 is the
+    centre map (an off-by-one quirk); ``channel_offset`` reproduces it (default 0 = as the code)."""
+
+    def __init__(self, channel_offset=0):
+        self.channel_offset = channel_offset
+
+    def adjust_keypoints(self, keypoints, heatmaps):
+        t, _ = _hm(heatmaps)
+        hm_cpu = None
+        for batch_id, kpt_list in enumerate(keypoints):
+            for bbox_id, kpt in enumerate(kpt_list):
+                if not len(kpt):
+                    continue
+                # grouped candidates are not plane argmaxima: refine at the given integer positions
+                if hm_cpu is None:
+                    hm_cpu = t.float().cpu()
+                for joint_id, joint in enumerate(kpt):
+                    x, y = joint[:2]
+                    xx, yy = int(x), int(y)
+                    tmp = hm_cpu[batch_id, joint_id + self.channel_offset]
+                    x += 0.25 if tmp[yy, min(xx + 1, tmp.shape[1] - 1)] > tmp[yy, max(xx - 1, 0)] else -0.25
+                    y += 0.25 if tmp[min(yy + 1, tmp.shape[0] - 1), xx] > tmp[max(yy - 1, 0), xx] else -0.25
+                    keypoints[batch_id][bbox_id][joint_id][0] = x
+                    keypoints[batch_id][bbox_id][joint_id][1] = y
+        return keypoints
+
+
+# ---- HRNet-style helpers (utils/transforms.py) ---------------------------------------------------------
+def get_max_preds(batch_heatmaps):
+    """utils/transforms.py:47-75 (coords * 0 where max <= 0)."""
+    if not isinstance(batch_heatmaps, (np.ndarray, torch.Tensor)):
+        raise AssertionError('batch_heatmaps should be numpy.ndarray')
+    assert batch_heatmaps.ndim == 4, 'batch_images should be 4-ndim'
+    t, was = _hm(batch_heatmaps)
+    r = ops.decode_heatmap(t, L.MASK_ZERO, L.REFINE_NONE, want_idx=False)["hm_kpts"]
+    return (r[..., :2], r[..., 2:]) if was else (_np(r[..., :2]), _np(r[..., 2:]))
+
+
+def get_coordinates_from_heatmap(batch_heatmaps):
+    """utils/evaluation.py:62-89 (torch in, torch out on the same device)."""
+    assert isinstance(batch_heatmaps, torch.Tensor), "batch_heatmaps should be torch.Tensor"
+    assert batch_heatmaps.dim() == 4, "batch_heatmaps should be 4-ndim"
+    t, was = _hm(batch_heatmaps)
+    r = ops.decode_heatmap(t, L.MASK_ZERO, L.REFINE_NONE, want_idx=False)["hm_kpts"]
+    preds, maxvals = r[..., :2].contiguous(), r[..., 2:].contiguous()
+    return (preds, maxvals) if was else (preds.cpu(), maxvals.cpu())
+
+
+def get_final_preds(batch_heatmaps, center, scale):
+    """utils/transforms.py:18-44 (A3 -> floor(x+0.5) guarded quarter shift -> back-transform).  The
+    reference's cv2-affine transform (rot = 0) is evaluated in closed form."""
+    t, was = _hm(batch_heatmaps)
+    c, _ = _up(center, torch.float32)
+    s, _ = _up(scale, torch.float32)
+    r = ops.decode_heatmap(t, L.MASK_ZERO, L.REFINE_SIGN_ROUND, L.XFORM_CENTER_SCALE, c, s, want_idx=False)
+    preds = r["kpts"][..., :2]
+    return preds if was else _np(preds)
+
+
+def flip_back(output_flipped, matched_parts):
+    """utils/transforms.py:78-92: reverse W and swap the matched channels."""
+    assert output_flipped.ndim == 4, 'output_flipped should be [batch_size, num_joints, height, width]'
+    t, was = _up(output_flipped)
+    fi = flip_index_from_pairs(t.shape[1], matched_parts, t.device)
+    out = ops.flip_back(t, fi)
+    return out if was else (_np(out) if isinstance(output_flipped, np.ndarray) else out.cpu())

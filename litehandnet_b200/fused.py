@@ -1,0 +1,251 @@
+"""The headline fused path (BASELINE config 2): Gaussian target render + target-weight masked MSE
+loss + flip-test average + argmax + DARK refinement + affine back-transform, with every heatmap
+plane read from HBM exactly once.
+
+It replaces this chain of reference calls:
+  datasets/data_pipeline/generateTarget.py:245  TopDownGenerateTarget.__call__      (per sample, CPU)
+  loss/heatmapLoss.py:242                       DistanceLoss.forward                (~9 eager kernels)
+  utils/transforms.py:78                        flip_back + (a + b) * 0.5
+  utils/post_processing/evaluation/top_down_eval.py:375  keypoints_from_heatmaps('unbiased')
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def flip_index_from_pairs(num_joints, flip_pairs, device):
+    """flip_back's channel swap (utils/transforms.py:86-90) as a gather index."""
+    idx = list(range(num_joints))
+    for a, b in flip_pairs or ():
+        idx[a], idx[b] = idx[b], idx[a]
+    return torch.tensor(idx, dtype=torch.int32, device=device)
+
+
+class FusedHeatmapStep:
+    """Reusable launcher: caches the parameter blocks and the output buffers for one shape, so a
+    steady-state call is three kernel launches (fused plane kernel, loss reduce, loss finalise)."""
+
+    def __init__(self, image_size=(256, 256), sigma=2, unbiased_encoding=True, balance=True,
+                 post_process="unbiased", kernel=11, flip_pairs=(), loss_weight=1.0, pos_value=0.5,
+                 loss_type="distance"):
+        self.image_size = tuple(image_size)
+        self.sigma = sigma
+        self.unbiased = bool(unbiased_encoding)
+        if loss_type == "joints_mse":
+            self.loss_mode = L.LOSS_JOINTS_MSE
+        elif loss_type is None:
+            self.loss_mode = L.LOSS_NONE
+        else:
+            self.loss_mode = L.LOSS_DISTANCE_BALANCE if balance else L.LOSS_DISTANCE
+        self.refine = {"unbiased": L.REFINE_DARK, "default": L.REFINE_SIGN, None: L.REFINE_NONE}[post_process]
+        self.kernel = int(kernel)
+        self.flip_pairs = tuple(flip_pairs)
+        self.loss_weight = float(loss_weight)
+        self.pos_value = float(pos_value)
+        self._flip_index = {}
+
+    def __call__(self, hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None):
+        dev = hm.device
+        K = hm.shape[-3]
+        fi = None
+        if hm_flip is not None and self.flip_pairs:
+            key = (K, dev)
+            if key not in self._flip_index:
+                self._flip_index[key] = flip_index_from_pairs(K, self.flip_pairs, dev)
+            fi = self._flip_index[key]
+        render = None
+        if self.loss_mode != L.LOSS_NONE:
+            render = dict(loss_mode=self.loss_mode, image_size=self.image_size, sigma=self.sigma,
+                          unbiased=self.unbiased, pos_value=self.pos_value)
+        r = ops.decode_heatmap(hm, L.MASK_NEG1, self.refine, L.XFORM_CENTER_SCALE, center, scale,
+                               hm_flip=hm_flip, flip_index=fi, blur_ksize=self.kernel,
+                               render=render, joints=joints_3d, vis=joints_3d_visible)
+        out = dict(preds=r["kpts"], hm_preds=r["hm_kpts"], idx=r["idx"], maxvals=r["kpts"][..., 2:])
+        if render is not None:
+            sums = ops.loss_reduce(r["partials"])
+            out["loss_sums"] = sums
+            out["loss"] = ops.loss_finalize(sums, self.loss_mode, "mean", self.loss_weight)[0]
+            out["target_weight"] = r["weight"].unsqueeze(-1)
+        return out
+
+
+def fused_render_loss_decode(hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None,
+                             image_size=(256, 256), sigma=2, unbiased_encoding=True, balance=True,
+                             post_process="unbiased", kernel=11, flip_pairs=(), loss_weight=1.0):
+    """hm [B,K,H,W] (f32/bf16/f16, CUDA), joints_3d [B,K,3] image pixels, joints_3d_visible [B,K,3],
+    center/scale [B,2] (scale = bbox/200), hm_flip = network output on the mirrored image or None.
+
+    Returns dict(loss 0-dim f32, preds [B,K,3] (X,Y,score) in image coords, hm_preds [B,K,3] in
+    heatmap coords, idx [B,K] int32 argmax, maxvals [B,K,1], target_weight [B,K,1], loss_sums f64[4]).
+    """
+    step = FusedHeatmapStep(image_size, sigma, unbiased_encoding, balance, post_process, kernel,
+                            flip_pairs, loss_weight)
+    return step(hm, joints_3d, joints_3d_visible, center, scale, hm_flip)
+
+
+class HostPipeline:
+    """End-to-end entry for HOST buffers (the call a reference user makes today hands CPU arrays to
+    the loss/decoder): the batch is cut into chunks; chunk i+1's host->device copy (pinned memory, copy
+    stream) overlaps chunk i's fused kernel (compute stream); the per-plane loss partials of all chunks
+    land in one buffer so the balanced loss still uses batch-global counts; the [B,K,3] predictions and
+    the loss scalar are copied back device->host at the end.
+
+    h2d_bytes / d2h_bytes report what one call moves."""
+
+    def __init__(self, step, B, K, H, W, dtype=torch.float32, flip=True, chunks=8, device="cuda"):
+        self.step, self.B, self.K, self.H, self.W = step, B, K, H, W
+        self.flip = flip
+        self.dev = torch.device(device)
+        chunks = max(1, min(chunks, B))
+        edges = [round(i * B / chunks) for i in range(chunks + 1)]
+        self.bounds = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        cb = max(b - a for a, b in self.bounds)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        # double-buffered device staging for the heatmap chunks
+        self.d_hm = [torch.empty((cb, K, H, W), dtype=dtype, device=self.dev) for _ in range(2)]
+        self.d_hf = [torch.empty((cb, K, H, W), dtype=dtype, device=self.dev) for _ in range(2)] if flip else None
+        self.d_joints = torch.empty((B, K, 3), device=self.dev)
+        self.d_vis = torch.empty((B, K, 3), device=self.dev)
+        self.d_center = torch.empty((B, 2), device=self.dev)
+        self.d_scale = torch.empty((B, 2), device=self.dev)
+        self.d_partials = torch.empty((B * K, 4), dtype=torch.float64, device=self.dev)
+        self.d_preds = torch.empty((B, K, 3), device=self.dev)
+        self.d_hmk = torch.empty((B, K, 3), device=self.dev)
+        self.d_weight = torch.empty((B, K), device=self.dev)
+        self.d_loss = torch.empty(1, device=self.dev)
+        self.h_preds = torch.empty((B, K, 3), pin_memory=True)
+        self.h_loss = torch.empty(1, pin_memory=True)
+        self.copied = [torch.cuda.Event() for _ in self.bounds]
+        self.freed = [torch.cuda.Event() for _ in range(2)]
+        esz = torch.empty((), dtype=dtype).element_size()
+        self.h2d_bytes = B * K * H * W * esz * (2 if flip else 1) + B * (K * 3 * 4 * 2 + 16)
+        self.d2h_bytes = B * K * 3 * 4 + 4
+        self.launches = 0
+
+    def __call__(self, hm, hm_flip, joints, vis, center, scale):
+        """All arguments are pinned HOST tensors.  Returns (h_preds [B,K,3], h_loss [1]) host tensors,
+        valid after the call returns (it synchronises on the final device->host copy)."""
+        step = self.step
+        comp = torch.cuda.current_stream(self.dev)
+        cs = self.copy_stream
+        cs.wait_stream(comp)
+        with torch.cuda.stream(cs):
+            self.d_joints.copy_(joints, non_blocking=True)
+            self.d_vis.copy_(vis, non_blocking=True)
+            self.d_center.copy_(center, non_blocking=True)
+            self.d_scale.copy_(scale, non_blocking=True)
+        render = dict(loss_mode=step.loss_mode, image_size=step.image_size, sigma=step.sigma,
+                      unbiased=step.unbiased, pos_value=step.pos_value)
+        self.launches = 0
+        for i, (a, b) in enumerate(self.bounds):
+            slot = i & 1
+            n = b - a
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(self.freed[slot])       # the kernel that read this slot is done
+                self.d_hm[slot][:n].copy_(hm[a:b], non_blocking=True)
+                if self.flip:
+                    self.d_hf[slot][:n].copy_(hm_flip[a:b], non_blocking=True)
+                self.copied[i].record(cs)
+            comp.wait_event(self.copied[i])
+            ops.decode_heatmap(self.d_hm[slot][:n], L.MASK_NEG1, step.refine, L.XFORM_CENTER_SCALE,
+                               self.d_center[a:b], self.d_scale[a:b],
+                               hm_flip=self.d_hf[slot][:n] if self.flip else None,
+                               blur_ksize=step.kernel, want_idx=False, render=render,
+                               joints=self.d_joints[a:b], vis=self.d_vis[a:b],
+                               out=dict(partials=self.d_partials[a * self.K:b * self.K], kpts=self.d_preds[a:b],
+                                        hm_kpts=self.d_hmk[a:b], weight=self.d_weight[a:b]))
+            self.freed[slot].record(comp)
+            self.launches += 1
+        sums = ops.loss_reduce(self.d_partials)
+        ops.loss_finalize(sums, step.loss_mode, "mean", step.loss_weight, out=self.d_loss)
+        self.launches += 2
+        self.h_preds.copy_(self.d_preds, non_blocking=True)
+        self.h_loss.copy_(self.d_loss, non_blocking=True)
+        comp.synchronize()
+        return self.h_preds, self.h_loss
+
+
+class BoundFusedStep:
+    """A FusedHeatmapStep bound to fixed device buffers: every ctypes argument is built once, outputs
+    are preallocated, so a steady-state step is three raw C-ABI launches (fused plane kernel, loss
+    reduce, loss finalise) — and ``capture()`` records them into a CUDA graph, which turns the step
+    into a single graph launch (the inner loop is launch-bound at ~0.1 ms of GPU work per step)."""
+
+    def __init__(self, step, hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None,
+                 finalize=True):
+        import ctypes as C
+        self.step = step
+        lib = L.lib()
+        self._lib = lib
+        hm, B, Cc, H, W, sb, sc = ops._plane_view(hm, "heatmaps")
+        dev = hm.device
+        self.B, self.K, self.H, self.W = B, Cc, H, W
+        fb = fc = 0
+        if hm_flip is not None:
+            hm_flip, _, _, _, _, fb, fc = ops._plane_view(hm_flip, "flipped heatmaps")
+        fi = None
+        if hm_flip is not None and step.flip_pairs:
+            fi = flip_index_from_pairs(Cc, step.flip_pairs, dev)
+        self._keep = [hm, hm_flip, fi]
+        joints = ops._f32c(joints_3d, "joints")
+        vis = ops._f32c(joints_3d_visible, "vis")
+        if vis.dim() == 2:
+            vis = vis.unsqueeze(-1).contiguous()
+        center, scale = ops._f32c(center, "center"), ops._f32c(scale, "scale")
+        self._keep += [joints, vis, center, scale]
+        self.dp = ops._decode_params(L.MASK_NEG1, step.refine, L.XFORM_CENTER_SCALE, blur_ksize=step.kernel)
+        self.rp = ops._render_params(step.loss_mode, step.image_size, step.sigma, step.unbiased, step.pos_value)
+        self.hm_preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
+        self.preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
+        self.idx = torch.empty((B, Cc), dtype=torch.int32, device=dev)
+        self.weight = torch.empty((B, Cc), dtype=torch.float32, device=dev)
+        self.partials = torch.empty((B * Cc, 4), dtype=torch.float64, device=dev)
+        self.sums = torch.empty(4, dtype=torch.float64, device=dev)
+        self.loss = torch.empty(1, dtype=torch.float32, device=dev)
+        self.finalize = finalize
+        self._decode_args = (
+            L.ptr(hm), L.ptr(hm_flip), L.ptr(fi), L.dtype_code(hm), B, Cc, H, W, sb, sc, fb, fc,
+            L.ptr(center), L.ptr(scale), C.byref(self.dp), L.ptr(self.hm_preds), L.ptr(self.preds),
+            L.ptr(self.idx), C.byref(self.rp), L.ptr(joints), joints.shape[2], L.ptr(vis), vis.shape[2],
+            L.ptr(self.weight), L.ptr(self.partials))
+        self._p_partials, self._p_sums, self._p_loss = L.ptr(self.partials), L.ptr(self.sums), L.ptr(self.loss)
+        self.n_planes = B * Cc
+        self.graph = None
+        self.launches_per_step = 3 if finalize else 2
+
+    def launch_kernel(self, stream):
+        L.check(self._lib.lhn_decode_heatmap(*self._decode_args, stream), "lhn_decode_heatmap")
+
+    def launch_reduce(self, stream):
+        L.check(self._lib.lhn_loss_reduce(self._p_partials, self.n_planes, self._p_sums, 0, stream), "lhn_loss_reduce")
+
+    def launch_finalize(self, stream):
+        L.check(self._lib.lhn_loss_finalize(self._p_sums, self.step.loss_mode, 0, self.step.loss_weight,
+                                            self._p_loss, 0, stream), "lhn_loss_finalize")
+
+    def launch(self, events=None):
+        """Issue the step on the current stream.  events=(before, after) brackets the fused kernel."""
+        st = L.stream()
+        if events is not None:
+            events[0].record()
+        self.launch_kernel(st)
+        if events is not None:
+            events[1].record()
+        self.launch_reduce(st)
+        if self.finalize:
+            self.launch_finalize(st)
+
+    def capture(self):
+        """Record the step into a CUDA graph (warm-up launch first so attributes are set eagerly)."""
+        self.launch()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.launch()
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()

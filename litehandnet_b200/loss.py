@@ -1,0 +1,208 @@
+"""Drop-in mirrors of the reference's loss modules (loss/heatmapLoss.py, loss/centernet_simdr_loss.py,
+loss/loss.py, loss/__init__.py) — same class names, constructor arguments, call signatures, return
+types and error behaviour; the arithmetic runs in the CUDA library.
+
+Scope: L2-type DistanceLoss (balance on/off, mean/sum), JointsDistanceLoss mse,
+KLDiscretLoss, SimDRLoss, TopdownHeatmapLoss, SRHandNetLoss (heatmap-only branch), get_loss.  The
+forward value is computed on the GPU; autograd through these losses is SURVEY §8f "next" (rank 1) and
+is not provided — the returned tensors carry no grad_fn.
+"""
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+
+
+def _as_cuda(t, device):
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    return t.to(device)          # the reference moves meta['target'] to the output's device (loss.py:97-98)
+
+
+class DistanceLoss(nn.Module):
+    """loss/heatmapLoss.py:228-265.  Only loss_type 'L2' is on the path (every config uses it)."""
+
+    def __init__(self, loss_type='L2', reduction='mean', balance=True, value=0.5):
+        super().__init__()
+        assert reduction in ['mean', 'sum', None], f"Error: {reduction=}"
+        if loss_type.lower() != 'l2':
+            raise NotImplementedError("only DistanceLoss(loss_type='L2') is on the B200 hot path "
+                                      "(SURVEY.md §2 row 1); L1/SmoothL1 are unused by every config")
+        if reduction is None:
+            raise NotImplementedError("reduction=None (unreduced loss map) is not on the hot path")
+        self.reduction = reduction
+        self.value = value
+        self.balance = balance
+
+    @property
+    def _mode(self):
+        return L.LOSS_DISTANCE_BALANCE if self.balance else L.LOSS_DISTANCE
+
+    def forward(self, output, target, target_weight):
+        """output/target [N,K,H,W] or [N,S,K,H,W]; target_weight [N,K,1] / [N,S,K,1] -> 0-dim f32."""
+        L.require_cuda(output, "output")
+        target = _as_cuda(target, output.device)
+        target_weight = _as_cuda(target_weight, output.device)
+        partials = ops.loss_partials(output.detach(), target, target_weight, self._mode, self.value)
+        sums = ops.loss_reduce(partials)
+        return ops.loss_finalize(sums, self._mode, self.reduction)[0]
+
+    def forward_fused(self, output, joints_3d, joints_3d_visible, image_size, sigma=2,
+                      unbiased_encoding=True):
+        """Additive fused entry: render the target in-kernel from the joints instead of
+        reading a target tensor.  Returns (loss, target_weight [.., 1])."""
+        L.require_cuda(output, "output")
+        r = ops.decode_heatmap(output.detach(), L.MASK_NEG1, L.REFINE_NONE, want_idx=False,
+                               render=dict(loss_mode=self._mode, image_size=image_size, sigma=sigma,
+                                           unbiased=unbiased_encoding, pos_value=self.value),
+                               joints=_as_cuda(joints_3d, output.device),
+                               vis=_as_cuda(joints_3d_visible, output.device))
+        sums = ops.loss_reduce(r["partials"])
+        return ops.loss_finalize(sums, self._mode, self.reduction)[0], r["weight"].unsqueeze(-1)
+
+
+class JointsDistanceLoss(nn.Module):
+    """loss/heatmapLoss.py:175-225 (HRNet per-joint 0.5*MSE; the weight multiplies both operands)."""
+
+    def __init__(self, use_target_weight=True, loss_type='mse'):
+        super().__init__()
+        assert loss_type.lower() in ['mse', 'mae', 'smoothl1']
+        if loss_type.lower() != 'mse':
+            raise NotImplementedError("only JointsDistanceLoss(loss_type='mse') is on the hot path")
+        self.use_target_weight = use_target_weight
+
+    def forward(self, output, target, target_weight=None):
+        L.require_cuda(output, "output")
+        if self.use_target_weight:
+            if target_weight is None:
+                raise NameError
+            w = _as_cuda(target_weight, output.device)
+        else:
+            w = torch.ones(output.shape[:2], device=output.device)
+        partials = ops.loss_partials(output.detach(), _as_cuda(target, output.device), w, L.LOSS_JOINTS_MSE)
+        return ops.loss_finalize(ops.loss_reduce(partials), L.LOSS_JOINTS_MSE)[0]
+
+
+class KLDiscretLoss(nn.Module):
+    """loss/centernet_simdr_loss.py:6-39 — despite the name: per-joint SmoothL1 mean, times the
+    batch-mean of the weight."""
+
+    def forward(self, output_x, output_y, target_x, target_y, target_weight):
+        L.require_cuda(output_x, "output_x")
+        dev = output_x.device
+        return ops.simdr_smoothl1(output_x.detach(), _as_cuda(output_y, dev).detach(), _as_cuda(target_x, dev),
+                                  _as_cuda(target_y, dev), _as_cuda(target_weight, dev))[0]
+
+
+class SimDRLoss(nn.Module):
+    """loss/centernet_simdr_loss.py:42-69.  The two nn.Linear heads are the criterion's own dense
+    contraction and stay in torch/cuBLAS; the SmoothL1 reduction is ours."""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+        image_size = cfg.DATASET.image_size
+        heatmap_size = cfg.DATASET.heatmap_size
+        k = cfg.PIPELINE.simdr_split_ratio
+        self.simdr_width = int(k * image_size[0])
+        self.simdr_height = int(k * image_size[1])
+        in_features = int(heatmap_size[0] * heatmap_size[1])
+        self.x_shared_decoder = nn.Linear(in_features, self.simdr_width)
+        self.y_shared_decoder = nn.Linear(in_features, self.simdr_height)
+        self.loss = KLDiscretLoss()
+
+    def forward(self, heatmap, simdr_x, simdr_y, target_weight):
+        pred_x = self.x_shared_decoder(heatmap.flatten(start_dim=2))
+        pred_y = self.y_shared_decoder(heatmap.flatten(start_dim=2))
+        return self.loss(pred_x, pred_y, simdr_x, simdr_y, target_weight)
+
+
+class TopdownHeatmapLoss(nn.Module):
+    """loss/loss.py:69-114.  criterion(output, meta) -> (loss, {name: float}).
+
+    Fused entry (additive): when ``meta`` has no 'target' but has 'joints_3d' / 'joints_3d_visible',
+    the target is rendered in-kernel (cfg.PIPELINE sigma / unbiased_encoding, cfg.DATASET.image_size)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        loss_type = cfg.LOSS.get('dl_type', 'L2')
+        balance = cfg.MODEL.name != 'atthandnet'
+        self.heatmap_loss = DistanceLoss(loss_type=loss_type, reduction='mean', balance=balance)
+        if cfg.PIPELINE.simdr_split_ratio > 0:
+            self.simdr_loss = SimDRLoss(cfg)
+        else:
+            self.simdr_loss = None
+        self.loss_weight = cfg.LOSS.loss_weight
+        self.auto_weight = cfg.LOSS.auto_weight
+        if self.auto_weight:
+            params = torch.ones(len(self.loss_weight), requires_grad=True)
+            self.p = nn.Parameter(params, requires_grad=True)
+        self._image_size = cfg.DATASET.get('image_size', None)
+        self._sigma = cfg.PIPELINE.get('sigma', 2)
+        self._unbiased = cfg.PIPELINE.get('unbiased_encoding', True)
+
+    def forward(self, output, meta):
+        loss_dict = {}
+        device = output.device
+        if 'target' in meta:
+            target = meta['target'].to(device)
+            target_weight = meta['target_weight'].to(device)
+            hl = self.heatmap_loss(output, target, target_weight)
+        else:
+            hl, target_weight = self.heatmap_loss.forward_fused(
+                output, meta['joints_3d'], meta['joints_3d_visible'], self._image_size, self._sigma,
+                self._unbiased)
+        loss_dict['heatmap'] = self.loss_weight[0] * hl
+        if self.simdr_loss is not None:
+            simdr_x = meta['simdr_x'].to(device)
+            simdr_y = meta['simdr_y'].to(device)
+            loss_dict['simdr'] = self.loss_weight[1] * self.simdr_loss(output, simdr_x, simdr_y, target_weight)
+        loss = 0
+        for k, v in loss_dict.items():
+            loss += v
+            loss_dict[k] = v.item()          # .item() syncs: the reference contract
+        return loss, loss_dict
+
+
+class SRHandNetLoss(nn.Module):
+    """loss/loss.py:7-66, heatmap-only branch (_forward_only_heatmap): sum_i loss_weight[i] *
+    DistanceLoss(outputs[i], targets[i], w[i]) over the 4 scales.  The region-map branch
+    (pred_bbox with 24 channels) is out of scope."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        out_c = cfg.MODEL.get('output_channel', 24)
+        pred_bbox = cfg.MODEL.get('pred_bbox', False)
+        self.mse_loss = DistanceLoss(loss_type='L2', reduction='mean')
+        if pred_bbox and out_c == 24:
+            raise NotImplementedError("SRHandNetLoss region-map branch is out of the hot-path scope")
+        self.smoothl1_loss = None
+        self.num_out = 4
+        self.loss_weight = cfg.LOSS.loss_weight
+        assert len(self.loss_weight) == self.num_out
+
+    def forward(self, outputs, meta):
+        target = meta['target']
+        target_weight = meta['target_weight']
+        return self._forward_only_heatmap(outputs, target, target_weight)
+
+    def _forward_only_heatmap(self, outputs, targets, target_weight):
+        device = outputs[-1].device
+        sums_out = torch.zeros(1, dtype=torch.float32, device=device)
+        mode = L.LOSS_DISTANCE_BALANCE
+        for i in range(self.num_out):
+            w = target_weight[i] if isinstance(target_weight, (list, tuple)) else target_weight
+            partials = ops.loss_partials(outputs[i].detach(), _as_cuda(targets[i], device), _as_cuda(w, device), mode)
+            ops.loss_finalize(ops.loss_reduce(partials), mode, 'mean', float(self.loss_weight[i]),
+                              out=sums_out, accumulate=True)
+        loss = sums_out[0]
+        return loss, dict(kpt_loss=loss.item())
+
+
+srhandnetloss = SRHandNetLoss
+topdownheatmaploss = TopdownHeatmapLoss
+
+
+def get_loss(cfg):
+    """loss/__init__.py:18-19."""
+    return {"srhandnetloss": SRHandNetLoss, "topdownheatmaploss": TopdownHeatmapLoss}[cfg.LOSS.type.lower()](cfg)

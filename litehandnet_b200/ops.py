@@ -1,0 +1,328 @@
+"""Tensor-level wrappers over the C ABI (include/lhn.h).  Every function takes CUDA tensors, launches
+on ``torch.cuda.current_stream()`` and returns CUDA tensors; nothing here synchronises or falls back.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_REFINE_KSIZE = {L.REFINE_DARK: 11, L.REFINE_DARK_LEGACY: 19}
+
+
+def _decode_params(mask_mode, refine, transform, scale_xy=(1.0, 1.0), blur_ksize=None, use_udp=False):
+    dp = L.DecodeParams()
+    dp.mask_mode, dp.refine, dp.transform, dp.use_udp = int(mask_mode), int(refine), int(transform), int(bool(use_udp))
+    dp.scale_x, dp.scale_y = float(scale_xy[0]), float(scale_xy[1])
+    if refine in _REFINE_KSIZE:
+        k = int(blur_ksize) if blur_ksize else _REFINE_KSIZE[refine]
+        dp.blur_ksize = k
+        for i, t in enumerate(L.gaussian_taps(k)):
+            dp.taps[i] = t
+    return dp
+
+
+def _render_params(loss_mode, image_size, sigma, unbiased=True, pos_value=0.5):
+    rp = L.RenderParams()
+    sig = list(sigma) if isinstance(sigma, (list, tuple)) else [sigma]
+    if len(sig) > L.MAX_STACKS:
+        raise L.LhnError(f"at most {L.MAX_STACKS} stacked sigmas")
+    rp.loss_mode, rp.unbiased, rp.num_stacks = int(loss_mode), int(bool(unbiased)), len(sig)
+    rp.image_w, rp.image_h = float(image_size[0]), float(image_size[1])
+    rp.pos_value = float(pos_value)
+    for i, s in enumerate(sig):
+        rp.sigma[i] = float(s)
+    return rp
+
+
+def _plane_view(hm, name):
+    """[B,C,H,W] or [B,S,K,H,W] tensor with contiguous planes -> (tensor, B, C, H, W, stride_b, stride_c)."""
+    L.require_cuda(hm, name)
+    if hm.dim() == 5:
+        B, S, K, H, W = hm.shape
+        if not hm[0].is_contiguous():
+            hm = hm.contiguous()
+        return hm, B, S * K, H, W, hm.stride(0), hm.stride(2)
+    if hm.dim() != 4:
+        raise L.LhnError(f"{name} must be [B,K,H,W] or [B,S,K,H,W], got {tuple(hm.shape)}")
+    B, Cc, H, W = hm.shape
+    if hm.stride(3) != 1 or hm.stride(2) != W or (Cc > 1 and hm.stride(1) < H * W):
+        hm = hm.contiguous()
+    return hm, B, Cc, H, W, hm.stride(0), hm.stride(1) if Cc > 1 else H * W
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    L.require_cuda(t, name)
+    return t.to(torch.float32).contiguous()
+
+
+def decode_heatmap(hm, mask_mode, refine, transform=L.XFORM_NONE, center=None, scale=None,
+                   scale_xy=(1.0, 1.0), hm_flip=None, flip_index=None, blur_ksize=None, use_udp=False,
+                   want_idx=True, render=None, joints=None, vis=None, out=None):
+    """K1.  Returns dict(hm_kpts [B,C,3], kpts [B,C,3], idx [B,C] int32[, weight [B,C], partials [B*C,4]]).
+
+    render: None or dict(loss_mode, image_size, sigma, unbiased, pos_value) to fuse the target render +
+    masked-MSE partial sums against joints [B,K,>=2] / vis [B,K,>=1] (column 0 = visibility).
+    out: optional dict of preallocated contiguous outputs (hm_kpts, kpts, idx, partials, weight) to
+    write into instead of allocating (steady-state loops, chunked pipelines).
+    """
+    out = out or {}
+    hm, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
+    dev = hm.device
+    fb = fc = 0
+    if hm_flip is not None:
+        hm_flip, B2, C2, H2, W2, fb, fc = _plane_view(hm_flip, "flipped heatmaps")
+        if (B2, C2, H2, W2) != (B, Cc, H, W) or hm_flip.dtype != hm.dtype:
+            raise L.LhnError("flipped heatmaps must match heatmaps in shape and dtype")
+    S = 1
+    rp = None
+    partials = weight = None
+    if render is not None and render.get("loss_mode", L.LOSS_NONE) != L.LOSS_NONE:
+        rp = _render_params(render["loss_mode"], render["image_size"], render["sigma"],
+                            render.get("unbiased", True), render.get("pos_value", 0.5))
+        S = rp.num_stacks
+        joints = _f32c(joints, "joints")
+        vis = _f32c(vis, "vis")
+        if joints.dim() != 3 or joints.shape[0] != B or joints.shape[2] < 2:
+            raise L.LhnError("joints must be [B,K,>=2]")
+        if vis.dim() == 2:
+            vis = vis.unsqueeze(-1).contiguous()
+        partials = out.get("partials")
+        if partials is None:
+            partials = torch.empty((B * Cc, 4), dtype=torch.float64, device=dev)
+        weight = out.get("weight")
+        if weight is None:
+            weight = torch.empty((B, Cc), dtype=torch.float32, device=dev)
+    if Cc % S:
+        raise L.LhnError("channel count is not a multiple of the number of stacks")
+    K = Cc // S
+    if flip_index is not None:
+        flip_index = L.require_cuda(flip_index, "flip_index").to(torch.int32).contiguous()
+        if flip_index.numel() != K:
+            raise L.LhnError("flip_index must have K entries")
+    center = _f32c(center, "center")
+    scale = _f32c(scale, "scale")
+    dp = _decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp)
+    out_hm = out.get("hm_kpts")
+    if out_hm is None:
+        out_hm = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
+    out_k = out.get("kpts")
+    if out_k is None:
+        out_k = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
+    out_idx = out.get("idx")
+    if out_idx is None and want_idx:
+        out_idx = torch.empty((B, Cc), dtype=torch.int32, device=dev)
+    for name, t, dt, n in (("hm_kpts", out_hm, torch.float32, B * Cc * 3), ("kpts", out_k, torch.float32, B * Cc * 3),
+                           ("idx", out_idx, torch.int32, B * Cc), ("partials", partials, torch.float64, B * Cc * 4),
+                           ("weight", weight, torch.float32, B * Cc)):
+        if t is not None and (t.dtype != dt or t.numel() != n or not t.is_contiguous() or t.device != dev):
+            raise L.LhnError(f"preallocated output '{name}' has the wrong dtype/size/layout/device")
+    rc = L.lib().lhn_decode_heatmap(
+        L.ptr(hm), L.ptr(hm_flip), L.ptr(flip_index), L.dtype_code(hm), B, K, H, W, sb, sc, fb, fc,
+        L.ptr(center), L.ptr(scale), C.byref(dp), L.ptr(out_hm), L.ptr(out_k), L.ptr(out_idx),
+        C.byref(rp) if rp is not None else None,
+        L.ptr(joints), joints.shape[2] if joints is not None else 0,
+        L.ptr(vis), vis.shape[2] if vis is not None else 0,
+        L.ptr(weight), L.ptr(partials), L.stream())
+    L.check(rc, "lhn_decode_heatmap")
+    res = dict(hm_kpts=out_hm, kpts=out_k, idx=out_idx)
+    if partials is not None:
+        res["partials"], res["weight"] = partials, weight
+    return res
+
+
+def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, counters,
+                       pck_thr=0.2, auc_nor=30.0, auc_steps=20, blur_ksize=None):
+    """K1 + fused PCK/AUC/EPE counters (BASELINE config 4).  `counters` int64 [(auc_steps+5)*K] is
+    ADDED to.  Returns dict(hm_kpts, kpts, idx)."""
+    hm, B, K, H, W, sb, sc = _plane_view(hm, "heatmaps")
+    dev = hm.device
+    dp = _decode_params(mask_mode, refine, L.XFORM_CENTER_SCALE, (1, 1), blur_ksize)
+    center, scale = _f32c(center, "center"), _f32c(scale, "scale")
+    gt = _f32c(gt, "gt")
+    bbox_wh = _f32c(bbox_wh, "bbox_wh")
+    mask = L.require_cuda(mask, "mask").to(torch.uint8).contiguous()
+    if counters.dtype != torch.int64 or counters.numel() != (auc_steps + 5) * K or not counters.is_contiguous():
+        raise L.LhnError("counters must be a contiguous int64 tensor of (auc_steps+5)*K entries")
+    out_hm = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
+    out_k = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
+    out_idx = torch.empty((B, K), dtype=torch.int32, device=dev)
+    rc = L.lib().lhn_decode_heatmap_pck(
+        L.ptr(hm), L.dtype_code(hm), B, K, H, W, sb, sc, L.ptr(center), L.ptr(scale), C.byref(dp),
+        L.ptr(out_hm), L.ptr(out_k), L.ptr(out_idx), L.ptr(gt), L.ptr(mask), L.ptr(bbox_wh),
+        float(pck_thr), float(auc_nor), int(auc_steps), L.ptr(counters), L.stream())
+    L.check(rc, "lhn_decode_heatmap_pck")
+    return dict(hm_kpts=out_hm, kpts=out_k, idx=out_idx)
+
+
+def loss_partials(output, target, weight, loss_mode, pos_value=0.5):
+    """Per-plane sums of DistanceLoss / JointsDistanceLoss against an explicit target tensor."""
+    L.require_cuda(output, "output")
+    L.require_cuda(target, "target")
+    if target.shape != output.shape:
+        raise L.LhnError("output and target shapes differ")
+    if target.dtype != output.dtype:
+        target = target.to(output.dtype)
+    output, target = output.contiguous(), target.contiguous()
+    H, W = output.shape[-2:]
+    P = output.numel() // (H * W)
+    weight = _f32c(weight, "target_weight").reshape(-1)
+    if weight.numel() != P:
+        raise L.LhnError(f"target_weight has {weight.numel()} entries for {P} planes")
+    partials = torch.empty((P, 4), dtype=torch.float64, device=output.device)
+    rc = L.lib().lhn_loss_partials(L.ptr(output), L.ptr(target), L.ptr(weight), L.dtype_code(output), P,
+                                   H * W, int(loss_mode), float(pos_value), L.ptr(partials), L.stream())
+    L.check(rc, "lhn_loss_partials")
+    return partials
+
+
+def loss_reduce(partials, sums=None, accumulate=False):
+    if sums is None:
+        sums = torch.empty(4, dtype=torch.float64, device=partials.device)
+    L.check(L.lib().lhn_loss_reduce(L.ptr(partials), partials.shape[0], L.ptr(sums), int(accumulate),
+                                    L.stream()), "lhn_loss_reduce")
+    return sums
+
+
+def loss_finalize(sums, loss_mode, reduction="mean", scale=1.0, out=None, accumulate=False):
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=sums.device)
+    L.check(L.lib().lhn_loss_finalize(L.ptr(sums), int(loss_mode), int(reduction == "sum"), float(scale),
+                                      L.ptr(out), int(accumulate), L.stream()), "lhn_loss_finalize")
+    return out
+
+
+def render_targets(joints, vis, image_size, heatmap_size, sigma, unbiased=True):
+    """Batched TopDownGenerateTarget: target [B,(S,)K,H,W] f32, target_weight [B,(S,)K,1] f32."""
+    joints = _f32c(joints, "joints")
+    vis = _f32c(vis, "vis")
+    if vis.dim() == 2:
+        vis = vis.unsqueeze(-1).contiguous()
+    B, K = joints.shape[:2]
+    W, H = int(heatmap_size[0]), int(heatmap_size[1])
+    rp = _render_params(L.LOSS_NONE, image_size, sigma, unbiased)
+    S = rp.num_stacks
+    stacked = isinstance(sigma, (list, tuple))
+    shape = (B, S, K, H, W) if stacked else (B, K, H, W)
+    target = torch.empty(shape, dtype=torch.float32, device=joints.device)
+    tw = torch.empty(shape[:-2] + (1,), dtype=torch.float32, device=joints.device)
+    rc = L.lib().lhn_render_targets(L.ptr(joints), joints.shape[2], L.ptr(vis), vis.shape[2], B, K, H, W,
+                                    C.byref(rp), L.ptr(target), L.ptr(tw), L.stream())
+    L.check(rc, "lhn_render_targets")
+    return target, tw
+
+
+def render_simdr(joints, vis, image_size, k=2, sigma=2):
+    joints = _f32c(joints, "joints")
+    vis = _f32c(vis, "vis")
+    if vis.dim() == 2:
+        vis = vis.unsqueeze(-1).contiguous()
+    B, K = joints.shape[:2]
+    Lx, Ly = int(image_size[0] * k), int(image_size[1] * k)
+    sx = torch.empty((B, K, Lx), dtype=torch.float32, device=joints.device)
+    sy = torch.empty((B, K, Ly), dtype=torch.float32, device=joints.device)
+    rc = L.lib().lhn_render_simdr(L.ptr(joints), joints.shape[2], L.ptr(vis), vis.shape[2], B, K, Lx, Ly,
+                                  float(k), float(sigma), L.ptr(sx), L.ptr(sy), L.stream())
+    L.check(rc, "lhn_render_simdr")
+    return sx, sy
+
+
+def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=None, want_idx=False):
+    L.require_cuda(x_vec, "x_vectors")
+    L.require_cuda(y_vec, "y_vectors")
+    if y_vec.dtype != x_vec.dtype:
+        y_vec = y_vec.to(x_vec.dtype)
+    x_vec, y_vec = x_vec.contiguous(), y_vec.contiguous()
+    B, K, Lx = x_vec.shape
+    Ly = y_vec.shape[2]
+    center, scale = _f32c(center, "center"), _f32c(scale, "scale")
+    if ranges is not None:
+        ranges = L.require_cuda(ranges, "ranges").to(torch.int32).contiguous()
+    out = torch.empty((B, K, 3), dtype=torch.float32, device=x_vec.device)
+    idx = torch.empty((B, K, 2), dtype=torch.int32, device=x_vec.device) if want_idx else None
+    rc = L.lib().lhn_decode_simdr(L.ptr(x_vec), L.ptr(y_vec), L.dtype_code(x_vec), B, K, Lx, Ly, int(k),
+                                  L.ptr(center), L.ptr(scale), int(bool(nms)), L.ptr(ranges), L.ptr(out),
+                                  L.ptr(idx), L.stream())
+    L.check(rc, "lhn_decode_simdr")
+    return (out, idx) if want_idx else out
+
+
+def simdr_smoothl1(out_x, out_y, tgt_x, tgt_y, weight):
+    for n, t in (("output_x", out_x), ("output_y", out_y), ("target_x", tgt_x), ("target_y", tgt_y)):
+        L.require_cuda(t, n)
+    dt = out_x.dtype
+    out_x, out_y = out_x.contiguous(), out_y.to(dt).contiguous()
+    tgt_x, tgt_y = tgt_x.to(dt).contiguous(), tgt_y.to(dt).contiguous()
+    B, K, Lx = out_x.shape
+    Ly = out_y.shape[2]
+    weight = _f32c(weight, "target_weight").reshape(B, K)
+    nbytes = L.lib().lhn_simdr_loss_workspace_bytes(B, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=out_x.device)
+    loss = torch.empty(1, dtype=torch.float32, device=out_x.device)
+    rc = L.lib().lhn_simdr_smoothl1(L.ptr(out_x), L.ptr(out_y), L.ptr(tgt_x), L.ptr(tgt_y), L.ptr(weight),
+                                    L.dtype_code(out_x), B, K, Lx, Ly, L.ptr(ws), nbytes, L.ptr(loss),
+                                    L.stream())
+    L.check(rc, "lhn_simdr_smoothl1")
+    return loss
+
+
+def pck_accumulate(pred, gt, mask, thr, normalize=None, norm_const=1.0, counters=None):
+    """Adds hits[T,K], valid[K], dist_fix[K] (int64, [(T+2)*K]) for one shard of samples."""
+    L.require_cuda(pred, "pred")
+    L.require_cuda(gt, "gt")
+    if pred.dtype not in (torch.float32, torch.float64):
+        pred = pred.float()
+    if gt.dtype not in (torch.float32, torch.float64):
+        gt = gt.float()
+    pred, gt = pred.contiguous(), gt.contiguous()
+    N, K = pred.shape[:2]
+    mask = L.require_cuda(mask, "mask").to(torch.uint8).contiguous()
+    if normalize is not None:
+        L.require_cuda(normalize, "normalize")
+        if normalize.dtype not in (torch.float32, torch.float64):
+            normalize = normalize.double()
+        normalize = normalize.contiguous()
+    T = len(thr)
+    if counters is None:
+        counters = torch.zeros((T + 2) * K, dtype=torch.int64, device=pred.device)
+    thr_arr = (C.c_float * max(T, 1))(*[float(t) for t in thr])
+    rc = L.lib().lhn_pck_accumulate(L.ptr(pred), L.dtype_code(pred), pred.shape[2], L.ptr(gt),
+                                    L.dtype_code(gt), gt.shape[2], L.ptr(mask), L.ptr(normalize),
+                                    L.dtype_code(normalize) if normalize is not None else L.F64,
+                                    float(norm_const), N, K, thr_arr, T, L.ptr(counters), L.stream())
+    L.check(rc, "lhn_pck_accumulate")
+    return counters
+
+
+def evaluate_pck(pred_hm, gt_hm, bbox_wh, weight, image_size, thr):
+    L.require_cuda(pred_hm, "pred_keypoints_hm")
+    L.require_cuda(gt_hm, "gt_keypoints_hm")
+    if gt_hm.dtype != pred_hm.dtype:
+        gt_hm = gt_hm.to(pred_hm.dtype)
+    pred_hm, gt_hm = pred_hm.contiguous(), gt_hm.contiguous()
+    B, K, H, W = pred_hm.shape
+    bbox_wh = _f32c(bbox_wh, "bbox")
+    weight = None if weight is None else _f32c(weight, "target_weight").reshape(B, K)
+    nbytes = L.lib().lhn_evaluate_pck_workspace_bytes(B, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=pred_hm.device)
+    pck = torch.empty(B, dtype=torch.float32, device=pred_hm.device)
+    mean = torch.empty(1, dtype=torch.float64, device=pred_hm.device)
+    rc = L.lib().lhn_evaluate_pck(L.ptr(pred_hm), L.ptr(gt_hm), L.dtype_code(pred_hm), B, K, H, W,
+                                  L.ptr(bbox_wh), L.ptr(weight), float(image_size[0]), float(image_size[1]),
+                                  float(thr), L.ptr(ws), nbytes, L.ptr(pck), L.ptr(mean), L.stream())
+    L.check(rc, "lhn_evaluate_pck")
+    return pck, mean
+
+
+def flip_back(x, flip_index=None):
+    L.require_cuda(x, "output_flipped")
+    x = x.contiguous()
+    B, K, H, W = x.shape
+    if flip_index is not None:
+        flip_index = L.require_cuda(flip_index, "flip_index").to(torch.int32).contiguous()
+    out = torch.empty_like(x)
+    L.check(L.lib().lhn_flip_back(L.ptr(x), L.ptr(out), L.dtype_code(x), B, K, H, W, L.ptr(flip_index),
+                                  L.stream()), "lhn_flip_back")
+    return out

@@ -74,6 +74,8 @@ def render_loss_case(ref, name, N, K, H, W, seed, image_size, hm):
     j, v = synth.hand_joints(N, K, image_size=image_size, seed=seed, outside_frac=0.12, vis_prob=0.8)
     v[0, 0, 0] = 0.3                       # fractional visibility: weight kept, target zero
     jn, vn = j.numpy(), v.numpy()
+    # losses are taken on a NaN/inf-free copy of the decode fixture (loss_input = nan_to_num(hm))
+    hm = torch.nan_to_num(hm, nan=0.25, posinf=1.0, neginf=-1.0)
     d = dict(joints_3d=jn, joints_3d_visible=vn, image_size=np.array(image_size),
              heatmap_size=np.array([W, H]))
     for unb, tag in ((True, "unbiased"), (False, "int")):
