@@ -1,0 +1,706 @@
+// K1 (primary) — persistent fused heatmap kernel: one TEAM of warps per shared-memory stage.
+//
+// One CTA per SM, cut into teams of TW warps; every team owns a private stage (plane [+ flipped
+// plane]) with its own mbarrier and named barrier — there is no CTA-wide barrier anywhere.  Per plane
+// a team: waits for its TMA bulk copy, makes ONE sweep over the plane (flip average, Gaussian target +
+// squared error, running max; 128-bit conflict-free shared-memory reads), combines the per-warp
+// partials, and then splits: warp 0 takes the positives' sum and the DARK window from the
+// still-resident stage, immediately re-arms the stage with the TMA load of the team's NEXT plane, and
+// finishes refinement / back-transform / stores while that load is in flight; the other warps of the
+// team meanwhile evaluate the next plane's render parameters and Gaussian tables (double-buffered).
+// 6 teams x 32 KB in flight per SM (f32 + flip) keep HBM busy; 24 warps per SM hide the latencies.
+#pragma once
+#include <math.h>
+#include <stdlib.h>
+
+#include "lhn_heatmap.cuh"
+
+namespace lhn {
+
+constexpr int kMaxWarpsPerCta = 24;
+constexpr int kMaxTeams = 12;
+
+__device__ __forceinline__ void team_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// per-team header at the start of the aux region
+struct TeamHeader {
+  uint64_t bar;               // TMA completion barrier of the stage
+  uint64_t pad;
+  uint32_t red_key[8];        // per-warp pass-1 partials
+  uint32_t red_q[8];
+  double red_s[8];
+  int red_nonfinite[8];
+  // render parameters of the two table buffers (written by whoever runs the prologue)
+  float w[2];
+  float mx[2], my[2];
+  int render_on[2];
+  // positives of the balanced loss (written by the last warp of the team before S3)
+  double spos;
+  int npos;
+  int pad2;
+};
+
+template <typename T>
+__device__ __forceinline__ float elem_f32(const T* p, int i) { return Elem<T>::to_f32(p[i]); }
+
+// fast f32 exp of a double argument: exp(a) = exp(ah) * (1 + al), ah = f32(a), al = a - ah
+__device__ __forceinline__ float exp_f32_from_f64(double a) {
+  const float ah = (float)a;
+  const float al = (float)(a - (double)ah);
+  const float v = expf(ah);
+  return fmaf(v, al, v);
+}
+
+// FAST: W = H = 64 and the team size is a compile-time constant (TWC warps), so the sweep is a fully
+//       unrolled 128-bit loop with a loop-invariant column quad per thread.
+// KS:   DARK Gaussian size known at compile time (11: the Gen-2 decoder) or 0 = run-time size.
+template <typename T, bool FAST, int TWC, bool FLIP, bool LOSS, int KS>
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
+heatmap_team_kernel(const __grid_constant__ HmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int H = FAST ? 64 : a.H, W = FAST ? 64 : a.W, HW = FAST ? 4096 : a.HW;
+  const int TW = FAST ? TWC : a.team_warps;          // warps per team
+  const int TT = TW * 32;                            // threads per team
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp / TW, wt = warp - team * TW; // team in CTA, warp in team
+  const int tl = wt * 32 + lane;                     // thread in team
+  const int nteams = (blockDim.x >> 5) / TW;
+  const int bar_id = 1 + team;
+
+  // ---- this team's private shared memory ----------------------------------------------------------
+  unsigned char* tbase = smem_raw + (size_t)team * a.warp_smem;
+  const T* plane0 = reinterpret_cast<const T*>(tbase);
+  const T* plane1 = FLIP ? reinterpret_cast<const T*>(tbase + (a.stage_bytes >> 1)) : nullptr;
+  unsigned char* aux = tbase + a.stage_bytes;
+  TeamHeader* th = reinterpret_cast<TeamHeader*>(aux);
+  const size_t tab_bytes = align_up((size_t)(W + H) * 4, 16);
+  float* tab0 = reinterpret_cast<float*>(aux + align_up(sizeof(TeamHeader), 16));   // two table buffers
+  const int ksize = KS > 0 ? KS : a.ksize;
+  const int TD = KS > 0 ? KS + 4 : a.tile_dim;
+  float* tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);
+  double* hbuf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile) + align_up((size_t)TD * TD * 4, 16));
+  float* hout = reinterpret_cast<float*>(hbuf + (size_t)TD * 5);
+
+  const uint32_t total_teams = gridDim.x * nteams;
+  const uint32_t gteam = blockIdx.x * nteams + team;
+  const uint32_t n_planes = (uint32_t)a.n_planes;
+  const uint32_t plane_bytes = (uint32_t)HW * sizeof(T);
+  const uint32_t C = (uint32_t)a.C, K = (uint32_t)a.K;
+  // plane -> (batch, channel) is advanced incrementally: no division in the loop
+  const uint32_t step_b = total_teams / C, step_c = total_teams - step_b * C;
+
+  auto split_channel = [&](uint32_t c, uint32_t& s, uint32_t& k) {
+    if (C == K) { s = 0; k = c; } else { s = c / K; k = c - s * K; }
+  };
+  auto advance = [&](uint32_t& b, uint32_t& c) {
+    b += step_b; c += step_c;
+    if (c >= C) { c -= C; b += 1; }
+  };
+  auto gptr0 = [&](uint32_t b, uint32_t c) {
+    return reinterpret_cast<const T*>(a.hm) + (int64_t)b * a.stride_b + (int64_t)c * a.stride_c;
+  };
+  auto gptr1 = [&](uint32_t b, uint32_t c) {
+    uint32_t s, k;
+    split_channel(c, s, k);
+    const uint32_t kf = a.flip_index ? (uint32_t)a.flip_index[k] : k;
+    return reinterpret_cast<const T*>(a.hm_flip) + (int64_t)b * a.fstride_b + (int64_t)(s * K + kf) * a.fstride_c;
+  };
+  uint64_t policy = 0;
+  auto issue = [&](uint32_t b, uint32_t c) {   // one thread of the team
+    mbar_arrive_expect_tx(&th->bar, FLIP ? 2 * plane_bytes : plane_bytes);
+    tma_load_1d(const_cast<T*>(plane0), gptr0(b, c), plane_bytes, &th->bar, policy);
+    if (FLIP) tma_load_1d(const_cast<T*>(plane1), gptr1(b, c), plane_bytes, &th->bar, policy);
+  };
+
+  // Render parameters + separable Gaussian factors of plane (b, c) into table buffer `buf`, computed
+  // by `nthr` threads of the team (thread index `t`).  exp() is evaluated on an f64 argument.
+  auto prologue = [&](uint32_t b, uint32_t c, int buf, int t, int nthr) {
+    if (!LOSS) return;
+    uint32_t s, k;
+    split_channel(c, s, k);
+    const uint32_t bk = b * K + k;
+    const float* jp = a.joints + (int64_t)bk * a.joints_stride;
+    float w = a.vis[(int64_t)bk * a.vis_stride];
+    const double sig = (double)a.sigma[s], tmp = sig * 3.0;
+    double mux = (double)jp[0] / a.feat_x, muy = (double)jp[1] / a.feat_y;
+    double x0p = 0, ulx, uly, brx, bry;
+    if (a.unbiased) {
+      ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1;
+    } else {
+      mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);                // int() truncates toward zero
+      ulx = trunc(mux - tmp); uly = trunc(muy - tmp);
+      brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
+      x0p = floor((2 * tmp + 1) * 0.5);                               // size // 2
+    }
+    if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
+    const bool render_on = w > 0.5f;
+    if (t == 0) {
+      th->w[buf] = w; th->mx[buf] = (float)mux; th->my[buf] = (float)muy; th->render_on[buf] = render_on ? 1 : 0;
+    }
+    const double i2 = a.inv2s2[s];
+    float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + (size_t)buf * tab_bytes);
+    for (int i = t; i < W + H; i += nthr) {
+      const bool isx = i < W;
+      const int pos = isx ? i : i - W;
+      float v = 0.f;
+      if (render_on) {
+        if (a.unbiased) {
+          const double d = (double)pos - (isx ? mux : muy);
+          v = exp_f32_from_f64(-(d * d) * i2);
+        } else {
+          const double ul = isx ? ulx : uly, br = isx ? brx : bry;
+          if ((double)pos >= ul && (double)pos < br) {
+            const double d = ((double)pos - ul) - x0p;
+            v = exp_f32_from_f64(-(d * d) * i2);
+          }
+        }
+      }
+      tab[i] = v;
+    }
+  };
+
+  uint32_t p = gteam;
+  if (p >= n_planes) return;                       // whole teams leave together
+  uint32_t pb = p / C, pc = p - pb * C;            // the only division: once per team
+  if (tl == 0) {
+    mbar_init(&th->bar, 1);
+    fence_mbar_init();
+    policy = policy_evict_first();
+    if (a.use_tma) issue(pb, pc);
+  }
+  prologue(pb, pc, 0, tl, TT);
+  uint32_t phase = 0;
+  int buf = 0;
+
+  const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
+  const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
+  const int QR = W >> 2, nq = HW >> 2;
+
+  for (; p < n_planes; p += total_teams, buf ^= 1, advance(pb, pc)) {
+    // S1: tables of this plane are written, the aux buffers of the previous plane are free
+    team_sync(bar_id, TT);
+    const float* ex = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(tab0) + (size_t)buf * tab_bytes);
+    const float* ey = ex + W;
+
+    // ---- wait for the plane ------------------------------------------------------------------------
+    if (a.use_tma) {
+      mbar_wait(&th->bar, phase);
+      phase ^= 1u;
+    } else {
+      const T* g0 = gptr0(pb, pc);
+      T* d0 = const_cast<T*>(plane0);
+      for (int e = tl; e < HW; e += TT) d0[e] = g0[e];
+      if (FLIP) {
+        const T* g1 = gptr1(pb, pc);
+        T* d1 = const_cast<T*>(plane1);
+        for (int e = tl; e < HW; e += TT) d1[e] = g1[e];
+      }
+      team_sync(bar_id, TT);
+    }
+
+    // decoded value (flip average) of quad q / of element (y, x)
+    auto load_quad = [&](int q) -> float4 {
+      const float4 o = load4<T>(plane0 + 4 * q);
+      if (!FLIP) return o;
+      const int row = FAST ? (q >> 4) : (q / QR);
+      const int cq = q - row * QR;
+      const float4 f = load4<T>(plane1 + row * W + (W - 4 - 4 * cq));
+      float4 v;
+      v.x = __fmul_rn(__fadd_rn(o.x, f.w), 0.5f);
+      v.y = __fmul_rn(__fadd_rn(o.y, f.z), 0.5f);
+      v.z = __fmul_rn(__fadd_rn(o.z, f.y), 0.5f);
+      v.w = __fmul_rn(__fadd_rn(o.w, f.x), 0.5f);
+      return v;
+    };
+    auto val = [&](int y, int x) -> float {
+      float o = elem_f32<T>(plane0, y * W + x);
+      if (FLIP) o = __fmul_rn(__fadd_rn(o, elem_f32<T>(plane1, y * W + (W - 1 - x))), 0.5f);
+      return o;
+    };
+
+    // ---- pass 1: one sweep, split over the team ------------------------------------------------------
+    constexpr bool kUseS = LOSS && !FLIP;   // S already turns non-finite on a NaN/inf input
+    float S0 = 0.f, S1 = 0.f, nacc = 0.f;
+    float best = -CUDART_INF_F;
+    int bq = -1;
+    auto sweep_quad = [&](int q, int row, const float4& gx) {
+      const float4 o = load4<T>(plane0 + 4 * q);
+      float4 v = o;
+      if (FLIP) {
+        const int cq = q - row * QR;
+        const float4 f = load4<T>(plane1 + row * W + (W - 4 - 4 * cq));
+        v.x = __fmul_rn(__fadd_rn(o.x, f.w), 0.5f);
+        v.y = __fmul_rn(__fadd_rn(o.y, f.z), 0.5f);
+        v.z = __fmul_rn(__fadd_rn(o.z, f.y), 0.5f);
+        v.w = __fmul_rn(__fadd_rn(o.w, f.x), 0.5f);
+      }
+      if (LOSS) {
+        const float gy = ey[row];
+        const float d0 = fmaf(-gx.x, gy, o.x), d1 = fmaf(-gx.y, gy, o.y);
+        const float d2 = fmaf(-gx.z, gy, o.z), d3 = fmaf(-gx.w, gy, o.w);
+        S0 = fmaf(d0, d0, S0); S1 = fmaf(d1, d1, S1); S0 = fmaf(d2, d2, S0); S1 = fmaf(d3, d3, S1);
+      }
+      if (!kUseS) {
+        nacc = fmaf(v.x, 0.f, nacc); nacc = fmaf(v.y, 0.f, nacc);
+        nacc = fmaf(v.z, 0.f, nacc); nacc = fmaf(v.w, 0.f, nacc);
+      }
+      const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));   // ignores NaN, like `>`
+      if (m4 > best) { best = m4; bq = q; }
+    };
+    if (FAST) {
+      // TT is a multiple of 16: the column quad of a thread is loop-invariant
+      float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (LOSS) gx = *reinterpret_cast<const float4*>(ex + 4 * (tl & 15));
+      constexpr int kIters = 1024 / ((TWC > 0 ? TWC : 1) * 32);
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int q = it * (TWC * 32) + tl;
+        sweep_quad(q, q >> 4, gx);
+      }
+    } else {
+      for (int q = tl; q < nq; q += TT) {
+        const int row = q / QR;
+        float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LOSS) gx = *reinterpret_cast<const float4*>(ex + 4 * (q - row * QR));
+        sweep_quad(q, row, gx);
+      }
+    }
+
+    // ---- per-warp partials -> shared, S2 ----------------------------------------------------------------
+    {
+      uint32_t key = order_key(best);
+      uint32_t qsel = (uint32_t)bq;            // -1 -> 0xffffffff
+      warp_argmax(key, qsel);
+      double ssum = 0.0;
+      if (LOSS) ssum = warp_sum((double)S0 + (double)S1);
+      const bool nonfinite_lane = kUseS ? !(fabsf(S0 + S1) < CUDART_INF_F) : (nacc != nacc);
+      const bool nf = __any_sync(0xffffffffu, nonfinite_lane);
+      if (lane == 0) { th->red_key[wt] = key; th->red_q[wt] = qsel; th->red_s[wt] = ssum; th->red_nonfinite[wt] = nf ? 1 : 0; }
+    }
+    team_sync(bar_id, TT);
+
+    // ---- every warp: the team-wide argmax (redundantly: cheaper than another barrier) --------------------
+    uint32_t key = lane < TW ? th->red_key[lane] : 0u;
+    uint32_t qsel = lane < TW ? th->red_q[lane] : 0xffffffffu;
+    warp_argmax(key, qsel);
+    const bool any_nonfinite = __any_sync(0xffffffffu, lane < TW && th->red_nonfinite[lane] != 0);
+    uint32_t idx = 0;
+    float maxval = key_to_float(key);
+    if (qsel != 0xffffffffu) {
+      const float4 v = load_quad((int)qsel);
+      const float m = key_to_float(key);
+      // `==` treats -0 and +0 as equal, like torch/numpy; report the element actually selected
+      if (v.x == m) { idx = 4 * qsel; maxval = v.x; }
+      else if (v.y == m) { idx = 4 * qsel + 1; maxval = v.y; }
+      else if (v.z == m) { idx = 4 * qsel + 2; maxval = v.z; }
+      else { idx = 4 * qsel + 3; maxval = v.w; }
+    } else {
+      maxval = val(0, 0);                     // every element is -inf (or NaN: fixed below)
+    }
+    if (any_nonfinite) {
+      // rare: the first NaN of the decoded plane is the argmax (np.argmax / torch.max semantics)
+      uint32_t first_nan = 0xffffffffu;
+      for (int q = lane; q < nq && first_nan == 0xffffffffu; q += 32) {
+        const float4 v = load_quad(q);
+        if (v.x != v.x) first_nan = 4 * q;
+        else if (v.y != v.y) first_nan = 4 * q + 1;
+        else if (v.z != v.z) first_nan = 4 * q + 2;
+        else if (v.w != v.w) first_nan = 4 * q + 3;
+      }
+      first_nan = __reduce_min_sync(0xffffffffu, first_nan);
+      if (first_nan != 0xffffffffu) { idx = first_nan; maxval = __uint_as_float(0x7fc00000u); }
+    }
+
+    // masked integer coordinates (A1-A4)
+    const int ipy = FAST ? (int)(idx >> 6) : (int)(idx / (uint32_t)W);
+    const int ipx = (int)idx - ipy * W;
+    float cx = (float)ipx, cy = (float)ipy;
+    const bool positive = maxval > 0.0f;
+    if (a.mask_mode == LHN_MASK_ZERO && !positive) { cx = 0.f; cy = 0.f; }
+    if (a.mask_mode == LHN_MASK_NEG1 && !positive) { cx = -1.f; cy = -1.f; }
+    const int px = (int)cx, py = (int)cy;
+    const bool dark_guard = is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2);
+    const int bb = (ksize - 1) >> 1;
+
+    // ---- stage the DARK window: zero-padded (ksize+4)^2 tile of the decoded plane, by the whole team ----
+    if (dark_guard) {
+      for (int e = tl; e < TD * TD; e += TT) {
+        const int r = e / TD, cc = e - r * TD;           // compile-time divisor when KS > 0
+        const int y = py - 2 - bb + r, x = px - 2 - bb + cc;
+        tile[e] = (y >= 0 && y < H && x >= 0 && x < W) ? val(y, x) : 0.f;
+      }
+    }
+    // ---- positives of the balanced loss: a small window around the joint, by the team's last warp ----------
+    if (LOSS && wt == TW - 1 && a.loss_mode == LHN_LOSS_DISTANCE_BALANCE) {
+      uint32_t s, k;
+      split_channel(pc, s, k);
+      double Spos = 0.0;
+      int Npos = 0;
+      int x_lo = 0, x_hi = W - 1, y_lo = 0, y_hi = H - 1;
+      if (a.pos_value > 0.f && a.pos_value < 1.f) {
+        // g > value  <=>  r^2 < -2 sigma^2 ln(value): a.pos_radius = that radius + a rounding margin
+        const float rad = a.pos_radius[s];
+        const float mxf = th->mx[buf], myf = th->my[buf];
+        x_lo = max(0, (int)ceilf(mxf - rad)); x_hi = min(W - 1, (int)floorf(mxf + rad));
+        y_lo = max(0, (int)ceilf(myf - rad)); y_hi = min(H - 1, (int)floorf(myf + rad));
+      } else if (a.pos_value >= 1.f) {
+        x_hi = -1;
+      }
+      if (th->render_on[buf] || a.pos_value < 0.f) {
+        float sp = 0.f;
+        // one column per lane, rows in a short loop (5 x 5 for sigma = 2)
+        for (int x0 = x_lo; x0 <= x_hi; x0 += 32) {
+          const int xx = x0 + lane;
+          if (xx <= x_hi) {
+            const float gxv = ex[xx];
+            for (int yy = y_lo; yy <= y_hi; ++yy) {
+              const float gyv = ey[yy];
+              if (gxv * gyv > a.pos_value) {
+                const float d = fmaf(-gxv, gyv, elem_f32<T>(plane0, yy * W + xx));
+                sp = fmaf(d, d, sp);
+                Npos += 1;
+              }
+            }
+          }
+        }
+        Spos = warp_sum((double)sp);
+        Npos = __reduce_add_sync(0xffffffffu, Npos);
+      }
+      if (lane == 0) { th->spos = Spos; th->npos = Npos; }
+    }
+    // ---- quarter-offset refinements read their neighbours while the plane is resident ----------------------
+    float rx = cx, ry = cy;
+    if (wt == 0) {
+      if (a.refine == LHN_REFINE_OFFSET_HALF || a.refine == LHN_REFINE_OFFSET) {
+        const int xx = min(max(px, 0), W - 1), yy = min(max(py, 0), H - 1);
+        // clamped neighbours; `>` false (equality, NaN) -> -0.25
+        rx += (val(yy, min(xx + 1, W - 1)) > val(yy, max(xx - 1, 0))) ? 0.25f : -0.25f;
+        ry += (val(min(yy + 1, H - 1), xx) > val(max(yy - 1, 0), xx)) ? 0.25f : -0.25f;
+        if (a.refine == LHN_REFINE_OFFSET_HALF) { rx += 0.5f; ry += 0.5f; }
+      } else if (a.refine == LHN_REFINE_SIGN || a.refine == LHN_REFINE_SIGN_ROUND) {
+        int qx = px, qy = py;
+        if (a.refine == LHN_REFINE_SIGN_ROUND) { qx = (int)floorf(cx + 0.5f); qy = (int)floorf(cy + 0.5f); }
+        if (1 < qx && qx < W - 1 && 1 < qy && qy < H - 1) {
+          const float ddx = val(qy, qx + 1) - val(qy, qx - 1);
+          const float ddy = val(qy + 1, qx) - val(qy - 1, qx);
+          const float sxn = (ddx != ddx) ? ddx : (float)((ddx > 0.f) - (ddx < 0.f));   // np.sign
+          const float syn = (ddy != ddy) ? ddy : (float)((ddy > 0.f) - (ddy < 0.f));
+          rx += sxn * 0.25f; ry += syn * 0.25f;
+        }
+      }
+    }
+    // S3: the tile and the positives' sum are staged
+    team_sync(bar_id, TT);
+
+    if (wt != 0) {
+      // helper warps: render parameters + tables of the team's NEXT plane, while warp 0 finishes this one
+      if (p + total_teams < n_planes) {
+        uint32_t nb = pb, nc = pc;
+        advance(nb, nc);
+        prologue(nb, nc, buf ^ 1, tl - 32, TT - 32);
+      }
+      continue;
+    }
+
+    // =========================== warp 0 of the team: the rest of the epilogue ===============================
+    bool need_slow = false;
+    float bmax = 0.f;
+    if (dark_guard) {
+      // row pass (sequential FMA over the taps), then column pass (centre + symmetric pairs) — the
+      // summation order of cv2's separable filter
+      if (legacy) {
+        for (int e = lane; e < TD * 5; e += 32) {
+          const int r = e / 5, c5 = e - r * 5;
+          double acc = 0.0;
+          for (int j = 0; j < ksize; ++j) acc = __fma_rn(a.tapsd[j], (double)tile[r * TD + c5 + j], acc);
+          hbuf[e] = acc;
+        }
+        __syncwarp();
+        if (lane < 25) {
+          const int dr = lane / 5, c5 = lane - dr * 5;
+          double acc = __dmul_rn(a.tapsd[bb], hbuf[(dr + bb) * 5 + c5]);
+          for (int j = 1; j <= bb; ++j)
+            acc = __fma_rn(a.tapsd[bb + j], __dadd_rn(hbuf[(dr + bb + j) * 5 + c5], hbuf[(dr + bb - j) * 5 + c5]), acc);
+          hout[lane] = (float)acc;
+        }
+      } else {
+        float* hb = reinterpret_cast<float*>(hbuf);
+        for (int e = lane; e < TD * 5; e += 32) {
+          const int r = e / 5, c5 = e - r * 5;
+          const float* trow = tile + r * TD + c5;
+          float acc = 0.f;
+          if (KS > 0) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);   // taps: constant-bank operands
+          } else {
+            for (int j = 0; j < ksize; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);
+          }
+          hb[e] = acc;
+        }
+        __syncwarp();
+        if (lane < 25) {
+          const int dr = lane / 5, c5 = lane - dr * 5;
+          const float* hcol = hb + (dr + bb) * 5 + c5;
+          float acc = __fmul_rn(a.tapsf[bb], hcol[0]);
+          if (KS > 0) {
+#pragma unroll
+            for (int j = 1; j <= (KS - 1) / 2; ++j)
+              acc = __fmaf_rn(a.tapsf[(KS - 1) / 2 + j], __fadd_rn(hcol[5 * j], hcol[-5 * j]), acc);
+          } else {
+            for (int j = 1; j <= bb; ++j) acc = __fmaf_rn(a.tapsf[bb + j], __fadd_rn(hcol[5 * j], hcol[-5 * j]), acc);
+          }
+          hout[lane] = acc;
+        }
+      }
+      __syncwarp();
+      // can the 1e-10 clamp of log() (or a non-finite value) touch the 13 stencil points?
+      const float hv = lane < 25 ? hout[lane] : CUDART_INF_F;
+      const int dr = lane / 5 - 2, dc = lane % 5 - 2;
+      const bool used = lane < 25 && (abs(dr) + abs(dc) <= 2);
+      const bool bad = used && !(hv >= 1e-9f);
+      const bool ok_origin = legacy ? (maxval >= 1e-3f) : (maxval > 0.f);
+      need_slow = __any_sync(0xffffffffu, bad) || !ok_origin || any_nonfinite;
+      if (need_slow) {
+        // exact emulation: max of the whole blurred plane (NaN propagates like np.max)
+        float m = -CUDART_INF_F;
+        bool first = true;
+        for (int e = lane; e < HW; e += 32) {
+          const int y = e / W, x = e - y * W;
+          float v;
+          if (legacy) {
+            auto rowv = [&](int yy) {
+              double r = 0.0;
+              if (yy < 0 || yy >= H) return r;
+              for (int j = 0; j < ksize; ++j) {
+                const int xx = x + j - bb;
+                r = __fma_rn(a.tapsd[j], (xx >= 0 && xx < W) ? (double)val(yy, xx) : 0.0, r);
+              }
+              return r;
+            };
+            double acc = __dmul_rn(a.tapsd[bb], rowv(y));
+            for (int j = 1; j <= bb; ++j) acc = __fma_rn(a.tapsd[bb + j], __dadd_rn(rowv(y + j), rowv(y - j)), acc);
+            v = (float)acc;
+          } else {
+            auto rowv = [&](int yy) {
+              float r = 0.f;
+              if (yy < 0 || yy >= H) return r;
+              for (int j = 0; j < ksize; ++j) {
+                const int xx = x + j - bb;
+                r = __fmaf_rn(a.tapsf[j], (xx >= 0 && xx < W) ? val(yy, xx) : 0.f, r);
+              }
+              return r;
+            };
+            float acc = __fmul_rn(a.tapsf[bb], rowv(y));
+            for (int j = 1; j <= bb; ++j) acc = __fmaf_rn(a.tapsf[bb + j], __fadd_rn(rowv(y + j), rowv(y - j)), acc);
+            v = acc;
+          }
+          m = first ? v : nanmax(m, v);
+          first = false;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        bmax = m;
+      }
+    }
+
+    // ---- the stage is free: re-arm it with the team's next plane, then finish from shared/registers ------
+    __syncwarp();
+    if (a.use_tma && p + total_teams < n_planes && lane == 0) {
+      uint32_t nb = pb, nc = pc;
+      advance(nb, nc);
+      fence_proxy_async();
+      issue(nb, nc);
+    }
+
+    if (dark_guard) {
+      // log of the 25 blurred values in parallel, then the Taylor step on lane 0
+      const float raw = lane < 25 ? hout[lane] : 1.f;
+      float hval;
+      if (need_slow) {
+        const float sc = legacy ? __fdiv_rn(maxval, __fadd_rn(bmax, 1e-6f)) : __fdiv_rn(maxval, bmax);
+        float v = __fmul_rn(raw, sc);
+        v = (v != v) ? v : fmaxf(v, 1e-10f);          // np.maximum propagates NaN
+        hval = logf(v);
+      } else {
+        hval = logf(raw);
+      }
+      __syncwarp();
+      if (lane < 25) hout[lane] = hval;
+      __syncwarp();
+    }
+
+    if (lane == 0) {
+      if (dark_guard) {
+#define HH(dy, dx) hout[((dy) + 2) * 5 + (dx) + 2]
+        const float h00 = HH(0, 0);
+        const float ddx = __fmul_rn(0.5f, __fsub_rn(HH(0, 1), HH(0, -1)));
+        const float ddy = __fmul_rn(0.5f, __fsub_rn(HH(1, 0), HH(-1, 0)));
+        const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(HH(0, 2), __fmul_rn(2.f, h00)), HH(0, -2)));
+        const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(HH(1, 1), HH(-1, 1)), HH(1, -1)), HH(-1, -1)));
+        const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(HH(2, 0), __fmul_rn(2.f, h00)), HH(-2, 0)));
+#undef HH
+        const float det = __fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy));
+        if (det != 0.f) {   // true for NaN, as in numpy
+          const float ox = -__fdiv_rn(__fsub_rn(__fmul_rn(dyy, ddx), __fmul_rn(dxy, ddy)), det);
+          const float oy = -__fdiv_rn(__fsub_rn(__fmul_rn(dxx, ddy), __fmul_rn(dxy, ddx)), det);
+          rx = __fadd_rn(rx, ox); ry = __fadd_rn(ry, oy);
+        }
+      }
+      // ---- back-transform (T1/T2) and stores --------------------------------------------------------
+      const uint32_t b = pb;
+      uint32_t s, k;
+      split_channel(pc, s, k);
+      const uint32_t bk = b * K + k;
+      float X = rx, Y = ry;
+      if (a.transform == LHN_XFORM_CENTER_SCALE) {
+        const float s0 = __fmul_rn(a.scale[2 * b], 200.0f), s1 = __fmul_rn(a.scale[2 * b + 1], 200.0f);
+        const float dw = a.use_udp ? (float)(W - 1) : (float)W, dh = a.use_udp ? (float)(H - 1) : (float)H;
+        const float fx = __fdiv_rn(s0, dw), fy = __fdiv_rn(s1, dh);
+        X = __fsub_rn(__fadd_rn(__fmul_rn(rx, fx), a.center[2 * b]), __fmul_rn(s0, 0.5f));
+        Y = __fsub_rn(__fadd_rn(__fmul_rn(ry, fy), a.center[2 * b + 1]), __fmul_rn(s1, 0.5f));
+      } else if (a.transform == LHN_XFORM_SCALE) {
+        X = __fmul_rn(rx, a.scale_x); Y = __fmul_rn(ry, a.scale_y);
+      }
+      if (a.out_hm) { float* o = a.out_hm + 3 * (int64_t)p; o[0] = rx; o[1] = ry; o[2] = maxval; }
+      if (a.out_kpts) { float* o = a.out_kpts + 3 * (int64_t)p; o[0] = X; o[1] = Y; o[2] = maxval; }
+      if (a.out_idx) a.out_idx[p] = (int32_t)idx;
+      if (LOSS) {
+        double S = 0.0;
+        for (int i = 0; i < TW; ++i) S += th->red_s[i];
+        const float w = th->w[buf];
+        const bool bal = a.loss_mode == LHN_LOSS_DISTANCE_BALANCE;
+        const float wp = (a.loss_mode == LHN_LOSS_JOINTS_MSE) ? w * w : w;
+        const double sall = S * (double)wp, spos = bal ? th->spos * (double)wp : 0.0;
+        *reinterpret_cast<double2*>(a.partials + 4 * (int64_t)p) = make_double2(spos, sall - spos);
+        *reinterpret_cast<double2*>(a.partials + 4 * (int64_t)p + 2) = make_double2(bal ? (double)th->npos : 0.0, (double)HW);
+        if (a.out_weight) a.out_weight[p] = w;
+      }
+      if (a.counters && a.mask[bk]) {
+        // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32)
+        const int Ki = (int)K;
+        const double gx = (double)a.gt[2 * (int64_t)bk], gy = (double)a.gt[2 * (int64_t)bk + 1];
+        const double ddx = (double)X - gx, ddy = (double)Y - gy;
+        unsigned long long* cnt = reinterpret_cast<unsigned long long*>(a.counters);
+        double nb = (double)fmaxf(a.bbox_wh[2 * b], a.bbox_wh[2 * b + 1]);
+        if (nb != 0.0) {
+          if (nb < 0.0) nb = 1e6;
+          const double qx = ddx / nb, qy = ddy / nb;
+          const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
+          atomicAdd(cnt + Ki + k, 1ull);
+          if (d < a.pck_thr) atomicAdd(cnt + k, 1ull);
+        }
+        {
+          const double qx = ddx / (double)a.auc_nor, qy = ddy / (double)a.auc_nor;
+          const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
+          unsigned long long* auc = cnt + 2 * Ki;
+          for (int t = 0; t < a.auc_steps; ++t) {
+            const float thr = (float)(1.0 * t / a.auc_steps);
+            if (d < thr) atomicAdd(auc + (int64_t)t * Ki + k, 1ull);
+          }
+          atomicAdd(auc + (int64_t)a.auc_steps * Ki + k, 1ull);
+        }
+        {
+          const float d = (float)sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+          unsigned long long* epe = cnt + (int64_t)(3 + a.auc_steps) * Ki;
+          atomicAdd(epe + k, 1ull);
+          atomicAdd(epe + Ki + k, (unsigned long long)llrint((double)d * 1048576.0));
+        }
+      }
+    }
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_sm_count = n > 0 ? n : 148;
+  }
+  return g_sm_count;
+}
+
+template <typename T, bool FAST, int TWC, bool FLIP, bool LOSS, int KS>
+static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {
+  auto kern = heatmap_team_kernel<T, FAST, TWC, FLIP, LOSS, KS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
+  int64_t ctas = (a.n_planes + nteams - 1) / nteams;
+  if (ctas > sm_count()) ctas = sm_count();
+  kern<<<(unsigned)ctas, nteams * a.team_warps * 32, smem, st>>>(a);
+  return check_launch();
+}
+
+template <typename T, bool FLIP, bool LOSS>
+static int dispatch_variant(HmArgs& a, bool fast, int nteams, size_t smem, cudaStream_t st) {
+  // compile-time team size of the fast 64x64 path: 32 KB stage -> 4 warps, smaller stages -> 2 warps
+  constexpr int TWF = (sizeof(T) == 4 && FLIP) ? 4 : 2;
+  const bool ks11 = a.refine == LHN_REFINE_DARK && a.ksize == 11;
+  if (fast && a.team_warps == TWF) {
+    if (ks11) return launch_one<T, true, TWF, FLIP, LOSS, 11>(a, nteams, smem, st);
+    return launch_one<T, true, TWF, FLIP, LOSS, 0>(a, nteams, smem, st);
+  }
+  if (ks11) return launch_one<T, false, 0, FLIP, LOSS, 11>(a, nteams, smem, st);
+  return launch_one<T, false, 0, FLIP, LOSS, 0>(a, nteams, smem, st);
+}
+
+template <typename T>
+int dispatch_team(HmArgs& a, bool flip, bool loss, bool fast, int nteams, size_t smem, cudaStream_t st) {
+  if (flip) return loss ? dispatch_variant<T, true, true>(a, fast, nteams, smem, st)
+                        : dispatch_variant<T, true, false>(a, fast, nteams, smem, st);
+  return loss ? dispatch_variant<T, false, true>(a, fast, nteams, smem, st)
+              : dispatch_variant<T, false, false>(a, fast, nteams, smem, st);
+}
+
+#ifndef LHN_TEAM_DTYPE_TU
+// instantiated per dtype in lhn_heatmap_team_{f32,bf16,f16}.cu so the three compile in parallel
+extern template int dispatch_team<float>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
+extern template int dispatch_team<__nv_bfloat16>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
+extern template int dispatch_team<__half>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
+
+int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
+  const bool flip = a.hm_flip != nullptr;
+  const bool loss = a.loss_mode != LHN_LOSS_NONE;
+  const size_t esz = dtype == LHN_F32 ? 4 : 2;
+  if ((a.W & 3) != 0) return 1;                       // quads must not straddle rows
+  const size_t plane_bytes = (size_t)a.HW * esz;
+  if (plane_bytes % 16) return 1;
+  const size_t plane_al = align_up(plane_bytes, 128);
+  a.stage_bytes = (int)(flip ? 2 * plane_al : plane_al);
+  const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY;
+  a.tile_dim = is_dark ? a.ksize + 4 : 0;
+  const size_t aux = align_up(sizeof(TeamHeader), 16) + 2 * align_up((size_t)(a.W + a.H) * 4, 16) +
+                     align_up((size_t)a.tile_dim * a.tile_dim * 4, 16) + (size_t)a.tile_dim * 5 * 8 + 32 * 4;
+  a.warp_smem = (int)align_up(a.stage_bytes + aux, 128);
+  const size_t budget = 227 * 1024;
+  int nteams = (int)(budget / a.warp_smem);
+  if (nteams > kMaxTeams) nteams = kMaxTeams;
+  if (nteams < 2) return 1;                           // plane pair too large: CTA-per-plane kernel
+  // ~24 warps per SM: 6 teams x 4 warps (f32 + flip, 64x64), 12 x 2 (one 16 KB plane), 3 x 8 (128x128)
+  int tw = kMaxWarpsPerCta / nteams;
+  tw = tw >= 8 ? 8 : (tw >= 4 ? 4 : 2);
+  const char* env = getenv("LHN_TEAM_WARPS");
+  if (env && atoi(env) >= 2 && atoi(env) <= 8) tw = atoi(env);
+  while (nteams * tw > kMaxWarpsPerCta) --nteams;
+  a.team_warps = tw;
+  for (int i = 0; i < LHN_MAX_STACKS; ++i) {
+    const double sg = (double)a.sigma[i];
+    a.inv2s2[i] = sg > 0 ? 1.0 / (2.0 * sg * sg) : 0.0;
+    a.pos_radius[i] = (a.pos_value > 0.f && a.pos_value < 1.f && sg > 0)
+                          ? (float)(sg * sqrt(-2.0 * log((double)a.pos_value)) * 1.001 + 0.01) : 0.f;
+  }
+  const bool fast = a.W == 64 && a.H == 64;
+  const size_t smem = (size_t)nteams * a.warp_smem;
+  switch (dtype) {
+    case LHN_F32: return dispatch_team<float>(a, flip, loss, fast, nteams, smem, st);
+    case LHN_BF16: return dispatch_team<__nv_bfloat16>(a, flip, loss, fast, nteams, smem, st);
+    case LHN_F16: return dispatch_team<__half>(a, flip, loss, fast, nteams, smem, st);
+    default: return LHN_EDTYPE;
+  }
+}
+#endif
+
+}  // namespace lhn

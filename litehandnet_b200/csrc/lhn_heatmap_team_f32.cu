@@ -1,0 +1,7 @@
+// Instantiation of the persistent team kernel for float heatmaps.
+#define LHN_TEAM_DTYPE_TU
+#include "lhn_heatmap_team.cuh"
+
+namespace lhn {
+template int dispatch_team<float>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
+}

@@ -4,6 +4,8 @@
 // SM count with grid-stride loops.
 #include <math_constants.h>
 
+#include <cooperative_groups.h>
+
 #include "lhn_common.cuh"
 
 namespace lhn {
@@ -74,31 +76,50 @@ __global__ void __launch_bounds__(256) loss_partials_kernel(const T* __restrict_
   }
 }
 
-// ---- deterministic reduction: one block, fixed strided order, f64 ------------------------------
-__global__ void __launch_bounds__(1024) loss_reduce_kernel(const double* __restrict__ partials,
-                                                           int64_t n_planes, double* __restrict__ sums,
-                                                           int accumulate) {
-  __shared__ double red[4][32];
+// ---- deterministic reduction: one thread-block cluster, fixed order, f64 --------------------------
+// 8 CTAs of one cluster each reduce a contiguous slice of the per-plane partials; CTA 0 then reads the
+// 8 slice sums through distributed shared memory in rank order.  One launch, no workspace, and the
+// summation order is a pure function of (n_planes) — bitwise reproducible run to run.
+constexpr int kReduceCtas = 8;
+constexpr int kReduceThreads = 512;
+
+__global__ void __cluster_dims__(kReduceCtas, 1, 1) __launch_bounds__(kReduceThreads)
+loss_reduce_kernel(const double* __restrict__ partials, int64_t n_planes, double* __restrict__ sums,
+                   int accumulate) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double red[4][kReduceThreads / 32];
+  __shared__ double block_sum[4];
+  const unsigned rank = cluster.block_rank();
+  const int64_t per = (n_planes + kReduceCtas - 1) / kReduceCtas;
+  const int64_t lo = rank * per, hi = (lo + per < n_planes) ? lo + per : n_planes;
   double acc[4] = {0, 0, 0, 0};
-  for (int64_t p = threadIdx.x; p < n_planes; p += blockDim.x) {
+  for (int64_t p = lo + threadIdx.x; p < hi; p += kReduceThreads) {
     const double4 v = *reinterpret_cast<const double4*>(partials + 4 * p);
     acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    double v = warp_sum(acc[i]);
+    const double v = warp_sum(acc[i]);
     if (lane == 0) red[i][warp] = v;
   }
   __syncthreads();
   if (warp == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double v = lane < (blockDim.x >> 5) ? red[i][lane] : 0.0;
+      double v = lane < (kReduceThreads / 32) ? red[i][lane] : 0.0;
       v = warp_sum(v);
-      if (lane == 0) sums[i] = accumulate ? sums[i] + v : v;
+      if (lane == 0) block_sum[i] = v;
     }
   }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x < 4) {
+    double t = 0.0;
+    for (unsigned r = 0; r < kReduceCtas; ++r) t += cluster.map_shared_rank(block_sum, r)[threadIdx.x];
+    sums[threadIdx.x] = accumulate ? sums[threadIdx.x] + t : t;
+  }
+  cluster.sync();   // keep every CTA's shared memory alive until rank 0 has read it
 }
 
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, int loss_mode, int sum_reduction,
@@ -260,7 +281,7 @@ extern "C" int lhn_loss_reduce(const double* partials, int64_t n_planes, double*
                                lhn_stream_t stream) {
   if (!partials || !sums || n_planes < 0) return LHN_EINVAL;
   if ((uintptr_t)partials % 32) return LHN_EALIGN;
-  loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_planes, sums, accumulate);
+  loss_reduce_kernel<<<kReduceCtas, kReduceThreads, 0, (cudaStream_t)stream>>>(partials, n_planes, sums, accumulate);
   return check_launch();
 }
 

@@ -88,9 +88,11 @@ class MetricAccumulator:
                                       self.counters, self.pck_thr, self.auc_nor, self.steps, kernel)
 
     def update_from_preds(self, preds, gt, mask, bbox_wh):
-        """Counters from already-decoded predictions [N,K,>=2] (f32 or f64)."""
+        """Counters from already-decoded predictions [N,K,>=2].  As in _report_metric the predictions
+        enter the distance arithmetic as float64 (they come back from JSON there)."""
         K, T = self.K, self.steps
         dev = self.counters.device
+        preds = preds.to(dev).double().contiguous()
         bb = torch.as_tensor(bbox_wh).to(dev)
         nor = bb.max(dim=1, keepdim=True).values.expand(-1, 2).to(torch.float64).contiguous()
         c = self.counters.view(T + 5, K)

@@ -1,0 +1,341 @@
+"""GPU: the drop-in mirrors of the reference interface (same names, arguments, return structure)
+against the golden vectors of the executed reference — these read like the reference's own call sites
+(test.py:114-135, train/topdown_trainer.py:34, utils/SPheatmapParser.py:220-240)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_coords_close, load_golden
+from oracle import np_oracle as O
+from oracle.ref_loader import _AttrDict
+from litehandnet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+
+
+def make_cfg(K=21, hm=(64, 64), img=(256, 256), unbiased=True, k=0, model="litehandnet", loss_weight=(1.0, 1.0)):
+    return _AttrDict(
+        DATASET=dict(image_size=list(img), heatmap_size=list(hm), num_joints=K),
+        PIPELINE=dict(unbiased_encoding=unbiased, kernel=(11, 11), use_udp=False, simdr_split_ratio=k, sigma=2),
+        MODEL=dict(name=model), LOSS=dict(type="TopdownHeatmapLoss", loss_weight=list(loss_weight), auto_weight=False))
+
+
+# ---- decode ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["decode_64.npz", "decode_56.npz", "decode_mpii16.npz"])
+def test_keypoints_from_heatmaps_numpy_in_numpy_out(case):
+    from litehandnet_b200.decode import keypoints_from_heatmaps, _get_max_preds
+    g = load_golden(case)
+    before = g["hm"].copy()
+    for pp, tag in (("default", "default"), ("unbiased", "unbiased"), (None, "none")):
+        hp, p, mv = keypoints_from_heatmaps(g["hm"], g["center"], g["scale"], post_process=pp, kernel=11)
+        assert isinstance(p, np.ndarray) and p.dtype == np.float32 and p.shape == g[f"ref_g2_{tag}_preds"].shape
+        assert_coords_close(hp, g[f"ref_g2_{tag}_hm_preds"], what=tag)
+        assert_coords_close(p, g[f"ref_g2_{tag}_preds"], what=tag)
+        assert np.array_equal(mv, g[f"ref_g2_{tag}_maxvals"], equal_nan=True)
+    p2, mv2 = keypoints_from_heatmaps(g["hm"], g["center"], g["scale"], only_original_preds=True)
+    assert np.array_equal(p2, g["ref_g2_default_preds"], equal_nan=True)
+    assert np.array_equal(g["hm"], before, equal_nan=True), "inputs must not be modified"
+    preds, maxvals = _get_max_preds(g["hm"])
+    assert np.array_equal(preds, g["ref_g2_none_hm_preds"]) and maxvals.shape == (g["hm"].shape[0], g["hm"].shape[1], 1)
+    with pytest.raises(AssertionError):
+        _get_max_preds(g["hm"][0])
+
+
+def test_keypoints_from_heatmaps_cuda_in_cuda_out():
+    from litehandnet_b200.decode import keypoints_from_heatmaps
+    g = load_golden("decode_64.npz")
+    hp, p, mv = keypoints_from_heatmaps(cu(g["hm"]), cu(g["center"]), cu(g["scale"]), post_process="default")
+    assert p.is_cuda and np.array_equal(p.cpu().numpy(), g["ref_g2_default_preds"], equal_nan=True)
+
+
+def test_topdown_decoder_facade():
+    from litehandnet_b200.decode import TopDownDecoder
+    g = load_golden("decode_64.npz")
+    N, K = g["hm"].shape[:2]
+    out = torch.cat([cu(g["hm"]), torch.rand(N, 3, 64, 64, device=DEV)], 1)     # extra channels are sliced off
+    meta = dict(bbox_score=torch.ones(N), bbox_id=torch.arange(N), image_file=[f"{i}.jpg" for i in range(N)],
+                center=torch.from_numpy(g["center"]), scale=torch.from_numpy(g["scale"]))
+    for unbiased, tag in ((True, "unbiased"), (False, "default")):
+        r = TopDownDecoder(make_cfg(K=K, unbiased=unbiased)).decode(meta, out)
+        assert set(r) == {"preds", "hm_preds", "boxes", "image_paths", "bbox_ids", "output_heatmap"}
+        assert r["preds"].shape == (N, K, 3) and r["preds"].dtype == np.float32
+        assert_coords_close(r["preds"][..., :2], g[f"ref_g2_{tag}_preds"], what="decoder preds")
+        assert np.array_equal(r["preds"][..., 2:], g[f"ref_g2_{tag}_maxvals"], equal_nan=True)
+        assert_coords_close(r["hm_preds"][..., :2], g[f"ref_g2_{tag}_hm_preds"] * 4, what="decoder hm_preds")
+        want_boxes = np.zeros((N, 6), np.float32)
+        want_boxes[:, 0:2] = g["center"]; want_boxes[:, 2:4] = g["scale"]
+        want_boxes[:, 4] = np.prod(g["scale"] * 200.0, axis=1); want_boxes[:, 5] = 1
+        assert np.array_equal(r["boxes"], want_boxes) and r["bbox_ids"] == list(range(N))
+        assert np.array_equal(r["output_heatmap"], g["hm"], equal_nan=True)
+
+
+def test_decode_simdr_facade():
+    from litehandnet_b200.decode import TopDownDecoder, keypoints_from_simdr
+    g = load_golden("render_loss_64.npz")
+    out = keypoints_from_simdr(g["simdr_xv"], g["simdr_yv"], g["center"], g["scale"], 2)
+    assert isinstance(out, np.ndarray) and np.array_equal(out, g["ref_simdr_decode"])
+    N = g["simdr_xv"].shape[0]
+    meta = dict(bbox_score=torch.ones(N), bbox_id=torch.arange(N), image_file=["a"] * N,
+                center=torch.from_numpy(g["center"]), scale=torch.from_numpy(g["scale"]),
+                simdr_x=torch.from_numpy(g["simdr_xv"]), simdr_y=torch.from_numpy(g["simdr_yv"]))
+    r = TopDownDecoder(make_cfg(K=8, k=2)).decode_simdr(meta, torch.zeros(N, 8, 64, 64, device=DEV))
+    assert np.array_equal(r["preds"], g["ref_simdr_decode"])
+
+
+@pytest.mark.parametrize("case", ["decode_64.npz", "decode_56.npz"])
+def test_legacy_parsers(case):
+    from litehandnet_b200.decode import (ResultParser, HeatmapParser_SH, adjust_keypoints_by_offset,
+                                         adjust_keypoints_by_DARK, get_max_preds, get_final_preds, flip_back,
+                                         get_coordinates_from_heatmap)
+    g = load_golden(case)
+    hm = cu(g["hm"])
+    H, W = g["hm"].shape[2:]
+    isz = [int(v) for v in g["image_size"]]
+    cfg = dict(image_size=isz, hm_size=[W, H], model="litehandnet", simdr_split_ratio=2, bbox_alpha=1.0,
+               with_region_map=False, cycle_detection_reduction=1, DARK=False)
+    rp = ResultParser(cfg)
+    kpts = rp.get_coordinates_from_heatmaps(hm)
+    assert kpts.is_cuda and np.array_equal(kpts.cpu().numpy()[..., :2], O.max_preds(g["hm"], "none")[0])
+    assert np.array_equal(rp.get_pred_kpt(hm).cpu().numpy(), g["ref_legacy_offset_hm"], equal_nan=True)
+    assert np.array_equal(rp.get_pred_kpt(hm, resized=True).cpu().numpy(), g["ref_legacy_offset_img"], equal_nan=True)
+    rp_dark = ResultParser(dict(cfg, DARK=True))
+    assert_coords_close(rp_dark.get_pred_kpt(hm, resized=True).cpu().numpy(), g["ref_legacy_dark_img"], what="DARK")
+    # the two-step legacy form: argmax -> adjust
+    adj = adjust_keypoints_by_offset(kpts.clone(), hm)
+    assert np.array_equal(adj.cpu().numpy(), g["ref_legacy_offset_hm"], equal_nan=True)
+    dk = adjust_keypoints_by_DARK(kpts.clone(), hm)
+    assert isinstance(dk, np.ndarray)
+    assert_coords_close(dk, g["ref_legacy_dark_hm"], what="adjust DARK")
+    assert np.array_equal(hm.cpu().numpy(), g["hm"], equal_nan=True), "heatmaps must stay untouched (CUDA semantics)"
+    k, bb = HeatmapParser_SH().parse(hm, image_size=tuple(isz))
+    assert bb is None and not k.is_cuda and np.array_equal(k.numpy(), g["ref_parse_sh"], equal_nan=True)
+    c = HeatmapParser_SH.get_coordinates(hm)
+    assert not c.is_cuda
+    a = HeatmapParser_SH.adjust_keypoints(c.clone(), hm)
+    assert np.array_equal((a.numpy()[..., :2] * (np.array(isz, np.float32) / np.array([W, H], np.float32))),
+                          g["ref_parse_sh"][..., :2], equal_nan=True)
+    p, mv = get_max_preds(g["hm"])
+    assert np.array_equal(p, g["ref_a3_preds"]) and np.array_equal(mv, g["ref_a3_maxvals"], equal_nan=True)
+    p, mv = get_coordinates_from_heatmap(hm)
+    assert np.array_equal(p.cpu().numpy(), g["ref_a1_preds"])
+    assert_coords_close(get_final_preds(hm, g["center"], g["scale"]).cpu().numpy(), g["ref_final_preds"],
+                        rtol=1e-5, atol=1e-4, what="final preds")
+    pairs = [tuple(int(v) for v in pr) for pr in g["flip_pairs"]]
+    assert np.array_equal(flip_back(g["hm"], pairs), g["ref_flip_back"], equal_nan=True)
+    with pytest.raises(Exception):
+        adjust_keypoints_by_offset(kpts + 1.0, hm)          # not the argmax: rejected loudly
+
+
+def test_sp_parser_main_fixture():
+    """utils/SPheatmapParser.py:221-233."""
+    from litehandnet_b200.decode import HeatmapParser_SH
+    kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
+    k, b = HeatmapParser_SH().parse(kpt_hm, image_size=(256, 256))
+    assert b is None and np.array_equal(k.numpy(), load_golden("sp_parser_main.npz")["ref_kpt"])
+    assert k[0, 0].tolist() == [11.0, 11.0, 1.0]
+
+
+def test_vector_nms_and_coordinates_from_vectors():
+    from litehandnet_b200.decode import ResultParser
+    cfg = dict(image_size=[256, 256], hm_size=[64, 64], model="litehandnet", simdr_split_ratio=2, bbox_alpha=1.0,
+               with_region_map=False, cycle_detection_reduction=1, DARK=False)
+    rp = ResultParser(cfg)
+    xv, yv = synth.simdr_vectors(4, 21, 512, seed=5)
+    assert np.array_equal(rp.vector_nms(xv.to(DEV)).cpu().numpy(), O.vector_nms(xv.numpy()))
+    bboxes = [[[128.0, 120.0, 100.0, 90.0, 1.0]], None, [[60.2, 200.7, 50.5, 80.0, 0.9]], [[250.0, 10.0, 40.0, 40.0, 0.5]]]
+    got = rp.get_coordinates_from_vectors(xv.to(DEV), yv.to(DEV), bboxes).cpu().numpy()
+    assert got.shape == (4, 1, 21, 3)
+    ranges = np.zeros((4, 4), np.int64)
+    for i, bb in enumerate(bboxes):
+        if bb is None:
+            continue
+        b = np.round(np.array(bb[0]) * 2)
+        x1, y1 = b[:2] - b[2:4] / 2; x2, y2 = b[:2] + b[2:4] / 2
+        ranges[i] = (max(int(x1), 0), min(int(x2), 512), max(int(y1), 0), min(int(y2), 512))
+    want = O.coordinates_from_vectors(xv.numpy(), yv.numpy(), ranges, 2)
+    want[1] = 0
+    assert np.array_equal(got[:, 0], want)
+
+
+# ---- losses ------------------------------------------------------------------------------------------
+def test_loss_modules_golden():
+    from litehandnet_b200.loss import DistanceLoss, JointsDistanceLoss, KLDiscretLoss
+    g = load_golden("render_loss_64.npz")
+    hm = cu(np.nan_to_num(load_golden("decode_64.npz")["hm"], nan=0.25, posinf=1.0, neginf=-1.0))
+    for tag in ("unbiased", "int"):
+        t, w = cu(g[f"ref_target_{tag}"]), cu(g[f"ref_weight_{tag}"])
+        for bal, bt in ((True, "bal"), (False, "nobal")):
+            out = DistanceLoss("L2", "mean", bal)(hm, t, w)
+            assert out.dim() == 0 and out.dtype == torch.float32 and out.is_cuda
+            np.testing.assert_allclose(out.item(), g[f"ref_distance_loss_{tag}_{bt}"], rtol=1e-5)
+        np.testing.assert_allclose(JointsDistanceLoss()(hm, t, w).item(), g[f"ref_joints_mse_{tag}"], rtol=1e-5)
+    with pytest.raises(NameError):
+        JointsDistanceLoss()(hm, cu(g["ref_target_int"]), None)
+    with pytest.raises(AssertionError):
+        DistanceLoss(reduction="avg")
+    s = DistanceLoss("L2", "sum", True)(hm, cu(g["ref_target_unbiased"]), cu(g["ref_weight_unbiased"]))
+    np.testing.assert_allclose(s.item(), float(g["ref_distance_loss_unbiased_bal"]) * hm.numel(), rtol=1e-5)
+    # 5-D hourglass shape
+    t5, w5 = O.render_targets(g["joints_3d"], g["joints_3d_visible"], (256, 256), (64, 64), [2, 2])
+    o5 = torch.stack([hm, hm * 0.5], 1)
+    np.testing.assert_allclose(DistanceLoss()(o5, cu(t5), cu(w5)).item(), g["ref_distance_loss_5d_bal"], rtol=1e-5)
+    # fused entry == explicit-target entry
+    fl, fw = DistanceLoss().forward_fused(hm, cu(g["joints_3d"]), cu(g["joints_3d_visible"]), (256, 256), 2, True)
+    np.testing.assert_allclose(fl.item(), g["ref_distance_loss_unbiased_bal"], rtol=1e-5)
+    assert np.array_equal(fw.cpu().numpy(), g["ref_weight_unbiased"])
+    sx, sy = O.render_simdr_batch(g["joints_3d"], g["joints_3d_visible"], (256, 256), 2, 2)
+    kl = KLDiscretLoss()(cu(g["simdr_xv"]), cu(g["simdr_yv"]), cu(sx), cu(sy), cu(g["ref_weight_unbiased"]))
+    np.testing.assert_allclose(kl.item(), g["ref_kld_loss"], rtol=1e-5)
+
+
+def test_topdown_heatmap_loss_wrapper():
+    from litehandnet_b200.loss import get_loss
+    g = load_golden("render_loss_64.npz")
+    hm = cu(np.nan_to_num(load_golden("decode_64.npz")["hm"], nan=0.25, posinf=1.0, neginf=-1.0))
+    cfg = make_cfg(K=8, loss_weight=(0.5, 1.0))
+    crit = get_loss(cfg).cuda()
+    meta = dict(target=torch.from_numpy(g["ref_target_unbiased"]), target_weight=torch.from_numpy(g["ref_weight_unbiased"]))
+    loss, ld = crit(hm, meta)                                    # meta tensors on CPU, as the dataloader hands them
+    np.testing.assert_allclose(loss.item(), 0.5 * float(g["ref_distance_loss_unbiased_bal"]), rtol=1e-5)
+    assert set(ld) == {"heatmap"} and isinstance(ld["heatmap"], float)
+    loss2, _ = crit(hm, dict(joints_3d=torch.from_numpy(g["joints_3d"]), joints_3d_visible=torch.from_numpy(g["joints_3d_visible"])))
+    np.testing.assert_allclose(loss2.item(), loss.item(), rtol=1e-5)
+    cfg_att = make_cfg(K=8, model="atthandnet")
+    loss3, _ = get_loss(cfg_att).cuda()(hm, meta)
+    np.testing.assert_allclose(loss3.item(), g["ref_distance_loss_unbiased_nobal"], rtol=1e-5)
+    # SimDR branch: two nn.Linear heads (torch/cuBLAS) + our SmoothL1 reduction
+    cfg_s = make_cfg(K=8, k=2)
+    crit_s = get_loss(cfg_s).cuda()
+    sx, sy = O.render_simdr_batch(g["joints_3d"], g["joints_3d_visible"], (256, 256), 2, 2)
+    meta_s = dict(meta, simdr_x=torch.from_numpy(sx), simdr_y=torch.from_numpy(sy))
+    loss4, ld4 = crit_s(hm, meta_s)
+    with torch.no_grad():
+        px = crit_s.simdr_loss.x_shared_decoder(hm.flatten(2)); py = crit_s.simdr_loss.y_shared_decoder(hm.flatten(2))
+    want = O.kl_discret_loss(px.cpu().numpy(), py.cpu().numpy(), sx, sy, g["ref_weight_unbiased"])
+    np.testing.assert_allclose(ld4["simdr"], want, rtol=1e-5)
+    np.testing.assert_allclose(loss4.item(), ld4["heatmap"] + ld4["simdr"], rtol=1e-6)
+
+
+def test_srhandnet_loss_multiscale():
+    from litehandnet_b200.loss import SRHandNetLoss
+    cfg = _AttrDict(MODEL=dict(output_channel=21, pred_bbox=False), LOSS=dict(loss_weight=[0.3, 0.3, 0.5, 1.0]))
+    sizes = [16, 16, 32, 64]
+    j, v = synth.hand_joints(3, 21, seed=7)
+    outs, tgs, tws, want = [], [], [], 0.0
+    for i, s in enumerate(sizes):
+        o, _ = synth.blob_heatmaps(3, 21, s, s, seed=40 + i, margin=2.0)
+        t, w = O.render_targets(j.numpy(), v.numpy(), (256, 256), (s, s), 2, False)
+        outs.append(o.to(DEV)); tgs.append(torch.from_numpy(t)); tws.append(torch.from_numpy(w))
+        want += float(O.distance_loss_l2(o.numpy(), t, w, True)) * cfg.LOSS.loss_weight[i]
+    loss, ld = SRHandNetLoss(cfg)(outs, dict(target=tgs, target_weight=tws))
+    np.testing.assert_allclose(loss.item(), want, rtol=1e-5)
+    assert set(ld) == {"kpt_loss"}
+
+
+# ---- metrics -------------------------------------------------------------------------------------------
+def test_metric_functions_golden():
+    from litehandnet_b200.metrics import (keypoint_pck_accuracy, keypoint_auc, keypoint_epe, report_metric,
+                                          evaluate_pck)
+    g = load_golden("metrics_16.npz")
+    p64 = g["preds"].astype(np.float64)
+    t = g["bbox_wh"].max(1).astype(np.float64)
+    nor = np.stack([t, t], 1)
+    acc, avg, cnt = keypoint_pck_accuracy(p64, g["gt"], g["mask"], 0.2, nor)
+    assert np.array_equal(acc, g["ref_pck_acc"]) and avg == g["ref_pck_avg"] and cnt == g["ref_pck_cnt"]
+    hs = g["head_size"]
+    acc, avg, _ = keypoint_pck_accuracy(p64, g["gt"], g["mask"], 0.5, np.stack([hs, hs], 1))
+    assert np.array_equal(acc, g["ref_pckh_acc"]) and avg == g["ref_pckh_avg"]
+    assert keypoint_auc(p64, g["gt"], g["mask"], 30) == g["ref_auc"]
+    np.testing.assert_allclose(keypoint_epe(p64, g["gt"], g["mask"]), g["ref_epe"], rtol=1e-5)
+    info = dict(report_metric(p64, g["gt"], g["mask"], bbox_wh=g["bbox_wh"], head_size=hs,
+                              metrics=("PCK", "PCKh", "AUC", "EPE")))
+    assert info["PCK"] == g["ref_pck_avg"] and info["PCKh"] == g["ref_pckh_avg"] and info["AUC"] == g["ref_auc"]
+    with np.errstate(all="ignore"):
+        a = evaluate_pck(torch.from_numpy(g["pck_pred_hm"]), torch.from_numpy(g["pck_gt_hm"]), torch.from_numpy(g["pck_bbox"]),
+                         256, torch.from_numpy(g["pck_tw"]), 0.2)
+        b = evaluate_pck(cu(g["pck_pred_hm"]), cu(g["pck_gt_hm"]), cu(g["pck_bbox"]), 256, None, 0.02)
+    np.testing.assert_allclose(a, g["ref_evaluate_pck_w"], rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(b, g["ref_evaluate_pck_now"], rtol=1e-6, equal_nan=True)
+
+
+def test_metric_accumulator_sharded_equals_monolithic():
+    """BASELINE config 4: MPII-style 16-joint decode + PCK@0.2/AUC/EPE, batch-sharded (8 shards here on
+    one GPU; the NCCL all-reduce of the same int64 block is covered by the gloo test on CPU)."""
+    from litehandnet_b200.metrics import MetricAccumulator
+    N, K = 256, 16
+    hm, cen = synth.blob_heatmaps(N, K, 64, 64, seed=101)
+    center, scale = synth.bbox_center_scale(N, fixed=True)
+    gt, mask, wh = synth.pck_inputs(cen, seed=102)
+    hm, center, scale, gt, mask, wh = [t.to(DEV) for t in (hm, center, scale, gt, mask, wh)]
+    mono = MetricAccumulator(K)
+    r = mono.update_from_heatmaps(hm, center, scale, gt, mask, wh)
+    shard = MetricAccumulator(K)
+    for s in np.array_split(np.arange(N), 8):
+        sl = slice(int(s[0]), int(s[-1]) + 1)
+        shard.update_from_heatmaps(hm[sl], center[sl], scale[sl], gt[sl], mask[sl], wh[sl])
+    assert torch.equal(mono.counters, shard.counters)
+    from_preds = MetricAccumulator(K)
+    from_preds.update_from_preds(r["kpts"], gt, mask, wh)
+    assert torch.equal(mono.counters, from_preds.counters)
+    out = mono.compute()
+    preds = r["kpts"][..., :2].cpu().numpy().astype(np.float64)
+    want = dict(O.report_metric(preds, gt.cpu().numpy(), mask.cpu().numpy(), bbox_wh=wh.cpu().numpy().astype(np.float64)))
+    assert out["PCK"] == want["PCK"] and out["AUC"] == want["AUC"]
+    np.testing.assert_allclose(out["EPE"], want["EPE"], rtol=1e-5)
+
+
+# ---- render ---------------------------------------------------------------------------------------------
+def test_render_transforms_dict_in_dict_out():
+    from litehandnet_b200.render import TopDownGenerateTarget, GenerateSimDR
+    g = load_golden("render_loss_64.npz")
+    ann = dict(num_joints=8, image_size=np.array([256, 256]), heatmap_size=np.array([64, 64]), joint_weights=None,
+               use_different_joint_weights=False)
+    for unb, tag in ((True, "unbiased"), (False, "int")):
+        res = TopDownGenerateTarget(sigma=2, unbiased_encoding=unb)(
+            dict(joints_3d=g["joints_3d"][0], joints_3d_visible=g["joints_3d_visible"][0], ann_info=ann))
+        assert res["target"].shape == (8, 64, 64) and res["target_weight"].shape == (8, 1)
+        np.testing.assert_allclose(res["target"], g[f"ref_target_{tag}"][0], rtol=1e-5, atol=1e-7)
+        assert np.array_equal(res["target_weight"], g[f"ref_weight_{tag}"][0])
+    res = TopDownGenerateTarget(sigma=[2, 2], unbiased_encoding=True)(
+        dict(joints_3d=g["joints_3d"][1], joints_3d_visible=g["joints_3d_visible"][1], ann_info=ann))
+    assert res["target"].shape == (2, 8, 64, 64) and res["target_weight"].shape == (2, 8, 1)
+    res = GenerateSimDR(sigma=2, k=2)(dict(joints_3d=g["joints_3d"][0], joints_3d_visible=g["joints_3d_visible"][0], ann_info=ann))
+    np.testing.assert_allclose(res["simdr_x"][0], g["ref_simdr_x_row0"][0], rtol=1e-5, atol=1e-7)
+
+
+# ---- the headline call at full size: size-independent properties -------------------------------------------
+def test_full_size_config2_properties():
+    """B=1024 x 21 x 64 x 64 (BASELINE config 2): the oracle is too slow here, so check properties:
+    batch-permutation equivariance, shard-additivity of the loss sums, flip symmetry, determinism."""
+    from litehandnet_b200 import fused
+    B, K = 1024, 21
+    hm, cen = synth.blob_heatmaps(B, K, 64, 64, seed=7, device=DEV)
+    hf = synth.flipped_blob_heatmaps(cen, 64, 64, seed=8, device=DEV)
+    j, v = synth.hand_joints(B, K, seed=9, device=DEV)
+    c, s = synth.bbox_center_scale(B, seed=10, device=DEV)
+    step = fused.FusedHeatmapStep()
+    a = step(hm, j, v, c, s, hf)
+    b = step(hm, j, v, c, s, hf)
+    assert torch.equal(a["preds"], b["preds"]) and torch.equal(a["loss"], b["loss"]), "must be deterministic"
+    perm = torch.randperm(B, device=DEV)
+    p = step(hm[perm], j[perm], v[perm], c[perm], s[perm], hf[perm])
+    assert torch.equal(p["preds"], a["preds"][perm]) and torch.equal(p["idx"], a["idx"][perm])
+    np.testing.assert_allclose(p["loss"].item(), a["loss"].item(), rtol=1e-6)
+    sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+    for sl in (slice(0, 300), slice(300, 1024)):
+        sums += step(hm[sl], j[sl], v[sl], c[sl], s[sl], hf[sl])["loss_sums"]
+    assert torch.allclose(sums, a["loss_sums"], rtol=1e-12)
+    # argmax of the average equals argmax computed by torch on the same average (first-index ties)
+    avg = (hm + hf.flip(-1)) * 0.5
+    assert torch.equal(a["idx"].long(), avg.flatten(2).argmax(-1))
+    # a slice of the batch against the oracle
+    n = 6
+    with np.errstate(all="ignore"):
+        ref = O.fused_render_loss_decode(hm[:n].cpu().numpy(), hf[:n].cpu().numpy(), j[:n].cpu().numpy(), v[:n].cpu().numpy(),
+                                         c[:n].cpu().numpy(), s[:n].cpu().numpy())
+    assert_coords_close(a["preds"][:n, :, :2].cpu().numpy(), ref["preds"], what="config-2 preds")
