@@ -55,6 +55,8 @@ struct HmArgs {
   int stage_bytes;                 // bytes of the TMA stage (plane0 [+ plane1]) at the start of it
   int tile_dim;                    // DARK window side = blur_ksize + 4 (0 when DARK is off)
   int force_cta_kernel;            // testing: bypass the warp kernel (env LHN_FORCE_CTA_KERNEL=1)
+  int feat_pow2;                   // feat_x, feat_y are powers of two: joint / feat == joint * inv_feat exactly
+  double inv_feat_x, inv_feat_y;
 };
 
 // ---- shared-memory layout --------------------------------------------------------------------

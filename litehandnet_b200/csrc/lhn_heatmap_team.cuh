@@ -2,13 +2,15 @@
 //
 // One CTA per SM, cut into teams of TW warps; every team owns a private stage (plane [+ flipped
 // plane]) with its own mbarrier and named barrier — there is no CTA-wide barrier anywhere.  Per plane
-// a team: waits for its TMA bulk copy, makes ONE sweep over the plane (flip average, Gaussian target +
-// squared error, running max; 128-bit conflict-free shared-memory reads), combines the per-warp
-// partials, and then splits: warp 0 takes the positives' sum and the DARK window from the
-// still-resident stage, immediately re-arms the stage with the TMA load of the team's NEXT plane, and
-// finishes refinement / back-transform / stores while that load is in flight; the other warps of the
-// team meanwhile evaluate the next plane's render parameters and Gaussian tables (double-buffered).
-// 6 teams x 32 KB in flight per SM (f32 + flip) keep HBM busy; 24 warps per SM hide the latencies.
+// a team: waits for its TMA bulk copy; makes ONE sweep over the plane (flip average, Gaussian target +
+// squared error as packed f32x2 FMAs, running NaN-propagating 3-input max; 128-bit conflict-free
+// shared-memory reads); combines the per-warp partials; copies the DARK window (quads of the decoded
+// plane) and the positives' sum out of the stage; and then RELEASES the stage: warp 0 re-arms it with
+// the TMA load of the team's next plane before it starts the blur / Taylor / back-transform / stores,
+// while warp 1 evaluates the next plane's render parameters and Gaussian tables (double-buffered).
+// The stage is therefore idle only for the sweep itself; 6 teams x 32 KB per SM (f32 + flip) keep
+// HBM busy.  The rare exact-emulation path of DARK (1e-10 clamp reachable) re-reads the plane from
+// global memory (L2), so it never holds a stage.
 #pragma once
 #include <math.h>
 #include <stdlib.h>
@@ -24,14 +26,43 @@ __device__ __forceinline__ void team_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- sm_100a packed-f32x2 / 3-input max / f32 warp-reduce primitives -------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {   // FFMA2: 2 x fma.rn
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {               // FMUL2: 2 x mul.rn
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {           // FMNMX3.NAN
+  float d;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float redux_max_nan(float v) {                         // CREDUX.MAX.F32.NAN
+  float d;
+  asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(d) : "f"(v));
+  return d;
+}
+
 // per-team header at the start of the aux region
 struct TeamHeader {
   uint64_t bar;               // TMA completion barrier of the stage
   uint64_t pad;
-  uint32_t red_key[8];        // per-warp pass-1 partials
+  float red_max[8];           // per-warp sweep partials: max (NaN-propagating), first quad holding it, sum
   uint32_t red_q[8];
-  double red_s[8];
-  int red_nonfinite[8];
+  float red_s[8];
   // render parameters of the two table buffers (written by whoever runs the prologue)
   float w[2];
   float mx[2], my[2];
@@ -52,6 +83,9 @@ __device__ __forceinline__ float exp_f32_from_f64(double a) {
   const float v = expf(ah);
   return fmaf(v, al, v);
 }
+
+// quads per row of the DARK tile: the (ksize+4)-wide window starts 0..3 columns into its first quad
+__host__ __device__ constexpr int tile_quads(int td) { return (td + 6) >> 2; }
 
 // FAST: W = H = 64 and the team size is a compile-time constant (TWC warps), so the sweep is a fully
 //       unrolled 128-bit loop with a loop-invariant column quad per thread.
@@ -78,9 +112,10 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   const size_t tab_bytes = align_up((size_t)(W + H) * 4, 16);
   float* tab0 = reinterpret_cast<float*>(aux + align_up(sizeof(TeamHeader), 16));   // two table buffers
   const int ksize = KS > 0 ? KS : a.ksize;
-  const int TD = KS > 0 ? KS + 4 : a.tile_dim;
+  const int TD = KS > 0 ? KS + 4 : a.tile_dim;       // DARK window side
+  const int NQ = tile_quads(TD), TCW = 4 * NQ;       // tile row = NQ quads
   float* tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);
-  double* hbuf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile) + align_up((size_t)TD * TD * 4, 16));
+  double* hbuf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile) + align_up((size_t)TD * TCW * 4, 16));
   float* hout = reinterpret_cast<float*>(hbuf + (size_t)TD * 5);
 
   const uint32_t total_teams = gridDim.x * nteams;
@@ -124,7 +159,10 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     const float* jp = a.joints + (int64_t)bk * a.joints_stride;
     float w = a.vis[(int64_t)bk * a.vis_stride];
     const double sig = (double)a.sigma[s], tmp = sig * 3.0;
-    double mux = (double)jp[0] / a.feat_x, muy = (double)jp[1] / a.feat_y;
+    // joint / feat_stride in f64 (numpy promotes f32 / f64); a power-of-two stride multiplies exactly
+    double mux, muy;
+    if (a.feat_pow2) { mux = (double)jp[0] * a.inv_feat_x; muy = (double)jp[1] * a.inv_feat_y; }
+    else { mux = (double)jp[0] / a.feat_x; muy = (double)jp[1] / a.feat_y; }
     double x0p = 0, ulx, uly, brx, bry;
     if (a.unbiased) {
       ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1;
@@ -177,8 +215,10 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
   const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
   const int QR = W >> 2, nq = HW >> 2;
+  const uint64_t half2 = pack2(0.5f, 0.5f);
 
   for (; p < n_planes; p += total_teams, buf ^= 1, advance(pb, pc)) {
+    const bool has_next = p + total_teams < n_planes;
     // S1: tables of this plane are written, the aux buffers of the previous plane are free
     team_sync(bar_id, TT);
     const float* ex = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(tab0) + (size_t)buf * tab_bytes);
@@ -200,19 +240,22 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       team_sync(bar_id, TT);
     }
 
-    // decoded value (flip average) of quad q / of element (y, x)
-    auto load_quad = [&](int q) -> float4 {
-      const float4 o = load4<T>(plane0 + 4 * q);
-      if (!FLIP) return o;
-      const int row = FAST ? (q >> 4) : (q / QR);
-      const int cq = q - row * QR;
-      const float4 f = load4<T>(plane1 + row * W + (W - 4 - 4 * cq));
+    // decoded values (flip average) of quad q = row * QR + cq
+    auto avg_quad = [&](const float4& o, const float4& f) -> float4 {
+      uint64_t lo = fmul2(pack2(__fadd_rn(o.x, f.w), __fadd_rn(o.y, f.z)), half2);
+      uint64_t hi = fmul2(pack2(__fadd_rn(o.z, f.y), __fadd_rn(o.w, f.x)), half2);
       float4 v;
-      v.x = __fmul_rn(__fadd_rn(o.x, f.w), 0.5f);
-      v.y = __fmul_rn(__fadd_rn(o.y, f.z), 0.5f);
-      v.z = __fmul_rn(__fadd_rn(o.z, f.y), 0.5f);
-      v.w = __fmul_rn(__fadd_rn(o.w, f.x), 0.5f);
+      unpack2(lo, v.x, v.y); unpack2(hi, v.z, v.w);
       return v;
+    };
+    auto load_quad_rc = [&](int row, int cq) -> float4 {
+      const float4 o = load4<T>(plane0 + row * W + 4 * cq);
+      if (!FLIP) return o;
+      return avg_quad(o, load4<T>(plane1 + row * W + (W - 4 - 4 * cq)));
+    };
+    auto load_quad = [&](int q) -> float4 {
+      const int row = FAST ? (q >> 4) : (q / QR);
+      return load_quad_rc(row, q - row * QR);
     };
     auto val = [&](int y, int x) -> float {
       float o = elem_f32<T>(plane0, y * W + x);
@@ -221,85 +264,78 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     };
 
     // ---- pass 1: one sweep, split over the team ------------------------------------------------------
-    constexpr bool kUseS = LOSS && !FLIP;   // S already turns non-finite on a NaN/inf input
-    float S0 = 0.f, S1 = 0.f, nacc = 0.f;
-    float best = -CUDART_INF_F;
-    int bq = -1;
-    auto sweep_quad = [&](int q, int row, const float4& gx) {
-      const float4 o = load4<T>(plane0 + 4 * q);
+    uint64_t S2acc = 0;                      // packed (S0, S1) squared-error accumulators
+    float best = -CUDART_INF_F;              // NaN-propagating running max of this thread
+    int bq = -1;                             // first quad that raised it
+    // o / f: pointers to the quad of the plane and to its mirror quad of the flipped plane
+    auto sweep_quad = [&](int q, const T* po, const T* pf, const float* pgy, uint64_t ngx01, uint64_t ngx23) {
+      const float4 o = load4<T>(po);
       float4 v = o;
-      if (FLIP) {
-        const int cq = q - row * QR;
-        const float4 f = load4<T>(plane1 + row * W + (W - 4 - 4 * cq));
-        v.x = __fmul_rn(__fadd_rn(o.x, f.w), 0.5f);
-        v.y = __fmul_rn(__fadd_rn(o.y, f.z), 0.5f);
-        v.z = __fmul_rn(__fadd_rn(o.z, f.y), 0.5f);
-        v.w = __fmul_rn(__fadd_rn(o.w, f.x), 0.5f);
-      }
+      if (FLIP) v = avg_quad(o, load4<T>(pf));
       if (LOSS) {
-        const float gy = ey[row];
-        const float d0 = fmaf(-gx.x, gy, o.x), d1 = fmaf(-gx.y, gy, o.y);
-        const float d2 = fmaf(-gx.z, gy, o.z), d3 = fmaf(-gx.w, gy, o.w);
-        S0 = fmaf(d0, d0, S0); S1 = fmaf(d1, d1, S1); S0 = fmaf(d2, d2, S0); S1 = fmaf(d3, d3, S1);
+        const float gy = *pgy;
+        const uint64_t gy2 = pack2(gy, gy);
+        const uint64_t d01 = ffma2(ngx01, gy2, pack2(o.x, o.y));     // o - gx*gy
+        const uint64_t d23 = ffma2(ngx23, gy2, pack2(o.z, o.w));
+        S2acc = ffma2(d01, d01, S2acc);
+        S2acc = ffma2(d23, d23, S2acc);
       }
-      if (!kUseS) {
-        nacc = fmaf(v.x, 0.f, nacc); nacc = fmaf(v.y, 0.f, nacc);
-        nacc = fmaf(v.z, 0.f, nacc); nacc = fmaf(v.w, 0.f, nacc);
-      }
-      const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));   // ignores NaN, like `>`
-      if (m4 > best) { best = m4; bq = q; }
+      const float m3 = fmax3_nan(v.x, v.y, v.z);
+      const float r = fmax3_nan(m3, v.w, best);
+      if (r != best) bq = q;                 // strictly greater (or NaN: resolved by the NaN path)
+      best = r;
     };
     if (FAST) {
-      // TT is a multiple of 16: the column quad of a thread is loop-invariant
-      float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (LOSS) gx = *reinterpret_cast<const float4*>(ex + 4 * (tl & 15));
-      constexpr int kIters = 1024 / ((TWC > 0 ? TWC : 1) * 32);
-#pragma unroll
-      for (int it = 0; it < kIters; ++it) {
-        const int q = it * (TWC * 32) + tl;
-        sweep_quad(q, q >> 4, gx);
+      // TT is a multiple of 16: the column quad of a thread is loop-invariant and every address is
+      // base + compile-time offset
+      uint64_t ngx01 = 0, ngx23 = 0;
+      if (LOSS) {
+        const float4 gx = *reinterpret_cast<const float4*>(ex + 4 * (tl & 15));
+        ngx01 = pack2(-gx.x, -gx.y); ngx23 = pack2(-gx.z, -gx.w);
       }
+      constexpr int kTT = (TWC > 0 ? TWC : 1) * 32;
+      constexpr int kIters = 1024 / kTT;
+      const T* po = plane0 + 4 * tl;
+      const T* pf = FLIP ? plane1 + (tl >> 4) * 64 + 60 - 4 * (tl & 15) : nullptr;
+      const float* pgy = ey + (tl >> 4);
+#pragma unroll
+      for (int it = 0; it < kIters; ++it)
+        sweep_quad(it * kTT + tl, po + it * kTT * 4, pf + it * kTT * 4, pgy + it * (kTT / 16), ngx01, ngx23);
     } else {
       for (int q = tl; q < nq; q += TT) {
-        const int row = q / QR;
-        float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (LOSS) gx = *reinterpret_cast<const float4*>(ex + 4 * (q - row * QR));
-        sweep_quad(q, row, gx);
+        const int row = q / QR, cq = q - row * QR;
+        uint64_t ngx01 = 0, ngx23 = 0;
+        if (LOSS) {
+          const float4 gx = *reinterpret_cast<const float4*>(ex + 4 * cq);
+          ngx01 = pack2(-gx.x, -gx.y); ngx23 = pack2(-gx.z, -gx.w);
+        }
+        sweep_quad(q, plane0 + 4 * q, FLIP ? plane1 + row * W + (W - 4 - 4 * cq) : nullptr, ey + row, ngx01, ngx23);
       }
     }
 
     // ---- per-warp partials -> shared, S2 ----------------------------------------------------------------
     {
-      uint32_t key = order_key(best);
-      uint32_t qsel = (uint32_t)bq;            // -1 -> 0xffffffff
-      warp_argmax(key, qsel);
-      double ssum = 0.0;
-      if (LOSS) ssum = warp_sum((double)S0 + (double)S1);
-      const bool nonfinite_lane = kUseS ? !(fabsf(S0 + S1) < CUDART_INF_F) : (nacc != nacc);
-      const bool nf = __any_sync(0xffffffffu, nonfinite_lane);
-      if (lane == 0) { th->red_key[wt] = key; th->red_q[wt] = qsel; th->red_s[wt] = ssum; th->red_nonfinite[wt] = nf ? 1 : 0; }
+      const float wmax = redux_max_nan(best);
+      const uint32_t cand = (best == wmax) ? (uint32_t)bq : 0xffffffffu;   // -1 -> 0xffffffff
+      const uint32_t wq = __reduce_min_sync(0xffffffffu, cand);
+      float ssum = 0.f;
+      if (LOSS) {
+        float s0, s1;
+        unpack2(S2acc, s0, s1);
+        ssum = warp_sum(s0 + s1);
+      }
+      if (lane == 0) { th->red_max[wt] = wmax; th->red_q[wt] = wq; th->red_s[wt] = ssum; }
     }
     team_sync(bar_id, TT);
 
     // ---- every warp: the team-wide argmax (redundantly: cheaper than another barrier) --------------------
-    uint32_t key = lane < TW ? th->red_key[lane] : 0u;
-    uint32_t qsel = lane < TW ? th->red_q[lane] : 0xffffffffu;
-    warp_argmax(key, qsel);
-    const bool any_nonfinite = __any_sync(0xffffffffu, lane < TW && th->red_nonfinite[lane] != 0);
+    const float tm = lane < TW ? th->red_max[lane] : -CUDART_INF_F;
+    const float tmax = redux_max_nan(tm);
+    const uint32_t qsel = __reduce_min_sync(0xffffffffu, (lane < TW && tm == tmax) ? th->red_q[lane] : 0xffffffffu);
+    const bool any_nan = tmax != tmax;
     uint32_t idx = 0;
-    float maxval = key_to_float(key);
-    if (qsel != 0xffffffffu) {
-      const float4 v = load_quad((int)qsel);
-      const float m = key_to_float(key);
-      // `==` treats -0 and +0 as equal, like torch/numpy; report the element actually selected
-      if (v.x == m) { idx = 4 * qsel; maxval = v.x; }
-      else if (v.y == m) { idx = 4 * qsel + 1; maxval = v.y; }
-      else if (v.z == m) { idx = 4 * qsel + 2; maxval = v.z; }
-      else { idx = 4 * qsel + 3; maxval = v.w; }
-    } else {
-      maxval = val(0, 0);                     // every element is -inf (or NaN: fixed below)
-    }
-    if (any_nonfinite) {
+    float maxval = tmax;
+    if (any_nan) {
       // rare: the first NaN of the decoded plane is the argmax (np.argmax / torch.max semantics)
       uint32_t first_nan = 0xffffffffu;
       for (int q = lane; q < nq && first_nan == 0xffffffffu; q += 32) {
@@ -309,8 +345,17 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         else if (v.z != v.z) first_nan = 4 * q + 2;
         else if (v.w != v.w) first_nan = 4 * q + 3;
       }
-      first_nan = __reduce_min_sync(0xffffffffu, first_nan);
-      if (first_nan != 0xffffffffu) { idx = first_nan; maxval = __uint_as_float(0x7fc00000u); }
+      idx = __reduce_min_sync(0xffffffffu, first_nan);
+      maxval = __uint_as_float(0x7fc00000u);
+    } else if (qsel != 0xffffffffu) {
+      const float4 v = load_quad((int)qsel);
+      // `==` treats -0 and +0 as equal, like torch/numpy; report the element actually selected
+      if (v.x == tmax) { idx = 4 * qsel; maxval = v.x; }
+      else if (v.y == tmax) { idx = 4 * qsel + 1; maxval = v.y; }
+      else if (v.z == tmax) { idx = 4 * qsel + 2; maxval = v.z; }
+      else { idx = 4 * qsel + 3; maxval = v.w; }
+    } else {
+      maxval = val(0, 0);                     // every element is -inf
     }
 
     // masked integer coordinates (A1-A4)
@@ -323,13 +368,17 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     const int px = (int)cx, py = (int)cy;
     const bool dark_guard = is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2);
     const int bb = (ksize - 1) >> 1;
+    const int wx0 = px - 2 - bb;                      // first window column (may be negative)
+    const int c0 = wx0 & ~3, xo = wx0 & 3;            // its quad-aligned start and the offset inside it
 
-    // ---- stage the DARK window: zero-padded (ksize+4)^2 tile of the decoded plane, by the whole team ----
+    // ---- stage the DARK window: zero-padded (ksize+4) rows x NQ quads of the decoded plane -----------------
     if (dark_guard) {
-      for (int e = tl; e < TD * TD; e += TT) {
-        const int r = e / TD, cc = e - r * TD;           // compile-time divisor when KS > 0
-        const int y = py - 2 - bb + r, x = px - 2 - bb + cc;
-        tile[e] = (y >= 0 && y < H && x >= 0 && x < W) ? val(y, x) : 0.f;
+      for (int e = tl; e < TD * NQ; e += TT) {
+        const int r = e / NQ, cq = e - r * NQ;          // compile-time divisor when KS > 0
+        const int y = py - 2 - bb + r, x = c0 + 4 * cq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = load_quad_rc(y, x >> 2);
+        *reinterpret_cast<float4*>(tile + r * TCW + 4 * cq) = v;
       }
     }
     // ---- positives of the balanced loss: a small window around the joint, by the team's last warp ----------
@@ -365,7 +414,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             }
           }
         }
-        Spos = warp_sum((double)sp);
+        Spos = (double)warp_sum(sp);
         Npos = __reduce_add_sync(0xffffffffu, Npos);
       }
       if (lane == 0) { th->spos = Spos; th->npos = Npos; }
@@ -391,20 +440,28 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         }
       }
     }
-    // S3: the tile and the positives' sum are staged
+    // S3: the window and the positives' sum are out of the stage — nobody reads it again
     team_sync(bar_id, TT);
 
     if (wt != 0) {
-      // helper warps: render parameters + tables of the team's NEXT plane, while warp 0 finishes this one
-      if (p + total_teams < n_planes) {
+      // warp 1: render parameters + tables of the team's NEXT plane, while warp 0 finishes this one
+      if (wt == 1 && has_next) {
         uint32_t nb = pb, nc = pc;
         advance(nb, nc);
-        prologue(nb, nc, buf ^ 1, tl - 32, TT - 32);
+        prologue(nb, nc, buf ^ 1, lane, 32);
       }
       continue;
     }
 
     // =========================== warp 0 of the team: the rest of the epilogue ===============================
+    // re-arm the stage with the team's next plane first; everything below works from aux / registers
+    if (a.use_tma && has_next && lane == 0) {
+      uint32_t nb = pb, nc = pc;
+      advance(nb, nc);
+      fence_proxy_async();
+      issue(nb, nc);
+    }
+
     bool need_slow = false;
     float bmax = 0.f;
     if (dark_guard) {
@@ -413,8 +470,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       if (legacy) {
         for (int e = lane; e < TD * 5; e += 32) {
           const int r = e / 5, c5 = e - r * 5;
+          const float* trow = tile + r * TCW + xo + c5;
           double acc = 0.0;
-          for (int j = 0; j < ksize; ++j) acc = __fma_rn(a.tapsd[j], (double)tile[r * TD + c5 + j], acc);
+          for (int j = 0; j < ksize; ++j) acc = __fma_rn(a.tapsd[j], (double)trow[j], acc);
           hbuf[e] = acc;
         }
         __syncwarp();
@@ -429,7 +487,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         float* hb = reinterpret_cast<float*>(hbuf);
         for (int e = lane; e < TD * 5; e += 32) {
           const int r = e / 5, c5 = e - r * 5;
-          const float* trow = tile + r * TD + c5;
+          const float* trow = tile + r * TCW + xo + c5;
           float acc = 0.f;
           if (KS > 0) {
 #pragma unroll
@@ -461,9 +519,17 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       const bool used = lane < 25 && (abs(dr) + abs(dc) <= 2);
       const bool bad = used && !(hv >= 1e-9f);
       const bool ok_origin = legacy ? (maxval >= 1e-3f) : (maxval > 0.f);
-      need_slow = __any_sync(0xffffffffu, bad) || !ok_origin || any_nonfinite;
+      need_slow = __any_sync(0xffffffffu, bad) || !ok_origin || any_nan;
       if (need_slow) {
-        // exact emulation: max of the whole blurred plane (NaN propagates like np.max)
+        // exact emulation: max of the whole blurred plane (NaN propagates like np.max).  The stage is
+        // already being refilled, so the decoded plane is re-read from global memory (L2-resident).
+        const T* g0 = gptr0(pb, pc);
+        const T* g1 = FLIP ? gptr1(pb, pc) : nullptr;
+        auto gval = [&](int y, int x) -> float {
+          float o = elem_f32<T>(g0, y * W + x);
+          if (FLIP) o = __fmul_rn(__fadd_rn(o, elem_f32<T>(g1, y * W + (W - 1 - x))), 0.5f);
+          return o;
+        };
         float m = -CUDART_INF_F;
         bool first = true;
         for (int e = lane; e < HW; e += 32) {
@@ -475,7 +541,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
               if (yy < 0 || yy >= H) return r;
               for (int j = 0; j < ksize; ++j) {
                 const int xx = x + j - bb;
-                r = __fma_rn(a.tapsd[j], (xx >= 0 && xx < W) ? (double)val(yy, xx) : 0.0, r);
+                r = __fma_rn(a.tapsd[j], (xx >= 0 && xx < W) ? (double)gval(yy, xx) : 0.0, r);
               }
               return r;
             };
@@ -488,7 +554,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
               if (yy < 0 || yy >= H) return r;
               for (int j = 0; j < ksize; ++j) {
                 const int xx = x + j - bb;
-                r = __fmaf_rn(a.tapsf[j], (xx >= 0 && xx < W) ? val(yy, xx) : 0.f, r);
+                r = __fmaf_rn(a.tapsf[j], (xx >= 0 && xx < W) ? gval(yy, xx) : 0.f, r);
               }
               return r;
             };
@@ -503,15 +569,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         for (int o = 16; o > 0; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
         bmax = m;
       }
-    }
-
-    // ---- the stage is free: re-arm it with the team's next plane, then finish from shared/registers ------
-    __syncwarp();
-    if (a.use_tma && p + total_teams < n_planes && lane == 0) {
-      uint32_t nb = pb, nc = pc;
-      advance(nb, nc);
-      fence_proxy_async();
-      issue(nb, nc);
     }
 
     if (dark_guard) {
@@ -673,7 +730,7 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY;
   a.tile_dim = is_dark ? a.ksize + 4 : 0;
   const size_t aux = align_up(sizeof(TeamHeader), 16) + 2 * align_up((size_t)(a.W + a.H) * 4, 16) +
-                     align_up((size_t)a.tile_dim * a.tile_dim * 4, 16) + (size_t)a.tile_dim * 5 * 8 + 32 * 4;
+                     align_up((size_t)a.tile_dim * 4 * tile_quads(a.tile_dim) * 4, 16) + (size_t)a.tile_dim * 5 * 8 + 32 * 4;
   a.warp_smem = (int)align_up(a.stage_bytes + aux, 128);
   const size_t budget = 227 * 1024;
   int nteams = (int)(budget / a.warp_smem);
@@ -686,6 +743,13 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   if (env && atoi(env) >= 2 && atoi(env) <= 8) tw = atoi(env);
   while (nteams * tw > kMaxWarpsPerCta) --nteams;
   a.team_warps = tw;
+  {
+    // joint / feat_stride: a power-of-two stride (256/64, 224/56, ...) is an exact multiplication
+    int ex = 0, ey = 0;
+    a.feat_pow2 = (a.feat_x > 0 && a.feat_y > 0 && frexp(a.feat_x, &ex) == 0.5 && frexp(a.feat_y, &ey) == 0.5) ? 1 : 0;
+    a.inv_feat_x = a.feat_x > 0 ? 1.0 / a.feat_x : 0.0;
+    a.inv_feat_y = a.feat_y > 0 ? 1.0 / a.feat_y : 0.0;
+  }
   for (int i = 0; i < LHN_MAX_STACKS; ++i) {
     const double sg = (double)a.sigma[i];
     a.inv2s2[i] = sg > 0 ? 1.0 / (2.0 * sg * sg) : 0.0;
