@@ -21,6 +21,8 @@ SOURCES = ["lhn_heatmap.cu", "lhn_heatmap_warp.cu", "lhn_heatmap_team_f32.cu", "
 HEADERS = [os.path.join(CSRC, "lhn_common.cuh"), os.path.join(CSRC, "lhn_heatmap.cuh"), os.path.join(CSRC, "lhn_heatmap_team.cuh"), os.path.join(HERE, "..", "include", "lhn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+if os.environ.get("LHN_TRACE") == "1":      # phase timestamps in the team kernel (profiles/probes/trace_run.py)
+    NVCC_FLAGS.append("-DLHN_TRACE")
 
 
 def _nvcc():

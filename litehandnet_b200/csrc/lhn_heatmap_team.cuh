@@ -56,6 +56,13 @@ __device__ __forceinline__ float redux_max_nan(float v) {                       
   return d;
 }
 
+// Phase timestamps for profiles/probes/trace_run.py (build with LHN_TRACE=1; compiled out otherwise).
+#ifdef LHN_TRACE
+static __device__ long long g_trace[148 * 6 * 16 * 8];
+#define TR(slot) do { if (wt == 0 && lane == 0 && it_no < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + it_no) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
 // per-team header at the start of the aux region
 struct TeamHeader {
   uint64_t bar;               // TMA completion barrier of the stage
@@ -70,8 +77,23 @@ struct TeamHeader {
   // positives of the balanced loss (written by the last warp of the team before S3)
   double spos;
   int npos;
-  int pad2;
+  int mask_pref;              // fused-metrics mask byte of the plane one ahead (register-pipelined by warp 1)
+  // Per-plane side inputs (joint x/y, visibility, center, scale, gt x/y, bbox w/h), prefetched
+  // kSideAhead planes ahead with 4-byte cp.async: under a saturated memory system a plain global load
+  // costs microseconds, which must never sit on a team's critical path.
+  float side[8][12];
+  int side_mask[8];
 };
+constexpr int kSideAhead = 3;
+enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_N };
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 template <typename T>
 __device__ __forceinline__ float elem_f32(const T* p, int i) { return Elem<T>::to_f32(p[i]); }
@@ -117,6 +139,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   float* tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);
   double* hbuf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile) + align_up((size_t)TD * TCW * 4, 16));
   float* hout = reinterpret_cast<float*>(hbuf + (size_t)TD * 5);
+  int* fidx = reinterpret_cast<int*>(hout + 32);     // this team's copy of flip_index[K]
 
   const uint32_t total_teams = gridDim.x * nteams;
   const uint32_t gteam = blockIdx.x * nteams + team;
@@ -139,7 +162,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   auto gptr1 = [&](uint32_t b, uint32_t c) {
     uint32_t s, k;
     split_channel(c, s, k);
-    const uint32_t kf = a.flip_index ? (uint32_t)a.flip_index[k] : k;
+    const uint32_t kf = a.flip_index ? (uint32_t)fidx[k] : k;
     return reinterpret_cast<const T*>(a.hm_flip) + (int64_t)b * a.fstride_b + (int64_t)(s * K + kf) * a.fstride_c;
   };
   uint64_t policy = 0;
@@ -151,18 +174,36 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
 
   // Render parameters + separable Gaussian factors of plane (b, c) into table buffer `buf`, computed
   // by `nthr` threads of the team (thread index `t`).  exp() is evaluated on an f64 argument.
-  auto prologue = [&](uint32_t b, uint32_t c, int buf, int t, int nthr) {
+  // Side inputs of plane (b, c) -> ring slot `slot` (lanes 0..SD_N-1 of one warp; asynchronous).
+  auto side_fetch = [&](uint32_t b, uint32_t c, int slot) {
+    uint32_t s, k;
+    split_channel(c, s, k);
+    const int64_t bk = (int64_t)b * K + k;
+    const float* src = nullptr;
+    switch (lane) {
+      case SD_JX: case SD_JY: if (LOSS) src = a.joints + bk * a.joints_stride + lane; break;
+      case SD_VIS: if (LOSS) src = a.vis + bk * a.vis_stride; break;
+      case SD_CX: case SD_CY: if (a.center) src = a.center + 2 * (int64_t)b + (lane - SD_CX); break;
+      case SD_SX: case SD_SY: if (a.scale) src = a.scale + 2 * (int64_t)b + (lane - SD_SX); break;
+      case SD_GX: case SD_GY: if (a.counters) src = a.gt + 2 * bk + (lane - SD_GX); break;
+      case SD_BW: case SD_BH: if (a.counters) src = a.bbox_wh + 2 * (int64_t)b + (lane - SD_BW); break;
+      default: break;
+    }
+    if (src) cp_async_4(&th->side[slot][lane], src);
+  };
+
+  auto prologue = [&](uint32_t c, int slot, int buf, int t, int nthr) {
     if (!LOSS) return;
     uint32_t s, k;
     split_channel(c, s, k);
-    const uint32_t bk = b * K + k;
-    const float* jp = a.joints + (int64_t)bk * a.joints_stride;
-    float w = a.vis[(int64_t)bk * a.vis_stride];
+    const float* sd = th->side[slot];
+    const float jx = sd[SD_JX], jy = sd[SD_JY];
+    float w = sd[SD_VIS];
     const double sig = (double)a.sigma[s], tmp = sig * 3.0;
     // joint / feat_stride in f64 (numpy promotes f32 / f64); a power-of-two stride multiplies exactly
     double mux, muy;
-    if (a.feat_pow2) { mux = (double)jp[0] * a.inv_feat_x; muy = (double)jp[1] * a.inv_feat_y; }
-    else { mux = (double)jp[0] / a.feat_x; muy = (double)jp[1] / a.feat_y; }
+    if (a.feat_pow2) { mux = (double)jx * a.inv_feat_x; muy = (double)jy * a.inv_feat_y; }
+    else { mux = (double)jx / a.feat_x; muy = (double)jy / a.feat_y; }
     double x0p = 0, ulx, uly, brx, bry;
     if (a.unbiased) {
       ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1;
@@ -202,32 +243,57 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   uint32_t p = gteam;
   if (p >= n_planes) return;                       // whole teams leave together
   uint32_t pb = p / C, pc = p - pb * C;            // the only division: once per team
+  if (a.flip_index) {
+    for (int i = tl; i < (int)K; i += TT) fidx[i] = a.flip_index[i];
+    team_sync(bar_id, TT);
+  }
   if (tl == 0) {
     mbar_init(&th->bar, 1);
     fence_mbar_init();
     policy = policy_evict_first();
     if (a.use_tma) issue(pb, pc);
   }
-  prologue(pb, pc, 0, tl, TT);
+  // side-input ring: warp 1 (every team has at least two warps) runs kSideAhead planes ahead
+  uint32_t qb = pb, qc = pc, pq = p;               // cursor of the next plane to fetch (warp 1 only)
+  int mask_reg = 0;
+  if (wt == 1) {
+#pragma unroll
+    for (int i = 0; i < kSideAhead; ++i) {
+      if (pq < n_planes) side_fetch(qb, qc, i);
+      cp_async_commit();
+      if (i == 0 && lane == 0 && a.counters) th->side_mask[0] = a.mask[(int64_t)qb * K + (C == K ? qc : qc % K)];
+      if (i == 1 && lane == 0 && a.counters && pq < n_planes) mask_reg = a.mask[(int64_t)qb * K + (C == K ? qc : qc % K)];
+      pq += total_teams; advance(qb, qc);
+    }
+    cp_async_wait<kSideAhead - 1>();               // the first plane's side inputs have landed
+  }
+  team_sync(bar_id, TT);
+  prologue(pc, 0, 0, tl, TT);
   uint32_t phase = 0;
   int buf = 0;
+  int n_it = 0;                                    // team-local plane counter (ring slot = n_it & 7)
 
   const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
   const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
   const int QR = W >> 2, nq = HW >> 2;
   const uint64_t half2 = pack2(0.5f, 0.5f);
 
-  for (; p < n_planes; p += total_teams, buf ^= 1, advance(pb, pc)) {
+  for (; p < n_planes; p += total_teams, buf ^= 1, ++n_it, advance(pb, pc)) {
     const bool has_next = p + total_teams < n_planes;
+#ifdef LHN_TRACE
+    const int it_no = (int)((p - gteam) / total_teams);
+#endif
     // S1: tables of this plane are written, the aux buffers of the previous plane are free
     team_sync(bar_id, TT);
     const float* ex = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(tab0) + (size_t)buf * tab_bytes);
     const float* ey = ex + W;
 
     // ---- wait for the plane ------------------------------------------------------------------------
+    TR(0);
     if (a.use_tma) {
       mbar_wait(&th->bar, phase);
       phase ^= 1u;
+      TR(1);
     } else {
       const T* g0 = gptr0(pb, pc);
       T* d0 = const_cast<T*>(plane0);
@@ -313,6 +379,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       }
     }
 
+    TR(2);
     // ---- per-warp partials -> shared, S2 ----------------------------------------------------------------
     {
       const float wmax = redux_max_nan(best);
@@ -328,6 +395,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     team_sync(bar_id, TT);
 
+    TR(3);
     // ---- every warp: the team-wide argmax (redundantly: cheaper than another barrier) --------------------
     const float tm = lane < TW ? th->red_max[lane] : -CUDART_INF_F;
     const float tmax = redux_max_nan(tm);
@@ -441,14 +509,32 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       }
     }
     // S3: the window and the positives' sum are out of the stage — nobody reads it again
+    TR(4);
     team_sync(bar_id, TT);
+    TR(5);
 
     if (wt != 0) {
-      // warp 1: render parameters + tables of the team's NEXT plane, while warp 0 finishes this one
-      if (wt == 1 && has_next) {
-        uint32_t nb = pb, nc = pc;
-        advance(nb, nc);
-        prologue(nb, nc, buf ^ 1, lane, 32);
+      // warp 1: fetch the side inputs kSideAhead planes ahead, then the render parameters + tables of the
+      // team's NEXT plane (its side inputs were requested two planes ago), while warp 0 finishes this one
+      if (wt == 1) {
+        if (lane == 0 && a.counters) {
+          th->side_mask[(n_it + 1) & 7] = mask_reg;            // loaded one plane ago
+          if (p + 2 * total_teams < n_planes) {
+            uint32_t mb = pb, mc = pc;
+            advance(mb, mc); advance(mb, mc);
+            mask_reg = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];
+          }
+        }
+        if (pq < n_planes) side_fetch(qb, qc, (n_it + kSideAhead) & 7);
+        cp_async_commit();
+        pq += total_teams; advance(qb, qc);
+        cp_async_wait<kSideAhead - 1>();
+        __syncwarp();
+        if (has_next) {
+          uint32_t nb = pb, nc = pc;
+          advance(nb, nc);
+          prologue(nc, (n_it + 1) & 7, buf ^ 1, lane, 32);
+        }
       }
       continue;
     }
@@ -611,12 +697,13 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       split_channel(pc, s, k);
       const uint32_t bk = b * K + k;
       float X = rx, Y = ry;
+      const float* sd = th->side[n_it & 7];
       if (a.transform == LHN_XFORM_CENTER_SCALE) {
-        const float s0 = __fmul_rn(a.scale[2 * b], 200.0f), s1 = __fmul_rn(a.scale[2 * b + 1], 200.0f);
+        const float s0 = __fmul_rn(sd[SD_SX], 200.0f), s1 = __fmul_rn(sd[SD_SY], 200.0f);
         const float dw = a.use_udp ? (float)(W - 1) : (float)W, dh = a.use_udp ? (float)(H - 1) : (float)H;
         const float fx = __fdiv_rn(s0, dw), fy = __fdiv_rn(s1, dh);
-        X = __fsub_rn(__fadd_rn(__fmul_rn(rx, fx), a.center[2 * b]), __fmul_rn(s0, 0.5f));
-        Y = __fsub_rn(__fadd_rn(__fmul_rn(ry, fy), a.center[2 * b + 1]), __fmul_rn(s1, 0.5f));
+        X = __fsub_rn(__fadd_rn(__fmul_rn(rx, fx), sd[SD_CX]), __fmul_rn(s0, 0.5f));
+        Y = __fsub_rn(__fadd_rn(__fmul_rn(ry, fy), sd[SD_CY]), __fmul_rn(s1, 0.5f));
       } else if (a.transform == LHN_XFORM_SCALE) {
         X = __fmul_rn(rx, a.scale_x); Y = __fmul_rn(ry, a.scale_y);
       }
@@ -634,13 +721,13 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         *reinterpret_cast<double2*>(a.partials + 4 * (int64_t)p + 2) = make_double2(bal ? (double)th->npos : 0.0, (double)HW);
         if (a.out_weight) a.out_weight[p] = w;
       }
-      if (a.counters && a.mask[bk]) {
+      if (a.counters && th->side_mask[n_it & 7]) {
         // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32)
         const int Ki = (int)K;
-        const double gx = (double)a.gt[2 * (int64_t)bk], gy = (double)a.gt[2 * (int64_t)bk + 1];
+        const double gx = (double)sd[SD_GX], gy = (double)sd[SD_GY];
         const double ddx = (double)X - gx, ddy = (double)Y - gy;
         unsigned long long* cnt = reinterpret_cast<unsigned long long*>(a.counters);
-        double nb = (double)fmaxf(a.bbox_wh[2 * b], a.bbox_wh[2 * b + 1]);
+        double nb = (double)fmaxf(sd[SD_BW], sd[SD_BH]);
         if (nb != 0.0) {
           if (nb < 0.0) nb = 1e6;
           const double qx = ddx / nb, qy = ddy / nb;
@@ -666,6 +753,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         }
       }
     }
+    TR(6);
   }
 }
 
@@ -712,6 +800,13 @@ int dispatch_team(HmArgs& a, bool flip, bool loss, bool fast, int nteams, size_t
               : dispatch_variant<T, false, false>(a, fast, nteams, smem, st);
 }
 
+#if defined(LHN_TEAM_DTYPE_TU) && defined(LHN_TRACE)
+#ifdef LHN_TRACE_EXPORT
+extern "C" __attribute__((visibility("default"))) int lhn_debug_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_trace, sizeof(g_trace));
+}
+#endif
+#endif
 #ifndef LHN_TEAM_DTYPE_TU
 // instantiated per dtype in lhn_heatmap_team_{f32,bf16,f16}.cu so the three compile in parallel
 extern template int dispatch_team<float>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
@@ -730,7 +825,8 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY;
   a.tile_dim = is_dark ? a.ksize + 4 : 0;
   const size_t aux = align_up(sizeof(TeamHeader), 16) + 2 * align_up((size_t)(a.W + a.H) * 4, 16) +
-                     align_up((size_t)a.tile_dim * 4 * tile_quads(a.tile_dim) * 4, 16) + (size_t)a.tile_dim * 5 * 8 + 32 * 4;
+                     align_up((size_t)a.tile_dim * 4 * tile_quads(a.tile_dim) * 4, 16) + (size_t)a.tile_dim * 5 * 8 + 32 * 4 +
+                     align_up((size_t)a.K * 4, 16);
   a.warp_smem = (int)align_up(a.stage_bytes + aux, 128);
   const size_t budget = 227 * 1024;
   int nteams = (int)(budget / a.warp_smem);
