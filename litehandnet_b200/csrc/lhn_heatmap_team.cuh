@@ -58,8 +58,8 @@ __device__ __forceinline__ float redux_max_nan(float v) {                       
 
 // Phase timestamps for profiles/probes/trace_run.py (build with LHN_TRACE=1; compiled out otherwise).
 #ifdef LHN_TRACE
-static __device__ long long g_trace[148 * 6 * 16 * 8];
-#define TR(slot) do { if (wt == 0 && lane == 0 && it_no < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + it_no) * 8 + (slot)] = clock64(); } while (0)
+static __device__ long long g_trace[148 * 6 * 16 * 16];
+#define TR(slot) do { if (role == 0 && lane == 0 && it_no < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + it_no) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TR(slot) do { } while (0)
 #endif
@@ -79,12 +79,12 @@ struct TeamHeader {
   int npos;
   int mask_pref;              // fused-metrics mask byte of the plane one ahead (register-pipelined by warp 1)
   // Per-plane side inputs (joint x/y, visibility, center, scale, gt x/y, bbox w/h), prefetched
-  // kSideAhead planes ahead with 4-byte cp.async: under a saturated memory system a plain global load
+  // kSideAhead planes ahead (two full plane periods before their first use) with 4-byte cp.async: under a saturated memory system a plain global load
   // costs microseconds, which must never sit on a team's critical path.
   float side[8][12];
   int side_mask[8];
 };
-constexpr int kSideAhead = 3;
+constexpr int kSideAhead = 4;
 enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_N };
 
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
@@ -106,9 +106,6 @@ __device__ __forceinline__ float exp_f32_from_f64(double a) {
   return fmaf(v, al, v);
 }
 
-// quads per row of the DARK tile: the (ksize+4)-wide window starts 0..3 columns into its first quad
-__host__ __device__ constexpr int tile_quads(int td) { return (td + 6) >> 2; }
-
 // FAST: W = H = 64 and the team size is a compile-time constant (TWC warps), so the sweep is a fully
 //       unrolled 128-bit loop with a loop-invariant column quad per thread.
 // KS:   DARK Gaussian size known at compile time (11: the Gen-2 decoder) or 0 = run-time size.
@@ -122,6 +119,11 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / TW, wt = warp - team * TW; // team in CTA, warp in team
   const int tl = wt * 32 + lane;                     // thread in team
+  // Roles rotate over the warps of a team so that the serial epilogues of the CTA's teams are spread
+  // over the four SM sub-partitions (warp w issues on SMSP w % 4): role 0 = epilogue, roles 1..2 = next
+  // plane's tables (+ side-input ring on role 1), role TW-1 = positives of the balanced loss.
+  const int ew = (TW >= 4 ? team : (team >> 1)) % TW;
+  const int role = (wt - ew + TW) % TW;
   const int nteams = (blockDim.x >> 5) / TW;
   const int bar_id = 1 + team;
 
@@ -135,9 +137,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   float* tab0 = reinterpret_cast<float*>(aux + align_up(sizeof(TeamHeader), 16));   // two table buffers
   const int ksize = KS > 0 ? KS : a.ksize;
   const int TD = KS > 0 ? KS + 4 : a.tile_dim;       // DARK window side
-  const int NQ = tile_quads(TD), TCW = 4 * NQ;       // tile row = NQ quads
-  float* tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);
-  double* hbuf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile) + align_up((size_t)TD * TCW * 4, 16));
+  double* hbuf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);   // row-pass sums
   float* hout = reinterpret_cast<float*>(hbuf + (size_t)TD * 5);
   int* fidx = reinterpret_cast<int*>(hout + 32);     // this team's copy of flip_index[K]
 
@@ -256,7 +256,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   // side-input ring: warp 1 (every team has at least two warps) runs kSideAhead planes ahead
   uint32_t qb = pb, qc = pc, pq = p;               // cursor of the next plane to fetch (warp 1 only)
   int mask_reg = 0;
-  if (wt == 1) {
+  if (role == 1) {
 #pragma unroll
     for (int i = 0; i < kSideAhead; ++i) {
       if (pq < n_planes) side_fetch(qb, qc, i);
@@ -265,7 +265,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       if (i == 1 && lane == 0 && a.counters && pq < n_planes) mask_reg = a.mask[(int64_t)qb * K + (C == K ? qc : qc % K)];
       pq += total_teams; advance(qb, qc);
     }
-    cp_async_wait<kSideAhead - 1>();               // the first plane's side inputs have landed
+    cp_async_wait<kSideAhead - 2>();               // the first two planes' side inputs have landed
   }
   team_sync(bar_id, TT);
   prologue(pc, 0, 0, tl, TT);
@@ -436,21 +436,43 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     const int px = (int)cx, py = (int)cy;
     const bool dark_guard = is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2);
     const int bb = (ksize - 1) >> 1;
-    const int wx0 = px - 2 - bb;                      // first window column (may be negative)
-    const int c0 = wx0 & ~3, xo = wx0 & 3;            // its quad-aligned start and the offset inside it
-
-    // ---- stage the DARK window: zero-padded (ksize+4) rows x NQ quads of the decoded plane -----------------
+    // ---- DARK row pass straight from the stage, one output per thread: the (ksize+4) x 5 row sums around
+    //      the peak (zero padding = skipped taps; sequential FMA over the taps = cv2's RowFilter order) ----
     if (dark_guard) {
-      for (int e = tl; e < TD * NQ; e += TT) {
-        const int r = e / NQ, cq = e - r * NQ;          // compile-time divisor when KS > 0
-        const int y = py - 2 - bb + r, x = c0 + 4 * cq;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < H && x >= 0 && x < W) v = load_quad_rc(y, x >> 2);
-        *reinterpret_cast<float4*>(tile + r * TCW + 4 * cq) = v;
+      const int nrow = TD * 5;
+      for (int e = tl; e < nrow; e += TT) {
+        const int r = e / 5, c5 = e - r * 5;
+        const int y = py - 2 - bb + r, x0 = px - 2 + c5 - bb;
+        if (legacy) {
+          double acc = 0.0;
+          if (y >= 0 && y < H)
+            for (int j = 0; j < ksize; ++j) {
+              const int x = x0 + j;
+              if ((unsigned)x < (unsigned)W) acc = __fma_rn(a.tapsd[j], (double)val(y, x), acc);
+            }
+          hbuf[e] = acc;
+        } else {
+          float acc = 0.f;
+          if (y >= 0 && y < H) {
+            if (KS > 0) {
+#pragma unroll
+              for (int j = 0; j < KS; ++j) {
+                const int x = x0 + j;
+                if ((unsigned)x < (unsigned)W) acc = __fmaf_rn(a.tapsf[j], val(y, x), acc);   // taps: constant bank
+              }
+            } else {
+              for (int j = 0; j < ksize; ++j) {
+                const int x = x0 + j;
+                if ((unsigned)x < (unsigned)W) acc = __fmaf_rn(a.tapsf[j], val(y, x), acc);
+              }
+            }
+          }
+          reinterpret_cast<float*>(hbuf)[e] = acc;
+        }
       }
     }
     // ---- positives of the balanced loss: a small window around the joint, by the team's last warp ----------
-    if (LOSS && wt == TW - 1 && a.loss_mode == LHN_LOSS_DISTANCE_BALANCE) {
+    if (LOSS && role == TW - 1 && a.loss_mode == LHN_LOSS_DISTANCE_BALANCE) {
       uint32_t s, k;
       split_channel(pc, s, k);
       double Spos = 0.0;
@@ -467,19 +489,15 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       }
       if (th->render_on[buf] || a.pos_value < 0.f) {
         float sp = 0.f;
-        // one column per lane, rows in a short loop (5 x 5 for sigma = 2)
-        for (int x0 = x_lo; x0 <= x_hi; x0 += 32) {
-          const int xx = x0 + lane;
-          if (xx <= x_hi) {
-            const float gxv = ex[xx];
-            for (int yy = y_lo; yy <= y_hi; ++yy) {
-              const float gyv = ey[yy];
-              if (gxv * gyv > a.pos_value) {
-                const float d = fmaf(-gxv, gyv, elem_f32<T>(plane0, yy * W + xx));
-                sp = fmaf(d, d, sp);
-                Npos += 1;
-              }
-            }
+        // one window element per lane (5 x 5 = 25 lanes for sigma = 2)
+        const int ww = x_hi - x_lo + 1, wn = ww > 0 ? ww * (y_hi - y_lo + 1) : 0;
+        for (int e = lane; e < wn; e += 32) {
+          const int ry = e / ww, xx = x_lo + (e - ry * ww), yy = y_lo + ry;
+          const float gxv = ex[xx], gyv = ey[yy];
+          if (gxv * gyv > a.pos_value) {
+            const float d = fmaf(-gxv, gyv, elem_f32<T>(plane0, yy * W + xx));
+            sp = fmaf(d, d, sp);
+            Npos += 1;
           }
         }
         Spos = (double)warp_sum(sp);
@@ -489,7 +507,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     // ---- quarter-offset refinements read their neighbours while the plane is resident ----------------------
     float rx = cx, ry = cy;
-    if (wt == 0) {
+    if (role == 0) {
       if (a.refine == LHN_REFINE_OFFSET_HALF || a.refine == LHN_REFINE_OFFSET) {
         const int xx = min(max(px, 0), W - 1), yy = min(max(py, 0), H - 1);
         // clamped neighbours; `>` false (equality, NaN) -> -0.25
@@ -513,10 +531,11 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     team_sync(bar_id, TT);
     TR(5);
 
-    if (wt != 0) {
-      // warp 1: fetch the side inputs kSideAhead planes ahead, then the render parameters + tables of the
-      // team's NEXT plane (its side inputs were requested two planes ago), while warp 0 finishes this one
-      if (wt == 1) {
+    if (role != 0) {
+      // role 1: fetch the side inputs kSideAhead planes ahead; roles 1..2: render parameters + tables of the
+      // team's NEXT plane (its side inputs were requested earlier), while the epilogue warp finishes this one
+      const int nh = TW > 2 ? 2 : 1;
+      if (role == 1) {
         if (lane == 0 && a.counters) {
           th->side_mask[(n_it + 1) & 7] = mask_reg;            // loaded one plane ago
           if (p + 2 * total_teams < n_planes) {
@@ -528,14 +547,14 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         if (pq < n_planes) side_fetch(qb, qc, (n_it + kSideAhead) & 7);
         cp_async_commit();
         pq += total_teams; advance(qb, qc);
-        cp_async_wait<kSideAhead - 1>();
-        __syncwarp();
-        if (has_next) {
-          uint32_t nb = pb, nc = pc;
-          advance(nb, nc);
-          prologue(nc, (n_it + 1) & 7, buf ^ 1, lane, 32);
-        }
       }
+      if (role <= nh && has_next) {
+        uint32_t nb = pb, nc = pc;
+        advance(nb, nc);
+        prologue(nc, (n_it + 1) & 7, buf ^ 1, (role - 1) * 32 + lane, nh * 32);
+      }
+      // side inputs of plane n+2 complete here; the S1 barrier publishes them to the other warps
+      if (role == 1) cp_async_wait<kSideAhead - 2>();
       continue;
     }
 
@@ -548,20 +567,13 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       issue(nb, nc);
     }
 
+    TR(7);
     bool need_slow = false;
     float bmax = 0.f;
     if (dark_guard) {
-      // row pass (sequential FMA over the taps), then column pass (centre + symmetric pairs) — the
-      // summation order of cv2's separable filter
+      // column pass over the staged row sums (centre tap, then symmetric pairs fused-added: the
+      // summation order of cv2's separable filter)
       if (legacy) {
-        for (int e = lane; e < TD * 5; e += 32) {
-          const int r = e / 5, c5 = e - r * 5;
-          const float* trow = tile + r * TCW + xo + c5;
-          double acc = 0.0;
-          for (int j = 0; j < ksize; ++j) acc = __fma_rn(a.tapsd[j], (double)trow[j], acc);
-          hbuf[e] = acc;
-        }
-        __syncwarp();
         if (lane < 25) {
           const int dr = lane / 5, c5 = lane - dr * 5;
           double acc = __dmul_rn(a.tapsd[bb], hbuf[(dr + bb) * 5 + c5]);
@@ -571,19 +583,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         }
       } else {
         float* hb = reinterpret_cast<float*>(hbuf);
-        for (int e = lane; e < TD * 5; e += 32) {
-          const int r = e / 5, c5 = e - r * 5;
-          const float* trow = tile + r * TCW + xo + c5;
-          float acc = 0.f;
-          if (KS > 0) {
-#pragma unroll
-            for (int j = 0; j < KS; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);   // taps: constant-bank operands
-          } else {
-            for (int j = 0; j < ksize; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);
-          }
-          hb[e] = acc;
-        }
-        __syncwarp();
         if (lane < 25) {
           const int dr = lane / 5, c5 = lane - dr * 5;
           const float* hcol = hb + (dr + bb) * 5 + c5;
@@ -599,6 +598,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         }
       }
       __syncwarp();
+      TR(8);
       // can the 1e-10 clamp of log() (or a non-finite value) touch the 13 stencil points?
       const float hv = lane < 25 ? hout[lane] : CUDART_INF_F;
       const int dr = lane / 5 - 2, dc = lane % 5 - 2;
@@ -657,6 +657,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       }
     }
 
+    TR(9);
     if (dark_guard) {
       // log of the 25 blurred values in parallel, then the Taylor step on lane 0
       const float raw = lane < 25 ? hout[lane] : 1.f;
@@ -691,6 +692,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           rx = __fadd_rn(rx, ox); ry = __fadd_rn(ry, oy);
         }
       }
+      TR(10);
       // ---- back-transform (T1/T2) and stores --------------------------------------------------------
       const uint32_t b = pb;
       uint32_t s, k;
@@ -710,6 +712,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       if (a.out_hm) { float* o = a.out_hm + 3 * (int64_t)p; o[0] = rx; o[1] = ry; o[2] = maxval; }
       if (a.out_kpts) { float* o = a.out_kpts + 3 * (int64_t)p; o[0] = X; o[1] = Y; o[2] = maxval; }
       if (a.out_idx) a.out_idx[p] = (int32_t)idx;
+      TR(11);
       if (LOSS) {
         double S = 0.0;
         for (int i = 0; i < TW; ++i) S += th->red_s[i];
@@ -825,7 +828,7 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY;
   a.tile_dim = is_dark ? a.ksize + 4 : 0;
   const size_t aux = align_up(sizeof(TeamHeader), 16) + 2 * align_up((size_t)(a.W + a.H) * 4, 16) +
-                     align_up((size_t)a.tile_dim * 4 * tile_quads(a.tile_dim) * 4, 16) + (size_t)a.tile_dim * 5 * 8 + 32 * 4 +
+                     (size_t)a.tile_dim * 5 * 8 + 32 * 4 +
                      align_up((size_t)a.K * 4, 16);
   a.warp_smem = (int)align_up(a.stage_bytes + aux, 128);
   const size_t budget = 227 * 1024;
