@@ -55,6 +55,13 @@ struct HmArgs {
   int stage_bytes;                 // bytes of the TMA stage (plane0 [+ plane1]) at the start of it
   int tile_dim;                    // DARK window side = blur_ksize + 4 (0 when DARK is off)
   int force_cta_kernel;            // testing: bypass the warp kernel (env LHN_FORCE_CTA_KERNEL=1)
+  // one-launch loss (team kernel only; all optional): per-team f64 sums + a self-resetting ticket
+  double* team_sums;               // [teams, 4] workspace
+  unsigned int* ticket;            // zero before the first launch; the kernel leaves it zero
+  double* sums_out;                // [4] (S_pos, S_neg, N_pos, numel) of the whole launch
+  float* loss_out;                 // [1] finalised loss (as lhn_loss_finalize)
+  float loss_scale;
+  int sum_reduction;
   int feat_pow2;                   // feat_x, feat_y are powers of two: joint / feat == joint * inv_feat exactly
   double inv_feat_x, inv_feat_y;
 };

@@ -1,16 +1,23 @@
-// K1 (primary) — persistent fused heatmap kernel: one TEAM of warps per shared-memory stage.
+// K1 (primary) — persistent fused heatmap kernel: sweeper warps + a lagging epilogue warp per TEAM.
 //
-// One CTA per SM, cut into teams of TW warps; every team owns a private stage (plane [+ flipped
-// plane]) with its own mbarrier and named barrier — there is no CTA-wide barrier anywhere.  Per plane
-// a team: waits for its TMA bulk copy; makes ONE sweep over the plane (flip average, Gaussian target +
-// squared error as packed f32x2 FMAs, running NaN-propagating 3-input max; 128-bit conflict-free
-// shared-memory reads); combines the per-warp partials; copies the DARK window (quads of the decoded
-// plane) and the positives' sum out of the stage; and then RELEASES the stage: warp 0 re-arms it with
-// the TMA load of the team's next plane before it starts the blur / Taylor / back-transform / stores,
-// while warp 1 evaluates the next plane's render parameters and Gaussian tables (double-buffered).
-// The stage is therefore idle only for the sweep itself; 6 teams x 32 KB per SM (f32 + flip) keep
-// HBM busy.  The rare exact-emulation path of DARK (1e-10 clamp reachable) re-reads the plane from
-// global memory (L2), so it never holds a stage.
+// One CTA per SM, cut into teams of TW warps; every team owns a private stage (plane [+ flipped plane])
+// filled by TMA bulk copies, and works as a two-stage pipeline with no CTA-wide barrier:
+//
+//   SWEEPERS (TW-1 warps)  wait for the stage's mbarrier; make ONE sweep over the plane (flip average,
+//       Gaussian target + squared error as packed f32x2 FMAs, running NaN-propagating 3-input max; 128-bit
+//       conflict-free shared-memory reads); combine the per-warp partials; resolve the argmax; compute the
+//       DARK row sums around it straight from the stage; sum the loss "positives"; write a small plane
+//       record; RELEASE the stage by re-arming it with the TMA load of the team's next plane; and, while
+//       that load is in flight, evaluate the next plane's render parameters and Gaussian tables and run the
+//       side-input ring (joints / visibility / center / scale prefetched four planes ahead with cp.async).
+//   EPILOGUE warp (1 warp)  lags up to two planes behind on double-buffered records: column pass of the
+//       blur, log, Taylor step, back-transform, stores, loss partial sums, PCK/AUC/EPE counters; at the end
+//       it publishes the team's loss sums and the last team to finish reduces them in a fixed order and
+//       finalises the loss (one launch per step, bitwise reproducible).
+//
+// The two sides hand records over through a full/empty mbarrier pair per buffer, so the latency-bound
+// scalar epilogue (~4k cycles) overlaps the next plane's load and sweep instead of serialising with them.
+// The rare exact-emulation path of DARK (1e-10 clamp reachable) re-reads the plane from global memory (L2).
 #pragma once
 #include <math.h>
 #include <stdlib.h>
@@ -22,7 +29,7 @@ namespace lhn {
 constexpr int kMaxWarpsPerCta = 24;
 constexpr int kMaxTeams = 12;
 
-__device__ __forceinline__ void team_sync(int id, int nthreads) {
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
@@ -55,38 +62,6 @@ __device__ __forceinline__ float redux_max_nan(float v) {                       
   asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(d) : "f"(v));
   return d;
 }
-
-// Phase timestamps for profiles/probes/trace_run.py (build with LHN_TRACE=1; compiled out otherwise).
-#ifdef LHN_TRACE
-static __device__ long long g_trace[148 * 6 * 16 * 16];
-#define TR(slot) do { if (role == 0 && lane == 0 && it_no < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + it_no) * 16 + (slot)] = clock64(); } while (0)
-#else
-#define TR(slot) do { } while (0)
-#endif
-// per-team header at the start of the aux region
-struct TeamHeader {
-  uint64_t bar;               // TMA completion barrier of the stage
-  uint64_t pad;
-  float red_max[8];           // per-warp sweep partials: max (NaN-propagating), first quad holding it, sum
-  uint32_t red_q[8];
-  float red_s[8];
-  // render parameters of the two table buffers (written by whoever runs the prologue)
-  float w[2];
-  float mx[2], my[2];
-  int render_on[2];
-  // positives of the balanced loss (written by the last warp of the team before S3)
-  double spos;
-  int npos;
-  int mask_pref;              // fused-metrics mask byte of the plane one ahead (register-pipelined by warp 1)
-  // Per-plane side inputs (joint x/y, visibility, center, scale, gt x/y, bbox w/h), prefetched
-  // kSideAhead planes ahead (two full plane periods before their first use) with 4-byte cp.async: under a saturated memory system a plain global load
-  // costs microseconds, which must never sit on a team's critical path.
-  float side[8][12];
-  int side_mask[8];
-};
-constexpr int kSideAhead = 4;
-enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_N };
-
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -94,6 +69,56 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// Phase timestamps for profiles/probes/trace_run.py (build with LHN_TRACE=1; compiled out otherwise).
+// slots 0-5: first sweeper warp (S1 passed, plane landed, sweep done, S2 passed, staged, released);
+// slots 8-11: epilogue warp (record received, blur/check done, Taylor done, plane finished).
+#ifdef LHN_TRACE
+static __device__ long long g_trace[148 * 6 * 16 * 16];
+#define TRS(slot) do { if (role == 1 && lane == 0 && n_it < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + n_it) * 16 + (slot)] = clock64(); } while (0)
+#define TRE(slot) do { if (lane == 0 && n_it < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + n_it) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRS(slot) do { } while (0)
+#define TRE(slot) do { } while (0)
+#endif
+
+// Record handed from the sweepers to the epilogue warp (double-buffered).
+struct PlaneRec {
+  uint32_t idx;               // first-maximal flat index
+  float maxval;
+  float rx, ry;               // coordinates after masking and the +-0.25 rules (DARK adds its offset later)
+  float w;                    // target weight after the visibility rule
+  float ssum;                 // sum of (output - target)^2 over the plane
+  float spos;                 // ... over the positives (target > value)
+  int npos;
+  int flags;                  // bit 0: DARK guard passed, bit 1: a NaN was found
+  int pad[3];
+};
+
+// per-team header at the start of the aux region
+struct TeamHeader {
+  uint64_t bar;               // TMA completion barrier of the stage
+  uint64_t full[2];           // record n is complete          (sweepers -> epilogue warp)
+  uint64_t empty[2];          // record/row-sum buffer is free (epilogue warp -> sweepers)
+  uint64_t pad;
+  float red_max[8];           // per-warp sweep partials: max (NaN-propagating), first quad holding it, sum
+  uint32_t red_q[8];
+  float red_s[8];
+  // render parameters of the two table buffers (written by the prologue)
+  float w[2];
+  float mx[2], my[2];
+  int render_on[2];
+  PlaneRec rec[2];
+  int mask_pad[2];
+  // Per-plane side inputs (joint x/y, visibility, center, scale, gt x/y, bbox w/h), prefetched
+  // kSideAhead planes ahead (two full plane periods before their first use) with 4-byte cp.async: under
+  // a saturated memory system a plain global load costs microseconds, which must never sit on a team's
+  // critical path.
+  float side[8][12];
+  int side_mask[8];
+};
+constexpr int kSideAhead = 4;
+enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_N };
 
 template <typename T>
 __device__ __forceinline__ float elem_f32(const T* p, int i) { return Elem<T>::to_f32(p[i]); }
@@ -106,8 +131,8 @@ __device__ __forceinline__ float exp_f32_from_f64(double a) {
   return fmaf(v, al, v);
 }
 
-// FAST: W = H = 64 and the team size is a compile-time constant (TWC warps), so the sweep is a fully
-//       unrolled 128-bit loop with a loop-invariant column quad per thread.
+// FAST: W = H = 64 and the team size is a compile-time constant (TWC warps = TWC-1 sweepers + 1 epilogue),
+//       so the sweep is a fully unrolled 128-bit loop with a loop-invariant column quad per thread.
 // KS:   DARK Gaussian size known at compile time (11: the Gen-2 decoder) or 0 = run-time size.
 template <typename T, bool FAST, int TWC, bool FLIP, bool LOSS, int KS>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
@@ -115,17 +140,17 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int H = FAST ? 64 : a.H, W = FAST ? 64 : a.W, HW = FAST ? 4096 : a.HW;
   const int TW = FAST ? TWC : a.team_warps;          // warps per team
-  const int TT = TW * 32;                            // threads per team
+  const int NS = TW - 1;                             // sweeper warps
+  const int ST = NS * 32;                            // sweeper threads
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / TW, wt = warp - team * TW; // team in CTA, warp in team
-  const int tl = wt * 32 + lane;                     // thread in team
-  // Roles rotate over the warps of a team so that the serial epilogues of the CTA's teams are spread
-  // over the four SM sub-partitions (warp w issues on SMSP w % 4): role 0 = epilogue, roles 1..2 = next
-  // plane's tables (+ side-input ring on role 1), role TW-1 = positives of the balanced loss.
+  const int nteams = (blockDim.x >> 5) / TW;
+  const int bar_id = 1 + team;                       // named barrier of this team's sweepers
+  // Roles rotate over the warps of a team so that the epilogue warps of the CTA's teams are spread over
+  // the four SM sub-partitions (warp w issues on SMSP w % 4): role 0 = epilogue, roles 1..TW-1 = sweepers.
   const int ew = (TW >= 4 ? team : (team >> 1)) % TW;
   const int role = (wt - ew + TW) % TW;
-  const int nteams = (blockDim.x >> 5) / TW;
-  const int bar_id = 1 + team;
+  const int sl = (role - 1) * 32 + lane;             // sweeper thread index (role >= 1)
 
   // ---- this team's private shared memory ----------------------------------------------------------
   unsigned char* tbase = smem_raw + (size_t)team * a.warp_smem;
@@ -137,8 +162,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   float* tab0 = reinterpret_cast<float*>(aux + align_up(sizeof(TeamHeader), 16));   // two table buffers
   const int ksize = KS > 0 ? KS : a.ksize;
   const int TD = KS > 0 ? KS + 4 : a.tile_dim;       // DARK window side
-  double* hbuf = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);   // row-pass sums
-  float* hout = reinterpret_cast<float*>(hbuf + (size_t)TD * 5);
+  const int bb = (ksize - 1) >> 1;
+  double* hbuf0 = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);   // 2 x row sums
+  float* hout = reinterpret_cast<float*>(hbuf0 + (size_t)2 * TD * 5);
   int* fidx = reinterpret_cast<int*>(hout + 32);     // this team's copy of flip_index[K]
 
   const uint32_t total_teams = gridDim.x * nteams;
@@ -165,6 +191,267 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     const uint32_t kf = a.flip_index ? (uint32_t)fidx[k] : k;
     return reinterpret_cast<const T*>(a.hm_flip) + (int64_t)b * a.fstride_b + (int64_t)(s * K + kf) * a.fstride_c;
   };
+  const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
+  const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
+
+  // ---- one-time setup: barriers visible to the whole CTA before anybody waits on them ------------------
+  if (wt == 0 && lane == 0) {
+    mbar_init(&th->bar, 1);
+    mbar_init(&th->full[0], 1); mbar_init(&th->full[1], 1);
+    mbar_init(&th->empty[0], 1); mbar_init(&th->empty[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t p = gteam;
+  if (p >= n_planes) return;                       // whole teams leave together
+  uint32_t pb = p / C, pc = p - pb * C;            // the only division: once per team
+
+  if (role == 0) {
+    // =====================================================================================================
+    // EPILOGUE WARP
+    // =====================================================================================================
+    double acc_sp = 0.0, acc_sn = 0.0, acc_np = 0.0, acc_ne = 0.0;   // this team's loss sums (lane 0)
+    int n_it = 0;
+    for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
+      const int buf = n_it & 1;
+      mbar_wait(&th->full[buf], (uint32_t)(n_it >> 1) & 1u);
+      TRE(8);
+      const PlaneRec* rec = &th->rec[buf];
+      const uint32_t idx = rec->idx;
+      const float maxval = rec->maxval;
+      float rx = rec->rx, ry = rec->ry;
+      const bool dark_guard = (rec->flags & 1) != 0, any_nan = (rec->flags & 2) != 0;
+      double* hbuf = hbuf0 + (size_t)buf * TD * 5;
+
+      bool need_slow = false;
+      float bmax = 0.f;
+      if (dark_guard) {
+        // column pass over the staged row sums (centre tap, then symmetric pairs fused-added: the
+        // summation order of cv2's separable filter)
+        if (legacy) {
+          if (lane < 25) {
+            const int dr = lane / 5, c5 = lane - dr * 5;
+            double acc = __dmul_rn(a.tapsd[bb], hbuf[(dr + bb) * 5 + c5]);
+            for (int j = 1; j <= bb; ++j)
+              acc = __fma_rn(a.tapsd[bb + j], __dadd_rn(hbuf[(dr + bb + j) * 5 + c5], hbuf[(dr + bb - j) * 5 + c5]), acc);
+            hout[lane] = (float)acc;
+          }
+        } else {
+          const float* hb = reinterpret_cast<const float*>(hbuf);
+          if (lane < 25) {
+            const int dr = lane / 5, c5 = lane - dr * 5;
+            const float* hcol = hb + (dr + bb) * 5 + c5;
+            float acc = __fmul_rn(a.tapsf[bb], hcol[0]);
+            if (KS > 0) {
+#pragma unroll
+              for (int j = 1; j <= (KS - 1) / 2; ++j)
+                acc = __fmaf_rn(a.tapsf[(KS - 1) / 2 + j], __fadd_rn(hcol[5 * j], hcol[-5 * j]), acc);
+            } else {
+              for (int j = 1; j <= bb; ++j) acc = __fmaf_rn(a.tapsf[bb + j], __fadd_rn(hcol[5 * j], hcol[-5 * j]), acc);
+            }
+            hout[lane] = acc;
+          }
+        }
+        __syncwarp();
+        // can the 1e-10 clamp of log() (or a non-finite value) touch the 13 stencil points?
+        const float hv = lane < 25 ? hout[lane] : CUDART_INF_F;
+        const int dr = lane / 5 - 2, dc = lane % 5 - 2;
+        const bool used = lane < 25 && (abs(dr) + abs(dc) <= 2);
+        const bool bad = used && !(hv >= 1e-9f);
+        const bool ok_origin = legacy ? (maxval >= 1e-3f) : (maxval > 0.f);
+        need_slow = __any_sync(0xffffffffu, bad) || !ok_origin || any_nan;
+        if (need_slow) {
+          // exact emulation: max of the whole blurred plane (NaN propagates like np.max).  The stage
+          // belongs to the sweepers, so the decoded plane is re-read from global memory (L2-resident).
+          const T* g0 = gptr0(pb, pc);
+          const T* g1 = FLIP ? gptr1(pb, pc) : nullptr;
+          auto gval = [&](int y, int x) -> float {
+            float o = elem_f32<T>(g0, y * W + x);
+            if (FLIP) o = __fmul_rn(__fadd_rn(o, elem_f32<T>(g1, y * W + (W - 1 - x))), 0.5f);
+            return o;
+          };
+          float m = -CUDART_INF_F;
+          bool first = true;
+          for (int e = lane; e < HW; e += 32) {
+            const int y = e / W, x = e - y * W;
+            float v;
+            if (legacy) {
+              auto rowv = [&](int yy) {
+                double r = 0.0;
+                if (yy < 0 || yy >= H) return r;
+                for (int j = 0; j < ksize; ++j) {
+                  const int xx = x + j - bb;
+                  r = __fma_rn(a.tapsd[j], (xx >= 0 && xx < W) ? (double)gval(yy, xx) : 0.0, r);
+                }
+                return r;
+              };
+              double acc = __dmul_rn(a.tapsd[bb], rowv(y));
+              for (int j = 1; j <= bb; ++j) acc = __fma_rn(a.tapsd[bb + j], __dadd_rn(rowv(y + j), rowv(y - j)), acc);
+              v = (float)acc;
+            } else {
+              auto rowv = [&](int yy) {
+                float r = 0.f;
+                if (yy < 0 || yy >= H) return r;
+                for (int j = 0; j < ksize; ++j) {
+                  const int xx = x + j - bb;
+                  r = __fmaf_rn(a.tapsf[j], (xx >= 0 && xx < W) ? gval(yy, xx) : 0.f, r);
+                }
+                return r;
+              };
+              float acc = __fmul_rn(a.tapsf[bb], rowv(y));
+              for (int j = 1; j <= bb; ++j) acc = __fmaf_rn(a.tapsf[bb + j], __fadd_rn(rowv(y + j), rowv(y - j)), acc);
+              v = acc;
+            }
+            m = first ? v : nanmax(m, v);
+            first = false;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+          bmax = m;
+        }
+        // log of the 25 blurred values in parallel, then the Taylor step on lane 0
+        const float raw = lane < 25 ? hout[lane] : 1.f;
+        float hval;
+        if (need_slow) {
+          const float sc = legacy ? __fdiv_rn(maxval, __fadd_rn(bmax, 1e-6f)) : __fdiv_rn(maxval, bmax);
+          float v = __fmul_rn(raw, sc);
+          v = (v != v) ? v : fmaxf(v, 1e-10f);          // np.maximum propagates NaN
+          hval = logf(v);
+        } else {
+          hval = logf(raw);
+        }
+        __syncwarp();
+        if (lane < 25) hout[lane] = hval;
+        __syncwarp();
+      }
+      TRE(9);
+
+      if (lane == 0) {
+        if (dark_guard) {
+#define HH(dy, dx) hout[((dy) + 2) * 5 + (dx) + 2]
+          const float h00 = HH(0, 0);
+          const float ddx = __fmul_rn(0.5f, __fsub_rn(HH(0, 1), HH(0, -1)));
+          const float ddy = __fmul_rn(0.5f, __fsub_rn(HH(1, 0), HH(-1, 0)));
+          const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(HH(0, 2), __fmul_rn(2.f, h00)), HH(0, -2)));
+          const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(HH(1, 1), HH(-1, 1)), HH(1, -1)), HH(-1, -1)));
+          const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(HH(2, 0), __fmul_rn(2.f, h00)), HH(-2, 0)));
+#undef HH
+          const float det = __fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy));
+          if (det != 0.f) {   // true for NaN, as in numpy
+            const float ox = -__fdiv_rn(__fsub_rn(__fmul_rn(dyy, ddx), __fmul_rn(dxy, ddy)), det);
+            const float oy = -__fdiv_rn(__fsub_rn(__fmul_rn(dxx, ddy), __fmul_rn(dxy, ddx)), det);
+            rx = __fadd_rn(rx, ox); ry = __fadd_rn(ry, oy);
+          }
+        }
+        TRE(10);
+        // ---- back-transform (T1/T2) and stores --------------------------------------------------------
+        uint32_t s, k;
+        split_channel(pc, s, k);
+        float X = rx, Y = ry;
+        const float* sd = th->side[n_it & 7];
+        if (a.transform == LHN_XFORM_CENTER_SCALE) {
+          const float s0 = __fmul_rn(sd[SD_SX], 200.0f), s1 = __fmul_rn(sd[SD_SY], 200.0f);
+          const float dw = a.use_udp ? (float)(W - 1) : (float)W, dh = a.use_udp ? (float)(H - 1) : (float)H;
+          const float fx = __fdiv_rn(s0, dw), fy = __fdiv_rn(s1, dh);
+          X = __fsub_rn(__fadd_rn(__fmul_rn(rx, fx), sd[SD_CX]), __fmul_rn(s0, 0.5f));
+          Y = __fsub_rn(__fadd_rn(__fmul_rn(ry, fy), sd[SD_CY]), __fmul_rn(s1, 0.5f));
+        } else if (a.transform == LHN_XFORM_SCALE) {
+          X = __fmul_rn(rx, a.scale_x); Y = __fmul_rn(ry, a.scale_y);
+        }
+        if (a.out_hm) { float* o = a.out_hm + 3 * (int64_t)p; o[0] = rx; o[1] = ry; o[2] = maxval; }
+        if (a.out_kpts) { float* o = a.out_kpts + 3 * (int64_t)p; o[0] = X; o[1] = Y; o[2] = maxval; }
+        if (a.out_idx) a.out_idx[p] = (int32_t)idx;
+        if (LOSS) {
+          const float w = rec->w;
+          const bool bal = a.loss_mode == LHN_LOSS_DISTANCE_BALANCE;
+          const float wp = (a.loss_mode == LHN_LOSS_JOINTS_MSE) ? w * w : w;
+          const double sall = (double)rec->ssum * (double)wp, spos = bal ? (double)rec->spos * (double)wp : 0.0;
+          const double npos = bal ? (double)rec->npos : 0.0;
+          if (a.partials) {
+            *reinterpret_cast<double2*>(a.partials + 4 * (int64_t)p) = make_double2(spos, sall - spos);
+            *reinterpret_cast<double2*>(a.partials + 4 * (int64_t)p + 2) = make_double2(npos, (double)HW);
+          }
+          acc_sp += spos; acc_sn += sall - spos; acc_np += npos; acc_ne += (double)HW;
+          if (a.out_weight) a.out_weight[p] = w;
+        }
+        if (a.counters && th->side_mask[n_it & 7]) {
+          // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32)
+          const int Ki = (int)K;
+          const double gx = (double)sd[SD_GX], gy = (double)sd[SD_GY];
+          const double ddx = (double)X - gx, ddy = (double)Y - gy;
+          unsigned long long* cnt = reinterpret_cast<unsigned long long*>(a.counters);
+          double nb = (double)fmaxf(sd[SD_BW], sd[SD_BH]);
+          if (nb != 0.0) {
+            if (nb < 0.0) nb = 1e6;
+            const double qx = ddx / nb, qy = ddy / nb;
+            const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
+            atomicAdd(cnt + Ki + k, 1ull);
+            if (d < a.pck_thr) atomicAdd(cnt + k, 1ull);
+          }
+          {
+            const double qx = ddx / (double)a.auc_nor, qy = ddy / (double)a.auc_nor;
+            const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
+            unsigned long long* auc = cnt + 2 * Ki;
+            for (int t = 0; t < a.auc_steps; ++t) {
+              const float thr = (float)(1.0 * t / a.auc_steps);
+              if (d < thr) atomicAdd(auc + (int64_t)t * Ki + k, 1ull);
+            }
+            atomicAdd(auc + (int64_t)a.auc_steps * Ki + k, 1ull);
+          }
+          {
+            const float d = (float)sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+            unsigned long long* epe = cnt + (int64_t)(3 + a.auc_steps) * Ki;
+            atomicAdd(epe + k, 1ull);
+            atomicAdd(epe + Ki + k, (unsigned long long)llrint((double)d * 1048576.0));
+          }
+        }
+      }
+      TRE(11);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&th->empty[buf]);   // release: the record and the row sums are free again
+    }
+
+    // ---- one-launch loss: publish this team's sums; the last team reduces all of them in a fixed order ----
+    if (LOSS && a.team_sums) {
+      const uint32_t active = n_planes < total_teams ? n_planes : total_teams;
+      unsigned int ticket = 0;
+      if (lane == 0) {
+        double* dst = a.team_sums + 4 * (size_t)gteam;
+        __stcg(reinterpret_cast<double2*>(dst), make_double2(acc_sp, acc_sn));
+        __stcg(reinterpret_cast<double2*>(dst) + 1, make_double2(acc_np, acc_ne));
+        __threadfence();
+        ticket = atomicAdd(a.ticket, 1u);
+      }
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      if (ticket == active - 1) {
+        __threadfence();
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        for (uint32_t t = lane; t < active; t += 32) {          // fixed order: lane-strided, then a fixed tree
+          const double2 x = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t));
+          const double2 y = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t) + 1);
+          v0 += x.x; v1 += x.y; v2 += y.x; v3 += y.y;
+        }
+        v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+        if (lane == 0) {
+          if (a.sums_out) { a.sums_out[0] = v0; a.sums_out[1] = v1; a.sums_out[2] = v2; a.sums_out[3] = v3; }
+          if (a.loss_out) {
+            double v;
+            if (a.loss_mode == LHN_LOSS_DISTANCE_BALANCE) v = 0.1 * v0 / (v2 + 1.0) + v1 / (v3 - v2 + 1.0);
+            else if (a.loss_mode == LHN_LOSS_JOINTS_MSE) v = 0.5 * (v0 + v1) / v3;
+            else v = (v0 + v1) / v3;
+            if (a.sum_reduction) v *= v3;
+            a.loss_out[0] = (float)(v * (double)a.loss_scale);
+          }
+          *a.ticket = 0u;                                       // leave the workspace ready for the next launch
+        }
+      }
+    }
+    return;
+  }
+
+  // =======================================================================================================
+  // SWEEPERS
+  // =======================================================================================================
   uint64_t policy = 0;
   auto issue = [&](uint32_t b, uint32_t c) {   // one thread of the team
     mbar_arrive_expect_tx(&th->bar, FLIP ? 2 * plane_bytes : plane_bytes);
@@ -172,8 +459,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     if (FLIP) tma_load_1d(const_cast<T*>(plane1), gptr1(b, c), plane_bytes, &th->bar, policy);
   };
 
-  // Render parameters + separable Gaussian factors of plane (b, c) into table buffer `buf`, computed
-  // by `nthr` threads of the team (thread index `t`).  exp() is evaluated on an f64 argument.
   // Side inputs of plane (b, c) -> ring slot `slot` (lanes 0..SD_N-1 of one warp; asynchronous).
   auto side_fetch = [&](uint32_t b, uint32_t c, int slot) {
     uint32_t s, k;
@@ -192,7 +477,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     if (src) cp_async_4(&th->side[slot][lane], src);
   };
 
-  auto prologue = [&](uint32_t c, int slot, int buf, int t, int nthr) {
+  // Render parameters + separable Gaussian factors of a plane (channel c, side-ring slot `slot`) into table
+  // buffer `buf`, computed by the sweepers.  exp() is evaluated on an f64 argument.
+  auto prologue = [&](uint32_t c, int slot, int buf) {
     if (!LOSS) return;
     uint32_t s, k;
     split_channel(c, s, k);
@@ -215,12 +502,12 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
     const bool render_on = w > 0.5f;
-    if (t == 0) {
+    if (sl == 0) {
       th->w[buf] = w; th->mx[buf] = (float)mux; th->my[buf] = (float)muy; th->render_on[buf] = render_on ? 1 : 0;
     }
     const double i2 = a.inv2s2[s];
     float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + (size_t)buf * tab_bytes);
-    for (int i = t; i < W + H; i += nthr) {
+    for (int i = sl; i < W + H; i += ST) {
       const bool isx = i < W;
       const int pos = isx ? i : i - W;
       float v = 0.f;
@@ -240,21 +527,16 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
   };
 
-  uint32_t p = gteam;
-  if (p >= n_planes) return;                       // whole teams leave together
-  uint32_t pb = p / C, pc = p - pb * C;            // the only division: once per team
   if (a.flip_index) {
-    for (int i = tl; i < (int)K; i += TT) fidx[i] = a.flip_index[i];
-    team_sync(bar_id, TT);
+    for (int i = sl; i < (int)K; i += ST) fidx[i] = a.flip_index[i];
+    named_sync(bar_id, ST);
   }
-  if (tl == 0) {
-    mbar_init(&th->bar, 1);
-    fence_mbar_init();
+  if (sl == 0) {
     policy = policy_evict_first();
     if (a.use_tma) issue(pb, pc);
   }
-  // side-input ring: warp 1 (every team has at least two warps) runs kSideAhead planes ahead
-  uint32_t qb = pb, qc = pc, pq = p;               // cursor of the next plane to fetch (warp 1 only)
+  // side-input ring: the first sweeper warp runs kSideAhead planes ahead
+  uint32_t qb = pb, qc = pc, pq = p;               // cursor of the next plane to fetch (role 1 only)
   int mask_reg = 0;
   if (role == 1) {
 #pragma unroll
@@ -267,44 +549,39 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     cp_async_wait<kSideAhead - 2>();               // the first two planes' side inputs have landed
   }
-  team_sync(bar_id, TT);
-  prologue(pc, 0, 0, tl, TT);
+  named_sync(bar_id, ST);
+  prologue(pc, 0, 0);
   uint32_t phase = 0;
-  int buf = 0;
   int n_it = 0;                                    // team-local plane counter (ring slot = n_it & 7)
 
-  const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
-  const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
   const int QR = W >> 2, nq = HW >> 2;
   const uint64_t half2 = pack2(0.5f, 0.5f);
 
-  for (; p < n_planes; p += total_teams, buf ^= 1, ++n_it, advance(pb, pc)) {
+  for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
+    const int buf = n_it & 1;
     const bool has_next = p + total_teams < n_planes;
-#ifdef LHN_TRACE
-    const int it_no = (int)((p - gteam) / total_teams);
-#endif
-    // S1: tables of this plane are written, the aux buffers of the previous plane are free
-    team_sync(bar_id, TT);
+    // S1: tables / side inputs of this plane are written, red_* of the previous plane are consumed
+    named_sync(bar_id, ST);
+    TRS(0);
     const float* ex = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(tab0) + (size_t)buf * tab_bytes);
     const float* ey = ex + W;
 
     // ---- wait for the plane ------------------------------------------------------------------------
-    TR(0);
     if (a.use_tma) {
       mbar_wait(&th->bar, phase);
       phase ^= 1u;
-      TR(1);
     } else {
       const T* g0 = gptr0(pb, pc);
       T* d0 = const_cast<T*>(plane0);
-      for (int e = tl; e < HW; e += TT) d0[e] = g0[e];
+      for (int e = sl; e < HW; e += ST) d0[e] = g0[e];
       if (FLIP) {
         const T* g1 = gptr1(pb, pc);
         T* d1 = const_cast<T*>(plane1);
-        for (int e = tl; e < HW; e += TT) d1[e] = g1[e];
+        for (int e = sl; e < HW; e += ST) d1[e] = g1[e];
       }
-      team_sync(bar_id, TT);
+      named_sync(bar_id, ST);
     }
+    TRS(1);
 
     // decoded values (flip average) of quad q = row * QR + cq
     auto avg_quad = [&](const float4& o, const float4& f) -> float4 {
@@ -314,14 +591,12 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       unpack2(lo, v.x, v.y); unpack2(hi, v.z, v.w);
       return v;
     };
-    auto load_quad_rc = [&](int row, int cq) -> float4 {
+    auto load_quad = [&](int q) -> float4 {
+      const int row = FAST ? (q >> 4) : (q / QR);
+      const int cq = q - row * QR;
       const float4 o = load4<T>(plane0 + row * W + 4 * cq);
       if (!FLIP) return o;
       return avg_quad(o, load4<T>(plane1 + row * W + (W - 4 - 4 * cq)));
-    };
-    auto load_quad = [&](int q) -> float4 {
-      const int row = FAST ? (q >> 4) : (q / QR);
-      return load_quad_rc(row, q - row * QR);
     };
     auto val = [&](int y, int x) -> float {
       float o = elem_f32<T>(plane0, y * W + x);
@@ -329,11 +604,11 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       return o;
     };
 
-    // ---- pass 1: one sweep, split over the team ------------------------------------------------------
+    // ---- pass 1: one sweep, split over the sweepers ----------------------------------------------------
     uint64_t S2acc = 0;                      // packed (S0, S1) squared-error accumulators
     float best = -CUDART_INF_F;              // NaN-propagating running max of this thread
     int bq = -1;                             // first quad that raised it
-    // o / f: pointers to the quad of the plane and to its mirror quad of the flipped plane
+    // po / pf: pointers to the quad of the plane and to its mirror quad of the flipped plane
     auto sweep_quad = [&](int q, const T* po, const T* pf, const float* pgy, uint64_t ngx01, uint64_t ngx23) {
       const float4 o = load4<T>(po);
       float4 v = o;
@@ -352,23 +627,25 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       best = r;
     };
     if (FAST) {
-      // TT is a multiple of 16: the column quad of a thread is loop-invariant and every address is
+      // ST is a multiple of 16: the column quad of a thread is loop-invariant and every address is
       // base + compile-time offset
       uint64_t ngx01 = 0, ngx23 = 0;
       if (LOSS) {
-        const float4 gx = *reinterpret_cast<const float4*>(ex + 4 * (tl & 15));
+        const float4 gx = *reinterpret_cast<const float4*>(ex + 4 * (sl & 15));
         ngx01 = pack2(-gx.x, -gx.y); ngx23 = pack2(-gx.z, -gx.w);
       }
-      constexpr int kTT = (TWC > 0 ? TWC : 1) * 32;
-      constexpr int kIters = 1024 / kTT;
-      const T* po = plane0 + 4 * tl;
-      const T* pf = FLIP ? plane1 + (tl >> 4) * 64 + 60 - 4 * (tl & 15) : nullptr;
-      const float* pgy = ey + (tl >> 4);
-#pragma unroll
-      for (int it = 0; it < kIters; ++it)
-        sweep_quad(it * kTT + tl, po + it * kTT * 4, pf + it * kTT * 4, pgy + it * (kTT / 16), ngx01, ngx23);
+      constexpr int kST = (TWC > 1 ? TWC - 1 : 1) * 32;
+      constexpr int kFull = 1024 / kST, kRem = 1024 - kFull * kST;
+      const T* po = plane0 + 4 * sl;
+      const T* pf = FLIP ? plane1 + (sl >> 4) * 64 + 60 - 4 * (sl & 15) : nullptr;
+      const float* pgy = ey + (sl >> 4);
+#pragma unroll (kFull <= 16 ? kFull : 8)
+      for (int it = 0; it < kFull; ++it)
+        sweep_quad(it * kST + sl, po + it * kST * 4, pf + it * kST * 4, pgy + it * (kST / 16), ngx01, ngx23);
+      if (kRem > 0 && sl < kRem)
+        sweep_quad(kFull * kST + sl, po + kFull * kST * 4, pf + kFull * kST * 4, pgy + kFull * (kST / 16), ngx01, ngx23);
     } else {
-      for (int q = tl; q < nq; q += TT) {
+      for (int q = sl; q < nq; q += ST) {
         const int row = q / QR, cq = q - row * QR;
         uint64_t ngx01 = 0, ngx23 = 0;
         if (LOSS) {
@@ -378,8 +655,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         sweep_quad(q, plane0 + 4 * q, FLIP ? plane1 + row * W + (W - 4 - 4 * cq) : nullptr, ey + row, ngx01, ngx23);
       }
     }
+    TRS(2);
 
-    TR(2);
     // ---- per-warp partials -> shared, S2 ----------------------------------------------------------------
     {
       const float wmax = redux_max_nan(best);
@@ -391,15 +668,15 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         unpack2(S2acc, s0, s1);
         ssum = warp_sum(s0 + s1);
       }
-      if (lane == 0) { th->red_max[wt] = wmax; th->red_q[wt] = wq; th->red_s[wt] = ssum; }
+      if (lane == 0) { th->red_max[role - 1] = wmax; th->red_q[role - 1] = wq; th->red_s[role - 1] = ssum; }
     }
-    team_sync(bar_id, TT);
+    named_sync(bar_id, ST);
+    TRS(3);
 
-    TR(3);
-    // ---- every warp: the team-wide argmax (redundantly: cheaper than another barrier) --------------------
-    const float tm = lane < TW ? th->red_max[lane] : -CUDART_INF_F;
+    // ---- every sweeper warp: the team-wide argmax (redundantly: cheaper than another barrier) ------------
+    const float tm = lane < NS ? th->red_max[lane] : -CUDART_INF_F;
     const float tmax = redux_max_nan(tm);
-    const uint32_t qsel = __reduce_min_sync(0xffffffffu, (lane < TW && tm == tmax) ? th->red_q[lane] : 0xffffffffu);
+    const uint32_t qsel = __reduce_min_sync(0xffffffffu, (lane < NS && tm == tmax) ? th->red_q[lane] : 0xffffffffu);
     const bool any_nan = tmax != tmax;
     uint32_t idx = 0;
     float maxval = tmax;
@@ -435,12 +712,17 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     if (a.mask_mode == LHN_MASK_NEG1 && !positive) { cx = -1.f; cy = -1.f; }
     const int px = (int)cx, py = (int)cy;
     const bool dark_guard = is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2);
-    const int bb = (ksize - 1) >> 1;
+
+    // the epilogue warp must be done with this record / row-sum buffer (it lags at most two planes)
+    if (n_it >= 2) mbar_wait(&th->empty[buf], (uint32_t)((n_it >> 1) - 1) & 1u);
+    PlaneRec* rec = &th->rec[buf];
+
     // ---- DARK row pass straight from the stage, one output per thread: the (ksize+4) x 5 row sums around
     //      the peak (zero padding = skipped taps; sequential FMA over the taps = cv2's RowFilter order) ----
     if (dark_guard) {
+      double* hbuf = hbuf0 + (size_t)buf * TD * 5;
       const int nrow = TD * 5;
-      for (int e = tl; e < nrow; e += TT) {
+      for (int e = sl; e < nrow; e += ST) {
         const int r = e / 5, c5 = e - r * 5;
         const int y = py - 2 - bb + r, x0 = px - 2 + c5 - bb;
         if (legacy) {
@@ -471,43 +753,45 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         }
       }
     }
-    // ---- positives of the balanced loss: a small window around the joint, by the team's last warp ----------
-    if (LOSS && role == TW - 1 && a.loss_mode == LHN_LOSS_DISTANCE_BALANCE) {
-      uint32_t s, k;
-      split_channel(pc, s, k);
-      double Spos = 0.0;
+    // ---- positives of the balanced loss: a small window around the joint, by the last sweeper warp ---------
+    if (LOSS && role == TW - 1) {
+      float Spos = 0.f;
       int Npos = 0;
-      int x_lo = 0, x_hi = W - 1, y_lo = 0, y_hi = H - 1;
-      if (a.pos_value > 0.f && a.pos_value < 1.f) {
-        // g > value  <=>  r^2 < -2 sigma^2 ln(value): a.pos_radius = that radius + a rounding margin
-        const float rad = a.pos_radius[s];
-        const float mxf = th->mx[buf], myf = th->my[buf];
-        x_lo = max(0, (int)ceilf(mxf - rad)); x_hi = min(W - 1, (int)floorf(mxf + rad));
-        y_lo = max(0, (int)ceilf(myf - rad)); y_hi = min(H - 1, (int)floorf(myf + rad));
-      } else if (a.pos_value >= 1.f) {
-        x_hi = -1;
-      }
-      if (th->render_on[buf] || a.pos_value < 0.f) {
-        float sp = 0.f;
-        // one window element per lane (5 x 5 = 25 lanes for sigma = 2)
-        const int ww = x_hi - x_lo + 1, wn = ww > 0 ? ww * (y_hi - y_lo + 1) : 0;
-        for (int e = lane; e < wn; e += 32) {
-          const int ry = e / ww, xx = x_lo + (e - ry * ww), yy = y_lo + ry;
-          const float gxv = ex[xx], gyv = ey[yy];
-          if (gxv * gyv > a.pos_value) {
-            const float d = fmaf(-gxv, gyv, elem_f32<T>(plane0, yy * W + xx));
-            sp = fmaf(d, d, sp);
-            Npos += 1;
-          }
+      if (a.loss_mode == LHN_LOSS_DISTANCE_BALANCE) {
+        uint32_t s, k;
+        split_channel(pc, s, k);
+        int x_lo = 0, x_hi = W - 1, y_lo = 0, y_hi = H - 1;
+        if (a.pos_value > 0.f && a.pos_value < 1.f) {
+          // g > value  <=>  r^2 < -2 sigma^2 ln(value): a.pos_radius = that radius + a rounding margin
+          const float rad = a.pos_radius[s];
+          const float mxf = th->mx[buf], myf = th->my[buf];
+          x_lo = max(0, (int)ceilf(mxf - rad)); x_hi = min(W - 1, (int)floorf(mxf + rad));
+          y_lo = max(0, (int)ceilf(myf - rad)); y_hi = min(H - 1, (int)floorf(myf + rad));
+        } else if (a.pos_value >= 1.f) {
+          x_hi = -1;
         }
-        Spos = (double)warp_sum(sp);
-        Npos = __reduce_add_sync(0xffffffffu, Npos);
+        if (th->render_on[buf] || a.pos_value < 0.f) {
+          float sp = 0.f;
+          // one window element per lane (5 x 5 = 25 lanes for sigma = 2)
+          const int ww = x_hi - x_lo + 1, wn = ww > 0 ? ww * (y_hi - y_lo + 1) : 0;
+          for (int e = lane; e < wn; e += 32) {
+            const int ry = e / ww, xx = x_lo + (e - ry * ww), yy = y_lo + ry;
+            const float gxv = ex[xx], gyv = ey[yy];
+            if (gxv * gyv > a.pos_value) {
+              const float d = fmaf(-gxv, gyv, elem_f32<T>(plane0, yy * W + xx));
+              sp = fmaf(d, d, sp);
+              Npos += 1;
+            }
+          }
+          Spos = warp_sum(sp);
+          Npos = __reduce_add_sync(0xffffffffu, Npos);
+        }
       }
-      if (lane == 0) { th->spos = Spos; th->npos = Npos; }
+      if (lane == 0) { rec->spos = Spos; rec->npos = Npos; }
     }
-    // ---- quarter-offset refinements read their neighbours while the plane is resident ----------------------
-    float rx = cx, ry = cy;
-    if (role == 0) {
+    // ---- the first sweeper warp: +-0.25 rules (neighbours read while the plane is resident) + the record ----
+    if (role == 1 && lane == 0) {
+      float rx = cx, ry = cy;
       if (a.refine == LHN_REFINE_OFFSET_HALF || a.refine == LHN_REFINE_OFFSET) {
         const int xx = min(max(px, 0), W - 1), yy = min(max(py, 0), H - 1);
         // clamped neighbours; `>` false (equality, NaN) -> -0.25
@@ -525,238 +809,48 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           rx += sxn * 0.25f; ry += syn * 0.25f;
         }
       }
+      float S = 0.f;
+      if (LOSS) for (int i = 0; i < NS; ++i) S += th->red_s[i];
+      rec->idx = idx; rec->maxval = maxval; rec->rx = rx; rec->ry = ry;
+      rec->w = LOSS ? th->w[buf] : 0.f; rec->ssum = S;
+      rec->flags = (dark_guard ? 1 : 0) | (any_nan ? 2 : 0);
     }
-    // S3: the window and the positives' sum are out of the stage — nobody reads it again
-    TR(4);
-    team_sync(bar_id, TT);
-    TR(5);
-
-    if (role != 0) {
-      // role 1: fetch the side inputs kSideAhead planes ahead; roles 1..2: render parameters + tables of the
-      // team's NEXT plane (its side inputs were requested earlier), while the epilogue warp finishes this one
-      const int nh = TW > 2 ? 2 : 1;
-      if (role == 1) {
-        if (lane == 0 && a.counters) {
-          th->side_mask[(n_it + 1) & 7] = mask_reg;            // loaded one plane ago
-          if (p + 2 * total_teams < n_planes) {
-            uint32_t mb = pb, mc = pc;
-            advance(mb, mc); advance(mb, mc);
-            mask_reg = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];
-          }
-        }
-        if (pq < n_planes) side_fetch(qb, qc, (n_it + kSideAhead) & 7);
-        cp_async_commit();
-        pq += total_teams; advance(qb, qc);
-      }
-      if (role <= nh && has_next) {
+    TRS(4);
+    // S3: everything the epilogue needs is out of the stage — nobody reads it again
+    named_sync(bar_id, ST);
+    if (sl == 0) {
+      // re-arm the stage with the team's next plane, then hand the record to the epilogue warp
+      if (a.use_tma && has_next) {
         uint32_t nb = pb, nc = pc;
         advance(nb, nc);
-        prologue(nc, (n_it + 1) & 7, buf ^ 1, (role - 1) * 32 + lane, nh * 32);
+        fence_proxy_async();
+        issue(nb, nc);
       }
-      // side inputs of plane n+2 complete here; the S1 barrier publishes them to the other warps
-      if (role == 1) cp_async_wait<kSideAhead - 2>();
-      continue;
+      mbar_arrive(&th->full[buf]);
     }
+    TRS(5);
 
-    // =========================== warp 0 of the team: the rest of the epilogue ===============================
-    // re-arm the stage with the team's next plane first; everything below works from aux / registers
-    if (a.use_tma && has_next && lane == 0) {
+    // ---- while the next plane is in flight: side-input ring + the next plane's tables -----------------------
+    if (role == 1) {
+      if (lane == 0 && a.counters) {
+        th->side_mask[(n_it + 1) & 7] = mask_reg;            // loaded one plane ago
+        if (p + 2 * total_teams < n_planes) {
+          uint32_t mb = pb, mc = pc;
+          advance(mb, mc); advance(mb, mc);
+          mask_reg = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];
+        }
+      }
+      if (pq < n_planes) side_fetch(qb, qc, (n_it + kSideAhead) & 7);
+      cp_async_commit();
+      pq += total_teams; advance(qb, qc);
+    }
+    if (has_next) {
       uint32_t nb = pb, nc = pc;
       advance(nb, nc);
-      fence_proxy_async();
-      issue(nb, nc);
+      prologue(nc, (n_it + 1) & 7, buf ^ 1);
     }
-
-    TR(7);
-    bool need_slow = false;
-    float bmax = 0.f;
-    if (dark_guard) {
-      // column pass over the staged row sums (centre tap, then symmetric pairs fused-added: the
-      // summation order of cv2's separable filter)
-      if (legacy) {
-        if (lane < 25) {
-          const int dr = lane / 5, c5 = lane - dr * 5;
-          double acc = __dmul_rn(a.tapsd[bb], hbuf[(dr + bb) * 5 + c5]);
-          for (int j = 1; j <= bb; ++j)
-            acc = __fma_rn(a.tapsd[bb + j], __dadd_rn(hbuf[(dr + bb + j) * 5 + c5], hbuf[(dr + bb - j) * 5 + c5]), acc);
-          hout[lane] = (float)acc;
-        }
-      } else {
-        float* hb = reinterpret_cast<float*>(hbuf);
-        if (lane < 25) {
-          const int dr = lane / 5, c5 = lane - dr * 5;
-          const float* hcol = hb + (dr + bb) * 5 + c5;
-          float acc = __fmul_rn(a.tapsf[bb], hcol[0]);
-          if (KS > 0) {
-#pragma unroll
-            for (int j = 1; j <= (KS - 1) / 2; ++j)
-              acc = __fmaf_rn(a.tapsf[(KS - 1) / 2 + j], __fadd_rn(hcol[5 * j], hcol[-5 * j]), acc);
-          } else {
-            for (int j = 1; j <= bb; ++j) acc = __fmaf_rn(a.tapsf[bb + j], __fadd_rn(hcol[5 * j], hcol[-5 * j]), acc);
-          }
-          hout[lane] = acc;
-        }
-      }
-      __syncwarp();
-      TR(8);
-      // can the 1e-10 clamp of log() (or a non-finite value) touch the 13 stencil points?
-      const float hv = lane < 25 ? hout[lane] : CUDART_INF_F;
-      const int dr = lane / 5 - 2, dc = lane % 5 - 2;
-      const bool used = lane < 25 && (abs(dr) + abs(dc) <= 2);
-      const bool bad = used && !(hv >= 1e-9f);
-      const bool ok_origin = legacy ? (maxval >= 1e-3f) : (maxval > 0.f);
-      need_slow = __any_sync(0xffffffffu, bad) || !ok_origin || any_nan;
-      if (need_slow) {
-        // exact emulation: max of the whole blurred plane (NaN propagates like np.max).  The stage is
-        // already being refilled, so the decoded plane is re-read from global memory (L2-resident).
-        const T* g0 = gptr0(pb, pc);
-        const T* g1 = FLIP ? gptr1(pb, pc) : nullptr;
-        auto gval = [&](int y, int x) -> float {
-          float o = elem_f32<T>(g0, y * W + x);
-          if (FLIP) o = __fmul_rn(__fadd_rn(o, elem_f32<T>(g1, y * W + (W - 1 - x))), 0.5f);
-          return o;
-        };
-        float m = -CUDART_INF_F;
-        bool first = true;
-        for (int e = lane; e < HW; e += 32) {
-          const int y = e / W, x = e - y * W;
-          float v;
-          if (legacy) {
-            auto rowv = [&](int yy) {
-              double r = 0.0;
-              if (yy < 0 || yy >= H) return r;
-              for (int j = 0; j < ksize; ++j) {
-                const int xx = x + j - bb;
-                r = __fma_rn(a.tapsd[j], (xx >= 0 && xx < W) ? (double)gval(yy, xx) : 0.0, r);
-              }
-              return r;
-            };
-            double acc = __dmul_rn(a.tapsd[bb], rowv(y));
-            for (int j = 1; j <= bb; ++j) acc = __fma_rn(a.tapsd[bb + j], __dadd_rn(rowv(y + j), rowv(y - j)), acc);
-            v = (float)acc;
-          } else {
-            auto rowv = [&](int yy) {
-              float r = 0.f;
-              if (yy < 0 || yy >= H) return r;
-              for (int j = 0; j < ksize; ++j) {
-                const int xx = x + j - bb;
-                r = __fmaf_rn(a.tapsf[j], (xx >= 0 && xx < W) ? gval(yy, xx) : 0.f, r);
-              }
-              return r;
-            };
-            float acc = __fmul_rn(a.tapsf[bb], rowv(y));
-            for (int j = 1; j <= bb; ++j) acc = __fmaf_rn(a.tapsf[bb + j], __fadd_rn(rowv(y + j), rowv(y - j)), acc);
-            v = acc;
-          }
-          m = first ? v : nanmax(m, v);
-          first = false;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        bmax = m;
-      }
-    }
-
-    TR(9);
-    if (dark_guard) {
-      // log of the 25 blurred values in parallel, then the Taylor step on lane 0
-      const float raw = lane < 25 ? hout[lane] : 1.f;
-      float hval;
-      if (need_slow) {
-        const float sc = legacy ? __fdiv_rn(maxval, __fadd_rn(bmax, 1e-6f)) : __fdiv_rn(maxval, bmax);
-        float v = __fmul_rn(raw, sc);
-        v = (v != v) ? v : fmaxf(v, 1e-10f);          // np.maximum propagates NaN
-        hval = logf(v);
-      } else {
-        hval = logf(raw);
-      }
-      __syncwarp();
-      if (lane < 25) hout[lane] = hval;
-      __syncwarp();
-    }
-
-    if (lane == 0) {
-      if (dark_guard) {
-#define HH(dy, dx) hout[((dy) + 2) * 5 + (dx) + 2]
-        const float h00 = HH(0, 0);
-        const float ddx = __fmul_rn(0.5f, __fsub_rn(HH(0, 1), HH(0, -1)));
-        const float ddy = __fmul_rn(0.5f, __fsub_rn(HH(1, 0), HH(-1, 0)));
-        const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(HH(0, 2), __fmul_rn(2.f, h00)), HH(0, -2)));
-        const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(HH(1, 1), HH(-1, 1)), HH(1, -1)), HH(-1, -1)));
-        const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(HH(2, 0), __fmul_rn(2.f, h00)), HH(-2, 0)));
-#undef HH
-        const float det = __fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy));
-        if (det != 0.f) {   // true for NaN, as in numpy
-          const float ox = -__fdiv_rn(__fsub_rn(__fmul_rn(dyy, ddx), __fmul_rn(dxy, ddy)), det);
-          const float oy = -__fdiv_rn(__fsub_rn(__fmul_rn(dxx, ddy), __fmul_rn(dxy, ddx)), det);
-          rx = __fadd_rn(rx, ox); ry = __fadd_rn(ry, oy);
-        }
-      }
-      TR(10);
-      // ---- back-transform (T1/T2) and stores --------------------------------------------------------
-      const uint32_t b = pb;
-      uint32_t s, k;
-      split_channel(pc, s, k);
-      const uint32_t bk = b * K + k;
-      float X = rx, Y = ry;
-      const float* sd = th->side[n_it & 7];
-      if (a.transform == LHN_XFORM_CENTER_SCALE) {
-        const float s0 = __fmul_rn(sd[SD_SX], 200.0f), s1 = __fmul_rn(sd[SD_SY], 200.0f);
-        const float dw = a.use_udp ? (float)(W - 1) : (float)W, dh = a.use_udp ? (float)(H - 1) : (float)H;
-        const float fx = __fdiv_rn(s0, dw), fy = __fdiv_rn(s1, dh);
-        X = __fsub_rn(__fadd_rn(__fmul_rn(rx, fx), sd[SD_CX]), __fmul_rn(s0, 0.5f));
-        Y = __fsub_rn(__fadd_rn(__fmul_rn(ry, fy), sd[SD_CY]), __fmul_rn(s1, 0.5f));
-      } else if (a.transform == LHN_XFORM_SCALE) {
-        X = __fmul_rn(rx, a.scale_x); Y = __fmul_rn(ry, a.scale_y);
-      }
-      if (a.out_hm) { float* o = a.out_hm + 3 * (int64_t)p; o[0] = rx; o[1] = ry; o[2] = maxval; }
-      if (a.out_kpts) { float* o = a.out_kpts + 3 * (int64_t)p; o[0] = X; o[1] = Y; o[2] = maxval; }
-      if (a.out_idx) a.out_idx[p] = (int32_t)idx;
-      TR(11);
-      if (LOSS) {
-        double S = 0.0;
-        for (int i = 0; i < TW; ++i) S += th->red_s[i];
-        const float w = th->w[buf];
-        const bool bal = a.loss_mode == LHN_LOSS_DISTANCE_BALANCE;
-        const float wp = (a.loss_mode == LHN_LOSS_JOINTS_MSE) ? w * w : w;
-        const double sall = S * (double)wp, spos = bal ? th->spos * (double)wp : 0.0;
-        *reinterpret_cast<double2*>(a.partials + 4 * (int64_t)p) = make_double2(spos, sall - spos);
-        *reinterpret_cast<double2*>(a.partials + 4 * (int64_t)p + 2) = make_double2(bal ? (double)th->npos : 0.0, (double)HW);
-        if (a.out_weight) a.out_weight[p] = w;
-      }
-      if (a.counters && th->side_mask[n_it & 7]) {
-        // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32)
-        const int Ki = (int)K;
-        const double gx = (double)sd[SD_GX], gy = (double)sd[SD_GY];
-        const double ddx = (double)X - gx, ddy = (double)Y - gy;
-        unsigned long long* cnt = reinterpret_cast<unsigned long long*>(a.counters);
-        double nb = (double)fmaxf(sd[SD_BW], sd[SD_BH]);
-        if (nb != 0.0) {
-          if (nb < 0.0) nb = 1e6;
-          const double qx = ddx / nb, qy = ddy / nb;
-          const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
-          atomicAdd(cnt + Ki + k, 1ull);
-          if (d < a.pck_thr) atomicAdd(cnt + k, 1ull);
-        }
-        {
-          const double qx = ddx / (double)a.auc_nor, qy = ddy / (double)a.auc_nor;
-          const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
-          unsigned long long* auc = cnt + 2 * Ki;
-          for (int t = 0; t < a.auc_steps; ++t) {
-            const float thr = (float)(1.0 * t / a.auc_steps);
-            if (d < thr) atomicAdd(auc + (int64_t)t * Ki + k, 1ull);
-          }
-          atomicAdd(auc + (int64_t)a.auc_steps * Ki + k, 1ull);
-        }
-        {
-          const float d = (float)sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
-          unsigned long long* epe = cnt + (int64_t)(3 + a.auc_steps) * Ki;
-          atomicAdd(epe + k, 1ull);
-          atomicAdd(epe + Ki + k, (unsigned long long)llrint((double)d * 1048576.0));
-        }
-      }
-    }
-    TR(6);
+    // side inputs of plane n+2 complete here; the S1 barrier publishes them to the other sweepers
+    if (role == 1) cp_async_wait<kSideAhead - 2>();
   }
 }
 
@@ -828,7 +922,7 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY;
   a.tile_dim = is_dark ? a.ksize + 4 : 0;
   const size_t aux = align_up(sizeof(TeamHeader), 16) + 2 * align_up((size_t)(a.W + a.H) * 4, 16) +
-                     (size_t)a.tile_dim * 5 * 8 + 32 * 4 +
+                     (size_t)2 * a.tile_dim * 5 * 8 + 32 * 4 +
                      align_up((size_t)a.K * 4, 16);
   a.warp_smem = (int)align_up(a.stage_bytes + aux, 128);
   const size_t budget = 227 * 1024;

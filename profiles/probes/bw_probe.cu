@@ -101,6 +101,40 @@ __global__ void read_tma_teams(const char* __restrict__ src, size_t bytes, int c
   if (acc == 123.456f) out[0] = acc;
 }
 
+
+// D: the fused heatmap kernel's exact traffic shape: each team stage = 16 KB from tensor A + 16 KB from tensor B
+// (plane + flipped plane), 21504 plane pairs (705 MB), teams walk planes g, g+888, ...
+__global__ void read_tma_teams2(const char* __restrict__ srcA, const char* __restrict__ srcB, size_t nplanes, int chunk, int tw, float* out) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = warp / tw, wt = warp % tw, tl = wt * 32 + lane, TT = tw * 32;
+  const int nteams = (blockDim.x >> 5) / tw;
+  unsigned char* stage = sm + (size_t)team * (2 * chunk + 128);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * chunk);
+  const size_t total = (size_t)gridDim.x * nteams;
+  size_t c = (size_t)blockIdx.x * nteams + team;
+  uint64_t pol = 0;
+  if (tl == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pol = pol_evict_first();
+    if (c < nplanes) { mbar_expect(bar, 2 * chunk); tma_1d(stage, srcA + c * chunk, chunk, bar, pol); tma_1d(stage + chunk, srcB + c * chunk, chunk, bar, pol); }
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TT) : "memory");
+  float acc = 0.f; uint32_t ph = 0;
+  for (; c < nplanes; c += total) {
+    mbar_wait(bar, ph); ph ^= 1;
+    const float4* p = reinterpret_cast<const float4*>(stage);
+    for (int q = tl; q < 2 * chunk / 16; q += TT) { float4 v = p[q]; acc += v.x + v.y + v.z + v.w; }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TT) : "memory");
+    if (tl == 0 && c + total < nplanes) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect(bar, 2 * chunk); tma_1d(stage, srcA + (c + total) * chunk, chunk, bar, pol); tma_1d(stage + chunk, srcB + (c + total) * chunk, chunk, bar, pol);
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
 template <typename F>
 static float best_ms(F f, int reps = 8) {
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -144,6 +178,20 @@ int main() {
     int nteams = (200 * 1024) / (chunk + 128); if (nteams * tw > 32) nteams = 32 / tw;
     float ms = best_ms([&] { read_tma_teams<<<sms, nteams * tw * 32, nteams * (chunk + 128)>>>(src, bytes, chunk, tw, out); });
     printf("TMA teams chunk %5d, %2d teams x %d warps : %8.1f GB/s\n", chunk, nteams, tw, bytes / ms / 1e6);
+  }
+  CK(cudaFuncSetAttribute(read_tma_teams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  {
+    const size_t np = 21504; const int chunk = 16384;
+    for (int tw : {2, 4}) {
+      int nteams = 6;
+      float ms = best_ms([&] { read_tma_teams2<<<sms, nteams * tw * 32, nteams * (2 * chunk + 128)>>>(src, src + (np * chunk), np, chunk, tw, out); }, 12);
+      printf("K1 shape: 2 x 16 KB per stage, 21504 plane pairs (705 MB), 6 teams x %d warps : %8.1f GB/s (%.1f us)\n", tw, 2.0 * np * chunk / ms / 1e6, ms * 1e3);
+    }
+    // same bytes as one contiguous tensor with 32 KB chunks
+    float ms = best_ms([&] { read_tma_teams<<<sms, 6 * 4 * 32, 6 * (32768 + 128)>>>(src, np * 2 * chunk, 32768, 4, out); }, 12);
+    printf("same 705 MB, one tensor, 32 KB chunks, 6 teams x 4 warps : %8.1f GB/s (%.1f us)\n", 2.0 * np * chunk / ms / 1e6, ms * 1e3);
+    ms = best_ms([&] { read_ldg<8><<<sms * 4, 512>>>((const float4*)src, np * 2 * chunk / 16, out); }, 12);
+    printf("same 705 MB, LDG.128 U8 4 CTA/SM x 512 : %8.1f GB/s (%.1f us)\n", 2.0 * np * chunk / ms / 1e6, ms * 1e3);
   }
   return 0;
 }

@@ -19,22 +19,19 @@ buf = np.zeros(148 * 6 * 16 * 16, dtype=np.int64)
 rc = lib.lhn_debug_trace(buf.ctypes.data_as(ctypes.c_void_p))
 print('rc', rc)
 T = buf.reshape(148 * 6, 16, 16).astype(np.float64)
-t = T[:, :, :7]
-names = ['S1->wait', 'wait(mbar)', 'sweep', 'reduce+S2', 'resolve+tile+pos', 'S3', 'epilogue(w0)']
 its = slice(3, 15)
-d = np.diff(t[:, its, :], axis=2)            # [team, it, 6]
-for i, n in enumerate(names[1:]):
-    x = d[:, :, i]
-    print(f'{n:18s} mean {x.mean():8.0f}  p10 {np.percentile(x,10):8.0f}  p50 {np.percentile(x,50):8.0f}  p90 {np.percentile(x,90):8.0f}')
-cyc = t[:, 4:15, 0] - t[:, 3:14, 0]
-print(f'cycle per plane    mean {cyc.mean():8.0f}  p10 {np.percentile(cyc,10):8.0f} p50 {np.percentile(cyc,50):8.0f} p90 {np.percentile(cyc,90):8.0f}')
-gap = t[:, 4:15, 0] - t[:, 3:14, 6]
-print(f'epilogue end -> next S1 pass  mean {gap.mean():8.0f} p50 {np.percentile(gap,50):8.0f}')
-
-# finer epilogue stamps (warp 0): 5 = S3 passed, 7 = TMA re-armed, 8 = blur window done, 9 = slow-path check done,
-# 10 = log + Taylor done, 11 = transform + keypoint stores done, 6 = loss partials / counters done
-order = [5, 7, 8, 9, 10, 11, 6]
-lab = ['re-arm TMA', 'row+col blur', 'clamp check', 'log+Taylor', 'transform+stores', 'loss partial']
-for a_, b_, n in zip(order[:-1], order[1:], lab):
-    x = T[:, its, b_] - T[:, its, a_]
-    print(f'  epi {n:18s} mean {x.mean():8.0f}  p50 {np.percentile(x,50):8.0f}  p90 {np.percentile(x,90):8.0f}')
+def stat(name, x):
+    print(f'{name:34s} mean {x.mean():8.0f}  p10 {np.percentile(x,10):8.0f}  p50 {np.percentile(x,50):8.0f}  p90 {np.percentile(x,90):8.0f}')
+# sweepers (first sweeper warp, lane 0): 0 = S1 passed, 1 = plane landed, 2 = sweep done, 3 = S2 passed,
+# 4 = row sums / positives / record staged, 5 = S3 passed + stage re-armed
+for a_, b_, n in [(0, 1, 'sweeper wait for plane (mbar)'), (1, 2, 'sweep'), (2, 3, 'warp reduce + S2'),
+                  (3, 4, 'resolve + row pass + positives'), (4, 5, 'S3 + re-arm TMA')]:
+    stat(n, T[:, its, b_] - T[:, its, a_])
+stat('tables for next plane + S1', T[:, 4:15, 0] - T[:, 3:14, 5])
+stat('sweeper cycle per plane', T[:, 4:15, 0] - T[:, 3:14, 0])
+# epilogue warp: 8 = record received, 9 = column pass / clamp check / log done, 10 = Taylor done, 11 = plane finished
+for a_, b_, n in [(8, 9, 'epilogue: blur column + log'), (9, 10, 'epilogue: Taylor'), (10, 11, 'epilogue: transform + stores + loss')]:
+    stat(n, T[:, its, b_] - T[:, its, a_])
+stat('epilogue busy per plane', T[:, its, 11] - T[:, its, 8])
+stat('epilogue wait for record', T[:, 4:15, 8] - T[:, 3:14, 11])
+stat('record ready -> epilogue picks it up', T[:, its, 8] - T[:, its, 5])
