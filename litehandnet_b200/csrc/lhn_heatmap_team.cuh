@@ -91,7 +91,7 @@ struct PlaneRec {
   float ssum;                 // sum of (output - target)^2 over the plane
   float spos;                 // ... over the positives (target > value)
   int npos;
-  int flags;                  // bit 0: DARK guard passed, bit 1: a NaN was found
+  int flags;                  // bit 0: DARK guard passed, bit 1: a NaN was found, bits 8-9: window offset in its first quad
   int pad[3];
 };
 
@@ -104,18 +104,16 @@ struct TeamHeader {
   float red_max[8];           // per-warp sweep partials: max (NaN-propagating), first quad holding it, sum
   uint32_t red_q[8];
   float red_s[8];
-  // render parameters of the two table buffers (written by the prologue)
-  float w[2];
-  float mx[2], my[2];
-  int render_on[2];
+  // render parameters of the three table buffers (written by the epilogue warp two planes ahead)
+  float w[3];
+  float mx[3], my[3];
+  int render_on[3];
   PlaneRec rec[2];
-  int mask_pad[2];
   // Per-plane side inputs (joint x/y, visibility, center, scale, gt x/y, bbox w/h), prefetched
   // kSideAhead planes ahead (two full plane periods before their first use) with 4-byte cp.async: under
   // a saturated memory system a plain global load costs microseconds, which must never sit on a team's
   // critical path.
   float side[8][12];
-  int side_mask[8];
 };
 constexpr int kSideAhead = 4;
 enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_N };
@@ -130,6 +128,9 @@ __device__ __forceinline__ float exp_f32_from_f64(double a) {
   const float v = expf(ah);
   return fmaf(v, al, v);
 }
+
+// quads per row of the DARK tile: the (ksize+4)-wide window starts 0..3 columns into its first quad
+__host__ __device__ constexpr int tile_quads(int td) { return (td + 6) >> 2; }
 
 // FAST: W = H = 64 and the team size is a compile-time constant (TWC warps = TWC-1 sweepers + 1 epilogue),
 //       so the sweep is a fully unrolled 128-bit loop with a loop-invariant column quad per thread.
@@ -163,12 +164,16 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   const int ksize = KS > 0 ? KS : a.ksize;
   const int TD = KS > 0 ? KS + 4 : a.tile_dim;       // DARK window side
   const int bb = (ksize - 1) >> 1;
-  double* hbuf0 = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tab0) + 2 * tab_bytes);   // 2 x row sums
-  float* hout = reinterpret_cast<float*>(hbuf0 + (size_t)2 * TD * 5);
+  const int NQ = tile_quads(TD), TCW = 4 * NQ;       // DARK tile row = NQ quads
+  const size_t tile_bytes = align_up((size_t)TD * TCW * 4, 16);
+  unsigned char* tile0 = reinterpret_cast<unsigned char*>(tab0) + 3 * tab_bytes;        // two DARK tiles
+  double* hbuf = reinterpret_cast<double*>(tile0 + 2 * tile_bytes);                     // row sums (epilogue warp)
+  float* hout = reinterpret_cast<float*>(hbuf + (size_t)TD * 5);
   int* fidx = reinterpret_cast<int*>(hout + 32);     // this team's copy of flip_index[K]
 
   const uint32_t total_teams = gridDim.x * nteams;
-  const uint32_t gteam = blockIdx.x * nteams + team;
+  // team-major numbering: the n_planes % total_teams leftover planes spread over all SMs instead of the first few
+  const uint32_t gteam = team * gridDim.x + blockIdx.x;
   const uint32_t n_planes = (uint32_t)a.n_planes;
   const uint32_t plane_bytes = (uint32_t)HW * sizeof(T);
   const uint32_t C = (uint32_t)a.C, K = (uint32_t)a.K;
@@ -194,6 +199,38 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
   const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
 
+  // Side inputs of plane (b, c) -> ring slot `slot` (lanes 0..SD_N-1 of one warp; asynchronous).
+  auto side_fetch = [&](uint32_t b, uint32_t c, int slot) {
+    uint32_t s, k;
+    split_channel(c, s, k);
+    const int64_t bk = (int64_t)b * K + k;
+    const float* src = nullptr;
+    switch (lane) {
+      case SD_JX: case SD_JY: if (LOSS) src = a.joints + bk * a.joints_stride + lane; break;
+      case SD_VIS: if (LOSS) src = a.vis + bk * a.vis_stride; break;
+      case SD_CX: case SD_CY: if (a.center) src = a.center + 2 * (int64_t)b + (lane - SD_CX); break;
+      case SD_SX: case SD_SY: if (a.scale) src = a.scale + 2 * (int64_t)b + (lane - SD_SX); break;
+      case SD_GX: case SD_GY: if (a.counters) src = a.gt + 2 * bk + (lane - SD_GX); break;
+      case SD_BW: case SD_BH: if (a.counters) src = a.bbox_wh + 2 * (int64_t)b + (lane - SD_BW); break;
+      default: break;
+    }
+    if (src) cp_async_4(&th->side[slot][lane], src);
+  };
+
+  uint32_t p = gteam;
+  uint32_t pb = p / C, pc = p - pb * C;            // the only division: once per team
+  // The epilogue warp requests the side inputs of its first two planes before anything else: issued ahead of
+  // the CTA's first bulk loads they return in ~1 us; queued behind 29 MB of plane traffic they take 5 us.
+  uint32_t qb = pb, qc = pc, pq = p;               // cursor of the next plane to fetch (epilogue warp)
+  if (role == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (pq < n_planes) side_fetch(qb, qc, i);
+      cp_async_commit();
+      pq += total_teams; advance(qb, qc);
+    }
+  }
+
   // ---- one-time setup: barriers visible to the whole CTA before anybody waits on them ------------------
   if (wt == 0 && lane == 0) {
     mbar_init(&th->bar, 1);
@@ -202,15 +239,96 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     fence_mbar_init();
   }
   __syncthreads();
-  uint32_t p = gteam;
+#ifdef LHN_TRACE
+  if (role == 1 && lane == 0 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 15] = clock64();
+#endif
   if (p >= n_planes) return;                       // whole teams leave together
-  uint32_t pb = p / C, pc = p - pb * C;            // the only division: once per team
+
+  // Render parameters + separable Gaussian factors of a plane (channel c, side-ring slot `slot`) into table
+  // buffer `buf`, computed by one warp.  exp() is evaluated on an f64 argument.
+  auto prologue = [&](uint32_t c, int slot, int buf) {
+    if (!LOSS) return;
+    uint32_t s, k;
+    split_channel(c, s, k);
+    const float* sd = th->side[slot];
+    const float jx = sd[SD_JX], jy = sd[SD_JY];
+    float w = sd[SD_VIS];
+    const double sig = (double)a.sigma[s], tmp = sig * 3.0;
+    // joint / feat_stride in f64 (numpy promotes f32 / f64); a power-of-two stride multiplies exactly
+    double mux, muy;
+    if (a.feat_pow2) { mux = (double)jx * a.inv_feat_x; muy = (double)jy * a.inv_feat_y; }
+    else { mux = (double)jx / a.feat_x; muy = (double)jy / a.feat_y; }
+    double x0p = 0, ulx, uly, brx, bry;
+    if (a.unbiased) {
+      ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1;
+    } else {
+      mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);                // int() truncates toward zero
+      ulx = trunc(mux - tmp); uly = trunc(muy - tmp);
+      brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
+      x0p = floor((2 * tmp + 1) * 0.5);                               // size // 2
+    }
+    if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
+    const bool render_on = w > 0.5f;
+    if (lane == 0) {
+      th->w[buf] = w; th->mx[buf] = (float)mux; th->my[buf] = (float)muy; th->render_on[buf] = render_on ? 1 : 0;
+    }
+    const double i2 = a.inv2s2[s];
+    float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + (size_t)buf * tab_bytes);
+    for (int i = lane; i < W + H; i += 32) {
+      const bool isx = i < W;
+      const int pos = isx ? i : i - W;
+      float v = 0.f;
+      if (render_on) {
+        if (a.unbiased) {
+          const double d = (double)pos - (isx ? mux : muy);
+          v = exp_f32_from_f64(-(d * d) * i2);
+        } else {
+          const double ul = isx ? ulx : uly, br = isx ? brx : bry;
+          if ((double)pos >= ul && (double)pos < br) {
+            const double d = ((double)pos - ul) - x0p;
+            v = exp_f32_from_f64(-(d * d) * i2);
+          }
+        }
+      }
+      tab[i] = v;
+    }
+  };
 
   if (role == 0) {
     // =====================================================================================================
     // EPILOGUE WARP
     // =====================================================================================================
     double acc_sp = 0.0, acc_sn = 0.0, acc_np = 0.0, acc_ne = 0.0;   // this team's loss sums (lane 0)
+    // side-input ring (kSideAhead planes ahead) and the tables of the first two planes; the sweepers start
+    // on plane 0 as soon as its tables exist
+    int mask_cur = 1, mask_nxt = 1;                  // fused-metrics mask bytes of planes n, n+1 (lane 0)
+    if (lane == 0 && a.counters) {
+      mask_cur = a.mask[(int64_t)pb * K + (C == K ? pc : pc % K)];
+      if (p + total_teams < n_planes) {
+        uint32_t mb = pb, mc = pc;
+        advance(mb, mc);
+        mask_nxt = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];
+      }
+    }
+#pragma unroll
+    for (int i = 2; i < kSideAhead; ++i) {
+      if (pq < n_planes) side_fetch(qb, qc, i);
+      cp_async_commit();
+      pq += total_teams; advance(qb, qc);
+    }
+    cp_async_wait<kSideAhead - 2>();               // the first two planes' side inputs have landed
+    __syncwarp();
+    prologue(pc, 0, 0);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&th->empty[0]);
+    if (p + total_teams < n_planes) {
+      uint32_t nb = pb, nc = pc;
+      advance(nb, nc);
+      prologue(nc, 1, 1);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&th->empty[1]);
+
     int n_it = 0;
     for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
       const int buf = n_it & 1;
@@ -221,14 +339,23 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       const float maxval = rec->maxval;
       float rx = rec->rx, ry = rec->ry;
       const bool dark_guard = (rec->flags & 1) != 0, any_nan = (rec->flags & 2) != 0;
-      double* hbuf = hbuf0 + (size_t)buf * TD * 5;
 
       bool need_slow = false;
       float bmax = 0.f;
       if (dark_guard) {
-        // column pass over the staged row sums (centre tap, then symmetric pairs fused-added: the
-        // summation order of cv2's separable filter)
+        // row pass over the staged window (sequential FMA over the taps), then column pass (centre tap,
+        // then symmetric pairs fused-added) — the summation order of cv2's separable filter
+        const float* tile = reinterpret_cast<const float*>(tile0 + (size_t)buf * tile_bytes);
+        const int xo = (rec->flags >> 8) & 3;
         if (legacy) {
+          for (int e = lane; e < TD * 5; e += 32) {
+            const int r = e / 5, c5 = e - r * 5;
+            const float* trow = tile + r * TCW + xo + c5;
+            double acc = 0.0;
+            for (int j = 0; j < ksize; ++j) acc = __fma_rn(a.tapsd[j], (double)trow[j], acc);
+            hbuf[e] = acc;
+          }
+          __syncwarp();
           if (lane < 25) {
             const int dr = lane / 5, c5 = lane - dr * 5;
             double acc = __dmul_rn(a.tapsd[bb], hbuf[(dr + bb) * 5 + c5]);
@@ -237,7 +364,20 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             hout[lane] = (float)acc;
           }
         } else {
-          const float* hb = reinterpret_cast<const float*>(hbuf);
+          float* hb = reinterpret_cast<float*>(hbuf);
+          for (int e = lane; e < TD * 5; e += 32) {
+            const int r = e / 5, c5 = e - r * 5;
+            const float* trow = tile + r * TCW + xo + c5;
+            float acc = 0.f;
+            if (KS > 0) {
+#pragma unroll
+              for (int j = 0; j < KS; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);   // taps: constant-bank operands
+            } else {
+              for (int j = 0; j < ksize; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);
+            }
+            hb[e] = acc;
+          }
+          __syncwarp();
           if (lane < 25) {
             const int dr = lane / 5, c5 = lane - dr * 5;
             const float* hcol = hb + (dr + bb) * 5 + c5;
@@ -362,7 +502,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         if (a.out_kpts) { float* o = a.out_kpts + 3 * (int64_t)p; o[0] = X; o[1] = Y; o[2] = maxval; }
         if (a.out_idx) a.out_idx[p] = (int32_t)idx;
         if (LOSS) {
-          const float w = rec->w;
+          const float w = th->w[n_it % 3];
           const bool bal = a.loss_mode == LHN_LOSS_DISTANCE_BALANCE;
           const float wp = (a.loss_mode == LHN_LOSS_JOINTS_MSE) ? w * w : w;
           const double sall = (double)rec->ssum * (double)wp, spos = bal ? (double)rec->spos * (double)wp : 0.0;
@@ -374,7 +514,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           acc_sp += spos; acc_sn += sall - spos; acc_np += npos; acc_ne += (double)HW;
           if (a.out_weight) a.out_weight[p] = w;
         }
-        if (a.counters && th->side_mask[n_it & 7]) {
+        if (a.counters && mask_cur) {
           // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32)
           const int Ki = (int)K;
           const double gx = (double)sd[SD_GX], gy = (double)sd[SD_GY];
@@ -407,10 +547,34 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         }
       }
       TRE(11);
+      // ---- side-input ring + the tables of plane n+2; then plane n+2 may start ------------------------------
+      if (lane == 0 && a.counters) {
+        mask_cur = mask_nxt;
+        mask_nxt = 1;
+        if (p + 2 * total_teams < n_planes) {
+          uint32_t mb = pb, mc = pc;
+          advance(mb, mc); advance(mb, mc);
+          mask_nxt = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];   // consumed two planes from now
+        }
+      }
+      if (pq < n_planes) side_fetch(qb, qc, (n_it + kSideAhead) & 7);
+      cp_async_commit();
+      pq += total_teams; advance(qb, qc);
+      cp_async_wait<kSideAhead - 2>();               // side inputs of plane n+2 have landed
       __syncwarp();
-      if (lane == 0) mbar_arrive(&th->empty[buf]);   // release: the record and the row sums are free again
+      if (p + 2 * total_teams < n_planes) {
+        uint32_t nb = pb, nc = pc;
+        advance(nb, nc); advance(nb, nc);
+        prologue(nc, (n_it + 2) & 7, (n_it + 2) % 3);
+      }
+      TRE(12);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&th->empty[buf]);   // release: record/tile buffer free, tables of n+2 ready
     }
 
+#ifdef LHN_TRACE
+    if (lane == 0 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 14] = clock64();
+#endif
     // ---- one-launch loss: publish this team's sums; the last team reduces all of them in a fixed order ----
     if (LOSS && a.team_sums) {
       const uint32_t active = n_planes < total_teams ? n_planes : total_teams;
@@ -459,74 +623,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     if (FLIP) tma_load_1d(const_cast<T*>(plane1), gptr1(b, c), plane_bytes, &th->bar, policy);
   };
 
-  // Side inputs of plane (b, c) -> ring slot `slot` (lanes 0..SD_N-1 of one warp; asynchronous).
-  auto side_fetch = [&](uint32_t b, uint32_t c, int slot) {
-    uint32_t s, k;
-    split_channel(c, s, k);
-    const int64_t bk = (int64_t)b * K + k;
-    const float* src = nullptr;
-    switch (lane) {
-      case SD_JX: case SD_JY: if (LOSS) src = a.joints + bk * a.joints_stride + lane; break;
-      case SD_VIS: if (LOSS) src = a.vis + bk * a.vis_stride; break;
-      case SD_CX: case SD_CY: if (a.center) src = a.center + 2 * (int64_t)b + (lane - SD_CX); break;
-      case SD_SX: case SD_SY: if (a.scale) src = a.scale + 2 * (int64_t)b + (lane - SD_SX); break;
-      case SD_GX: case SD_GY: if (a.counters) src = a.gt + 2 * bk + (lane - SD_GX); break;
-      case SD_BW: case SD_BH: if (a.counters) src = a.bbox_wh + 2 * (int64_t)b + (lane - SD_BW); break;
-      default: break;
-    }
-    if (src) cp_async_4(&th->side[slot][lane], src);
-  };
-
-  // Render parameters + separable Gaussian factors of a plane (channel c, side-ring slot `slot`) into table
-  // buffer `buf`, computed by the sweepers.  exp() is evaluated on an f64 argument.
-  auto prologue = [&](uint32_t c, int slot, int buf) {
-    if (!LOSS) return;
-    uint32_t s, k;
-    split_channel(c, s, k);
-    const float* sd = th->side[slot];
-    const float jx = sd[SD_JX], jy = sd[SD_JY];
-    float w = sd[SD_VIS];
-    const double sig = (double)a.sigma[s], tmp = sig * 3.0;
-    // joint / feat_stride in f64 (numpy promotes f32 / f64); a power-of-two stride multiplies exactly
-    double mux, muy;
-    if (a.feat_pow2) { mux = (double)jx * a.inv_feat_x; muy = (double)jy * a.inv_feat_y; }
-    else { mux = (double)jx / a.feat_x; muy = (double)jy / a.feat_y; }
-    double x0p = 0, ulx, uly, brx, bry;
-    if (a.unbiased) {
-      ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1;
-    } else {
-      mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);                // int() truncates toward zero
-      ulx = trunc(mux - tmp); uly = trunc(muy - tmp);
-      brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
-      x0p = floor((2 * tmp + 1) * 0.5);                               // size // 2
-    }
-    if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
-    const bool render_on = w > 0.5f;
-    if (sl == 0) {
-      th->w[buf] = w; th->mx[buf] = (float)mux; th->my[buf] = (float)muy; th->render_on[buf] = render_on ? 1 : 0;
-    }
-    const double i2 = a.inv2s2[s];
-    float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + (size_t)buf * tab_bytes);
-    for (int i = sl; i < W + H; i += ST) {
-      const bool isx = i < W;
-      const int pos = isx ? i : i - W;
-      float v = 0.f;
-      if (render_on) {
-        if (a.unbiased) {
-          const double d = (double)pos - (isx ? mux : muy);
-          v = exp_f32_from_f64(-(d * d) * i2);
-        } else {
-          const double ul = isx ? ulx : uly, br = isx ? brx : bry;
-          if ((double)pos >= ul && (double)pos < br) {
-            const double d = ((double)pos - ul) - x0p;
-            v = exp_f32_from_f64(-(d * d) * i2);
-          }
-        }
-      }
-      tab[i] = v;
-    }
-  };
-
   if (a.flip_index) {
     for (int i = sl; i < (int)K; i += ST) fidx[i] = a.flip_index[i];
     named_sync(bar_id, ST);
@@ -535,35 +631,20 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     policy = policy_evict_first();
     if (a.use_tma) issue(pb, pc);
   }
-  // side-input ring: the first sweeper warp runs kSideAhead planes ahead
-  uint32_t qb = pb, qc = pc, pq = p;               // cursor of the next plane to fetch (role 1 only)
-  int mask_reg = 0;
-  if (role == 1) {
-#pragma unroll
-    for (int i = 0; i < kSideAhead; ++i) {
-      if (pq < n_planes) side_fetch(qb, qc, i);
-      cp_async_commit();
-      if (i == 0 && lane == 0 && a.counters) th->side_mask[0] = a.mask[(int64_t)qb * K + (C == K ? qc : qc % K)];
-      if (i == 1 && lane == 0 && a.counters && pq < n_planes) mask_reg = a.mask[(int64_t)qb * K + (C == K ? qc : qc % K)];
-      pq += total_teams; advance(qb, qc);
-    }
-    cp_async_wait<kSideAhead - 2>();               // the first two planes' side inputs have landed
-  }
-  named_sync(bar_id, ST);
-  prologue(pc, 0, 0);
   uint32_t phase = 0;
-  int n_it = 0;                                    // team-local plane counter (ring slot = n_it & 7)
+  int n_it = 0;                                    // team-local plane counter
 
   const int QR = W >> 2, nq = HW >> 2;
   const uint64_t half2 = pack2(0.5f, 0.5f);
 
   for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
-    const int buf = n_it & 1;
+    const int buf = n_it & 1, tb = n_it % 3;
     const bool has_next = p + total_teams < n_planes;
-    // S1: tables / side inputs of this plane are written, red_* of the previous plane are consumed
-    named_sync(bar_id, ST);
+    // the epilogue warp has written this plane's tables and is done with the record/tile buffer `buf`
+    // (it finished plane n-2; it lags at most two planes)
+    mbar_wait(&th->empty[buf], (uint32_t)(n_it >> 1) & 1u);
     TRS(0);
-    const float* ex = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(tab0) + (size_t)buf * tab_bytes);
+    const float* ex = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(tab0) + (size_t)tb * tab_bytes);
     const float* ey = ex + W;
 
     // ---- wait for the plane ------------------------------------------------------------------------
@@ -713,44 +794,19 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     const int px = (int)cx, py = (int)cy;
     const bool dark_guard = is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2);
 
-    // the epilogue warp must be done with this record / row-sum buffer (it lags at most two planes)
-    if (n_it >= 2) mbar_wait(&th->empty[buf], (uint32_t)((n_it >> 1) - 1) & 1u);
     PlaneRec* rec = &th->rec[buf];
+    const int wx0 = px - 2 - bb;                      // first window column (may be negative)
+    const int c0 = wx0 & ~3, xo = wx0 & 3;            // its quad-aligned start and the offset inside it
 
-    // ---- DARK row pass straight from the stage, one output per thread: the (ksize+4) x 5 row sums around
-    //      the peak (zero padding = skipped taps; sequential FMA over the taps = cv2's RowFilter order) ----
+    // ---- stage the DARK window: zero-padded (ksize+4) rows x NQ quads of the decoded plane -----------------
     if (dark_guard) {
-      double* hbuf = hbuf0 + (size_t)buf * TD * 5;
-      const int nrow = TD * 5;
-      for (int e = sl; e < nrow; e += ST) {
-        const int r = e / 5, c5 = e - r * 5;
-        const int y = py - 2 - bb + r, x0 = px - 2 + c5 - bb;
-        if (legacy) {
-          double acc = 0.0;
-          if (y >= 0 && y < H)
-            for (int j = 0; j < ksize; ++j) {
-              const int x = x0 + j;
-              if ((unsigned)x < (unsigned)W) acc = __fma_rn(a.tapsd[j], (double)val(y, x), acc);
-            }
-          hbuf[e] = acc;
-        } else {
-          float acc = 0.f;
-          if (y >= 0 && y < H) {
-            if (KS > 0) {
-#pragma unroll
-              for (int j = 0; j < KS; ++j) {
-                const int x = x0 + j;
-                if ((unsigned)x < (unsigned)W) acc = __fmaf_rn(a.tapsf[j], val(y, x), acc);   // taps: constant bank
-              }
-            } else {
-              for (int j = 0; j < ksize; ++j) {
-                const int x = x0 + j;
-                if ((unsigned)x < (unsigned)W) acc = __fmaf_rn(a.tapsf[j], val(y, x), acc);
-              }
-            }
-          }
-          reinterpret_cast<float*>(hbuf)[e] = acc;
-        }
+      float* tile = reinterpret_cast<float*>(tile0 + (size_t)buf * tile_bytes);
+      for (int e = sl; e < TD * NQ; e += ST) {
+        const int r = e / NQ, cq = e - r * NQ;          // compile-time divisor when KS > 0
+        const int y = py - 2 - bb + r, x = c0 + 4 * cq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = load_quad(y * QR + (x >> 2));
+        *reinterpret_cast<float4*>(tile + r * TCW + 4 * cq) = v;
       }
     }
     // ---- positives of the balanced loss: a small window around the joint, by the last sweeper warp ---------
@@ -764,13 +820,13 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         if (a.pos_value > 0.f && a.pos_value < 1.f) {
           // g > value  <=>  r^2 < -2 sigma^2 ln(value): a.pos_radius = that radius + a rounding margin
           const float rad = a.pos_radius[s];
-          const float mxf = th->mx[buf], myf = th->my[buf];
+          const float mxf = th->mx[tb], myf = th->my[tb];
           x_lo = max(0, (int)ceilf(mxf - rad)); x_hi = min(W - 1, (int)floorf(mxf + rad));
           y_lo = max(0, (int)ceilf(myf - rad)); y_hi = min(H - 1, (int)floorf(myf + rad));
         } else if (a.pos_value >= 1.f) {
           x_hi = -1;
         }
-        if (th->render_on[buf] || a.pos_value < 0.f) {
+        if (th->render_on[tb] || a.pos_value < 0.f) {
           float sp = 0.f;
           // one window element per lane (5 x 5 = 25 lanes for sigma = 2)
           const int ww = x_hi - x_lo + 1, wn = ww > 0 ? ww * (y_hi - y_lo + 1) : 0;
@@ -812,8 +868,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       float S = 0.f;
       if (LOSS) for (int i = 0; i < NS; ++i) S += th->red_s[i];
       rec->idx = idx; rec->maxval = maxval; rec->rx = rx; rec->ry = ry;
-      rec->w = LOSS ? th->w[buf] : 0.f; rec->ssum = S;
-      rec->flags = (dark_guard ? 1 : 0) | (any_nan ? 2 : 0);
+      rec->ssum = S;
+      rec->flags = (dark_guard ? 1 : 0) | (any_nan ? 2 : 0) | (xo << 8);
     }
     TRS(4);
     // S3: everything the epilogue needs is out of the stage — nobody reads it again
@@ -830,27 +886,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     TRS(5);
 
-    // ---- while the next plane is in flight: side-input ring + the next plane's tables -----------------------
-    if (role == 1) {
-      if (lane == 0 && a.counters) {
-        th->side_mask[(n_it + 1) & 7] = mask_reg;            // loaded one plane ago
-        if (p + 2 * total_teams < n_planes) {
-          uint32_t mb = pb, mc = pc;
-          advance(mb, mc); advance(mb, mc);
-          mask_reg = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];
-        }
-      }
-      if (pq < n_planes) side_fetch(qb, qc, (n_it + kSideAhead) & 7);
-      cp_async_commit();
-      pq += total_teams; advance(qb, qc);
-    }
-    if (has_next) {
-      uint32_t nb = pb, nc = pc;
-      advance(nb, nc);
-      prologue(nc, (n_it + 1) & 7, buf ^ 1);
-    }
-    // side inputs of plane n+2 complete here; the S1 barrier publishes them to the other sweepers
-    if (role == 1) cp_async_wait<kSideAhead - 2>();
   }
 }
 
@@ -870,8 +905,8 @@ static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {
   auto kern = heatmap_team_kernel<T, FAST, TWC, FLIP, LOSS, KS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
-  int64_t ctas = (a.n_planes + nteams - 1) / nteams;
-  if (ctas > sm_count()) ctas = sm_count();
+  // one CTA per SM; small problems still spread over as many SMs as they have planes (team-major numbering)
+  int64_t ctas = a.n_planes < sm_count() ? a.n_planes : sm_count();
   kern<<<(unsigned)ctas, nteams * a.team_warps * 32, smem, st>>>(a);
   return check_launch();
 }
@@ -921,9 +956,9 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   a.stage_bytes = (int)(flip ? 2 * plane_al : plane_al);
   const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY;
   a.tile_dim = is_dark ? a.ksize + 4 : 0;
-  const size_t aux = align_up(sizeof(TeamHeader), 16) + 2 * align_up((size_t)(a.W + a.H) * 4, 16) +
-                     (size_t)2 * a.tile_dim * 5 * 8 + 32 * 4 +
-                     align_up((size_t)a.K * 4, 16);
+  const size_t aux = align_up(sizeof(TeamHeader), 16) + 3 * align_up((size_t)(a.W + a.H) * 4, 16) +
+                     2 * align_up((size_t)a.tile_dim * 4 * tile_quads(a.tile_dim) * 4, 16) +
+                     (size_t)a.tile_dim * 5 * 8 + 32 * 4 + align_up((size_t)a.K * 4, 16);
   a.warp_smem = (int)align_up(a.stage_bytes + aux, 128);
   const size_t budget = 227 * 1024;
   int nteams = (int)(budget / a.warp_smem);

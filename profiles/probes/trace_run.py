@@ -25,13 +25,24 @@ def stat(name, x):
 # sweepers (first sweeper warp, lane 0): 0 = S1 passed, 1 = plane landed, 2 = sweep done, 3 = S2 passed,
 # 4 = row sums / positives / record staged, 5 = S3 passed + stage re-armed
 for a_, b_, n in [(0, 1, 'sweeper wait for plane (mbar)'), (1, 2, 'sweep'), (2, 3, 'warp reduce + S2'),
-                  (3, 4, 'resolve + row pass + positives'), (4, 5, 'S3 + re-arm TMA')]:
+                  (3, 4, 'resolve + window + positives'), (4, 5, 'S3 + re-arm TMA')]:
     stat(n, T[:, its, b_] - T[:, its, a_])
-stat('tables for next plane + S1', T[:, 4:15, 0] - T[:, 3:14, 5])
+stat('wait for tables/empty (next plane)', T[:, 4:15, 0] - T[:, 3:14, 5])
 stat('sweeper cycle per plane', T[:, 4:15, 0] - T[:, 3:14, 0])
-# epilogue warp: 8 = record received, 9 = column pass / clamp check / log done, 10 = Taylor done, 11 = plane finished
-for a_, b_, n in [(8, 9, 'epilogue: blur column + log'), (9, 10, 'epilogue: Taylor'), (10, 11, 'epilogue: transform + stores + loss')]:
+# epilogue warp: 8 = record received, 9 = blur / clamp check / log done, 10 = Taylor done, 11 = plane finished,
+# 12 = side ring + tables of plane n+2 done
+for a_, b_, n in [(8, 9, 'epilogue: blur + log'), (9, 10, 'epilogue: Taylor'), (10, 11, 'epilogue: transform + stores + loss'),
+                  (11, 12, 'epilogue: side ring + tables n+2')]:
     stat(n, T[:, its, b_] - T[:, its, a_])
-stat('epilogue busy per plane', T[:, its, 11] - T[:, its, 8])
-stat('epilogue wait for record', T[:, 4:15, 8] - T[:, 3:14, 11])
-stat('record ready -> epilogue picks it up', T[:, its, 8] - T[:, its, 5])
+stat('epilogue busy per plane', T[:, its, 12] - T[:, its, 8])
+stat('epilogue wait for record', T[:, 4:15, 8] - T[:, 3:14, 12])
+
+# whole-kernel view per team (clock64 is per SM: only differences within a team are meaningful)
+entry, finish = T[:, 0, 15], T[:, 0, 14]
+stat('team: entry -> first plane landed', T[:, 0, 1] - entry)
+stat('team: entry -> tables ready (it 0)', T[:, 0, 0] - entry)
+stat('team: first 3 planes (entry -> it3)', T[:, 3, 0] - entry)
+stat('team: total (entry -> finish)', finish - entry)
+per_sm = (finish - entry).reshape(148, 6)
+stat('SM: slowest team total', per_sm.max(axis=1))
+print('kernel cycles if every SM ran at its slowest team:', per_sm.max())
