@@ -5,7 +5,9 @@ Metric (BASELINE.json): heatmap render+loss+decode samples/s @ 21x64x64 (+ % of 
 Workload at every N: BASELINE config[1] — FreiHAND 21x64x64 fused Gaussian target render +
 target-weight MSE loss (DistanceLoss L2, balance=True) + flip-test average + DARK decode (k=11) +
 affine back-transform, batch 1024 PER GPU (weak scaling: the batch is sharded by rank, the only
-collective is an all-reduce of the four f64 loss sums).
+collective is an all-reduce of the four f64 loss sums).  A step is ONE launch of the persistent fused kernel
+(lhn_fused_render_loss_decode: it also reduces and finalises the loss); at N > 1 the kernel leaves the f64 sums,
+NCCL all-reduces them and lhn_loss_finalize runs as a second, tiny launch.
 
   python bench.py --gpus N --steps K --warmup W           (torchrun launches N ranks for N > 1)
   python bench.py --impl reference ...                    the reference's CPU path (oracle port) on the
@@ -208,9 +210,11 @@ def run_gpu_arm(args, rank, local_rank, world):
         joints, vis = synth.hand_joints(B, K_JOINTS, IMAGE_SIZE, seed=seed + 2, device=dev)
         center, scale = synth.bbox_center_scale(B, seed=seed + 3, device=dev)
         sets.append((hm, hf, joints, vis, center, scale))
-    bound = [fused.BoundFusedStep(step_cfg, s[0], s[2], s[3], s[4], s[5], hm_flip=s[1], finalize=(world == 1))
+    # consecutive steps work on disjoint buffer sets (R >= 2), so each launch may overlap the tail of the previous one
+    bound = [fused.BoundFusedStep(step_cfg, s[0], s[2], s[3], s[4], s[5], hm_flip=s[1], finalize=(world == 1),
+                                  overlap_previous=(R >= 2 and not args.no_overlap))
              for s in sets]
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = (world == 1) and args.graph
     if use_graph:
         for b in bound:
             b.capture()
@@ -246,13 +250,19 @@ def run_gpu_arm(args, rank, local_rank, world):
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
 
-    # ---- the fused kernel alone, bracketed by events inside a second pass over the same steps ----------
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- the fused kernel alone: a second pass of K back-to-back launches (no collective, no finalise)
+    #      between two events on the launching stream; average launch duration = elapsed / K ---------------
     fence()
+    st = fused.L.stream()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(min(3, args.steps)):
+        bound[i % R].launch_kernel(st)
+    k0.record()
     for i in range(args.steps):
-        one_step(i, kev[i])
+        bound[i % R].launch_kernel(st)
+    k1.record()
     fence()
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    kernel_ms = k0.elapsed_time(k1) / args.steps
 
     # ---- end to end through the host-buffer API ---------------------------------------------------------
     e2e = None
@@ -294,14 +304,16 @@ def run_gpu_arm(args, rank, local_rank, world):
                        "decode": "argmax + DARK k=11 + transform_preds", "parallelism": f"batch-shard x{world}",
                        "l2_policy": f"inputs {2 * B * K_JOINTS * H * W * 4 / 1e6:.0f} MB/step > 126 MB L2, "
                                     f"{R} rotating input sets, L2 evict_first loads",
-                       "launch": "CUDA graph replay" if use_graph else "eager C-ABI launches",
+                       "launch": ("CUDA graph replay" if use_graph else "eager C-ABI launches, one per step") +
+                                 ("" if args.no_overlap or R < 2 else
+                                  "; LHN_FLAG_OVERLAP_PREVIOUS (programmatic dependent launch over rotating buffer sets)"),
                        "loss_check": loss_val},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(B),
-                         "kernel": "heatmap_plane_kernel<f32,W=64,FLIP,LOSS>", "kernel_ms": kernel_ms,
+                         "kernel": "heatmap_team_kernel<f32,64x64,TW=4,FLIP,LOSS,KS=11>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src},
-            "gpu_launches": args.steps * (3 if world == 1 else 3),
+            "gpu_launches": args.steps * (1 if world == 1 else 2),
         }
         if e2e:
             line["e2e"] = {"value": world * B * args.steps / e2e_s, "unit": UNIT,
@@ -333,7 +345,9 @@ def main():
     ap.add_argument("--rotate", type=int, default=2, help="distinct device-resident input sets")
     ap.add_argument("--chunks", type=int, default=8, help="H2D/compute pipeline chunks of the e2e path")
     ap.add_argument("--cpu-sample", type=int, default=0)
-    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per step instead of eager launches")
+    ap.add_argument("--no-graph", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-overlap", action="store_true", help="do not let a launch overlap the previous one's tail")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -72,6 +72,13 @@ typedef void* lhn_stream_t; /* cudaStream_t */
 #define LHN_LOSS_DISTANCE_BALANCE 2 /* L2: DistanceLoss L2 balance=True */
 #define LHN_LOSS_JOINTS_MSE 3       /* L3: JointsDistanceLoss mse, heatmapLoss.py:195-225 */
 
+/* lhn_decode_params.flags */
+#define LHN_FLAG_OVERLAP_PREVIOUS 1 /* This launch touches no buffer (inputs, outputs, workspace) that the previous
+                                       launch on the same stream writes: it may begin while that launch is still
+                                       draining (programmatic dependent launch), which hides the ~10 us launch gap
+                                       of back-to-back steps over rotating buffers.  Stream order is unchanged for
+                                       everything launched afterwards. */
+
 #define LHN_MAX_TAPS 31
 #define LHN_MAX_STACKS 8
 
@@ -82,7 +89,7 @@ typedef struct {
   int32_t transform;  /* LHN_XFORM_* */
   int32_t use_udp;    /* T1: divide by (W-1),(H-1) instead of W,H (post_transforms.py:37-39) */
   int32_t blur_ksize; /* DARK Gaussian kernel size (odd, 3..31): 11 for D5, 19 for D6 */
-  int32_t reserved;
+  int32_t flags;      /* LHN_FLAG_* (0 = none) */
   float scale_x, scale_y;         /* LHN_XFORM_SCALE factors */
   double taps[LHN_MAX_TAPS];      /* cv2.getGaussianKernel(blur_ksize, 0) in double; host fills it
                                      with lhn_gaussian_taps() */
@@ -131,7 +138,7 @@ LHN_API int lhn_gaussian_taps(int ksize, double* taps);
  * vis           f32 [B, K, vis_stride] (column 0 = visibility / weight).
  * out_weight    f32 [B*C] target_weight after the visibility rule, or NULL.
  * partials      f64 [B*C, 4] per-plane (w^p*S_pos, w^p*S_neg, N_pos, H*W); reduce with
- *               lhn_loss_reduce + lhn_loss_finalize.  The loss is taken on `hm` (not the flip
+ *               lhn_loss_reduce + lhn_loss_finalize (or use lhn_fused_render_loss_decode below).  The loss is taken on `hm` (not the flip
  *               average), as the training loss is.
  */
 LHN_API int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int32_t* flip_index,
@@ -146,6 +153,36 @@ LHN_API int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int32_
                                const float* vis, int vis_stride,
                                float* out_weight, double* partials,
                                lhn_stream_t stream);
+
+/* ---- the headline step in ONE launch ------------------------------------------------------------
+ * lhn_decode_heatmap (with the fused render + loss) followed by lhn_loss_reduce and
+ * lhn_loss_finalize, as a single kernel: every team of the persistent kernel keeps its own f64
+ * loss sums and the last team to finish reduces them in a fixed order (bitwise reproducible for a
+ * given shape) and finalises the loss.  Replaces the same reference calls as lhn_decode_heatmap +
+ * DistanceLoss.forward / JointsDistanceLoss.forward (heatmapLoss.py:242-265, :195-225).
+ *
+ * workspace  device buffer of lhn_fused_workspace_bytes(B, K, num_stacks) bytes; zero it ONCE
+ *            (cudaMemsetAsync) before the first call — every call leaves it zeroed.  One workspace
+ *            per concurrently running stream.
+ * partials   optional here (NULL = do not write the per-plane sums).
+ * sums       f64 [4] = (S_pos, S_neg, N_pos, numel) of the whole call, or NULL: all-reduce these across
+ *            ranks and call lhn_loss_finalize for a batch-sharded loss with global counts.
+ * loss       f32 [1] = loss_scale * f(sums) as lhn_loss_finalize (sum_reduction as there), or NULL.
+ * Shapes outside the persistent kernel's envelope (a plane pair larger than half the shared memory)
+ * run the same arithmetic as three launches; results are identical. */
+LHN_API int64_t lhn_fused_workspace_bytes(int64_t B, int K, int num_stacks);
+LHN_API int lhn_fused_render_loss_decode(const void* hm, const void* hm_flip,
+                                         const int32_t* flip_index, int dtype, int64_t B, int K, int H,
+                                         int W, int64_t stride_b, int64_t stride_c,
+                                         int64_t flip_stride_b, int64_t flip_stride_c,
+                                         const float* center, const float* scale,
+                                         const lhn_decode_params* dp, float* out_hm, float* out_kpts,
+                                         int32_t* out_idx, const lhn_render_params* rp,
+                                         const float* joints, int joints_stride, const float* vis,
+                                         int vis_stride, float* out_weight, double* partials,
+                                         void* workspace, int64_t workspace_bytes, double* sums,
+                                         int sum_reduction, float loss_scale, float* loss,
+                                         lhn_stream_t stream);
 
 /* ---- loss against an explicit target tensor (the un-fused drop-in) ----------------------------
  * DistanceLoss.forward(output, target, target_weight) / JointsDistanceLoss.forward

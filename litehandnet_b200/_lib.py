@@ -19,6 +19,7 @@ REFINE_NONE, REFINE_OFFSET_HALF, REFINE_OFFSET, REFINE_SIGN, REFINE_SIGN_ROUND, 
     REFINE_DARK_LEGACY = range(7)
 XFORM_NONE, XFORM_CENTER_SCALE, XFORM_SCALE = 0, 1, 2
 LOSS_NONE, LOSS_DISTANCE, LOSS_DISTANCE_BALANCE, LOSS_JOINTS_MSE = 0, 1, 2, 3
+FLAG_OVERLAP_PREVIOUS = 1
 MAX_TAPS, MAX_STACKS = 31, 8
 
 ERRORS = {-1: "LHN_EINVAL (bad shape / null pointer / bad enum)", -2: "LHN_EDTYPE (unsupported dtype)",
@@ -30,13 +31,13 @@ EXPORTS = [
     "lhn_decode_heatmap_pck", "lhn_loss_partials", "lhn_loss_reduce", "lhn_loss_finalize",
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_simdr_loss_workspace_bytes",
     "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_evaluate_pck_workspace_bytes",
-    "lhn_evaluate_pck", "lhn_flip_back",
+    "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
 ]
 
 
 class DecodeParams(C.Structure):
     _fields_ = [("mask_mode", C.c_int32), ("refine", C.c_int32), ("transform", C.c_int32),
-                ("use_udp", C.c_int32), ("blur_ksize", C.c_int32), ("reserved", C.c_int32),
+                ("use_udp", C.c_int32), ("blur_ksize", C.c_int32), ("flags", C.c_int32),
                 ("scale_x", C.c_float), ("scale_y", C.c_float), ("taps", C.c_double * MAX_TAPS)]
 
 
@@ -61,6 +62,11 @@ def _declare(lib):
     lib.lhn_decode_heatmap.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, i64, i64, i64, i64, vp, vp,
                                        C.POINTER(DecodeParams), vp, vp, vp, C.POINTER(RenderParams),
                                        vp, i32, vp, i32, vp, vp, vp]
+    lib.lhn_fused_workspace_bytes.argtypes = [i64, i32, i32]
+    lib.lhn_fused_workspace_bytes.restype = i64
+    lib.lhn_fused_render_loss_decode.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, i64, i64, i64, i64, vp, vp,
+                                                 C.POINTER(DecodeParams), vp, vp, vp, C.POINTER(RenderParams),
+                                                 vp, i32, vp, i32, vp, vp, vp, i64, vp, i32, f32, vp, vp]
     lib.lhn_decode_heatmap_pck.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp,
                                            C.POINTER(DecodeParams), vp, vp, vp, vp, vp, vp, f32, f32,
                                            i32, vp, vp]

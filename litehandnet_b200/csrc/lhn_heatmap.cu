@@ -463,7 +463,7 @@ static int dispatch_shape(const HmArgs& a, bool flip, bool loss, cudaStream_t st
 #undef LHN_GO
 }
 
-static int run_heatmap(HmArgs& a, int dtype, cudaStream_t st) {
+static int run_heatmap(HmArgs& a, int dtype, cudaStream_t st, int* used_team_kernel = nullptr) {
   const bool flip = a.hm_flip != nullptr;
   const bool loss = a.loss_mode != LHN_LOSS_NONE;
   const size_t esz = dtype == LHN_F32 ? 4 : 2;
@@ -482,8 +482,9 @@ static int run_heatmap(HmArgs& a, int dtype, cudaStream_t st) {
   }
   if (!a.force_cta_kernel) {
     const int rc = launch_heatmap_warp_kernel(a, dtype, st);
-    if (rc <= 0) return rc;
+    if (rc <= 0) { if (used_team_kernel) *used_team_kernel = 1; return rc; }
   }
+  if (a.fallback_partials) a.partials = a.fallback_partials;   // the CTA-per-plane kernel needs per-plane sums
   switch (dtype) {
     case LHN_F32: return dispatch_shape<float>(a, flip, loss, st);
     case LHN_BF16: return dispatch_shape<__nv_bfloat16>(a, flip, loss, st);
@@ -500,6 +501,7 @@ static int fill_decode(HmArgs& a, const lhn_decode_params* dp) {
   a.mask_mode = dp->mask_mode; a.refine = dp->refine; a.transform = dp->transform;
   a.use_udp = dp->use_udp; a.scale_x = dp->scale_x; a.scale_y = dp->scale_y;
   a.ksize = dp->blur_ksize;
+  a.overlap_previous = (dp->flags & LHN_FLAG_OVERLAP_PREVIOUS) ? 1 : 0;
   if (dp->refine == LHN_REFINE_DARK || dp->refine == LHN_REFINE_DARK_LEGACY) {
     if (a.ksize < 3 || a.ksize > LHN_MAX_TAPS || (a.ksize & 1) == 0) return LHN_EINVAL;
     for (int i = 0; i < a.ksize; ++i) { a.tapsd[i] = dp->taps[i]; a.tapsf[i] = (float)dp->taps[i]; }
@@ -512,6 +514,50 @@ static int fill_decode(HmArgs& a, const lhn_decode_params* dp) {
 
 using namespace lhn;
 
+namespace lhn { int num_sms(); }
+
+// workspace layout of the one-launch step: [ticket u32 | pad to 256 B][team sums: teams x 4 f64][partials of
+// the three-launch fallback: n_planes x 4 f64]
+static const int64_t kWsHeader = 256;
+static int64_t ws_team_bytes() { return (int64_t)lhn::num_sms() * lhn::kMaxTeamsPerCta * 32; }
+
+extern "C" int64_t lhn_fused_workspace_bytes(int64_t B, int K, int num_stacks) {
+  if (B < 0 || K <= 0) return 0;
+  const int S = num_stacks > 0 ? num_stacks : 1;
+  return kWsHeader + ws_team_bytes() + B * K * S * 32;
+}
+
+static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_t* flip_index,
+                               int dtype, int64_t B, int K, int H, int W, int64_t stride_b,
+                               int64_t stride_c, int64_t flip_stride_b, int64_t flip_stride_c,
+                               const float* center, const float* scale,
+                               const lhn_decode_params* dp, float* out_hm, float* out_kpts,
+                               int32_t* out_idx, const lhn_render_params* rp, const float* joints,
+                               int joints_stride, const float* vis, int vis_stride,
+                               float* out_weight, double* partials, bool fused, void* workspace,
+                               int64_t workspace_bytes, double* sums, int sum_reduction,
+                               float loss_scale, float* loss, lhn_stream_t stream);
+
+extern "C" int lhn_fused_render_loss_decode(const void* hm, const void* hm_flip,
+                                            const int32_t* flip_index, int dtype, int64_t B, int K,
+                                            int H, int W, int64_t stride_b, int64_t stride_c,
+                                            int64_t flip_stride_b, int64_t flip_stride_c,
+                                            const float* center, const float* scale,
+                                            const lhn_decode_params* dp, float* out_hm,
+                                            float* out_kpts, int32_t* out_idx,
+                                            const lhn_render_params* rp, const float* joints,
+                                            int joints_stride, const float* vis, int vis_stride,
+                                            float* out_weight, double* partials, void* workspace,
+                                            int64_t workspace_bytes, double* sums, int sum_reduction,
+                                            float loss_scale, float* loss, lhn_stream_t stream) {
+  if (!rp || rp->loss_mode == LHN_LOSS_NONE || !workspace) return LHN_EINVAL;
+  if ((uintptr_t)workspace % 16) return LHN_EALIGN;
+  return decode_heatmap_impl(hm, hm_flip, flip_index, dtype, B, K, H, W, stride_b, stride_c,
+                             flip_stride_b, flip_stride_c, center, scale, dp, out_hm, out_kpts, out_idx,
+                             rp, joints, joints_stride, vis, vis_stride, out_weight, partials, true,
+                             workspace, workspace_bytes, sums, sum_reduction, loss_scale, loss, stream);
+}
+
 extern "C" int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int32_t* flip_index,
                                   int dtype, int64_t B, int K, int H, int W, int64_t stride_b,
                                   int64_t stride_c, int64_t flip_stride_b, int64_t flip_stride_c,
@@ -520,6 +566,22 @@ extern "C" int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int
                                   int32_t* out_idx, const lhn_render_params* rp, const float* joints,
                                   int joints_stride, const float* vis, int vis_stride,
                                   float* out_weight, double* partials, lhn_stream_t stream) {
+  return decode_heatmap_impl(hm, hm_flip, flip_index, dtype, B, K, H, W, stride_b, stride_c,
+                             flip_stride_b, flip_stride_c, center, scale, dp, out_hm, out_kpts, out_idx,
+                             rp, joints, joints_stride, vis, vis_stride, out_weight, partials, false,
+                             nullptr, 0, nullptr, 0, 1.f, nullptr, stream);
+}
+
+static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_t* flip_index,
+                               int dtype, int64_t B, int K, int H, int W, int64_t stride_b,
+                               int64_t stride_c, int64_t flip_stride_b, int64_t flip_stride_c,
+                               const float* center, const float* scale,
+                               const lhn_decode_params* dp, float* out_hm, float* out_kpts,
+                               int32_t* out_idx, const lhn_render_params* rp, const float* joints,
+                               int joints_stride, const float* vis, int vis_stride,
+                               float* out_weight, double* partials, bool fused, void* workspace,
+                               int64_t workspace_bytes, double* sums, int sum_reduction,
+                               float loss_scale, float* loss, lhn_stream_t stream) {
   if (B < 0 || K <= 0 || H <= 0 || W <= 0) return LHN_EINVAL;
   if (B == 0) return LHN_OK;
   if (!hm) return LHN_EINVAL;
@@ -536,7 +598,7 @@ extern "C" int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int
   if (rc) return rc;
   a.loss_mode = rp ? rp->loss_mode : LHN_LOSS_NONE;
   if (a.loss_mode != LHN_LOSS_NONE) {
-    if (a.loss_mode < 0 || a.loss_mode > 3 || !joints || !vis || !partials || joints_stride < 2 ||
+    if (a.loss_mode < 0 || a.loss_mode > 3 || !joints || !vis || (!partials && !fused) || joints_stride < 2 ||
         vis_stride < 1 || rp->image_w <= 0 || rp->image_h <= 0)
       return LHN_EINVAL;
     a.unbiased = rp->unbiased;
@@ -548,7 +610,24 @@ extern "C" int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int
   }
   if (a.n_planes == 0) return LHN_OK;
   if (a.n_planes > 0x7fffffffLL) return LHN_EINVAL;
-  return run_heatmap(a, dtype, (cudaStream_t)stream);
+  if (!fused) return run_heatmap(a, dtype, (cudaStream_t)stream);
+  // ---- one-launch step ------------------------------------------------------------------------------
+  if (workspace_bytes < kWsHeader + ws_team_bytes() + a.n_planes * 32) return LHN_EWORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  a.ticket = reinterpret_cast<unsigned int*>(ws);
+  a.team_sums = reinterpret_cast<double*>(ws + kWsHeader);
+  a.sums_out = sums; a.loss_out = loss; a.loss_scale = loss_scale; a.sum_reduction = sum_reduction;
+  int used_team_kernel = 0;
+  double* fallback_partials = partials ? partials : reinterpret_cast<double*>(ws + kWsHeader + ws_team_bytes());
+  a.fallback_partials = fallback_partials;
+  rc = run_heatmap(a, dtype, (cudaStream_t)stream, &used_team_kernel);
+  if (rc || used_team_kernel) return rc;
+  // CTA-per-plane fallback wrote per-plane partials: reduce + finalise as separate launches
+  double* tmp_sums = sums ? sums : reinterpret_cast<double*>(ws + kWsHeader);
+  rc = lhn_loss_reduce(fallback_partials, a.n_planes, tmp_sums, 0, stream);
+  if (rc) return rc;
+  if (loss) rc = lhn_loss_finalize(tmp_sums, a.loss_mode, sum_reduction, loss_scale, loss, 0, stream);
+  return rc;
 }
 
 extern "C" int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, int H, int W,

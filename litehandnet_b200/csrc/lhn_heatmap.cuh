@@ -10,6 +10,7 @@
 namespace lhn {
 
 constexpr int kMaxWarps = 8;
+constexpr int kMaxTeamsPerCta = 12;   // persistent team kernel: teams per CTA (sizes the one-launch workspace)
 
 struct HmArgs {
   const void* hm;
@@ -62,6 +63,8 @@ struct HmArgs {
   float* loss_out;                 // [1] finalised loss (as lhn_loss_finalize)
   float loss_scale;
   int sum_reduction;
+  double* fallback_partials;       // per-plane sums for the CTA-per-plane fallback of the one-launch step
+  int overlap_previous;            // LHN_FLAG_OVERLAP_PREVIOUS: launch with programmatic stream serialization
   int feat_pow2;                   // feat_x, feat_y are powers of two: joint / feat == joint * inv_feat exactly
   double inv_feat_x, inv_feat_y;
 };

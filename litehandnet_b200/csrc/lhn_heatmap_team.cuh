@@ -27,7 +27,7 @@
 namespace lhn {
 
 constexpr int kMaxWarpsPerCta = 24;
-constexpr int kMaxTeams = 12;
+constexpr int kMaxTeams = kMaxTeamsPerCta;
 
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -231,6 +231,10 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
   }
 
+  // Let the next launch on the stream (if it was launched with LHN_FLAG_OVERLAP_PREVIOUS) take over SMs as
+  // this grid's CTAs retire; a no-op otherwise.
+  asm volatile("griddepcontrol.launch_dependents;");
+
   // ---- one-time setup: barriers visible to the whole CTA before anybody waits on them ------------------
   if (wt == 0 && lane == 0) {
     mbar_init(&th->bar, 1);
@@ -240,7 +244,12 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   }
   __syncthreads();
 #ifdef LHN_TRACE
-  if (role == 1 && lane == 0 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 15] = clock64();
+  if (role == 1 && lane == 0 && nteams <= 6) {
+    g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 15] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 13] = (long long)gt;
+  }
 #endif
   if (p >= n_planes) return;                       // whole teams leave together
 
@@ -573,10 +582,18 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
 
 #ifdef LHN_TRACE
-    if (lane == 0 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 14] = clock64();
+    if (lane == 0 && nteams <= 6) {
+      g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 14] = clock64();
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      g_trace[((blockIdx.x * 6 + team) * 16 + 1) * 16 + 13] = (long long)gt;
+    }
 #endif
     // ---- one-launch loss: publish this team's sums; the last team reduces all of them in a fixed order ----
     if (LOSS && a.team_sums) {
+      // the workspace is shared with the previous launch on the stream: it must have completed (it has, long
+      // ago; this only orders the memory operations when the launches overlap)
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       const uint32_t active = n_planes < total_teams ? n_planes : total_teams;
       unsigned int ticket = 0;
       if (lane == 0) {
@@ -907,7 +924,15 @@ static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {
   if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
   // one CTA per SM; small problems still spread over as many SMs as they have planes (team-major numbering)
   int64_t ctas = a.n_planes < sm_count() ? a.n_planes : sm_count();
-  kern<<<(unsigned)ctas, nteams * a.team_warps * 32, smem, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3((unsigned)(nteams * a.team_warps * 32));
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = a.overlap_previous ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
   return check_launch();
 }
 

@@ -23,8 +23,8 @@ def flip_index_from_pairs(num_joints, flip_pairs, device):
 
 
 class FusedHeatmapStep:
-    """Reusable launcher: caches the parameter blocks and the output buffers for one shape, so a
-    steady-state call is three kernel launches (fused plane kernel, loss reduce, loss finalise)."""
+    """Reusable launcher for one configuration; a call is ONE kernel launch (decode + render + loss sums +
+    fixed-order reduction + finalisation, lhn_fused_render_loss_decode)."""
 
     def __init__(self, image_size=(256, 256), sigma=2, unbiased_encoding=True, balance=True,
                  post_process="unbiased", kernel=11, flip_pairs=(), loss_weight=1.0, pos_value=0.5,
@@ -58,16 +58,16 @@ class FusedHeatmapStep:
         if self.loss_mode != L.LOSS_NONE:
             render = dict(loss_mode=self.loss_mode, image_size=self.image_size, sigma=self.sigma,
                           unbiased=self.unbiased, pos_value=self.pos_value)
-        r = ops.decode_heatmap(hm, L.MASK_NEG1, self.refine, L.XFORM_CENTER_SCALE, center, scale,
-                               hm_flip=hm_flip, flip_index=fi, blur_ksize=self.kernel,
-                               render=render, joints=joints_3d, vis=joints_3d_visible)
-        out = dict(preds=r["kpts"], hm_preds=r["hm_kpts"], idx=r["idx"], maxvals=r["kpts"][..., 2:])
-        if render is not None:
-            sums = ops.loss_reduce(r["partials"])
-            out["loss_sums"] = sums
-            out["loss"] = ops.loss_finalize(sums, self.loss_mode, "mean", self.loss_weight)[0]
-            out["target_weight"] = r["weight"].unsqueeze(-1)
-        return out
+        if render is None:
+            r = ops.decode_heatmap(hm, L.MASK_NEG1, self.refine, L.XFORM_CENTER_SCALE, center, scale,
+                                   hm_flip=hm_flip, flip_index=fi, blur_ksize=self.kernel)
+            return dict(preds=r["kpts"], hm_preds=r["hm_kpts"], idx=r["idx"], maxvals=r["kpts"][..., 2:])
+        # one launch: decode + render + loss sums + fixed-order reduction + finalisation
+        r = ops.fused_render_loss_decode(hm, L.MASK_NEG1, self.refine, L.XFORM_CENTER_SCALE, center, scale,
+                                         render, joints_3d, joints_3d_visible, hm_flip=hm_flip, flip_index=fi,
+                                         blur_ksize=self.kernel, loss_scale=self.loss_weight)
+        return dict(preds=r["kpts"], hm_preds=r["hm_kpts"], idx=r["idx"], maxvals=r["kpts"][..., 2:],
+                    loss_sums=r["sums"], loss=r["loss"][0], target_weight=r["weight"].unsqueeze(-1))
 
 
 def fused_render_loss_decode(hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None,
@@ -168,13 +168,15 @@ class HostPipeline:
 
 
 class BoundFusedStep:
-    """A FusedHeatmapStep bound to fixed device buffers: every ctypes argument is built once, outputs
-    are preallocated, so a steady-state step is three raw C-ABI launches (fused plane kernel, loss
-    reduce, loss finalise) — and ``capture()`` records them into a CUDA graph, which turns the step
-    into a single graph launch (the inner loop is launch-bound at ~0.1 ms of GPU work per step)."""
+    """A FusedHeatmapStep bound to fixed device buffers: every ctypes argument is built once, outputs are
+    preallocated, and a steady-state step is ONE raw C-ABI launch (lhn_fused_render_loss_decode: the kernel
+    reduces and finalises the loss itself).  ``capture()`` records it into a CUDA graph (the inner loop is
+    launch-bound at ~0.1 ms of GPU work per step)."""
 
     def __init__(self, step, hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None,
-                 finalize=True):
+                 finalize=True, overlap_previous=False):
+        """overlap_previous: this step shares no buffer with the step launched just before it on the stream
+        (rotating input/output sets), so its kernel may start while that one drains (LHN_FLAG_OVERLAP_PREVIOUS)."""
         import ctypes as C
         self.step = step
         lib = L.lib()
@@ -195,7 +197,8 @@ class BoundFusedStep:
             vis = vis.unsqueeze(-1).contiguous()
         center, scale = ops._f32c(center, "center"), ops._f32c(scale, "scale")
         self._keep += [joints, vis, center, scale]
-        self.dp = ops._decode_params(L.MASK_NEG1, step.refine, L.XFORM_CENTER_SCALE, blur_ksize=step.kernel)
+        self.dp = ops._decode_params(L.MASK_NEG1, step.refine, L.XFORM_CENTER_SCALE, blur_ksize=step.kernel,
+                                     flags=L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0)
         self.rp = ops._render_params(step.loss_mode, step.image_size, step.sigma, step.unbiased, step.pos_value)
         self.hm_preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
         self.preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
@@ -205,6 +208,16 @@ class BoundFusedStep:
         self.sums = torch.empty(4, dtype=torch.float64, device=dev)
         self.loss = torch.empty(1, dtype=torch.float32, device=dev)
         self.finalize = finalize
+        # one-launch step: the kernel reduces the loss sums itself; `finalize=False` (multi-GPU) leaves the
+        # f64 sums for the cross-rank all-reduce and finalises afterwards with launch_finalize()
+        self.workspace = torch.zeros(int(lib.lhn_fused_workspace_bytes(B, Cc // self.rp.num_stacks, self.rp.num_stacks)),
+                                     dtype=torch.uint8, device=dev)
+        self._fused_args = (
+            L.ptr(hm), L.ptr(hm_flip), L.ptr(fi), L.dtype_code(hm), B, Cc // self.rp.num_stacks, H, W, sb, sc, fb, fc,
+            L.ptr(center), L.ptr(scale), C.byref(self.dp), L.ptr(self.hm_preds), L.ptr(self.preds),
+            L.ptr(self.idx), C.byref(self.rp), L.ptr(joints), joints.shape[2], L.ptr(vis), vis.shape[2],
+            L.ptr(self.weight), None, L.ptr(self.workspace), self.workspace.numel(), L.ptr(self.sums), 0,
+            float(step.loss_weight), L.ptr(self.loss) if finalize else None)
         self._decode_args = (
             L.ptr(hm), L.ptr(hm_flip), L.ptr(fi), L.dtype_code(hm), B, Cc, H, W, sb, sc, fb, fc,
             L.ptr(center), L.ptr(scale), C.byref(self.dp), L.ptr(self.hm_preds), L.ptr(self.preds),
@@ -213,9 +226,13 @@ class BoundFusedStep:
         self._p_partials, self._p_sums, self._p_loss = L.ptr(self.partials), L.ptr(self.sums), L.ptr(self.loss)
         self.n_planes = B * Cc
         self.graph = None
-        self.launches_per_step = 3 if finalize else 2
+        self.launches_per_step = 1 if finalize else 2     # N > 1: + finalize after the all-reduce
 
     def launch_kernel(self, stream):
+        L.check(self._lib.lhn_fused_render_loss_decode(*self._fused_args, stream), "lhn_fused_render_loss_decode")
+
+    def launch_kernel_partials(self, stream):
+        """The three-launch form (per-plane partials -> reduce -> finalise), kept for comparison tests."""
         L.check(self._lib.lhn_decode_heatmap(*self._decode_args, stream), "lhn_decode_heatmap")
 
     def launch_reduce(self, stream):
@@ -233,9 +250,6 @@ class BoundFusedStep:
         self.launch_kernel(st)
         if events is not None:
             events[1].record()
-        self.launch_reduce(st)
-        if self.finalize:
-            self.launch_finalize(st)
 
     def capture(self):
         """Record the step into a CUDA graph (warm-up launch first so attributes are set eagerly)."""

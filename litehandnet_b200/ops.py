@@ -10,10 +10,11 @@ from . import _lib as L
 _REFINE_KSIZE = {L.REFINE_DARK: 11, L.REFINE_DARK_LEGACY: 19}
 
 
-def _decode_params(mask_mode, refine, transform, scale_xy=(1.0, 1.0), blur_ksize=None, use_udp=False):
+def _decode_params(mask_mode, refine, transform, scale_xy=(1.0, 1.0), blur_ksize=None, use_udp=False, flags=0):
     dp = L.DecodeParams()
     dp.mask_mode, dp.refine, dp.transform, dp.use_udp = int(mask_mode), int(refine), int(transform), int(bool(use_udp))
     dp.scale_x, dp.scale_y = float(scale_xy[0]), float(scale_xy[1])
+    dp.flags = int(flags)
     if refine in _REFINE_KSIZE:
         k = int(blur_ksize) if blur_ksize else _REFINE_KSIZE[refine]
         dp.blur_ksize = k
@@ -130,6 +131,91 @@ def decode_heatmap(hm, mask_mode, refine, transform=L.XFORM_NONE, center=None, s
     res = dict(hm_kpts=out_hm, kpts=out_k, idx=out_idx)
     if partials is not None:
         res["partials"], res["weight"] = partials, weight
+    return res
+
+
+_WORKSPACES = {}
+
+
+def fused_workspace(device, B, K, S=1, stream_key=None):
+    """Zero-initialised workspace of the one-launch step, cached per (device, stream, size): the kernel
+    leaves it zeroed, so it is memset only once."""
+    need = int(L.lib().lhn_fused_workspace_bytes(int(B), int(K), int(S)))
+    if stream_key is None:
+        stream_key = torch.cuda.current_stream(device).cuda_stream
+    key = (str(device), stream_key)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def fused_render_loss_decode(hm, mask_mode, refine, transform, center, scale, render, joints, vis,
+                             hm_flip=None, flip_index=None, blur_ksize=None, use_udp=False, scale_xy=(1.0, 1.0),
+                             want_idx=True, want_partials=False, reduction="mean", loss_scale=1.0,
+                             want_loss=True, out=None, workspace=None):
+    """The headline step in ONE launch (lhn_fused_render_loss_decode): as decode_heatmap(render=...) plus
+    the deterministic loss reduction and finalisation.  Returns dict(hm_kpts, kpts, idx, weight,
+    sums f64[4], loss f32[1] (if want_loss)[, partials])."""
+    out = out or {}
+    hm, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
+    dev = hm.device
+    fb = fc = 0
+    if hm_flip is not None:
+        hm_flip, B2, C2, H2, W2, fb, fc = _plane_view(hm_flip, "flipped heatmaps")
+        if (B2, C2, H2, W2) != (B, Cc, H, W) or hm_flip.dtype != hm.dtype:
+            raise L.LhnError("flipped heatmaps must match heatmaps in shape and dtype")
+    if render is None or render.get("loss_mode", L.LOSS_NONE) == L.LOSS_NONE:
+        raise L.LhnError("fused_render_loss_decode needs a loss mode")
+    rp = _render_params(render["loss_mode"], render["image_size"], render["sigma"],
+                        render.get("unbiased", True), render.get("pos_value", 0.5))
+    S = rp.num_stacks
+    if Cc % S:
+        raise L.LhnError("channel count is not a multiple of the number of stacks")
+    K = Cc // S
+    joints = _f32c(joints, "joints")
+    vis = _f32c(vis, "vis")
+    if joints.dim() != 3 or joints.shape[0] != B or joints.shape[2] < 2:
+        raise L.LhnError("joints must be [B,K,>=2]")
+    if vis.dim() == 2:
+        vis = vis.unsqueeze(-1).contiguous()
+    if flip_index is not None:
+        flip_index = L.require_cuda(flip_index, "flip_index").to(torch.int32).contiguous()
+        if flip_index.numel() != K:
+            raise L.LhnError("flip_index must have K entries")
+    center = _f32c(center, "center")
+    scale = _f32c(scale, "scale")
+    dp = _decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp)
+
+    def _get(name, shape, dtype, want=True):
+        t = out.get(name)
+        if t is None and want:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+        if t is not None and (t.dtype != dtype or t.numel() != int(torch.Size(shape).numel()) or
+                              not t.is_contiguous() or t.device != dev):
+            raise L.LhnError(f"preallocated output '{name}' has the wrong dtype/size/layout/device")
+        return t
+
+    out_hm = _get("hm_kpts", (B, Cc, 3), torch.float32)
+    out_k = _get("kpts", (B, Cc, 3), torch.float32)
+    out_idx = _get("idx", (B, Cc), torch.int32, want_idx)
+    weight = _get("weight", (B, Cc), torch.float32)
+    partials = _get("partials", (B * Cc, 4), torch.float64, want_partials)
+    sums = _get("sums", (4,), torch.float64)
+    loss = _get("loss", (1,), torch.float32, want_loss)
+    ws = workspace if workspace is not None else fused_workspace(dev, B, K, S)
+    rc = L.lib().lhn_fused_render_loss_decode(
+        L.ptr(hm), L.ptr(hm_flip), L.ptr(flip_index), L.dtype_code(hm), B, K, H, W, sb, sc, fb, fc,
+        L.ptr(center), L.ptr(scale), C.byref(dp), L.ptr(out_hm), L.ptr(out_k), L.ptr(out_idx),
+        C.byref(rp), L.ptr(joints), joints.shape[2], L.ptr(vis), vis.shape[2], L.ptr(weight), L.ptr(partials),
+        L.ptr(ws), ws.numel(), L.ptr(sums), int(reduction == "sum"), float(loss_scale), L.ptr(loss), L.stream())
+    L.check(rc, "lhn_fused_render_loss_decode")
+    res = dict(hm_kpts=out_hm, kpts=out_k, idx=out_idx, weight=weight, sums=sums)
+    if loss is not None:
+        res["loss"] = loss
+    if partials is not None:
+        res["partials"] = partials
     return res
 
 

@@ -46,3 +46,10 @@ stat('team: total (entry -> finish)', finish - entry)
 per_sm = (finish - entry).reshape(148, 6)
 stat('SM: slowest team total', per_sm.max(axis=1))
 print('kernel cycles if every SM ran at its slowest team:', per_sm.max())
+
+# wall-clock view (globaltimer, ns): SM clock actually seen by the kernel and its span across the chip
+g0, g1 = T[:, 0, 13], T[:, 1, 13]
+mhz = (finish - entry) / (g1 - g0) * 1e3
+stat('SM clock seen by the kernel (MHz)', mhz)
+print(f'first entry -> last finish: {(g1.max() - g0.min()) / 1e3:.1f} us; entry skew {(g0.max() - g0.min()) / 1e3:.1f} us; '
+      f'finish skew {(g1.max() - g1.min()) / 1e3:.1f} us')

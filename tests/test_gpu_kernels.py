@@ -238,6 +238,44 @@ def test_fused_render_loss_decode(ops, L, flip, unbiased):
     assert np.array_equal(nump(r["idx"]) if hf is None else O.argmax_planes(avg)[0], O.argmax_planes(avg)[0])
 
 
+@pytest.mark.parametrize("shape,flip", [((37, 21, 64, 64), True), ((1000, 21, 64, 64), True), ((9, 16, 56, 56), False),
+                                        ((3, 4, 128, 128), True), ((2, 3, 21, 64, 64), False)])
+def test_one_launch_step_equals_three_launches(ops, L, shape, flip):
+    """lhn_fused_render_loss_decode (kernel-side fixed-order reduction + finalisation) against
+    lhn_decode_heatmap -> lhn_loss_reduce -> lhn_loss_finalize; also the CTA-per-plane fallback shape
+    (128x128 f32 with flip), a stacked [N,S,K,H,W] shape, determinism and the self-resetting workspace."""
+    stacked = len(shape) == 5
+    N, K, H, W = (shape[0], shape[2], shape[3], shape[4]) if stacked else shape
+    S = shape[1] if stacked else 1
+    hm, cen = synth.blob_heatmaps(N, S * K, H, W, seed=41, zero_frac=0.03, tie_frac=0.03)
+    hf = synth.flipped_blob_heatmaps(cen, H, W, seed=42) if flip else None
+    center, scale = synth.bbox_center_scale(N, seed=43)
+    j, v = synth.hand_joints(N, K, (4 * W, 4 * H), seed=44, outside_frac=0.05, vis_prob=0.9)
+    sig = [2.0, 3.0, 2.5][:S] if stacked else 2
+    render = dict(loss_mode=L.LOSS_DISTANCE_BALANCE, image_size=(4 * W, 4 * H), sigma=sig, unbiased=True)
+    args = (cu(hm.numpy()), L.MASK_NEG1, L.REFINE_DARK, L.XFORM_CENTER_SCALE, cu(center.numpy()), cu(scale.numpy()))
+    kw = dict(hm_flip=None if hf is None else cu(hf.numpy()), blur_ksize=11)
+    a = ops.decode_heatmap(*args, render=render, joints=cu(j.numpy()), vis=cu(v.numpy()), **kw)
+    sums3 = ops.loss_reduce(a["partials"])
+    loss3 = ops.loss_finalize(sums3, L.LOSS_DISTANCE_BALANCE, "mean", 0.7)
+    ws = torch.zeros(int(L.lib().lhn_fused_workspace_bytes(N, K, S)), dtype=torch.uint8, device=DEV)
+    b = ops.fused_render_loss_decode(*args, render, cu(j.numpy()), cu(v.numpy()), loss_scale=0.7, want_partials=True,
+                                     workspace=ws, **kw)
+    torch.cuda.synchronize()
+    for k in ("hm_kpts", "kpts", "idx", "weight", "partials"):
+        assert torch.equal(a[k], b[k]), k
+    np.testing.assert_allclose(nump(b["sums"]), nump(sums3), rtol=1e-12)
+    assert nump(b["sums"])[2] == nump(sums3)[2] and nump(b["sums"])[3] == nump(sums3)[3]      # integer counts
+    np.testing.assert_allclose(nump(b["loss"]), nump(loss3), rtol=2e-7)
+    assert int(torch.count_nonzero(ws[:256])) == 0, "the ticket must be left at zero"
+    c = ops.fused_render_loss_decode(*args, render, cu(j.numpy()), cu(v.numpy()), loss_scale=0.7, workspace=ws, **kw)
+    assert torch.equal(b["sums"], c["sums"]) and torch.equal(b["loss"], c["loss"]), "reduction must be reproducible"
+    assert "partials" not in c
+    # sums only (multi-GPU form): no loss pointer
+    d = ops.fused_render_loss_decode(*args, render, cu(j.numpy()), cu(v.numpy()), want_loss=False, workspace=ws, **kw)
+    assert torch.equal(d["sums"], b["sums"]) and "loss" not in d
+
+
 def test_fused_golden_loss(ops, L):
     g = load_golden("render_loss_64.npz")
     hm = np.nan_to_num(load_golden("decode_64.npz")["hm"], nan=0.25, posinf=1.0, neginf=-1.0)
