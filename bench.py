@@ -219,6 +219,14 @@ def run_gpu_arm(args, rank, local_rank, world):
         for b in bound:
             b.capture()
 
+    pending = []                                          # (async all-reduce, step) awaiting finalisation
+
+    def flush():
+        while pending:
+            work, pb_ = pending.pop(0)
+            work.wait()                                   # compute stream waits for the NCCL stream
+            pb_.launch_finalize(fused.L.stream())
+
     def one_step(i, events=None):
         b = bound[i % R]
         if use_graph and events is None:
@@ -226,8 +234,10 @@ def run_gpu_arm(args, rank, local_rank, world):
         else:
             b.launch(events)
         if world > 1:
-            dist.all_reduce(b.sums)                       # global N_pos / sums for the balanced loss
-            b.launch_finalize(fused.L.stream())
+            # Global N_pos / sums for the balanced loss: the 32-byte all-reduce of step i runs on the NCCL stream
+            # while the kernel of step i+1 runs; step i is finalised right after that kernel is queued.
+            flush()
+            pending.append((dist.all_reduce(b.sums, async_op=True), b))
 
     def fence():
         torch.cuda.synchronize()
@@ -238,6 +248,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- warm-up, then the timed region ------------------------------------------------------------
     for i in range(args.warmup):
         one_step(i)
+    flush()
     fence()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
@@ -245,6 +256,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     e0.record()
     for i in range(args.steps):
         one_step(i)
+    flush()
     e1.record()
     fence()
     clocks = sampler.stop()

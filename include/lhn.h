@@ -206,6 +206,41 @@ LHN_API int lhn_loss_reduce(const double* partials, int64_t n_planes, double* su
 LHN_API int lhn_loss_finalize(const double* sums, int loss_mode, int sum_reduction, float scale,
                               float* loss, int accumulate, lhn_stream_t stream);
 
+/* ---- backward of the losses (lets the drop-in losses sit in train_one_epoch,
+ * train/topdown_trainer.py:68-87, behind torch.autograd.Function) ---------------------------------
+ * grad[p,e] = grad_out[0] * scale * coef(p,e) * (output[p,e] - target[p,e]), coef from the forward's
+ * f64 sums (S_pos, S_neg, N_pos, numel):
+ *   LHN_LOSS_DISTANCE          2 w / numel
+ *   LHN_LOSS_DISTANCE_BALANCE  2 w * 0.1/(N_pos+1) where target > pos_value, else 2 w / (N_neg+1)
+ *   LHN_LOSS_JOINTS_MSE        w^2 / numel
+ * (x numel when sum_reduction != 0) — the derivative of DistanceLoss.forward / JointsDistanceLoss.forward
+ * (heatmapLoss.py:242-265, :195-225) as torch autograd computes it.  grad_out: f32 [1] device pointer
+ * (the upstream gradient of the scalar loss) or NULL (= 1).  grad: same dtype and [P, HW] layout as
+ * output.  One pass: reads output and target once, writes grad once. */
+LHN_API int lhn_loss_backward(const void* output, const void* target, const float* weight, int dtype,
+                              int64_t n_planes, int64_t plane_elems, int loss_mode, float pos_value,
+                              const double* sums, int sum_reduction, float scale, const float* grad_out,
+                              void* grad, lhn_stream_t stream);
+
+/* The same with the target rendered in-kernel from the joints (the backward of the fused entry):
+ * hm [B, S*K, H, W] with element strides as lhn_decode_heatmap, rp->loss_mode selects the loss;
+ * grad is contiguous [B, S*K, H, W] of the heatmap dtype. */
+LHN_API int lhn_render_loss_backward(const void* hm, int dtype, int64_t B, int K, int H, int W,
+                                     int64_t stride_b, int64_t stride_c, const lhn_render_params* rp,
+                                     const float* joints, int joints_stride, const float* vis,
+                                     int vis_stride, const double* sums, int sum_reduction, float scale,
+                                     const float* grad_out, void* grad, lhn_stream_t stream);
+
+/* KLDiscretLoss backward (centernet_simdr_loss.py:27-39): grad_x[b,j,i] = grad_out * scale *
+ * SmoothL1'(out_x - tgt_x) * mean_b(weight[b,j]) / (K * B * Lx), likewise grad_y.  workspace:
+ * lhn_simdr_backward_workspace_bytes(K) bytes. */
+LHN_API int64_t lhn_simdr_backward_workspace_bytes(int K);
+LHN_API int lhn_simdr_smoothl1_backward(const void* out_x, const void* out_y, const void* tgt_x,
+                                        const void* tgt_y, const float* weight, int dtype, int64_t B,
+                                        int K, int Lx, int Ly, float scale, const float* grad_out,
+                                        void* workspace, int64_t workspace_bytes, void* grad_x,
+                                        void* grad_y, lhn_stream_t stream);
+
 /* ---- render (the un-fused drop-in; write-bound) -----------------------------------------------
  * TopDownGenerateTarget (generateTarget.py:100-154,245-300) for a batch: target f32
  * [B, S, K, H, W] contiguous, target_weight f32 [B, S, K]. */

@@ -32,6 +32,8 @@ EXPORTS = [
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_simdr_loss_workspace_bytes",
     "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
+    "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
+    "lhn_simdr_smoothl1_backward",
 ]
 
 
@@ -67,6 +69,13 @@ def _declare(lib):
     lib.lhn_fused_render_loss_decode.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, i64, i64, i64, i64, vp, vp,
                                                  C.POINTER(DecodeParams), vp, vp, vp, C.POINTER(RenderParams),
                                                  vp, i32, vp, i32, vp, vp, vp, i64, vp, i32, f32, vp, vp]
+    lib.lhn_loss_backward.argtypes = [vp, vp, vp, i32, i64, i64, i32, f32, vp, i32, f32, vp, vp, vp]
+    lib.lhn_render_loss_backward.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, C.POINTER(RenderParams),
+                                             vp, i32, vp, i32, vp, i32, f32, vp, vp, vp]
+    lib.lhn_simdr_backward_workspace_bytes.argtypes = [i32]
+    lib.lhn_simdr_backward_workspace_bytes.restype = i64
+    lib.lhn_simdr_smoothl1_backward.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, i64,
+                                                vp, vp, vp]
     lib.lhn_decode_heatmap_pck.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp,
                                            C.POINTER(DecodeParams), vp, vp, vp, vp, vp, vp, f32, f32,
                                            i32, vp, vp]

@@ -3,9 +3,12 @@ loss/loss.py, loss/__init__.py) — same class names, constructor arguments, cal
 types and error behaviour; the arithmetic runs in the CUDA library.
 
 Scope: L2-type DistanceLoss (balance on/off, mean/sum), JointsDistanceLoss mse,
-KLDiscretLoss, SimDRLoss, TopdownHeatmapLoss, SRHandNetLoss (heatmap-only branch), get_loss.  The
-forward value is computed on the GPU; autograd through these losses is SURVEY §8f "next" (rank 1) and
-is not provided — the returned tensors carry no grad_fn.
+KLDiscretLoss, SimDRLoss, TopdownHeatmapLoss, SRHandNetLoss (heatmap-only branch), get_loss.
+
+Autograd: every loss is a torch.autograd.Function whose backward is one streaming CUDA
+kernel (lhn_loss_backward / lhn_render_loss_backward / lhn_simdr_smoothl1_backward) driven by the forward's
+f64 sums, so ``loss, d = criterion(outputs, meta); loss.backward()`` works as in
+train/topdown_trainer.py:68-87.  Gradients flow to the network output only (targets and weights are data).
 """
 import torch
 from torch import nn
@@ -18,6 +21,58 @@ def _as_cuda(t, device):
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(t)
     return t.to(device)          # the reference moves meta['target'] to the output's device (loss.py:97-98)
+
+
+class _HeatmapLossFn(torch.autograd.Function):
+    """forward: per-plane sums -> fixed-order reduce -> finalise; backward: lhn_loss_backward."""
+
+    @staticmethod
+    def forward(ctx, output, target, weight, mode, value, reduction):
+        partials = ops.loss_partials(output.detach(), target, weight, mode, value)
+        sums = ops.loss_reduce(partials)
+        ctx.save_for_backward(output.detach(), target, weight, sums)
+        ctx.cfg = (mode, value, reduction)
+        return ops.loss_finalize(sums, mode, reduction)[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        output, target, weight, sums = ctx.saved_tensors
+        mode, value, reduction = ctx.cfg
+        g = ops.loss_backward(output, target, weight, mode, sums, value, reduction, 1.0, grad_out)
+        return g, None, None, None, None, None
+
+
+class _FusedHeatmapLossFn(torch.autograd.Function):
+    """The fused entry: target rendered in-kernel from the joints, one launch forward
+    (lhn_fused_render_loss_decode without a refinement), lhn_render_loss_backward backward."""
+
+    @staticmethod
+    def forward(ctx, output, joints, vis, render, reduction):
+        r = ops.fused_render_loss_decode(output.detach(), L.MASK_NEG1, L.REFINE_NONE, L.XFORM_NONE, None, None,
+                                         render, joints, vis, want_idx=False, reduction=reduction)
+        ctx.save_for_backward(output.detach(), joints, vis, r["sums"])
+        ctx.cfg = (render, reduction)
+        ctx.mark_non_differentiable(r["weight"])
+        return r["loss"][0], r["weight"]
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_w):
+        output, joints, vis, sums = ctx.saved_tensors
+        render, reduction = ctx.cfg
+        return ops.render_loss_backward(output, joints, vis, render, sums, reduction, 1.0, grad_out), None, None, None, None
+
+
+class _SimDRLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out_x, out_y, tgt_x, tgt_y, weight):
+        ctx.save_for_backward(out_x.detach(), out_y.detach(), tgt_x, tgt_y, weight)
+        return ops.simdr_smoothl1(out_x.detach(), out_y.detach(), tgt_x, tgt_y, weight)[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out_x, out_y, tgt_x, tgt_y, weight = ctx.saved_tensors
+        gx, gy = ops.simdr_smoothl1_backward(out_x, out_y, tgt_x, tgt_y, weight, 1.0, grad_out)
+        return gx, gy.to(out_y.dtype), None, None, None
 
 
 class DistanceLoss(nn.Module):
@@ -44,22 +99,18 @@ class DistanceLoss(nn.Module):
         L.require_cuda(output, "output")
         target = _as_cuda(target, output.device)
         target_weight = _as_cuda(target_weight, output.device)
-        partials = ops.loss_partials(output.detach(), target, target_weight, self._mode, self.value)
-        sums = ops.loss_reduce(partials)
-        return ops.loss_finalize(sums, self._mode, self.reduction)[0]
+        return _HeatmapLossFn.apply(output, target, target_weight, self._mode, self.value, self.reduction)
 
     def forward_fused(self, output, joints_3d, joints_3d_visible, image_size, sigma=2,
                       unbiased_encoding=True):
         """Additive fused entry: render the target in-kernel from the joints instead of
         reading a target tensor.  Returns (loss, target_weight [.., 1])."""
         L.require_cuda(output, "output")
-        r = ops.decode_heatmap(output.detach(), L.MASK_NEG1, L.REFINE_NONE, want_idx=False,
-                               render=dict(loss_mode=self._mode, image_size=image_size, sigma=sigma,
-                                           unbiased=unbiased_encoding, pos_value=self.value),
-                               joints=_as_cuda(joints_3d, output.device),
-                               vis=_as_cuda(joints_3d_visible, output.device))
-        sums = ops.loss_reduce(r["partials"])
-        return ops.loss_finalize(sums, self._mode, self.reduction)[0], r["weight"].unsqueeze(-1)
+        render = dict(loss_mode=self._mode, image_size=image_size, sigma=sigma, unbiased=unbiased_encoding,
+                      pos_value=self.value)
+        loss, weight = _FusedHeatmapLossFn.apply(output, _as_cuda(joints_3d, output.device),
+                                                 _as_cuda(joints_3d_visible, output.device), render, self.reduction)
+        return loss, weight.unsqueeze(-1)
 
 
 class JointsDistanceLoss(nn.Module):
@@ -80,8 +131,7 @@ class JointsDistanceLoss(nn.Module):
             w = _as_cuda(target_weight, output.device)
         else:
             w = torch.ones(output.shape[:2], device=output.device)
-        partials = ops.loss_partials(output.detach(), _as_cuda(target, output.device), w, L.LOSS_JOINTS_MSE)
-        return ops.loss_finalize(ops.loss_reduce(partials), L.LOSS_JOINTS_MSE)[0]
+        return _HeatmapLossFn.apply(output, _as_cuda(target, output.device), w, L.LOSS_JOINTS_MSE, 0.5, "mean")
 
 
 class KLDiscretLoss(nn.Module):
@@ -91,8 +141,8 @@ class KLDiscretLoss(nn.Module):
     def forward(self, output_x, output_y, target_x, target_y, target_weight):
         L.require_cuda(output_x, "output_x")
         dev = output_x.device
-        return ops.simdr_smoothl1(output_x.detach(), _as_cuda(output_y, dev).detach(), _as_cuda(target_x, dev),
-                                  _as_cuda(target_y, dev), _as_cuda(target_weight, dev))[0]
+        return _SimDRLossFn.apply(output_x, _as_cuda(output_y, dev), _as_cuda(target_x, dev),
+                                  _as_cuda(target_y, dev), _as_cuda(target_weight, dev))
 
 
 class SimDRLoss(nn.Module):
@@ -188,14 +238,11 @@ class SRHandNetLoss(nn.Module):
 
     def _forward_only_heatmap(self, outputs, targets, target_weight):
         device = outputs[-1].device
-        sums_out = torch.zeros(1, dtype=torch.float32, device=device)
-        mode = L.LOSS_DISTANCE_BALANCE
+        loss = 0
         for i in range(self.num_out):
             w = target_weight[i] if isinstance(target_weight, (list, tuple)) else target_weight
-            partials = ops.loss_partials(outputs[i].detach(), _as_cuda(targets[i], device), _as_cuda(w, device), mode)
-            ops.loss_finalize(ops.loss_reduce(partials), mode, 'mean', float(self.loss_weight[i]),
-                              out=sums_out, accumulate=True)
-        loss = sums_out[0]
+            loss = loss + self.loss_weight[i] * self.mse_loss(outputs[i], _as_cuda(targets[i], device),
+                                                              _as_cuda(w, device))
         return loss, dict(kpt_loss=loss.item())
 
 

@@ -264,6 +264,70 @@ def loss_partials(output, target, weight, loss_mode, pos_value=0.5):
     return partials
 
 
+def _grad_out_ptr(grad_out, device):
+    if grad_out is None:
+        return None, None
+    g = L.require_cuda(grad_out, "grad_output").detach().to(torch.float32).reshape(1).contiguous()
+    return g, L.ptr(g)
+
+
+def loss_backward(output, target, weight, loss_mode, sums, pos_value=0.5, reduction="mean", scale=1.0,
+                  grad_out=None):
+    """d loss / d output for the explicit-target losses (lhn_loss_backward); returns a tensor like output."""
+    L.require_cuda(output, "output")
+    L.require_cuda(target, "target")
+    if target.dtype != output.dtype:
+        target = target.to(output.dtype)
+    output, target = output.contiguous(), target.contiguous()
+    H, W = output.shape[-2:]
+    P = output.numel() // (H * W)
+    weight = _f32c(weight, "target_weight").reshape(-1)
+    grad = torch.empty_like(output)
+    keep, gp = _grad_out_ptr(grad_out, output.device)
+    rc = L.lib().lhn_loss_backward(L.ptr(output), L.ptr(target), L.ptr(weight), L.dtype_code(output), P, H * W,
+                                   int(loss_mode), float(pos_value), L.ptr(sums), int(reduction == "sum"),
+                                   float(scale), gp, L.ptr(grad), L.stream())
+    L.check(rc, "lhn_loss_backward")
+    return grad
+
+
+def render_loss_backward(hm, joints, vis, render, sums, reduction="mean", scale=1.0, grad_out=None):
+    """d loss / d hm for the fused (render-in-kernel) losses (lhn_render_loss_backward)."""
+    hm_v, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
+    rp = _render_params(render["loss_mode"], render["image_size"], render["sigma"],
+                        render.get("unbiased", True), render.get("pos_value", 0.5))
+    K = Cc // rp.num_stacks
+    joints = _f32c(joints, "joints")
+    vis = _f32c(vis, "vis")
+    if vis.dim() == 2:
+        vis = vis.unsqueeze(-1).contiguous()
+    grad = torch.empty(hm.shape, dtype=hm.dtype, device=hm.device)
+    keep, gp = _grad_out_ptr(grad_out, hm.device)
+    rc = L.lib().lhn_render_loss_backward(L.ptr(hm_v), L.dtype_code(hm_v), B, K, H, W, sb, sc, C.byref(rp),
+                                          L.ptr(joints), joints.shape[2], L.ptr(vis), vis.shape[2], L.ptr(sums),
+                                          int(reduction == "sum"), float(scale), gp, L.ptr(grad), L.stream())
+    L.check(rc, "lhn_render_loss_backward")
+    return grad
+
+
+def simdr_smoothl1_backward(out_x, out_y, tgt_x, tgt_y, weight, scale=1.0, grad_out=None):
+    dt = out_x.dtype
+    out_x, out_y = out_x.contiguous(), out_y.to(dt).contiguous()
+    tgt_x, tgt_y = tgt_x.to(dt).contiguous(), tgt_y.to(dt).contiguous()
+    B, K, Lx = out_x.shape
+    Ly = out_y.shape[2]
+    weight = _f32c(weight, "target_weight").reshape(B, K)
+    nbytes = int(L.lib().lhn_simdr_backward_workspace_bytes(K))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=out_x.device)
+    gx, gy = torch.empty_like(out_x), torch.empty_like(out_y)
+    keep, gp = _grad_out_ptr(grad_out, out_x.device)
+    rc = L.lib().lhn_simdr_smoothl1_backward(L.ptr(out_x), L.ptr(out_y), L.ptr(tgt_x), L.ptr(tgt_y), L.ptr(weight),
+                                             L.dtype_code(out_x), B, K, Lx, Ly, float(scale), gp, L.ptr(ws), nbytes,
+                                             L.ptr(gx), L.ptr(gy), L.stream())
+    L.check(rc, "lhn_simdr_smoothl1_backward")
+    return gx, gy
+
+
 def loss_reduce(partials, sums=None, accumulate=False):
     if sums is None:
         sums = torch.empty(4, dtype=torch.float64, device=partials.device)

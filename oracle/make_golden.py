@@ -165,6 +165,46 @@ def metrics_case(ref, name, N, K, seed):
     np.savez_compressed(os.path.join(OUT, name), **d)
 
 
+def backward_case(ref, name, seed):
+    """Gradients of the reference losses by torch autograd on the CPU: the explicit-target
+    heatmap losses on a rendered target, and KLDiscretLoss on SimDR vectors."""
+    N, K, H, W = 2, 4, 32, 32
+    hm, _ = synth.blob_heatmaps(N, K, H, W, seed=seed, sigma=1.5, margin=3.0)
+    joints, vis = synth.hand_joints(N, K, (128, 128), seed=seed + 1, vis_prob=0.8)
+    gen = ref.generateTarget.TopDownGenerateTarget(sigma=1.5, unbiased_encoding=True)
+    tg, tw = [], []
+    for b in range(N):
+        res = dict(joints_3d=joints[b].numpy().copy(), joints_3d_visible=vis[b].numpy().copy(),
+                   ann_info=_ann(K, (128, 128), (W, H)))
+        out = gen(res)
+        tg.append(out["target"]); tw.append(out["target_weight"])
+    tg, tw = torch.from_numpy(np.stack(tg)), torch.from_numpy(np.stack(tw))
+    tw[0, 1, 0] = 0.5                                  # a fractional weight: w vs w^2 must differ
+    d = dict(hm=hm.numpy(), target=tg.numpy(), target_weight=tw.numpy(), joints_3d=joints.numpy(),
+             joints_3d_visible=vis.numpy(), sigma=np.float32(1.5), image_size=np.array([128, 128]))
+    HL = ref.loss.heatmapLoss if hasattr(ref.loss, "heatmapLoss") else ref.loss
+    for tag, crit in (("bal", HL.DistanceLoss(loss_type="L2", balance=True)),
+                      ("nobal", HL.DistanceLoss(loss_type="L2", balance=False)),
+                      ("sum", HL.DistanceLoss(loss_type="L2", balance=True, reduction="sum")),
+                      ("jmse", HL.JointsDistanceLoss(use_target_weight=True, loss_type="mse"))):
+        x = hm.clone().requires_grad_(True)
+        loss = crit(x, tg, tw)
+        (loss * 0.7).backward()                        # a non-unit upstream gradient
+        d[f"ref_loss_{tag}"] = np.float32(loss.item())
+        d[f"ref_grad_{tag}"] = x.grad.numpy()
+    # KLDiscretLoss
+    xv, yv = synth.simdr_vectors(N, K, 96, seed=seed + 2)
+    tx, ty = synth.simdr_vectors(N, K, 96, seed=seed + 3)
+    xv, yv = xv * 3.0, yv * 3.0                       # some |d| > 1 so both SmoothL1 branches are hit
+    SL = ref.loss.centernet_simdr_loss if hasattr(ref.loss, "centernet_simdr_loss") else ref.loss
+    px, py = xv.clone().requires_grad_(True), yv.clone().requires_grad_(True)
+    loss = SL.KLDiscretLoss()(px, py, tx, ty, tw)
+    (loss * 1.3).backward()
+    d.update(simdr_out_x=xv.numpy(), simdr_out_y=yv.numpy(), simdr_tgt_x=tx.numpy(), simdr_tgt_y=ty.numpy(),
+             ref_loss_simdr=np.float32(loss.item()), ref_grad_simdr_x=px.grad.numpy(), ref_grad_simdr_y=py.grad.numpy())
+    np.savez_compressed(os.path.join(OUT, name), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -176,6 +216,7 @@ def main():
     hm56, _ = synth.blob_heatmaps(2, 6, 56, 56, seed=12)
     render_loss_case(ref, "render_loss_56.npz", N=2, K=6, H=56, W=56, seed=22, image_size=(224, 224), hm=hm56)
     metrics_case(ref, "metrics_16.npz", N=48, K=16, seed=31)
+    backward_case(ref, "loss_backward.npz", seed=41)
     # the reference's only hand-derivable known answer (utils/SPheatmapParser.py:221-233)
     kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
     k, _ = ref.SPheatmapParser.HeatmapParser_SH().parse(kpt_hm.clone(), image_size=(256, 256))
