@@ -51,13 +51,13 @@ template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
 // streaming 128-bit global load (read-once data: do not allocate in L1)
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
   uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 template <typename T> __device__ __forceinline__ float4 ldg_stream4(const T* p);

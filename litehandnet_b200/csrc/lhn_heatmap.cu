@@ -650,6 +650,8 @@ extern "C" int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int 
   a.loss_mode = LHN_LOSS_NONE;
   a.gt = gt; a.mask = mask; a.bbox_wh = bbox_wh; a.pck_thr = pck_thr; a.auc_nor = auc_nor;
   a.auc_steps = auc_steps; a.counters = counters;
+  if (auc_steps > 64) return LHN_EINVAL;
+  for (int t = 0; t < auc_steps; ++t) a.auc_thr[t] = (float)(1.0 * t / auc_steps);
   if (a.n_planes == 0) return LHN_OK;
   if (a.n_planes > 0x7fffffffLL) return LHN_EINVAL;
   return run_heatmap(a, dtype, (cudaStream_t)stream);

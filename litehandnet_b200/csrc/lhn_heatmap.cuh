@@ -47,13 +47,15 @@ struct HmArgs {
   const float* bbox_wh;
   float pck_thr, auc_nor;
   int auc_steps;
+  float auc_thr[64];               // (float)(t / auc_steps) in double, t < auc_steps (top_down_eval.py:190-193)
   int64_t* counters;
   // persistent warp-per-plane kernel
   double inv2s2[LHN_MAX_STACKS];   // 1 / (2 sigma^2), host-computed in double
   float pos_radius[LHN_MAX_STACKS];// radius (px) inside which target > pos_value can hold
   int warp_smem;                   // bytes of shared memory owned by one team (stage + aux)
   int team_warps;                  // warps per team
-  int stage_bytes;                 // bytes of the TMA stage (plane0 [+ plane1]) at the start of it
+  int stage_bytes;                 // bytes of one TMA stage (plane0 [+ plane1])
+  int stages;                      // stages per team (1, 2 or 4), at the start of the team's shared memory
   int tile_dim;                    // DARK window side = blur_ksize + 4 (0 when DARK is off)
   int force_cta_kernel;            // testing: bypass the warp kernel (env LHN_FORCE_CTA_KERNEL=1)
   // one-launch loss (team kernel only; all optional): per-team f64 sums + a self-resetting ticket

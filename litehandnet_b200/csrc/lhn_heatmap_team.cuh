@@ -97,7 +97,7 @@ struct PlaneRec {
 
 // per-team header at the start of the aux region
 struct TeamHeader {
-  uint64_t bar;               // TMA completion barrier of the stage
+  uint64_t bar[4];            // TMA completion barriers of the stages
   uint64_t full[2];           // record n is complete          (sweepers -> epilogue warp)
   uint64_t empty[2];          // record/row-sum buffer is free (epilogue warp -> sweepers)
   uint64_t pad;
@@ -132,14 +132,16 @@ __device__ __forceinline__ float exp_f32_from_f64(double a) {
 // quads per row of the DARK tile: the (ksize+4)-wide window starts 0..3 columns into its first quad
 __host__ __device__ constexpr int tile_quads(int td) { return (td + 6) >> 2; }
 
-// FAST: W = H = 64 and the team size is a compile-time constant (TWC warps = TWC-1 sweepers + 1 epilogue),
-//       so the sweep is a fully unrolled 128-bit loop with a loop-invariant column quad per thread.
-// KS:   DARK Gaussian size known at compile time (11: the Gen-2 decoder) or 0 = run-time size.
-template <typename T, bool FAST, int TWC, bool FLIP, bool LOSS, int KS>
+// WC:  compile-time square plane size (64 or 56: 89 of the reference's 108 configs) with a compile-time team
+//      size (TWC warps = TWC-1 sweepers + 1 epilogue), so the sweep is a fully unrolled 128-bit loop with a
+//      loop-invariant column quad per thread and immediate address offsets; 0 = run-time H, W and team size.
+// KS:  DARK Gaussian size known at compile time (11: the Gen-2 decoder) or 0 = run-time size.
+template <typename T, int WC, int TWC, bool FLIP, bool LOSS, int KS>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
 heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int H = FAST ? 64 : a.H, W = FAST ? 64 : a.W, HW = FAST ? 4096 : a.HW;
+  constexpr bool FAST = WC > 0;
+  const int H = FAST ? WC : a.H, W = FAST ? WC : a.W, HW = FAST ? WC * WC : a.HW;
   const int TW = FAST ? TWC : a.team_warps;          // warps per team
   const int NS = TW - 1;                             // sweeper warps
   const int ST = NS * 32;                            // sweeper threads
@@ -155,9 +157,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
 
   // ---- this team's private shared memory ----------------------------------------------------------
   unsigned char* tbase = smem_raw + (size_t)team * a.warp_smem;
-  const T* plane0 = reinterpret_cast<const T*>(tbase);
-  const T* plane1 = FLIP ? reinterpret_cast<const T*>(tbase + (a.stage_bytes >> 1)) : nullptr;
-  unsigned char* aux = tbase + a.stage_bytes;
+  const int nstg = a.stages;                         // stages per team (1, 2 or 4): plane n lives in stage n % nstg
+  unsigned char* aux = tbase + (size_t)nstg * a.stage_bytes;
   TeamHeader* th = reinterpret_cast<TeamHeader*>(aux);
   const size_t tab_bytes = align_up((size_t)(W + H) * 4, 16);
   float* tab0 = reinterpret_cast<float*>(aux + align_up(sizeof(TeamHeader), 16));   // two table buffers
@@ -231,13 +232,21 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
   }
 
+  // Fused metrics: one CTA-shared set of u64 counters in shared memory (same layout as the global ones, with
+  // the AUC rows holding a histogram of "thresholds passed"), flushed once by the last epilogue warp of the CTA.
+  unsigned long long* cta_cnt = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)nteams * a.warp_smem);
+  const int n_cnt = a.counters ? (a.auc_steps + 5) * (int)K : 0;
+  unsigned int* cta_done = reinterpret_cast<unsigned int*>(cta_cnt + n_cnt);
+  for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cta_cnt[i] = 0ull;
+  if (threadIdx.x == 0 && a.counters) *cta_done = 0u;
+
   // Let the next launch on the stream (if it was launched with LHN_FLAG_OVERLAP_PREVIOUS) take over SMs as
   // this grid's CTAs retire; a no-op otherwise.
   asm volatile("griddepcontrol.launch_dependents;");
 
   // ---- one-time setup: barriers visible to the whole CTA before anybody waits on them ------------------
   if (wt == 0 && lane == 0) {
-    mbar_init(&th->bar, 1);
+    for (int i = 0; i < nstg; ++i) mbar_init(&th->bar[i], 1);
     mbar_init(&th->full[0], 1); mbar_init(&th->full[1], 1);
     mbar_init(&th->empty[0], 1); mbar_init(&th->empty[1], 1);
     fence_mbar_init();
@@ -347,6 +356,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       const uint32_t idx = rec->idx;
       const float maxval = rec->maxval;
       float rx = rec->rx, ry = rec->ry;
+      float keepX = 0.f, keepY = 0.f;                  // image-space coordinates of this plane (lane 0)
       const bool dark_guard = (rec->flags & 1) != 0, any_nan = (rec->flags & 2) != 0;
 
       bool need_slow = false;
@@ -523,33 +533,41 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           acc_sp += spos; acc_sn += sall - spos; acc_np += npos; acc_ne += (double)HW;
           if (a.out_weight) a.out_weight[p] = w;
         }
-        if (a.counters && mask_cur) {
-          // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32)
+        keepX = X; keepY = Y;
+      }
+      if (a.counters) {
+        // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32): lanes 0..2 take one
+        // normaliser each (bbox, AUC constant, 1) so the three divide / sqrt chains run side by side
+        const float Xb = __shfl_sync(0xffffffffu, keepX, 0), Yb = __shfl_sync(0xffffffffu, keepY, 0);
+        const int mk = __shfl_sync(0xffffffffu, mask_cur, 0);
+        if (mk) {
+          uint32_t s_, k;
+          split_channel(pc, s_, k);
           const int Ki = (int)K;
-          const double gx = (double)sd[SD_GX], gy = (double)sd[SD_GY];
-          const double ddx = (double)X - gx, ddy = (double)Y - gy;
-          unsigned long long* cnt = reinterpret_cast<unsigned long long*>(a.counters);
-          double nb = (double)fmaxf(sd[SD_BW], sd[SD_BH]);
-          if (nb != 0.0) {
-            if (nb < 0.0) nb = 1e6;
-            const double qx = ddx / nb, qy = ddy / nb;
-            const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
-            atomicAdd(cnt + Ki + k, 1ull);
-            if (d < a.pck_thr) atomicAdd(cnt + k, 1ull);
+          const float* sd = th->side[n_it & 7];
+          const double ddx = (double)Xb - (double)sd[SD_GX], ddy = (double)Yb - (double)sd[SD_GY];
+          double nb = lane == 0 ? (double)fmaxf(sd[SD_BW], sd[SD_BH]) : (lane == 1 ? (double)a.auc_nor : 1.0);
+          const bool counted = nb != 0.0;                   // normalize == 0 masks the sample out (PCK only)
+          if (nb < 0.0) nb = 1e6;
+          float d = 0.f;
+          if (lane < 3 && counted) {
+            const double qx = lane == 2 ? ddx : ddx / nb, qy = lane == 2 ? ddy : ddy / nb;
+            d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
           }
-          {
-            const double qx = ddx / (double)a.auc_nor, qy = ddy / (double)a.auc_nor;
-            const float d = (float)sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
-            unsigned long long* auc = cnt + 2 * Ki;
-            for (int t = 0; t < a.auc_steps; ++t) {
-              const float thr = (float)(1.0 * t / a.auc_steps);
-              if (d < thr) atomicAdd(auc + (int64_t)t * Ki + k, 1ull);
-            }
-            atomicAdd(auc + (int64_t)a.auc_steps * Ki + k, 1ull);
+          // AUC: one threshold per lane, ballot -> how many of the (increasing) thresholds d is below
+          const float d_auc = __shfl_sync(0xffffffffu, d, 1);
+          int nh = 0;
+          for (int t0 = 0; t0 < a.auc_steps; t0 += 32) {
+            const int t = t0 + lane;
+            nh += __popc(__ballot_sync(0xffffffffu, t < a.auc_steps && d_auc < a.auc_thr[t]));
           }
-          {
-            const float d = (float)sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
-            unsigned long long* epe = cnt + (int64_t)(3 + a.auc_steps) * Ki;
+          if (lane == 0 && counted) {
+            atomicAdd(cta_cnt + Ki + k, 1ull);
+            if (d < a.pck_thr) atomicAdd(cta_cnt + k, 1ull);
+          } else if (lane == 1) {
+            atomicAdd(cta_cnt + (int64_t)(2 + nh) * Ki + k, 1ull);
+          } else if (lane == 2) {
+            unsigned long long* epe = cta_cnt + (int64_t)(3 + a.auc_steps) * Ki;
             atomicAdd(epe + k, 1ull);
             atomicAdd(epe + Ki + k, (unsigned long long)llrint((double)d * 1048576.0));
           }
@@ -581,6 +599,39 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       if (lane == 0) mbar_arrive(&th->empty[buf]);   // release: record/tile buffer free, tables of n+2 ready
     }
 
+    if (a.counters) {
+      // the last epilogue warp of the CTA to finish adds the CTA's counters to the global ones
+      __syncwarp();
+      unsigned int last = 0;
+      if (lane == 0) {
+        unsigned int active = 0;
+        for (int t = 0; t < nteams; ++t) active += ((uint64_t)t * gridDim.x + blockIdx.x < n_planes) ? 1u : 0u;
+        __threadfence_block();
+        last = (atomicAdd(cta_done, 1u) == active - 1u) ? 1u : 0u;
+      }
+      if (__shfl_sync(0xffffffffu, last, 0)) {
+        __threadfence_block();
+        const int Ki = (int)K, steps = a.auc_steps;
+        unsigned long long* gcnt = reinterpret_cast<unsigned long long*>(a.counters);
+        // rows outside the AUC histogram map one to one
+        for (int e = lane; e < n_cnt; e += 32) {
+          const int row = e / Ki;
+          if (row >= 2 && row <= 2 + steps) continue;
+          const unsigned long long v = cta_cnt[e];
+          if (v) atomicAdd(gcnt + e, v);
+        }
+        // AUC: one joint per lane, a running sum down the histogram: auc_hits[t] = planes that passed at least
+        // steps - t thresholds, auc_valid = all planes
+        for (int k = lane; k < Ki; k += 32) {
+          unsigned long long run = 0ull;
+          for (int nh = steps; nh >= 0; --nh) {
+            run += cta_cnt[(int64_t)(2 + nh) * Ki + k];
+            const int row = nh >= 1 ? 2 + (steps - nh) : 2 + steps;
+            if (run) atomicAdd(gcnt + (int64_t)row * Ki + k, run);
+          }
+        }
+      }
+    }
 #ifdef LHN_TRACE
     if (lane == 0 && nteams <= 6) {
       g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 14] = clock64();
@@ -634,10 +685,11 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   // SWEEPERS
   // =======================================================================================================
   uint64_t policy = 0;
-  auto issue = [&](uint32_t b, uint32_t c) {   // one thread of the team
-    mbar_arrive_expect_tx(&th->bar, FLIP ? 2 * plane_bytes : plane_bytes);
-    tma_load_1d(const_cast<T*>(plane0), gptr0(b, c), plane_bytes, &th->bar, policy);
-    if (FLIP) tma_load_1d(const_cast<T*>(plane1), gptr1(b, c), plane_bytes, &th->bar, policy);
+  auto issue = [&](uint32_t b, uint32_t c, int stg) {   // one thread of the team
+    unsigned char* dst = tbase + (size_t)stg * a.stage_bytes;
+    mbar_arrive_expect_tx(&th->bar[stg], FLIP ? 2 * plane_bytes : plane_bytes);
+    tma_load_1d(dst, gptr0(b, c), plane_bytes, &th->bar[stg], policy);
+    if (FLIP) tma_load_1d(dst + (a.stage_bytes >> 1), gptr1(b, c), plane_bytes, &th->bar[stg], policy);
   };
 
   if (a.flip_index) {
@@ -646,17 +698,20 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   }
   if (sl == 0) {
     policy = policy_evict_first();
-    if (a.use_tma) issue(pb, pc);
+    if (a.use_tma) {
+      uint32_t ib = pb, ic = pc, ip = p;
+      for (int i = 0; i < nstg && ip < n_planes; ++i, ip += total_teams, advance(ib, ic)) issue(ib, ic, i);
+    }
   }
-  uint32_t phase = 0;
   int n_it = 0;                                    // team-local plane counter
 
   const int QR = W >> 2, nq = HW >> 2;
   const uint64_t half2 = pack2(0.5f, 0.5f);
 
   for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
-    const int buf = n_it & 1, tb = n_it % 3;
-    const bool has_next = p + total_teams < n_planes;
+    const int buf = n_it & 1, tb = n_it % 3, stg = n_it & (nstg - 1);
+    const T* plane0 = reinterpret_cast<const T*>(tbase + (size_t)stg * a.stage_bytes);
+    const T* plane1 = FLIP ? reinterpret_cast<const T*>(tbase + (size_t)stg * a.stage_bytes + (a.stage_bytes >> 1)) : nullptr;
     // the epilogue warp has written this plane's tables and is done with the record/tile buffer `buf`
     // (it finished plane n-2; it lags at most two planes)
     mbar_wait(&th->empty[buf], (uint32_t)(n_it >> 1) & 1u);
@@ -666,8 +721,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
 
     // ---- wait for the plane ------------------------------------------------------------------------
     if (a.use_tma) {
-      mbar_wait(&th->bar, phase);
-      phase ^= 1u;
+      mbar_wait(&th->bar[stg], (uint32_t)(n_it / nstg) & 1u);
     } else {
       const T* g0 = gptr0(pb, pc);
       T* d0 = const_cast<T*>(plane0);
@@ -690,7 +744,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       return v;
     };
     auto load_quad = [&](int q) -> float4 {
-      const int row = FAST ? (q >> 4) : (q / QR);
+      const int row = FAST ? (q / (WC > 0 ? WC / 4 : 1)) : (q / QR);
       const int cq = q - row * QR;
       const float4 o = load4<T>(plane0 + row * W + 4 * cq);
       if (!FLIP) return o;
@@ -725,23 +779,28 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       best = r;
     };
     if (FAST) {
-      // ST is a multiple of 16: the column quad of a thread is loop-invariant and every address is
-      // base + compile-time offset
-      uint64_t ngx01 = 0, ngx23 = 0;
-      if (LOSS) {
-        const float4 gx = *reinterpret_cast<const float4*>(ex + 4 * (sl & 15));
-        ngx01 = pack2(-gx.x, -gx.y); ngx23 = pack2(-gx.z, -gx.w);
-      }
+      // The first kAST sweeper threads (a multiple of the quads per row) take part: the column quad of a thread
+      // is loop-invariant and every address is base + compile-time offset.
+      constexpr int kQR = (WC > 0 ? WC : 4) / 4, kNQ = kQR * (WC > 0 ? WC : 4);
       constexpr int kST = (TWC > 1 ? TWC - 1 : 1) * 32;
-      constexpr int kFull = 1024 / kST, kRem = 1024 - kFull * kST;
-      const T* po = plane0 + 4 * sl;
-      const T* pf = FLIP ? plane1 + (sl >> 4) * 64 + 60 - 4 * (sl & 15) : nullptr;
-      const float* pgy = ey + (sl >> 4);
+      constexpr int kAST = kST / kQR * kQR, kRPI = kAST / kQR;      // active threads, rows per iteration
+      constexpr int kFull = kNQ / kAST, kRem = kNQ - kFull * kAST;
+      if (sl < kAST) {
+        const int srow = sl / kQR, scq = sl - srow * kQR;
+        uint64_t ngx01 = 0, ngx23 = 0;
+        if (LOSS) {
+          const float4 gx = *reinterpret_cast<const float4*>(ex + 4 * scq);
+          ngx01 = pack2(-gx.x, -gx.y); ngx23 = pack2(-gx.z, -gx.w);
+        }
+        const T* po = plane0 + 4 * sl;
+        const T* pf = FLIP ? plane1 + srow * WC + (WC - 4) - 4 * scq : nullptr;
+        const float* pgy = ey + srow;
 #pragma unroll (kFull <= 16 ? kFull : 8)
-      for (int it = 0; it < kFull; ++it)
-        sweep_quad(it * kST + sl, po + it * kST * 4, pf + it * kST * 4, pgy + it * (kST / 16), ngx01, ngx23);
-      if (kRem > 0 && sl < kRem)
-        sweep_quad(kFull * kST + sl, po + kFull * kST * 4, pf + kFull * kST * 4, pgy + kFull * (kST / 16), ngx01, ngx23);
+        for (int it = 0; it < kFull; ++it)
+          sweep_quad(it * kAST + sl, po + it * kAST * 4, pf + it * kAST * 4, pgy + it * kRPI, ngx01, ngx23);
+        if (kRem > 0 && sl < kRem)
+          sweep_quad(kFull * kAST + sl, po + kFull * kAST * 4, pf + kFull * kAST * 4, pgy + kFull * kRPI, ngx01, ngx23);
+      }
     } else {
       for (int q = sl; q < nq; q += ST) {
         const int row = q / QR, cq = q - row * QR;
@@ -802,7 +861,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
 
     // masked integer coordinates (A1-A4)
-    const int ipy = FAST ? (int)(idx >> 6) : (int)(idx / (uint32_t)W);
+    const int ipy = FAST ? (int)(idx / (uint32_t)(WC > 0 ? WC : 1)) : (int)(idx / (uint32_t)W);
     const int ipx = (int)idx - ipy * W;
     float cx = (float)ipx, cy = (float)ipy;
     const bool positive = maxval > 0.0f;
@@ -892,12 +951,12 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     // S3: everything the epilogue needs is out of the stage — nobody reads it again
     named_sync(bar_id, ST);
     if (sl == 0) {
-      // re-arm the stage with the team's next plane, then hand the record to the epilogue warp
-      if (a.use_tma && has_next) {
+      // re-arm the stage with the plane `nstg` ahead, then hand the record to the epilogue warp
+      if (a.use_tma && (uint64_t)p + (uint64_t)nstg * total_teams < n_planes) {
         uint32_t nb = pb, nc = pc;
-        advance(nb, nc);
+        for (int i = 0; i < nstg; ++i) advance(nb, nc);
         fence_proxy_async();
-        issue(nb, nc);
+        issue(nb, nc, stg);
       }
       mbar_arrive(&th->full[buf]);
     }
@@ -917,9 +976,9 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <typename T, bool FAST, int TWC, bool FLIP, bool LOSS, int KS>
+template <typename T, int WC, int TWC, bool FLIP, bool LOSS, int KS>
 static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {
-  auto kern = heatmap_team_kernel<T, FAST, TWC, FLIP, LOSS, KS>;
+  auto kern = heatmap_team_kernel<T, WC, TWC, FLIP, LOSS, KS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
   // one CTA per SM; small problems still spread over as many SMs as they have planes (team-major numbering)
@@ -937,24 +996,28 @@ static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {
 }
 
 template <typename T, bool FLIP, bool LOSS>
-static int dispatch_variant(HmArgs& a, bool fast, int nteams, size_t smem, cudaStream_t st) {
-  // compile-time team size of the fast 64x64 path: 32 KB stage -> 4 warps, smaller stages -> 2 warps
+static int dispatch_variant(HmArgs& a, int wc, int nteams, size_t smem, cudaStream_t st) {
+  // compile-time team size of the fixed-size paths (64x64, 56x56): stage > 16 KB (f32 + flip) -> 4 warps, else 2
   constexpr int TWF = (sizeof(T) == 4 && FLIP) ? 4 : 2;
   const bool ks11 = a.refine == LHN_REFINE_DARK && a.ksize == 11;
-  if (fast && a.team_warps == TWF) {
-    if (ks11) return launch_one<T, true, TWF, FLIP, LOSS, 11>(a, nteams, smem, st);
-    return launch_one<T, true, TWF, FLIP, LOSS, 0>(a, nteams, smem, st);
+  if (wc == 64 && a.team_warps == TWF) {
+    if (ks11) return launch_one<T, 64, TWF, FLIP, LOSS, 11>(a, nteams, smem, st);
+    return launch_one<T, 64, TWF, FLIP, LOSS, 0>(a, nteams, smem, st);
   }
-  if (ks11) return launch_one<T, false, 0, FLIP, LOSS, 11>(a, nteams, smem, st);
-  return launch_one<T, false, 0, FLIP, LOSS, 0>(a, nteams, smem, st);
+  if (wc == 56 && a.team_warps == TWF) {
+    if (ks11) return launch_one<T, 56, TWF, FLIP, LOSS, 11>(a, nteams, smem, st);
+    return launch_one<T, 56, TWF, FLIP, LOSS, 0>(a, nteams, smem, st);
+  }
+  if (ks11) return launch_one<T, 0, 0, FLIP, LOSS, 11>(a, nteams, smem, st);
+  return launch_one<T, 0, 0, FLIP, LOSS, 0>(a, nteams, smem, st);
 }
 
 template <typename T>
-int dispatch_team(HmArgs& a, bool flip, bool loss, bool fast, int nteams, size_t smem, cudaStream_t st) {
-  if (flip) return loss ? dispatch_variant<T, true, true>(a, fast, nteams, smem, st)
-                        : dispatch_variant<T, true, false>(a, fast, nteams, smem, st);
-  return loss ? dispatch_variant<T, false, true>(a, fast, nteams, smem, st)
-              : dispatch_variant<T, false, false>(a, fast, nteams, smem, st);
+int dispatch_team(HmArgs& a, bool flip, bool loss, int wc, int nteams, size_t smem, cudaStream_t st) {
+  if (flip) return loss ? dispatch_variant<T, true, true>(a, wc, nteams, smem, st)
+                        : dispatch_variant<T, true, false>(a, wc, nteams, smem, st);
+  return loss ? dispatch_variant<T, false, true>(a, wc, nteams, smem, st)
+              : dispatch_variant<T, false, false>(a, wc, nteams, smem, st);
 }
 
 #if defined(LHN_TEAM_DTYPE_TU) && defined(LHN_TRACE)
@@ -966,9 +1029,9 @@ extern "C" __attribute__((visibility("default"))) int lhn_debug_trace(long long*
 #endif
 #ifndef LHN_TEAM_DTYPE_TU
 // instantiated per dtype in lhn_heatmap_team_{f32,bf16,f16}.cu so the three compile in parallel
-extern template int dispatch_team<float>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
-extern template int dispatch_team<__nv_bfloat16>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
-extern template int dispatch_team<__half>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
+extern template int dispatch_team<float>(HmArgs&, bool, bool, int, int, size_t, cudaStream_t);
+extern template int dispatch_team<__nv_bfloat16>(HmArgs&, bool, bool, int, int, size_t, cudaStream_t);
+extern template int dispatch_team<__half>(HmArgs&, bool, bool, int, int, size_t, cudaStream_t);
 
 int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const bool flip = a.hm_flip != nullptr;
@@ -984,18 +1047,25 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const size_t aux = align_up(sizeof(TeamHeader), 16) + 3 * align_up((size_t)(a.W + a.H) * 4, 16) +
                      2 * align_up((size_t)a.tile_dim * 4 * tile_quads(a.tile_dim) * 4, 16) +
                      (size_t)a.tile_dim * 5 * 8 + 32 * 4 + align_up((size_t)a.K * 4, 16);
-  a.warp_smem = (int)align_up(a.stage_bytes + aux, 128);
+  // Teams: the serial epilogue of a plane costs ~4-5k cycles of one warp whatever the plane size, so small planes
+  // need MANY epilogue warps: stages of <= 16 KB run up to 12 teams of 2 warps (1 sweeper + 1 epilogue), larger
+  // ones 6 teams of 4 warps (3 sweepers + 1 epilogue) or 3 / 2 teams of 8 warps.  Spare shared memory then
+  // multiplies the stages per team (2 or 4): the next planes of a team are already in flight while it sweeps.
   const size_t budget = 227 * 1024;
-  int nteams = (int)(budget / a.warp_smem);
-  if (nteams > kMaxTeams) nteams = kMaxTeams;
+  const size_t aux_al = align_up(aux, 128);
+  const size_t per_team = a.stage_bytes + aux_al;
+  int nteams, tw;
+  if (a.stage_bytes <= 16 * 1024) { tw = 2; nteams = (int)(budget / per_team); if (nteams > kMaxTeams) nteams = kMaxTeams; }
+  else if (6 * per_team <= budget) { tw = 4; nteams = 6; }
+  else { tw = 8; nteams = (int)(budget / per_team); if (nteams > 3) nteams = 3; }
   if (nteams < 2) return 1;                           // plane pair too large: CTA-per-plane kernel
-  // ~24 warps per SM: 6 teams x 4 warps (f32 + flip, 64x64), 12 x 2 (one 16 KB plane), 3 x 8 (128x128)
-  int tw = kMaxWarpsPerCta / nteams;
-  tw = tw >= 8 ? 8 : (tw >= 4 ? 4 : 2);
-  const char* env = getenv("LHN_TEAM_WARPS");
-  if (env && atoi(env) >= 2 && atoi(env) <= 8) tw = atoi(env);
-  while (nteams * tw > kMaxWarpsPerCta) --nteams;
+  int nstg = 1;
+  while (nstg < 4 && (size_t)nteams * (2 * nstg * a.stage_bytes + aux_al) <= budget) nstg *= 2;
+  const char* env = getenv("LHN_TEAM_STAGES");
+  if (env && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4) && atoi(env) <= nstg) nstg = atoi(env);
+  a.stages = nstg;
   a.team_warps = tw;
+  a.warp_smem = (int)((size_t)nstg * a.stage_bytes + aux_al);
   {
     // joint / feat_stride: a power-of-two stride (256/64, 224/56, ...) is an exact multiplication
     int ex = 0, ey = 0;
@@ -1009,12 +1079,19 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
     a.pos_radius[i] = (a.pos_value > 0.f && a.pos_value < 1.f && sg > 0)
                           ? (float)(sg * sqrt(-2.0 * log((double)a.pos_value)) * 1.001 + 0.01) : 0.f;
   }
-  const bool fast = a.W == 64 && a.H == 64;
-  const size_t smem = (size_t)nteams * a.warp_smem;
+  const int wc = (a.W == 64 && a.H == 64) ? 64 : ((a.W == 56 && a.H == 56) ? 56 : 0);
+  size_t smem = (size_t)nteams * a.warp_smem;
+  if (a.counters) {
+    // CTA-shared metric counters after the teams' regions; drop a team if they do not fit
+    const size_t cnt_bytes = (size_t)(a.auc_steps + 5) * a.K * 8 + 16;
+    while (nteams > 2 && (size_t)nteams * a.warp_smem + cnt_bytes > budget) --nteams;
+    smem = (size_t)nteams * a.warp_smem + cnt_bytes;
+    if (smem > budget) return 1;
+  }
   switch (dtype) {
-    case LHN_F32: return dispatch_team<float>(a, flip, loss, fast, nteams, smem, st);
-    case LHN_BF16: return dispatch_team<__nv_bfloat16>(a, flip, loss, fast, nteams, smem, st);
-    case LHN_F16: return dispatch_team<__half>(a, flip, loss, fast, nteams, smem, st);
+    case LHN_F32: return dispatch_team<float>(a, flip, loss, wc, nteams, smem, st);
+    case LHN_BF16: return dispatch_team<__nv_bfloat16>(a, flip, loss, wc, nteams, smem, st);
+    case LHN_F16: return dispatch_team<__half>(a, flip, loss, wc, nteams, smem, st);
     default: return LHN_EDTYPE;
   }
 }

@@ -3,5 +3,5 @@
 #include "lhn_heatmap_team.cuh"
 
 namespace lhn {
-template int dispatch_team<__half>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
+template int dispatch_team<__half>(HmArgs&, bool, bool, int, int, size_t, cudaStream_t);
 }

@@ -4,5 +4,5 @@
 #include "lhn_heatmap_team.cuh"
 
 namespace lhn {
-template int dispatch_team<float>(HmArgs&, bool, bool, bool, int, size_t, cudaStream_t);
+template int dispatch_team<float>(HmArgs&, bool, bool, int, int, size_t, cudaStream_t);
 }

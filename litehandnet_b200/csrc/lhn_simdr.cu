@@ -62,6 +62,57 @@ __device__ __forceinline__ void warp_vec_argmax(const T* __restrict__ v, int L, 
   out_val = key_to_float(bkey);
 }
 
+// Fast path (no NMS, 16-byte aligned vectors): both vectors of a (b, k) pair are scanned in ONE loop so that all
+// of their 128-bit loads are in flight together (one memory latency per pair instead of two), NaN detection is one
+// NaN-propagating 3-input max per quad, and the exact first-NaN element is only looked up when one was seen.
+struct LaneBest { float best; uint32_t idx; uint32_t nanq; };
+
+__device__ __forceinline__ void lane_scan4(const float4& a, uint32_t q, LaneBest& s) {
+  const uint32_t e = 4u * q;
+  if (a.x > s.best) { s.best = a.x; s.idx = e; }
+  if (a.y > s.best) { s.best = a.y; s.idx = e + 1; }
+  if (a.z > s.best) { s.best = a.z; s.idx = e + 2; }
+  if (a.w > s.best) { s.best = a.w; s.idx = e + 3; }
+  float m;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a.x), "f"(a.y), "f"(a.z));
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "f"(a.w));
+  if (m != m && s.nanq == 0xffffffffu) s.nanq = q;       // lanes visit their quads in increasing order
+}
+
+template <typename T>
+__device__ __forceinline__ void warp_finish(const T* __restrict__ v, LaneBest s, uint32_t& out_idx, float& out_val) {
+  const uint32_t nanq = __reduce_min_sync(0xffffffffu, s.nanq);
+  if (nanq != 0xffffffffu) {                               // rare: first NaN of the vector is the argmax
+    const float4 a = load4<T>(v + 4 * nanq);
+    out_idx = 4 * nanq + ((a.x != a.x) ? 0 : (a.y != a.y) ? 1 : (a.z != a.z) ? 2 : 3);
+    out_val = __uint_as_float(0x7fc00000u);
+    return;
+  }
+  uint32_t key = s.idx == 0xffffffffu ? 0u : order_key(s.best), idx = s.idx;
+  warp_argmax(key, idx);
+  if (idx == 0xffffffffu) idx = 0;
+  out_idx = idx;
+  out_val = key_to_float(key);
+}
+
+template <typename T>
+__device__ __forceinline__ void warp_pair_argmax(const T* __restrict__ xv, const T* __restrict__ yv, int Lx, int Ly,
+                                                 int lane, uint32_t& ix, float& mx, uint32_t& iy, float& my) {
+  LaneBest sx{-CUDART_INF_F, 0xffffffffu, 0xffffffffu}, sy = sx;
+  const int nqx = Lx >> 2, nqy = Ly >> 2, nq = nqx > nqy ? nqx : nqy;
+#pragma unroll 4
+  for (int q = lane; q < nq; q += 32) {
+    float4 a, b;
+    const bool hx = q < nqx, hy = q < nqy;
+    if (hx) a = ldg_stream4<T>(xv + 4 * q);
+    if (hy) b = ldg_stream4<T>(yv + 4 * q);
+    if (hx) lane_scan4(a, (uint32_t)q, sx);
+    if (hy) lane_scan4(b, (uint32_t)q, sy);
+  }
+  warp_finish<T>(xv, sx, ix, mx);
+  warp_finish<T>(yv, sy, iy, my);
+}
+
 template <typename T, bool NMS>
 __global__ void __launch_bounds__(256) decode_simdr_kernel(const T* __restrict__ xv, const T* __restrict__ yv,
                                                            int64_t n_bk, int K, int Lx, int Ly, int k,
@@ -78,17 +129,34 @@ __global__ void __launch_bounds__(256) decode_simdr_kernel(const T* __restrict__
     int x1 = 0, x2 = Lx, y1 = 0, y2 = Ly;
     if (NMS && ranges) { x1 = ranges[4 * b]; x2 = ranges[4 * b + 1]; y1 = ranges[4 * b + 2]; y2 = ranges[4 * b + 3]; }
     uint32_t ix, iy; float mx, my;
-    warp_vec_argmax<T, NMS>(xv + bk * Lx, Lx, x1, x2, lane, ix, mx);
-    warp_vec_argmax<T, NMS>(yv + bk * Ly, Ly, y1, y2, lane, iy, my);
+    // per-sample side inputs are requested before the vectors so their latency overlaps the scan
+    float cx = 0.f, cy = 0.f, sc0 = 0.f, sc1 = 0.f;
+    if (center) { cx = center[2 * b]; cy = center[2 * b + 1]; sc0 = scale[2 * b]; sc1 = scale[2 * b + 1]; }
+    const T* xp = xv + bk * Lx;
+    const T* yp = yv + bk * Ly;
+    const bool fast = !NMS && ((Lx | Ly) & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(xp) | reinterpret_cast<uintptr_t>(yp)) % (4 * sizeof(T)) == 0);
+    if (fast) {
+      warp_pair_argmax<T>(xp, yp, Lx, Ly, lane, ix, mx, iy, my);
+    } else {
+      warp_vec_argmax<T, NMS>(xp, Lx, x1, x2, lane, ix, mx);
+      warp_vec_argmax<T, NMS>(yp, Ly, y1, y2, lane, iy, my);
+    }
     if (lane == 0) {
-      // preds = idx / k (int64 / int -> f64 -> f32), score = (max_x + max_y) / 2
-      float px = (float)((double)ix / (double)k), py = (float)((double)iy / (double)k);
+      // preds = idx / k (int64 / int -> f64 -> f32: one rounding of the exact quotient, which is what the
+      // correctly rounded f32 division of the exactly representable operands gives), score = (max_x + max_y) / 2
+      float px, py;
+      if (ix < (1u << 24) && iy < (1u << 24) && k < (1 << 24)) {
+        px = __fdiv_rn((float)ix, (float)k); py = __fdiv_rn((float)iy, (float)k);
+      } else {
+        px = (float)((double)ix / (double)k); py = (float)((double)iy / (double)k);
+      }
       const float score = __fdiv_rn(__fadd_rn(mx, my), 2.f);
       if (center) {
-        const float s0 = __fmul_rn(scale[2 * b], 200.f), s1 = __fmul_rn(scale[2 * b + 1], 200.f);
+        const float s0 = __fmul_rn(sc0, 200.f), s1 = __fmul_rn(sc1, 200.f);
         const float fx = __fdiv_rn(s0, (float)(Lx / k)), fy = __fdiv_rn(s1, (float)(Ly / k));
-        px = __fsub_rn(__fadd_rn(__fmul_rn(px, fx), center[2 * b]), __fmul_rn(s0, 0.5f));
-        py = __fsub_rn(__fadd_rn(__fmul_rn(py, fy), center[2 * b + 1]), __fmul_rn(s1, 0.5f));
+        px = __fsub_rn(__fadd_rn(__fmul_rn(px, fx), cx), __fmul_rn(s0, 0.5f));
+        py = __fsub_rn(__fadd_rn(__fmul_rn(py, fy), cy), __fmul_rn(s1, 0.5f));
       }
       float* o = out + 3 * bk;
       o[0] = px; o[1] = py; o[2] = score;
