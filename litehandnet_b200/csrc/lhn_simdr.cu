@@ -65,40 +65,54 @@ __device__ __forceinline__ void warp_vec_argmax(const T* __restrict__ v, int L, 
 // Fast path (no NMS, 16-byte aligned vectors): both vectors of a (b, k) pair are scanned in ONE loop so that all
 // of their 128-bit loads are in flight together (one memory latency per pair instead of two), NaN detection is one
 // NaN-propagating 3-input max per quad, and the exact first-NaN element is only looked up when one was seen.
-struct LaneBest { float best; uint32_t idx; uint32_t nanq; };
+struct LaneBest { float best; uint32_t q; };
 
+// 4 instructions per quad: two NaN-propagating 3-input maxima (FMNMX3.NAN), one compare, one predicated move.
+// `best` becomes NaN as soon as the lane meets one; `q` is the first quad that raised the running maximum.
 __device__ __forceinline__ void lane_scan4(const float4& a, uint32_t q, LaneBest& s) {
-  const uint32_t e = 4u * q;
-  if (a.x > s.best) { s.best = a.x; s.idx = e; }
-  if (a.y > s.best) { s.best = a.y; s.idx = e + 1; }
-  if (a.z > s.best) { s.best = a.z; s.idx = e + 2; }
-  if (a.w > s.best) { s.best = a.w; s.idx = e + 3; }
-  float m;
+  float m, r;
   asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a.x), "f"(a.y), "f"(a.z));
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "f"(a.w));
-  if (m != m && s.nanq == 0xffffffffu) s.nanq = q;       // lanes visit their quads in increasing order
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(a.w), "f"(s.best));
+  if (r != s.best) s.q = q;
+  s.best = r;
 }
 
+// warp-wide (max, first quad holding it); then the winning quad is read again (L1/L2 hit) to name the element
 template <typename T>
-__device__ __forceinline__ void warp_finish(const T* __restrict__ v, LaneBest s, uint32_t& out_idx, float& out_val) {
-  const uint32_t nanq = __reduce_min_sync(0xffffffffu, s.nanq);
-  if (nanq != 0xffffffffu) {                               // rare: first NaN of the vector is the argmax
-    const float4 a = load4<T>(v + 4 * nanq);
-    out_idx = 4 * nanq + ((a.x != a.x) ? 0 : (a.y != a.y) ? 1 : (a.z != a.z) ? 2 : 3);
+__device__ __forceinline__ void warp_finish(const T* __restrict__ v, int nq, int lane, LaneBest s, uint32_t& out_idx,
+                                            float& out_val) {
+  float wmax;
+  asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(wmax) : "f"(s.best));
+  if (wmax != wmax) {                                      // rare: the first NaN of the vector is the argmax
+    uint32_t first = 0xffffffffu;
+    for (int q = lane; q < nq && first == 0xffffffffu; q += 32) {
+      const float4 a = load4<T>(v + 4 * q);
+      if (a.x != a.x) first = 4 * q;
+      else if (a.y != a.y) first = 4 * q + 1;
+      else if (a.z != a.z) first = 4 * q + 2;
+      else if (a.w != a.w) first = 4 * q + 3;
+    }
+    out_idx = __reduce_min_sync(0xffffffffu, first);
     out_val = __uint_as_float(0x7fc00000u);
     return;
   }
-  uint32_t key = s.idx == 0xffffffffu ? 0u : order_key(s.best), idx = s.idx;
-  warp_argmax(key, idx);
-  if (idx == 0xffffffffu) idx = 0;
-  out_idx = idx;
-  out_val = key_to_float(key);
+  const uint32_t qsel = __reduce_min_sync(0xffffffffu, (s.best == wmax) ? s.q : 0xffffffffu);
+  if (qsel == 0xffffffffu) {                               // every element is -inf: index 0
+    out_idx = 0; out_val = Elem<T>::to_f32(v[0]);
+    return;
+  }
+  const float4 a = load4<T>(v + 4 * qsel);
+  // `==` treats -0 and +0 as equal, like torch/numpy; report the element actually selected
+  if (a.x == wmax) { out_idx = 4 * qsel; out_val = a.x; }
+  else if (a.y == wmax) { out_idx = 4 * qsel + 1; out_val = a.y; }
+  else if (a.z == wmax) { out_idx = 4 * qsel + 2; out_val = a.z; }
+  else { out_idx = 4 * qsel + 3; out_val = a.w; }
 }
 
 template <typename T>
 __device__ __forceinline__ void warp_pair_argmax(const T* __restrict__ xv, const T* __restrict__ yv, int Lx, int Ly,
                                                  int lane, uint32_t& ix, float& mx, uint32_t& iy, float& my) {
-  LaneBest sx{-CUDART_INF_F, 0xffffffffu, 0xffffffffu}, sy = sx;
+  LaneBest sx{-CUDART_INF_F, 0xffffffffu}, sy = sx;
   const int nqx = Lx >> 2, nqy = Ly >> 2, nq = nqx > nqy ? nqx : nqy;
 #pragma unroll 4
   for (int q = lane; q < nq; q += 32) {
@@ -109,12 +123,12 @@ __device__ __forceinline__ void warp_pair_argmax(const T* __restrict__ xv, const
     if (hx) lane_scan4(a, (uint32_t)q, sx);
     if (hy) lane_scan4(b, (uint32_t)q, sy);
   }
-  warp_finish<T>(xv, sx, ix, mx);
-  warp_finish<T>(yv, sy, iy, my);
+  warp_finish<T>(xv, nqx, lane, sx, ix, mx);
+  warp_finish<T>(yv, nqy, lane, sy, iy, my);
 }
 
 template <typename T, bool NMS>
-__global__ void __launch_bounds__(256) decode_simdr_kernel(const T* __restrict__ xv, const T* __restrict__ yv,
+__global__ void __launch_bounds__(256, 6) decode_simdr_kernel(const T* __restrict__ xv, const T* __restrict__ yv,
                                                            int64_t n_bk, int K, int Lx, int Ly, int k,
                                                            const float* __restrict__ center,
                                                            const float* __restrict__ scale,
@@ -235,7 +249,8 @@ static int launch_simdr(const void* xv, const void* yv, int64_t n_bk, int K, int
                         const float* center, const float* scale, int nms, const int32_t* ranges,
                         float* out, int32_t* out_idx, cudaStream_t st) {
   const int threads = 256;
-  int64_t need = (n_bk * 32 + threads - 1) / threads, cap = (int64_t)num_sms() * 8;
+  // grid-stride over (b, k) pairs: exactly the resident CTAs (6 per SM at 40 registers), so there is no second wave
+  int64_t need = (n_bk * 32 + threads - 1) / threads, cap = (int64_t)num_sms() * 6;
   int blocks = (int)(need < cap ? need : cap);
   if (nms)
     decode_simdr_kernel<T, true><<<blocks, threads, 0, st>>>((const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k,
