@@ -263,8 +263,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   if (p >= n_planes) return;                       // whole teams leave together
 
   // Render parameters + separable Gaussian factors of a plane (channel c, side-ring slot `slot`) into table
-  // buffer `buf`, computed by one warp.  exp() is evaluated on an f64 argument.
-  auto prologue = [&](uint32_t c, int slot, int buf) {
+  // buffer `buf`, computed by `nthr` threads (thread index `t`).  exp() is evaluated on an f64 argument.
+  auto prologue = [&](uint32_t c, int slot, int buf, int t, int nthr) {
     if (!LOSS) return;
     uint32_t s, k;
     split_channel(c, s, k);
@@ -287,12 +287,12 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
     const bool render_on = w > 0.5f;
-    if (lane == 0) {
+    if (t == 0) {
       th->w[buf] = w; th->mx[buf] = (float)mux; th->my[buf] = (float)muy; th->render_on[buf] = render_on ? 1 : 0;
     }
     const double i2 = a.inv2s2[s];
     float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + (size_t)buf * tab_bytes);
-    for (int i = lane; i < W + H; i += 32) {
+    for (int i = t; i < W + H; i += nthr) {
       const bool isx = i < W;
       const int pos = isx ? i : i - W;
       float v = 0.f;
@@ -336,13 +336,13 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     cp_async_wait<kSideAhead - 2>();               // the first two planes' side inputs have landed
     __syncwarp();
-    prologue(pc, 0, 0);
+    if (!a.sweeper_tables) prologue(pc, 0, 0, lane, 32);
     __syncwarp();
     if (lane == 0) mbar_arrive(&th->empty[0]);
-    if (p + total_teams < n_planes) {
+    if (!a.sweeper_tables && p + total_teams < n_planes) {
       uint32_t nb = pb, nc = pc;
       advance(nb, nc);
-      prologue(nc, 1, 1);
+      prologue(nc, 1, 1, lane, 32);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&th->empty[1]);
@@ -589,10 +589,10 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       pq += total_teams; advance(qb, qc);
       cp_async_wait<kSideAhead - 2>();               // side inputs of plane n+2 have landed
       __syncwarp();
-      if (p + 2 * total_teams < n_planes) {
+      if (!a.sweeper_tables && p + 2 * total_teams < n_planes) {
         uint32_t nb = pb, nc = pc;
         advance(nb, nc); advance(nb, nc);
-        prologue(nc, (n_it + 2) & 7, (n_it + 2) % 3);
+        prologue(nc, (n_it + 2) & 7, (n_it + 2) % 3, lane, 32);
       }
       TRE(12);
       __syncwarp();
@@ -715,6 +715,12 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     // the epilogue warp has written this plane's tables and is done with the record/tile buffer `buf`
     // (it finished plane n-2; it lags at most two planes)
     mbar_wait(&th->empty[buf], (uint32_t)(n_it >> 1) & 1u);
+    if (LOSS && a.sweeper_tables) {
+      // multi-stage teams: the plane is usually resident already and the sweepers have slack, the epilogue warp
+      // has none — so the sweepers evaluate this plane's tables (its side inputs were published with `empty`)
+      prologue(pc, n_it & 7, tb, sl, ST);
+      named_sync(bar_id, ST);
+    }
     TRS(0);
     const float* ex = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(tab0) + (size_t)tb * tab_bytes);
     const float* ey = ex + W;
@@ -1055,7 +1061,11 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const size_t aux_al = align_up(aux, 128);
   const size_t per_team = a.stage_bytes + aux_al;
   int nteams, tw;
-  if (a.stage_bytes <= 16 * 1024) { tw = 2; nteams = (int)(budget / per_team); if (nteams > kMaxTeams) nteams = kMaxTeams; }
+  const char* pol = getenv("LHN_TEAM_POLICY");
+  // measured (profiles/r01_configs.txt): for <= 16 KB stages up to 12 teams of 2 warps beat 6 teams of 4 warps
+  // with two stages each (78 vs 67 % of peak at 64x64 f32 with loss + DARK); LHN_TEAM_POLICY=0 selects the latter
+  const bool many_small = !(pol && pol[0] == '0');
+  if (a.stage_bytes <= 16 * 1024 && many_small) { tw = 2; nteams = (int)(budget / per_team); if (nteams > kMaxTeams) nteams = kMaxTeams; }
   else if (6 * per_team <= budget) { tw = 4; nteams = 6; }
   else { tw = 8; nteams = (int)(budget / per_team); if (nteams > 3) nteams = 3; }
   if (nteams < 2) return 1;                           // plane pair too large: CTA-per-plane kernel
@@ -1064,6 +1074,7 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const char* env = getenv("LHN_TEAM_STAGES");
   if (env && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4) && atoi(env) <= nstg) nstg = atoi(env);
   a.stages = nstg;
+  a.sweeper_tables = (nstg >= 2 && tw >= 4) ? 1 : 0;
   a.team_warps = tw;
   a.warp_smem = (int)((size_t)nstg * a.stage_bytes + aux_al);
   {
