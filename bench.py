@@ -210,9 +210,18 @@ def run_gpu_arm(args, rank, local_rank, world):
         joints, vis = synth.hand_joints(B, K_JOINTS, IMAGE_SIZE, seed=seed + 2, device=dev)
         center, scale = synth.bbox_center_scale(B, seed=seed + 3, device=dev)
         sets.append((hm, hf, joints, vis, center, scale))
+    # N > 1, default: the reference's DDP semantics — every rank finalises the loss of its own shard (local N_pos,
+    # loss/heatmapLoss.py:253-258 sees only the rank's batch) inside the one-launch kernel, adds it into a
+    # device-resident epoch sum (train_one_epoch's loss_dict['sum'] += v) and the ranks all-reduce that scalar
+    # ONCE at the end of the timed region (train/distributed_utils.py:65-76 reduce_value).  --global-loss keeps
+    # global N_pos instead: the kernel leaves the f64 sums, NCCL all-reduces them every step (pipelined behind the
+    # next step's kernel) and lhn_loss_finalize runs as a second launch.
+    global_loss = world > 1 and args.global_loss
+    epoch_loss = torch.zeros(1, dtype=torch.float32, device=dev) if (world > 1 and not global_loss) else None
     # consecutive steps work on disjoint buffer sets (R >= 2), so each launch may overlap the tail of the previous one
-    bound = [fused.BoundFusedStep(step_cfg, s[0], s[2], s[3], s[4], s[5], hm_flip=s[1], finalize=(world == 1),
-                                  overlap_previous=(R >= 2 and not args.no_overlap))
+    bound = [fused.BoundFusedStep(step_cfg, s[0], s[2], s[3], s[4], s[5], hm_flip=s[1], finalize=not global_loss,
+                                  overlap_previous=(R >= 2 and not args.no_overlap),
+                                  spare_sms=(args.spare_sms if global_loss else 0), accumulate_into=epoch_loss)
              for s in sets]
     use_graph = (world == 1) and args.graph
     if use_graph:
@@ -233,11 +242,16 @@ def run_gpu_arm(args, rank, local_rank, world):
             b.replay()
         else:
             b.launch(events)
-        if world > 1:
+        if global_loss:
             # Global N_pos / sums for the balanced loss: the 32-byte all-reduce of step i runs on the NCCL stream
             # while the kernel of step i+1 runs; step i is finalised right after that kernel is queued.
             flush()
             pending.append((dist.all_reduce(b.sums, async_op=True), b))
+
+    def end_of_epoch():
+        flush()
+        if epoch_loss is not None:
+            dist.all_reduce(epoch_loss)                   # the one collective of the timed region
 
     def fence():
         torch.cuda.synchronize()
@@ -248,19 +262,26 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- warm-up, then the timed region ------------------------------------------------------------
     for i in range(args.warmup):
         one_step(i)
-    flush()
+    end_of_epoch()
     fence()
+    if epoch_loss is not None:
+        epoch_loss.zero_()
+        fence()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         one_step(i)
-    flush()
+    end_of_epoch()
     e1.record()
     fence()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
+    if epoch_loss is not None:
+        loss_val = float(epoch_loss.item()) / (world * args.steps)      # mean over ranks and steps
+    else:
+        loss_val = float(bound[(args.steps - 1) % R].loss.item())
 
     # ---- the fused kernel alone: a second pass of K back-to-back launches (no collective, no finalise)
     #      between two events on the launching stream; average launch duration = elapsed / K ---------------
@@ -300,7 +321,6 @@ def run_gpu_arm(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     ms_total, kernel_ms, e2e_s = [float(v) for v in stats.tolist()]
-    loss_val = float(bound[(args.steps - 1) % R].loss.item())
 
     if rank == 0:
         value = world * B * args.steps / (ms_total * 1e-3)
@@ -313,7 +333,11 @@ def run_gpu_arm(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world,
                        "joints": K_JOINTS, "heatmap": f"{H}x{W}", "flip_test": True, "loss": "DistanceLoss L2 balance=True",
-                       "decode": "argmax + DARK k=11 + transform_preds", "parallelism": f"batch-shard x{world}",
+                       "decode": "argmax + DARK k=11 + transform_preds", "parallelism": f"batch-shard x{world}" + (
+                           "" if world == 1 else
+                           (f"; global-N_pos loss: one 32-byte NCCL all-reduce per step, {args.spare_sms} SMs left to NCCL"
+                            if global_loss else
+                            "; per-rank loss (reference DDP semantics), ONE NCCL all-reduce of the epoch loss sum per timed region")),
                        "l2_policy": f"inputs {2 * B * K_JOINTS * H * W * 4 / 1e6:.0f} MB/step > 126 MB L2, "
                                     f"{R} rotating input sets, L2 evict_first loads",
                        "launch": ("CUDA graph replay" if use_graph else "eager C-ABI launches, one per step") +
@@ -325,7 +349,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                          "frac": achieved / peak, "traffic": recorded_traffic(B),
                          "kernel": "heatmap_team_kernel<f32,64x64,TW=4,FLIP,LOSS,KS=11>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src},
-            "gpu_launches": args.steps * (1 if world == 1 else 2),
+            "gpu_launches": args.steps * (2 if global_loss else 1),
         }
         if e2e:
             line["e2e"] = {"value": world * B * args.steps / e2e_s, "unit": UNIT,
@@ -359,6 +383,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per step instead of eager launches")
     ap.add_argument("--no-graph", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--global-loss", action="store_true",
+                    help="N > 1: balanced loss with batch-global N_pos (an all-reduce of the f64 sums every step) "
+                         "instead of the reference's per-rank loss")
+    ap.add_argument("--spare-sms", type=int, default=4,
+                    help="N > 1: SMs the persistent kernel leaves free so the NCCL all-reduce of the previous step "
+                         "can run beside it")
     ap.add_argument("--no-overlap", action="store_true", help="do not let a launch overlap the previous one's tail")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

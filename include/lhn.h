@@ -79,6 +79,15 @@ typedef void* lhn_stream_t; /* cudaStream_t */
                                        of back-to-back steps over rotating buffers.  Stream order is unchanged for
                                        everything launched afterwards. */
 
+#define LHN_FLAG_ACCUMULATE_LOSS 2  /* lhn_fused_render_loss_decode adds the finalised loss into loss[0] instead of
+                                       overwriting it: the epoch sum of train_one_epoch's loss_dict['sum'] += v
+                                       (train/topdown_trainer.py:82-84) kept on the device, all-reduced once per
+                                       epoch (train/distributed_utils.py:65-76) instead of once per step. */
+#define LHN_FLAG_SPARE_SMS(n) (((n) & 0xff) << 8) /* leave n SMs to other work: the persistent kernel otherwise
+                                       fills every SM (216 KB of shared memory each), so a concurrent NCCL kernel —
+                                       the 32-byte all-reduce of the previous step's loss sums — could not start
+                                       before it ends.  The kernel is HBM-bound: 4 of 148 SMs cost < 1 %. */
+
 #define LHN_MAX_TAPS 31
 #define LHN_MAX_STACKS 8
 

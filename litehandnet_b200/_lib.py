@@ -20,6 +20,7 @@ REFINE_NONE, REFINE_OFFSET_HALF, REFINE_OFFSET, REFINE_SIGN, REFINE_SIGN_ROUND, 
 XFORM_NONE, XFORM_CENTER_SCALE, XFORM_SCALE = 0, 1, 2
 LOSS_NONE, LOSS_DISTANCE, LOSS_DISTANCE_BALANCE, LOSS_JOINTS_MSE = 0, 1, 2, 3
 FLAG_OVERLAP_PREVIOUS = 1
+FLAG_ACCUMULATE_LOSS = 2
 MAX_TAPS, MAX_STACKS = 31, 8
 
 ERRORS = {-1: "LHN_EINVAL (bad shape / null pointer / bad enum)", -2: "LHN_EDTYPE (unsupported dtype)",

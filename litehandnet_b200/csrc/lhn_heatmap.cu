@@ -502,6 +502,8 @@ static int fill_decode(HmArgs& a, const lhn_decode_params* dp) {
   a.use_udp = dp->use_udp; a.scale_x = dp->scale_x; a.scale_y = dp->scale_y;
   a.ksize = dp->blur_ksize;
   a.overlap_previous = (dp->flags & LHN_FLAG_OVERLAP_PREVIOUS) ? 1 : 0;
+  a.spare_sms = (dp->flags >> 8) & 0xff;
+  a.loss_accumulate = (dp->flags & LHN_FLAG_ACCUMULATE_LOSS) ? 1 : 0;
   if (dp->refine == LHN_REFINE_DARK || dp->refine == LHN_REFINE_DARK_LEGACY) {
     if (a.ksize < 3 || a.ksize > LHN_MAX_TAPS || (a.ksize & 1) == 0) return LHN_EINVAL;
     for (int i = 0; i < a.ksize; ++i) { a.tapsd[i] = dp->taps[i]; a.tapsf[i] = (float)dp->taps[i]; }
@@ -626,7 +628,7 @@ static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_
   double* tmp_sums = sums ? sums : reinterpret_cast<double*>(ws + kWsHeader);
   rc = lhn_loss_reduce(fallback_partials, a.n_planes, tmp_sums, 0, stream);
   if (rc) return rc;
-  if (loss) rc = lhn_loss_finalize(tmp_sums, a.loss_mode, sum_reduction, loss_scale, loss, 0, stream);
+  if (loss) rc = lhn_loss_finalize(tmp_sums, a.loss_mode, sum_reduction, loss_scale, loss, a.loss_accumulate, stream);
   return rc;
 }
 

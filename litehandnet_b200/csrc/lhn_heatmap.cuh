@@ -67,6 +67,8 @@ struct HmArgs {
   float loss_scale;
   int sum_reduction;
   double* fallback_partials;       // per-plane sums for the CTA-per-plane fallback of the one-launch step
+  int loss_accumulate;             // LHN_FLAG_ACCUMULATE_LOSS
+  int spare_sms;                   // LHN_FLAG_SPARE_SMS: SMs left free for concurrent kernels
   int overlap_previous;            // LHN_FLAG_OVERLAP_PREVIOUS: launch with programmatic stream serialization
   int feat_pow2;                   // feat_x, feat_y are powers of two: joint / feat == joint * inv_feat exactly
   double inv_feat_x, inv_feat_y;

@@ -672,7 +672,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             else if (a.loss_mode == LHN_LOSS_JOINTS_MSE) v = 0.5 * (v0 + v1) / v3;
             else v = (v0 + v1) / v3;
             if (a.sum_reduction) v *= v3;
-            a.loss_out[0] = (float)(v * (double)a.loss_scale);
+            const float lv = (float)(v * (double)a.loss_scale);
+            a.loss_out[0] = a.loss_accumulate ? a.loss_out[0] + lv : lv;
           }
           *a.ticket = 0u;                                       // leave the workspace ready for the next launch
         }
@@ -988,7 +989,9 @@ static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
   // one CTA per SM; small problems still spread over as many SMs as they have planes (team-major numbering)
-  int64_t ctas = a.n_planes < sm_count() ? a.n_planes : sm_count();
+  int sms = sm_count() - a.spare_sms;
+  if (sms < 1) sms = 1;
+  int64_t ctas = a.n_planes < sms ? a.n_planes : sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3((unsigned)(nteams * a.team_warps * 32));
   cfg.dynamicSmemBytes = smem; cfg.stream = st;

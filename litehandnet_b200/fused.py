@@ -174,9 +174,11 @@ class BoundFusedStep:
     launch-bound at ~0.1 ms of GPU work per step)."""
 
     def __init__(self, step, hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None,
-                 finalize=True, overlap_previous=False):
+                 finalize=True, overlap_previous=False, spare_sms=0, accumulate_into=None):
         """overlap_previous: this step shares no buffer with the step launched just before it on the stream
-        (rotating input/output sets), so its kernel may start while that one drains (LHN_FLAG_OVERLAP_PREVIOUS)."""
+        (rotating input/output sets), so its kernel may start while that one drains (LHN_FLAG_OVERLAP_PREVIOUS).
+        accumulate_into: f32 [1] device tensor that receives ``+= loss`` of every step (the epoch sum that
+        train_one_epoch keeps in loss_dict['sum'], left on the device; LHN_FLAG_ACCUMULATE_LOSS)."""
         import ctypes as C
         self.step = step
         lib = L.lib()
@@ -198,7 +200,9 @@ class BoundFusedStep:
         center, scale = ops._f32c(center, "center"), ops._f32c(scale, "scale")
         self._keep += [joints, vis, center, scale]
         self.dp = ops._decode_params(L.MASK_NEG1, step.refine, L.XFORM_CENTER_SCALE, blur_ksize=step.kernel,
-                                     flags=L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0)
+                                     flags=(L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0) |
+                                     (L.FLAG_ACCUMULATE_LOSS if accumulate_into is not None else 0) |
+                                     ((int(spare_sms) & 0xff) << 8))
         self.rp = ops._render_params(step.loss_mode, step.image_size, step.sigma, step.unbiased, step.pos_value)
         self.hm_preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
         self.preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
@@ -206,7 +210,7 @@ class BoundFusedStep:
         self.weight = torch.empty((B, Cc), dtype=torch.float32, device=dev)
         self.partials = torch.empty((B * Cc, 4), dtype=torch.float64, device=dev)
         self.sums = torch.empty(4, dtype=torch.float64, device=dev)
-        self.loss = torch.empty(1, dtype=torch.float32, device=dev)
+        self.loss = torch.empty(1, dtype=torch.float32, device=dev) if accumulate_into is None else accumulate_into
         self.finalize = finalize
         # one-launch step: the kernel reduces the loss sums itself; `finalize=False` (multi-GPU) leaves the
         # f64 sums for the cross-rank all-reduce and finalises afterwards with launch_finalize()
