@@ -74,9 +74,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 // slots 0-5: first sweeper warp (S1 passed, plane landed, sweep done, S2 passed, staged, released);
 // slots 8-11: epilogue warp (record received, blur/check done, Taylor done, plane finished).
 #ifdef LHN_TRACE
-static __device__ long long g_trace[148 * 6 * 16 * 16];
-#define TRS(slot) do { if (role == 1 && lane == 0 && n_it < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + n_it) * 16 + (slot)] = clock64(); } while (0)
-#define TRE(slot) do { if (lane == 0 && n_it < 16 && nteams <= 6) g_trace[((blockIdx.x * 6 + team) * 16 + n_it) * 16 + (slot)] = clock64(); } while (0)
+static __device__ long long g_trace[148 * 12 * 16 * 16];
+#define TRS(slot) do { if (role == 1 && lane == 0 && n_it < 16 && nteams <= 12) g_trace[((blockIdx.x * 12 + team) * 16 + n_it) * 16 + (slot)] = clock64(); } while (0)
+#define TRE(slot) do { if (lane == 0 && n_it < 16 && nteams <= 12) g_trace[((blockIdx.x * 12 + team) * 16 + n_it) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TRS(slot) do { } while (0)
 #define TRE(slot) do { } while (0)
@@ -253,11 +253,11 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   }
   __syncthreads();
 #ifdef LHN_TRACE
-  if (role == 1 && lane == 0 && nteams <= 6) {
-    g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 15] = clock64();
+  if (role == 1 && lane == 0 && nteams <= 12) {
+    g_trace[((blockIdx.x * 12 + team) * 16 + 0) * 16 + 15] = clock64();
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 13] = (long long)gt;
+    g_trace[((blockIdx.x * 12 + team) * 16 + 0) * 16 + 13] = (long long)gt;
   }
 #endif
   if (p >= n_planes) return;                       // whole teams leave together
@@ -292,24 +292,30 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     }
     const double i2 = a.inv2s2[s];
     float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + (size_t)buf * tab_bytes);
-    for (int i = t; i < W + H; i += nthr) {
+    auto entry = [&](int i) -> float {
       const bool isx = i < W;
       const int pos = isx ? i : i - W;
       float v = 0.f;
-      if (render_on) {
-        if (a.unbiased) {
-          const double d = (double)pos - (isx ? mux : muy);
+      if (a.unbiased) {
+        const double d = (double)pos - (isx ? mux : muy);
+        v = exp_f32_from_f64(-(d * d) * i2);
+      } else {
+        const double ul = isx ? ulx : uly, br = isx ? brx : bry;
+        if ((double)pos >= ul && (double)pos < br) {
+          const double d = ((double)pos - ul) - x0p;
           v = exp_f32_from_f64(-(d * d) * i2);
-        } else {
-          const double ul = isx ? ulx : uly, br = isx ? brx : bry;
-          if ((double)pos >= ul && (double)pos < br) {
-            const double d = ((double)pos - ul) - x0p;
-            v = exp_f32_from_f64(-(d * d) * i2);
-          }
         }
       }
-      tab[i] = v;
+      return render_on ? v : 0.f;
+    };
+    // four independent f64 chains per thread at a time: the loop is latency-bound, not throughput-bound
+    const int n = W + H;
+    int i0 = t;
+    for (; i0 + 3 * nthr < n; i0 += 4 * nthr) {
+      const float v0 = entry(i0), v1 = entry(i0 + nthr), v2 = entry(i0 + 2 * nthr), v3 = entry(i0 + 3 * nthr);
+      tab[i0] = v0; tab[i0 + nthr] = v1; tab[i0 + 2 * nthr] = v2; tab[i0 + 3 * nthr] = v3;
     }
+    for (; i0 < n; i0 += nthr) tab[i0] = entry(i0);
   };
 
   if (role == 0) {
@@ -384,17 +390,34 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           }
         } else {
           float* hb = reinterpret_cast<float*>(hbuf);
-          for (int e = lane; e < TD * 5; e += 32) {
-            const int r = e / 5, c5 = e - r * 5;
-            const float* trow = tile + r * TCW + xo + c5;
-            float acc = 0.f;
-            if (KS > 0) {
+          if (KS > 0) {
+            // (KS+4)*5 row sums over 32 lanes: the (up to 3) sums of a lane are independent FMA chains, interleaved
+            constexpr int kN = (KS + 4) * 5, kPer = (kN + 31) / 32;
+            float acc[kPer];
+            const float* trow[kPer];
 #pragma unroll
-              for (int j = 0; j < KS; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);   // taps: constant-bank operands
-            } else {
-              for (int j = 0; j < ksize; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);
+            for (int u = 0; u < kPer; ++u) {
+              const int e = min(lane + 32 * u, kN - 1);
+              const int r = e / 5, c5 = e - r * 5;
+              trow[u] = tile + r * TCW + xo + c5;
+              acc[u] = 0.f;
             }
-            hb[e] = acc;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+#pragma unroll
+              for (int u = 0; u < kPer; ++u) acc[u] = __fmaf_rn(a.tapsf[j], trow[u][j], acc[u]);   // taps: constant bank
+            }
+#pragma unroll
+            for (int u = 0; u < kPer; ++u)
+              if (lane + 32 * u < kN) hb[lane + 32 * u] = acc[u];
+          } else {
+            for (int e = lane; e < TD * 5; e += 32) {
+              const int r = e / 5, c5 = e - r * 5;
+              const float* trow = tile + r * TCW + xo + c5;
+              float acc = 0.f;
+              for (int j = 0; j < ksize; ++j) acc = __fmaf_rn(a.tapsf[j], trow[j], acc);
+              hb[e] = acc;
+            }
           }
           __syncwarp();
           if (lane < 25) {
@@ -633,11 +656,11 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       }
     }
 #ifdef LHN_TRACE
-    if (lane == 0 && nteams <= 6) {
-      g_trace[((blockIdx.x * 6 + team) * 16 + 0) * 16 + 14] = clock64();
+    if (lane == 0 && nteams <= 12) {
+      g_trace[((blockIdx.x * 12 + team) * 16 + 0) * 16 + 14] = clock64();
       unsigned long long gt;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-      g_trace[((blockIdx.x * 6 + team) * 16 + 1) * 16 + 13] = (long long)gt;
+      g_trace[((blockIdx.x * 12 + team) * 16 + 1) * 16 + 13] = (long long)gt;
     }
 #endif
     // ---- one-launch loss: publish this team's sums; the last team reduces all of them in a fixed order ----

@@ -61,13 +61,15 @@ def _f32c(t, name):
 
 def decode_heatmap(hm, mask_mode, refine, transform=L.XFORM_NONE, center=None, scale=None,
                    scale_xy=(1.0, 1.0), hm_flip=None, flip_index=None, blur_ksize=None, use_udp=False,
-                   want_idx=True, render=None, joints=None, vis=None, out=None):
+                   want_idx=True, render=None, joints=None, vis=None, out=None, overlap_previous=False):
     """K1.  Returns dict(hm_kpts [B,C,3], kpts [B,C,3], idx [B,C] int32[, weight [B,C], partials [B*C,4]]).
 
     render: None or dict(loss_mode, image_size, sigma, unbiased, pos_value) to fuse the target render +
     masked-MSE partial sums against joints [B,K,>=2] / vis [B,K,>=1] (column 0 = visibility).
     out: optional dict of preallocated contiguous outputs (hm_kpts, kpts, idx, partials, weight) to
     write into instead of allocating (steady-state loops, chunked pipelines).
+    overlap_previous: this call touches no buffer the previous launch on the stream writes (rotating buffer sets),
+    so its kernel may start while that one drains (LHN_FLAG_OVERLAP_PREVIOUS).
     """
     out = out or {}
     hm, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
@@ -105,7 +107,8 @@ def decode_heatmap(hm, mask_mode, refine, transform=L.XFORM_NONE, center=None, s
             raise L.LhnError("flip_index must have K entries")
     center = _f32c(center, "center")
     scale = _f32c(scale, "scale")
-    dp = _decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp)
+    dp = _decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp,
+                        flags=L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0)
     out_hm = out.get("hm_kpts")
     if out_hm is None:
         out_hm = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
@@ -154,7 +157,7 @@ def fused_workspace(device, B, K, S=1, stream_key=None):
 def fused_render_loss_decode(hm, mask_mode, refine, transform, center, scale, render, joints, vis,
                              hm_flip=None, flip_index=None, blur_ksize=None, use_udp=False, scale_xy=(1.0, 1.0),
                              want_idx=True, want_partials=False, reduction="mean", loss_scale=1.0,
-                             want_loss=True, out=None, workspace=None):
+                             want_loss=True, out=None, workspace=None, overlap_previous=False):
     """The headline step in ONE launch (lhn_fused_render_loss_decode): as decode_heatmap(render=...) plus
     the deterministic loss reduction and finalisation.  Returns dict(hm_kpts, kpts, idx, weight,
     sums f64[4], loss f32[1] (if want_loss)[, partials])."""
@@ -186,7 +189,8 @@ def fused_render_loss_decode(hm, mask_mode, refine, transform, center, scale, re
             raise L.LhnError("flip_index must have K entries")
     center = _f32c(center, "center")
     scale = _f32c(scale, "scale")
-    dp = _decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp)
+    dp = _decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp,
+                        flags=L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0)
 
     def _get(name, shape, dtype, want=True):
         t = out.get(name)
@@ -220,12 +224,13 @@ def fused_render_loss_decode(hm, mask_mode, refine, transform, center, scale, re
 
 
 def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, counters,
-                       pck_thr=0.2, auc_nor=30.0, auc_steps=20, blur_ksize=None):
+                       pck_thr=0.2, auc_nor=30.0, auc_steps=20, blur_ksize=None, overlap_previous=False):
     """K1 + fused PCK/AUC/EPE counters (BASELINE config 4).  `counters` int64 [(auc_steps+5)*K] is
     ADDED to.  Returns dict(hm_kpts, kpts, idx)."""
     hm, B, K, H, W, sb, sc = _plane_view(hm, "heatmaps")
     dev = hm.device
-    dp = _decode_params(mask_mode, refine, L.XFORM_CENTER_SCALE, (1, 1), blur_ksize)
+    dp = _decode_params(mask_mode, refine, L.XFORM_CENTER_SCALE, (1, 1), blur_ksize,
+                        flags=L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0)
     center, scale = _f32c(center, "center"), _f32c(scale, "scale")
     gt = _f32c(gt, "gt")
     bbox_wh = _f32c(bbox_wh, "bbox_wh")

@@ -34,6 +34,9 @@ def timed(fns, reps=20, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+OVERLAP = "--overlap" in sys.argv     # consecutive launches work on disjoint buffer sets: LHN_FLAG_OVERLAP_PREVIOUS
+
+
 def heatmap_case(name, B, K, H, W, dtype=torch.float32, flip=False, refine=L.REFINE_DARK, loss=True, pck=False,
                  sets=None):
     esz = torch.empty((), dtype=dtype).element_size()
@@ -48,19 +51,20 @@ def heatmap_case(name, B, K, H, W, dtype=torch.float32, flip=False, refine=L.REF
             gt, mask, wh = synth.pck_inputs(cen, seed=5, device=DEV)
             cnt = torch.zeros((1 + 20 + 4) * K, dtype=torch.int64, device=DEV)
             fns.append(lambda hm=hm, c=c, s=s, gt=gt, mask=mask, wh=wh, cnt=cnt:
-                       ops.decode_heatmap_pck(hm, L.MASK_NEG1, refine, c, s, gt, mask, wh, cnt))
+                       ops.decode_heatmap_pck(hm, L.MASK_NEG1, refine, c, s, gt, mask, wh, cnt, overlap_previous=OVERLAP))
         elif loss:
             j, v = synth.hand_joints(B, K, (4 * W, 4 * H), seed=2, device=DEV)
             render = dict(loss_mode=L.LOSS_DISTANCE_BALANCE, image_size=(4 * W, 4 * H), sigma=2.0 * W / 64, unbiased=True)
             out = {}
             fns.append(lambda hm=hm, hf=hf, c=c, s=s, j=j, v=v, out=out:
                        out.update(ops.fused_render_loss_decode(hm, L.MASK_NEG1, refine, L.XFORM_CENTER_SCALE, c, s, render,
-                                                               j, v, hm_flip=hf, blur_ksize=11, out=out or None)))
+                                                               j, v, hm_flip=hf, blur_ksize=11, out=out or None,
+                                                               overlap_previous=OVERLAP)))
         else:
             out = {}
             fns.append(lambda hm=hm, hf=hf, c=c, s=s, out=out:
                        out.update(ops.decode_heatmap(hm, L.MASK_NEG1, refine, L.XFORM_CENTER_SCALE, c, s, hm_flip=hf,
-                                                     blur_ksize=11, out=out or None)))
+                                                     blur_ksize=11, out=out or None, overlap_previous=OVERLAP)))
     ms = timed(fns)
     return dict(config=name, bytes=nbytes, ms=ms, gbs=nbytes / ms / 1e6, frac=nbytes / ms / 1e6 / PEAK,
                 samples_per_s=B / ms * 1e3)
@@ -94,6 +98,7 @@ def main():
         heatmap_case("cfg5 21x128x128 render + loss + DARK, batch 1024/GPU f32", 1024, 21, 128, 128),
         heatmap_case("56x56 (33 reference configs), render + loss + DARK, 1024x21 f32", 1024, 21, 56, 56),
     ]
+    print("launch overlap (LHN_FLAG_OVERLAP_PREVIOUS over rotating buffer sets):", "on" if OVERLAP else "off")
     for r in rows:
         print(f"{r['config']:95s} {r['ms'] * 1e3:9.1f} us  {r['gbs']:8.1f} GB/s  {r['frac'] * 100:5.1f}% of {PEAK:.0f}  "
               f"{r['samples_per_s'] / 1e6:7.2f} M samples/s")

@@ -341,6 +341,93 @@ def test_full_size_config2_properties():
     assert_coords_close(a["preds"][:n, :, :2].cpu().numpy(), ref["preds"], what="config-2 preds")
 
 
+def test_full_size_config1_and_3_properties():
+    """BASELINE config 1 (64 x 21 x 64 x 64, argmax + quarter offset) against the oracle in full, and config 3
+    (SimDR, 2 x [4096, 21, 512], k = 2) through torch.argmax as an independent first-index argmax plus the oracle
+    on a slice."""
+    from litehandnet_b200 import decode as D
+    hm, _ = synth.blob_heatmaps(64, 21, 64, 64, seed=11, zero_frac=0.02, tie_frac=0.01)
+    c, s = synth.bbox_center_scale(64, seed=12)
+    hp, p, mv = D.keypoints_from_heatmaps(hm.numpy(), c.numpy(), s.numpy(), post_process="default")
+    rhp, rp_, rmv = O.keypoints_from_heatmaps(hm.numpy(), c.numpy(), s.numpy(), "default", 11)
+    assert np.array_equal(hp, rhp) and np.array_equal(p, rp_) and np.array_equal(mv, rmv)
+    rpk = D.ResultParser(dict(image_size=[256, 256], hm_size=[64, 64], model="litehandnet", simdr_split_ratio=2,
+                              bbox_alpha=1.0, with_region_map=False, cycle_detection_reduction=1, DARK=False))
+    k = rpk.get_pred_kpt(hm.to(DEV), resized=True)
+    assert np.array_equal(k.cpu().numpy(), O.get_pred_kpt(hm.numpy(), dark=False, resized=True, feature_stride=(4, 4)))
+    B, K, Lv = 4096, 21, 512
+    xv, yv = synth.simdr_vectors(B, K, Lv, seed=13, device=DEV)
+    c, s = synth.bbox_center_scale(B, seed=14, device=DEV)
+    out = D.keypoints_from_simdr(xv, yv, c, s, k=2)
+    ix, iy = xv.argmax(-1), yv.argmax(-1)
+    score = (xv.amax(-1) + yv.amax(-1)) / 2
+    assert torch.equal(out[..., 2], score)
+    # undo transform_preds on a slice through the oracle
+    n = 64
+    ref = O.keypoints_from_simdr(xv[:n].cpu().numpy(), yv[:n].cpu().numpy(), c[:n].cpu().numpy(), s[:n].cpu().numpy(), 2)
+    assert np.array_equal(out[:n].cpu().numpy(), ref)
+    # and the raw indices (bit-exact against torch's first-index argmax) through the ops layer
+    from litehandnet_b200 import ops as OPS
+    r = OPS.decode_simdr(xv, yv, 2, None, None, want_idx=True)
+    idx = r[1] if isinstance(r, tuple) else r["idx"]
+    assert torch.equal(idx[..., 0].long().reshape(B, K), ix) and torch.equal(idx[..., 1].long().reshape(B, K), iy)
+
+
+def test_full_size_config4_sharded_counters():
+    """BASELINE config 4: MPII 16 x 64 x 64, B = 8192 in 8 shards of 1024 — fused decode + PCK/AUC/EPE counters per
+    shard, summed, must equal the monolithic counters bit for bit and the metric functions on the decoded points."""
+    from litehandnet_b200 import metrics as M
+    B, K = 8192, 16
+    hm, cen = synth.blob_heatmaps(B, K, 64, 64, seed=15, device=DEV)
+    c, s = synth.bbox_center_scale(B, seed=16, device=DEV)
+    gt, mask, wh = synth.pck_inputs(cen, seed=17, device=DEV)
+    mono = M.MetricAccumulator(K, device=DEV)
+    mono.update_from_heatmaps(hm, c, s, gt, mask, wh, post_process="default")
+    shard = M.MetricAccumulator(K, device=DEV)
+    for r in range(8):
+        sl = slice(r * 1024, (r + 1) * 1024)
+        part = M.MetricAccumulator(K, device=DEV)
+        part.update_from_heatmaps(hm[sl], c[sl], s[sl], gt[sl], mask[sl], wh[sl], post_process="default")
+        shard.counters += part.counters
+    assert torch.equal(mono.counters, shard.counters), "integer counters must be shard-additive"
+    res = mono.compute(("PCK", "AUC", "EPE"))
+    # independent route: decode, then the metric functions on the points (float64 like the JSON round trip)
+    from litehandnet_b200 import decode as D
+    _, preds, _ = D.keypoints_from_heatmaps(hm, c, s, post_process="default")
+    p64 = preds.double().cpu().numpy()
+    t = wh.max(1).values.double().cpu().numpy()
+    acc, avg, cnt = O.keypoint_pck_accuracy(p64, gt.cpu().numpy(), mask.cpu().numpy(), 0.2, np.stack([t, t], 1))
+    got = dict(res)
+    np.testing.assert_allclose(got["PCK"], avg, rtol=1e-12)
+    np.testing.assert_allclose(got["AUC"], O.keypoint_auc(p64, gt.cpu().numpy(), mask.cpu().numpy(), 30), rtol=1e-12)
+    np.testing.assert_allclose(got["EPE"], O.keypoint_epe(p64, gt.cpu().numpy(), mask.cpu().numpy()), rtol=1e-5)
+
+
+def test_full_size_config5_properties():
+    """BASELINE config 5 shape, one GPU's shard: 1024 x 21 x 128 x 128 f32 (1.4 GB), fused render + loss + DARK."""
+    from litehandnet_b200 import fused
+    B, K, H, W = 1024, 21, 128, 128
+    hm, cen = synth.blob_heatmaps(B, K, H, W, seed=18, device=DEV, sigma=4.0)
+    j, v = synth.hand_joints(B, K, (512, 512), seed=19, device=DEV)
+    c, s = synth.bbox_center_scale(B, seed=20, device=DEV)
+    step = fused.FusedHeatmapStep(image_size=(512, 512), sigma=4)
+    a = step(hm, j, v, c, s)
+    assert torch.equal(a["idx"].long(), hm.flatten(2).argmax(-1)), "argmax must equal torch's first-index argmax"
+    b = step(hm, j, v, c, s)
+    assert torch.equal(a["preds"], b["preds"]) and torch.equal(a["loss"], b["loss"])
+    sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+    for sl in (slice(0, 500), slice(500, 1024)):
+        sums += step(hm[sl], j[sl], v[sl], c[sl], s[sl])["loss_sums"]
+    assert torch.allclose(sums, a["loss_sums"], rtol=1e-12)
+    n = 3
+    with np.errstate(all="ignore"):
+        ref = O.fused_render_loss_decode(hm[:n].cpu().numpy(), None, j[:n].cpu().numpy(), v[:n].cpu().numpy(),
+                                         c[:n].cpu().numpy(), s[:n].cpu().numpy(), image_size=(512, 512), sigma=4)
+    assert_coords_close(a["preds"][:n, :, :2].cpu().numpy(), ref["preds"], what="config-5 preds")
+    sub = step(hm[:n], j[:n], v[:n], c[:n], s[:n])
+    np.testing.assert_allclose(sub["loss"].item(), float(ref["loss"]), rtol=1e-5)
+
+
 # ---- autograd through the drop-in losses (SURVEY §8f rank 1) -----------------------------------------------
 def _close(a, b, what, rtol=1e-5):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
