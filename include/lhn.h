@@ -107,8 +107,10 @@ typedef struct {
 /* Render + loss parameters (fused op and lhn_render_targets). */
 typedef struct {
   int32_t loss_mode;    /* LHN_LOSS_* (LHN_LOSS_NONE = decode only) */
-  int32_t unbiased;     /* 1: R1 sub-pixel full-plane Gaussian, generateTarget.py:100-123;
-                           0: R2 integer-centre (2*3*sigma+1)^2 patch, generateTarget.py:124-154 */
+  int32_t unbiased;     /* 1: R1 MSRA sub-pixel full-plane Gaussian, generateTarget.py:100-123;
+                           0: R2 MSRA integer-centre (2*3*sigma+1)^2 patch, generateTarget.py:124-154;
+                           2: UDP GaussianHeatmap — integer patch position, sub-pixel centre inside it,
+                              feat_stride = (image_size-1)/(heatmap_size-1), generateTarget.py:162-243 */
   int32_t num_stacks;   /* S >= 1 (R3: sigma list -> [B,S,K,H,W], generateTarget.py:252-268) */
   int32_t reserved;
   float image_w, image_h;        /* cfg image_size; feat_stride = image_size / [W, H] */

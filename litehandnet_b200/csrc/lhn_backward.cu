@@ -107,13 +107,6 @@ struct RenderBwdArgs {
   const double* sums; const float* grad_out;
 };
 
-__device__ __forceinline__ float exp_f32_from_f64_b(double a) {   // as the forward kernel evaluates it
-  const float ah = (float)a;
-  const float al = (float)(a - (double)ah);
-  const float v = expf(ah);
-  return fmaf(v, al, v);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(128) render_loss_backward_kernel(const __grid_constant__ RenderBwdArgs a) {
   extern __shared__ float tab[];   // ex[W], ey[H]
@@ -125,29 +118,16 @@ __global__ void __launch_bounds__(128) render_loss_backward_kernel(const __grid_
   const int c = (int)(p - b * C);
   const int s = c / a.K, k = c - s * a.K;
   const float* jp = a.joints + (b * a.K + k) * (int64_t)a.joints_stride;
-  float w = a.vis[(b * a.K + k) * (int64_t)a.vis_stride];
-  const double sig = (double)a.sigma[s], tmp = sig * 3.0;
-  double mux = (double)jp[0] / a.feat_x, muy = (double)jp[1] / a.feat_y;
-  double x0p = 0, ulx, uly, brx, bry;
-  if (a.unbiased) { ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1; }
-  else {
-    mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);
-    ulx = trunc(mux - tmp); uly = trunc(muy - tmp); brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
-    x0p = floor((2 * tmp + 1) * 0.5);
-  }
-  if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
-  const bool on = w > 0.5f;
+  const double sig = (double)a.sigma[s];
+  const RenderGeom g = render_geom(jp[0], jp[1], a.vis[(b * a.K + k) * (int64_t)a.vis_stride], sig, a.unbiased,
+                                   a.feat_x, a.feat_y, 0, 0.0, 0.0, W, H);
+  float w = g.w;
   const double inv2s2 = 1.0 / (2.0 * sig * sig);
   for (int i = threadIdx.x; i < W + H; i += blockDim.x) {
-    const bool isx = i < W;
-    const int pos = isx ? i : i - W;
     float v = 0.f;
-    if (on) {
-      if (a.unbiased) { const double d = (double)pos - (isx ? mux : muy); v = exp_f32_from_f64_b(-(d * d) * inv2s2); }
-      else {
-        const double ul = isx ? ulx : uly, br = isx ? brx : bry;
-        if ((double)pos >= ul && (double)pos < br) { const double d = ((double)pos - ul) - x0p; v = exp_f32_from_f64_b(-(d * d) * inv2s2); }
-      }
+    if (g.on) {
+      const double arg = render_arg(g, i, W, a.unbiased, inv2s2);
+      if (arg <= 0.0) v = exp_f32_from_f64(arg);         // as the forward kernel evaluates it
     }
     tab[i] = v;
   }
@@ -257,7 +237,13 @@ extern "C" int lhn_render_loss_backward(const void* hm, int dtype, int64_t B, in
   a.joints = joints; a.joints_stride = joints_stride; a.vis = vis; a.vis_stride = vis_stride;
   a.S = S; a.K = K; a.H = H; a.W = W; a.unbiased = rp->unbiased; a.loss_mode = rp->loss_mode;
   a.sum_reduction = sum_reduction; a.n_planes = B * S * K;
-  a.feat_x = (double)rp->image_w / W; a.feat_y = (double)rp->image_h / H;
+  if (rp->unbiased < 0 || rp->unbiased > 2) return LHN_EINVAL;
+  if (rp->unbiased == 2) {
+    if (W < 2 || H < 2) return LHN_EINVAL;
+    a.feat_x = ((double)rp->image_w - 1.0) / (W - 1.0); a.feat_y = ((double)rp->image_h - 1.0) / (H - 1.0);
+  } else {
+    a.feat_x = (double)rp->image_w / W; a.feat_y = (double)rp->image_h / H;
+  }
   for (int i = 0; i < S; ++i) { if (!(rp->sigma[i] > 0.f)) return LHN_EINVAL; a.sigma[i] = rp->sigma[i]; }
   a.pos_value = rp->pos_value; a.scale = scale; a.sums = sums; a.grad_out = grad_out;
   if (a.n_planes == 0) return LHN_OK;

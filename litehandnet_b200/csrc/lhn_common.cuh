@@ -111,6 +111,75 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gaussian target geometry (generateTarget.py:100-154 MSRA, :162-243 UDP), shared by the fused kernel,
+// the CTA-per-plane fallback, lhn_render_targets and the backward kernel so that all four render the
+// same target.  mode = lhn_render_params.unbiased: 1 = MSRA sub-pixel full plane, 0 = MSRA integer
+// centre patch, 2 = UDP (integer patch position, sub-pixel Gaussian centre inside it).
+// ---------------------------------------------------------------------------------------------
+struct RenderGeom {
+  double mux, muy;            // mode 1: the sub-pixel centre
+  double ulx, uly, brx, bry;  // patch bounds [ul, br) (modes 0, 2) / visibility-rule bounds (mode 1)
+  double x0x, x0y;            // modes 0, 2: centre inside the patch
+  float w;                    // target weight after the visibility rule
+  float cx, cy;               // centre in plane coordinates, f32 (window of the loss "positives")
+  bool on;                    // w > 0.5: the plane carries a Gaussian
+};
+
+__device__ __forceinline__ RenderGeom render_geom(float jx, float jy, float w, double sig, int mode, double feat_x,
+                                                  double feat_y, int feat_pow2, double inv_feat_x, double inv_feat_y,
+                                                  int W, int H) {
+  RenderGeom g;
+  const double tmp = sig * 3.0;
+  // joint / feat_stride in f64 (numpy promotes f32 / f64); a power-of-two stride multiplies exactly
+  double mux, muy;
+  if (feat_pow2) { mux = (double)jx * inv_feat_x; muy = (double)jy * inv_feat_y; }
+  else { mux = (double)jx / feat_x; muy = (double)jy / feat_y; }
+  g.x0x = g.x0y = 0.0;
+  if (mode == 1) {
+    g.ulx = mux - tmp; g.uly = muy - tmp; g.brx = mux + tmp + 1; g.bry = muy + tmp + 1;
+    g.cx = (float)mux; g.cy = (float)muy;
+  } else {
+    const double mix = trunc(mux + 0.5), miy = trunc(muy + 0.5);      // int() truncates toward zero
+    g.ulx = trunc(mix - tmp); g.uly = trunc(miy - tmp);
+    g.brx = trunc(mix + tmp + 1); g.bry = trunc(miy + tmp + 1);
+    const double half = floor((2 * tmp + 1) * 0.5);                   // size // 2
+    g.x0x = half; g.x0y = half;
+    if (mode == 2) { g.x0x += mux - mix; g.x0y += muy - miy; }        // UDP: x0 += mu_x_ac - mu_x
+    g.cx = (float)(g.ulx + g.x0x); g.cy = (float)(g.uly + g.x0y);
+    mux = mix; muy = miy;
+  }
+  g.mux = mux; g.muy = muy;
+  if (g.ulx >= W || g.uly >= H || g.brx < 0 || g.bry < 0) w = 0.f;
+  g.w = w;
+  g.on = w > 0.5f;
+  return g;
+}
+
+// exponent argument (<= 0) of table entry i (i < W: x table, else y table), or +1 for "no Gaussian here"
+__device__ __forceinline__ double render_arg(const RenderGeom& g, int i, int W, int mode, double inv2s2) {
+  const bool isx = i < W;
+  const int pos = isx ? i : i - W;
+  if (mode == 1) {
+    const double d = (double)pos - (isx ? g.mux : g.muy);
+    return -(d * d) * inv2s2;
+  }
+  const double ul = isx ? g.ulx : g.uly, br = isx ? g.brx : g.bry;
+  if ((double)pos >= ul && (double)pos < br) {
+    const double d = ((double)pos - ul) - (isx ? g.x0x : g.x0y);
+    return -(d * d) * inv2s2;
+  }
+  return 1.0;
+}
+
+// fast f32 exp of a double argument: exp(a) = exp(ah) * (1 + al), ah = f32(a), al = a - ah
+__device__ __forceinline__ float exp_f32_from_f64(double a) {
+  const float ah = (float)a;
+  const float al = (float)(a - (double)ah);
+  const float v = expf(ah);
+  return fmaf(v, al, v);
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier + TMA bulk copy (cp.async.bulk, 1-D: no tensor map needed for contiguous planes)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

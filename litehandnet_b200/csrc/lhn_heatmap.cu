@@ -71,41 +71,22 @@ __global__ void __launch_bounds__(NT) heatmap_plane_kernel(const __grid_constant
   }
 
   // ---- per-plane render parameters + separable Gaussian tables (overlaps the load) -----------
-  float w = 0.f;
+  float w = 0.f, gcx = 0.f, gcy = 0.f;
   bool render_on = false;
   if (LOSS) {
     const float* jp = a.joints + (b * a.K + k) * (int64_t)a.joints_stride;
-    w = a.vis[(b * a.K + k) * (int64_t)a.vis_stride];
     const double sig = (double)a.sigma[s];
-    const double tmp = sig * 3.0;
-    double mux = (double)jp[0] / a.feat_x, muy = (double)jp[1] / a.feat_y;
-    double x0p = 0, ulx = 0, uly = 0, brx = 0, bry = 0;
-    if (a.unbiased) {
-      ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1;
-    } else {
-      mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);          // int() truncates toward zero
-      ulx = trunc(mux - tmp); uly = trunc(muy - tmp);
-      brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
-      x0p = floor((2 * tmp + 1) * 0.5);                         // size // 2
-    }
-    if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
-    render_on = w > 0.5f;
+    const RenderGeom g = render_geom(jp[0], jp[1], a.vis[(b * a.K + k) * (int64_t)a.vis_stride], sig, a.unbiased,
+                                     a.feat_x, a.feat_y, 0, 0.0, 0.0, W, H);
+    w = g.w;
+    render_on = g.on;
+    gcx = g.cx; gcy = g.cy;
     const double inv2s2 = 1.0 / (2.0 * sig * sig);
     for (int i = tid; i < W + H; i += NT) {
-      const bool isx = i < W;
-      const int pos = isx ? i : i - W;
       float v = 0.f;
       if (render_on) {
-        if (a.unbiased) {
-          double d = (double)pos - (isx ? mux : muy);
-          v = (float)exp(-(d * d) * inv2s2);
-        } else {
-          double ul = isx ? ulx : uly, br = isx ? brx : bry;
-          if ((double)pos >= ul && (double)pos < br) {
-            double d = ((double)pos - ul) - x0p;
-            v = (float)exp(-(d * d) * inv2s2);
-          }
-        }
+        const double arg = render_arg(g, i, W, a.unbiased, inv2s2);
+        if (arg <= 0.0) v = (float)exp(arg);
       }
       ex[i] = v;   // ey follows ex contiguously
     }
@@ -281,8 +262,7 @@ __global__ void __launch_bounds__(NT) heatmap_plane_kernel(const __grid_constant
     if (a.pos_value > 0.f && a.pos_value < 1.f) {
       // g > value  <=>  r^2 < -2 sigma^2 ln(value); per axis |d| < sqrt(-2 ln value) * sigma
       const float rad = sqrtf(-2.f * logf(a.pos_value)) * sig + 1.5f;
-      float mx = (float)((double)jp[0] / a.feat_x), my = (float)((double)jp[1] / a.feat_y);
-      if (!a.unbiased) { mx = truncf(mx + 0.5f); my = truncf(my + 0.5f); }
+      const float mx = gcx, my = gcy;                     // Gaussian centre in plane coordinates
       x_lo = max(0, (int)floorf(mx - rad)); x_hi = min(W - 1, (int)ceilf(mx + rad));
       y_lo = max(0, (int)floorf(my - rad)); y_hi = min(H - 1, (int)ceilf(my + rad));
     } else if (a.pos_value >= 1.f) {
@@ -604,7 +584,13 @@ static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_
         vis_stride < 1 || rp->image_w <= 0 || rp->image_h <= 0)
       return LHN_EINVAL;
     a.unbiased = rp->unbiased;
-    a.feat_x = (double)rp->image_w / (double)W; a.feat_y = (double)rp->image_h / (double)H;
+    if (rp->unbiased < 0 || rp->unbiased > 2) return LHN_EINVAL;
+    if (rp->unbiased == 2) {   // UDP: feat_stride = (image_size - 1) / (heatmap_size - 1), generateTarget.py:208
+      if (W < 2 || H < 2) return LHN_EINVAL;
+      a.feat_x = ((double)rp->image_w - 1.0) / ((double)W - 1.0); a.feat_y = ((double)rp->image_h - 1.0) / ((double)H - 1.0);
+    } else {
+      a.feat_x = (double)rp->image_w / (double)W; a.feat_y = (double)rp->image_h / (double)H;
+    }
     a.pos_value = rp->pos_value;
     for (int i = 0; i < S; ++i) { if (!(rp->sigma[i] > 0.f)) return LHN_EINVAL; a.sigma[i] = rp->sigma[i]; }
     a.joints = joints; a.joints_stride = joints_stride; a.vis = vis; a.vis_stride = vis_stride;

@@ -121,14 +121,6 @@ enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW
 template <typename T>
 __device__ __forceinline__ float elem_f32(const T* p, int i) { return Elem<T>::to_f32(p[i]); }
 
-// fast f32 exp of a double argument: exp(a) = exp(ah) * (1 + al), ah = f32(a), al = a - ah
-__device__ __forceinline__ float exp_f32_from_f64(double a) {
-  const float ah = (float)a;
-  const float al = (float)(a - (double)ah);
-  const float v = expf(ah);
-  return fmaf(v, al, v);
-}
-
 // quads per row of the DARK tile: the (ksize+4)-wide window starts 0..3 columns into its first quad
 __host__ __device__ constexpr int tile_quads(int td) { return (td + 6) >> 2; }
 
@@ -269,43 +261,17 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     uint32_t s, k;
     split_channel(c, s, k);
     const float* sd = th->side[slot];
-    const float jx = sd[SD_JX], jy = sd[SD_JY];
-    float w = sd[SD_VIS];
-    const double sig = (double)a.sigma[s], tmp = sig * 3.0;
-    // joint / feat_stride in f64 (numpy promotes f32 / f64); a power-of-two stride multiplies exactly
-    double mux, muy;
-    if (a.feat_pow2) { mux = (double)jx * a.inv_feat_x; muy = (double)jy * a.inv_feat_y; }
-    else { mux = (double)jx / a.feat_x; muy = (double)jy / a.feat_y; }
-    double x0p = 0, ulx, uly, brx, bry;
-    if (a.unbiased) {
-      ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1;
-    } else {
-      mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);                // int() truncates toward zero
-      ulx = trunc(mux - tmp); uly = trunc(muy - tmp);
-      brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
-      x0p = floor((2 * tmp + 1) * 0.5);                               // size // 2
-    }
-    if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
-    const bool render_on = w > 0.5f;
+    const RenderGeom g = render_geom(sd[SD_JX], sd[SD_JY], sd[SD_VIS], (double)a.sigma[s], a.unbiased, a.feat_x, a.feat_y,
+                                     a.feat_pow2, a.inv_feat_x, a.inv_feat_y, W, H);
+    const bool render_on = g.on;
     if (t == 0) {
-      th->w[buf] = w; th->mx[buf] = (float)mux; th->my[buf] = (float)muy; th->render_on[buf] = render_on ? 1 : 0;
+      th->w[buf] = g.w; th->mx[buf] = g.cx; th->my[buf] = g.cy; th->render_on[buf] = render_on ? 1 : 0;
     }
     const double i2 = a.inv2s2[s];
     float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab0) + (size_t)buf * tab_bytes);
     auto entry = [&](int i) -> float {
-      const bool isx = i < W;
-      const int pos = isx ? i : i - W;
-      float v = 0.f;
-      if (a.unbiased) {
-        const double d = (double)pos - (isx ? mux : muy);
-        v = exp_f32_from_f64(-(d * d) * i2);
-      } else {
-        const double ul = isx ? ulx : uly, br = isx ? brx : bry;
-        if ((double)pos >= ul && (double)pos < br) {
-          const double d = ((double)pos - ul) - x0p;
-          v = exp_f32_from_f64(-(d * d) * i2);
-        }
-      }
+      const double arg = render_arg(g, i, W, a.unbiased, i2);
+      const float v = arg <= 0.0 ? exp_f32_from_f64(arg) : 0.f;
       return render_on ? v : 0.f;
     };
     // four independent f64 chains per thread at a time: the loop is latency-bound, not throughput-bound

@@ -158,29 +158,16 @@ __global__ void __launch_bounds__(128) render_targets_kernel(const __grid_consta
   const int c = (int)(p - b * C);
   const int s = c / a.K, k = c - s * a.K;
   const float* jp = a.joints + (b * a.K + k) * (int64_t)a.joints_stride;
-  float w = a.vis[(b * a.K + k) * (int64_t)a.vis_stride];
-  const double sig = (double)a.sigma[s], tmp = sig * 3.0;
-  double mux = (double)jp[0] / a.feat_x, muy = (double)jp[1] / a.feat_y;
-  double x0p = 0, ulx, uly, brx, bry;
-  if (a.unbiased) { ulx = mux - tmp; uly = muy - tmp; brx = mux + tmp + 1; bry = muy + tmp + 1; }
-  else {
-    mux = trunc(mux + 0.5); muy = trunc(muy + 0.5);
-    ulx = trunc(mux - tmp); uly = trunc(muy - tmp); brx = trunc(mux + tmp + 1); bry = trunc(muy + tmp + 1);
-    x0p = floor((2 * tmp + 1) * 0.5);
-  }
-  if (ulx >= W || uly >= H || brx < 0 || bry < 0) w = 0.f;
-  const bool on = w > 0.5f;
+  const double sig = (double)a.sigma[s];
+  const RenderGeom g = render_geom(jp[0], jp[1], a.vis[(b * a.K + k) * (int64_t)a.vis_stride], sig, a.unbiased,
+                                   a.feat_x, a.feat_y, 0, 0.0, 0.0, W, H);
+  const float w = g.w;
   const double inv2s2 = 1.0 / (2.0 * sig * sig);
   for (int i = threadIdx.x; i < W + H; i += blockDim.x) {
-    const bool isx = i < W;
-    const int pos = isx ? i : i - W;
     float v = 0.f;
-    if (on) {
-      if (a.unbiased) { double d = (double)pos - (isx ? mux : muy); v = (float)exp(-(d * d) * inv2s2); }
-      else {
-        double ul = isx ? ulx : uly, br = isx ? brx : bry;
-        if ((double)pos >= ul && (double)pos < br) { double d = ((double)pos - ul) - x0p; v = (float)exp(-(d * d) * inv2s2); }
-      }
+    if (g.on) {
+      const double arg = render_arg(g, i, W, a.unbiased, inv2s2);
+      if (arg <= 0.0) v = (float)exp(arg);
     }
     tab[i] = v;
   }
@@ -306,7 +293,13 @@ extern "C" int lhn_render_targets(const float* joints, int joints_stride, const 
   a.joints = joints; a.joints_stride = joints_stride; a.vis = vis; a.vis_stride = vis_stride;
   a.S = S; a.K = K; a.H = H; a.W = W; a.unbiased = rp->unbiased;
   a.n_planes = B * S * K;
-  a.feat_x = (double)rp->image_w / W; a.feat_y = (double)rp->image_h / H;
+  if (rp->unbiased < 0 || rp->unbiased > 2) return LHN_EINVAL;
+  if (rp->unbiased == 2) {
+    if (W < 2 || H < 2) return LHN_EINVAL;
+    a.feat_x = ((double)rp->image_w - 1.0) / (W - 1.0); a.feat_y = ((double)rp->image_h - 1.0) / (H - 1.0);
+  } else {
+    a.feat_x = (double)rp->image_w / W; a.feat_y = (double)rp->image_h / H;
+  }
   for (int i = 0; i < S; ++i) { if (!(rp->sigma[i] > 0.f)) return LHN_EINVAL; a.sigma[i] = rp->sigma[i]; }
   a.target = target; a.target_weight = target_weight;
   if (a.n_planes == 0) return LHN_OK;

@@ -28,7 +28,9 @@ def _render_params(loss_mode, image_size, sigma, unbiased=True, pos_value=0.5):
     sig = list(sigma) if isinstance(sigma, (list, tuple)) else [sigma]
     if len(sig) > L.MAX_STACKS:
         raise L.LhnError(f"at most {L.MAX_STACKS} stacked sigmas")
-    rp.loss_mode, rp.unbiased, rp.num_stacks = int(loss_mode), int(bool(unbiased)), len(sig)
+    # unbiased: False/0 = MSRA integer-centre patch, True/1 = MSRA sub-pixel plane, 'udp'/2 = UDP GaussianHeatmap
+    mode = 2 if (unbiased == 2 or (isinstance(unbiased, str) and unbiased.lower() == "udp")) else int(bool(unbiased))
+    rp.loss_mode, rp.unbiased, rp.num_stacks = int(loss_mode), mode, len(sig)
     rp.image_w, rp.image_h = float(image_size[0]), float(image_size[1])
     rp.pos_value = float(pos_value)
     for i, s in enumerate(sig):

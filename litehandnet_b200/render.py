@@ -1,13 +1,12 @@
 """Drop-in mirrors of the target renderers (per-sample dict-in/dict-out transforms of the dataset
 pipeline) plus the batched GPU entry points.
 
-  datasets/data_pipeline/generateTarget.py:33   TopDownGenerateTarget (MSRA, unbiased + integer-centre,
-                                                sigma lists -> stacked targets)
+  datasets/data_pipeline/generateTarget.py:33   TopDownGenerateTarget (MSRA unbiased + integer-centre, UDP
+                                                GaussianHeatmap, sigma lists -> stacked targets)
   datasets/data_pipeline/generate_simder.py:3   GenerateSimDR
 
 The fused training path never materialises targets (see loss.TopdownHeatmapLoss / fused.py); these
 classes exist so a pipeline that wants the tensors still gets them, rendered on the GPU.
-UDP encoding is SURVEY §8f 'next' (1 of 108 configs).
 """
 import numpy as np
 import torch
@@ -40,8 +39,9 @@ class TopDownGenerateTarget:
         """results['joints_3d'] [K,3], ['joints_3d_visible'] [K,3], ['ann_info'] -> adds 'target'
         [K,H,W] (or [S,K,H,W]) and 'target_weight' [K,1] (or [S,K,1]) as NumPy arrays."""
         assert self.encoding in ['MSRA', 'UDP']
-        if self.encoding == 'UDP':
-            raise NotImplementedError("UDP target encoding is SURVEY §8f 'next' (rank 3)")
+        if self.encoding == 'UDP' and self.target_type.lower() != 'gaussianheatmap':
+            raise NotImplementedError("UDP 'CombinedTarget' (offset maps) is not produced by the reference either "
+                                      "(generateTarget.py:162-243 renders the GaussianHeatmap only)")
         cfg = results['ann_info']
         if cfg.get('use_different_joint_weights', False):
             raise NotImplementedError("joint_weights are forced off by every hand dataset (freihand_dataset.py:62)")
@@ -50,7 +50,7 @@ class TopDownGenerateTarget:
         v = torch.as_tensor(np.asarray(results['joints_3d_visible'], dtype=np.float32)).to(dev)[None]
         sigma = list(self.sigma) if isinstance(self.sigma, (list, tuple)) else self.sigma
         t, w = ops.render_targets(j, v, tuple(cfg['image_size']), tuple(cfg['heatmap_size']), sigma,
-                                  self.unbiased_encoding)
+                                  'udp' if self.encoding == 'UDP' else self.unbiased_encoding)
         results['target'] = _np(t[0])
         results['target_weight'] = _np(w[0])
         return results

@@ -165,6 +165,29 @@ def metrics_case(ref, name, N, K, seed):
     np.savez_compressed(os.path.join(OUT, name), **d)
 
 
+def udp_case(ref, name, seed):
+    """UDP GaussianHeatmap targets (generateTarget.py:162-243) for two sigmas incl. a non-integer 3*sigma, joints
+    outside the image and invisible joints; plus DistanceLoss on them."""
+    N, K, H, W = 3, 8, 64, 48
+    isz = (192, 256)
+    joints, vis = synth.hand_joints(N, K, isz, seed=seed, vis_prob=0.85, outside_frac=0.15)
+    d = dict(joints_3d=joints.numpy(), joints_3d_visible=vis.numpy(), image_size=np.array(isz), heatmap_size=np.array([W, H]))
+    for sg, tag in ((2, "s2"), (1.5, "s15"), ([2, 3], "list")):
+        gen = ref.generateTarget.TopDownGenerateTarget(sigma=sg, encoding="UDP", target_type="GaussianHeatmap")
+        tg, tw = [], []
+        for b in range(N):
+            out = gen(dict(joints_3d=joints[b].numpy().copy(), joints_3d_visible=vis[b].numpy().copy(),
+                           ann_info=_ann(K, isz, (W, H))))
+            tg.append(out["target"]); tw.append(out["target_weight"])
+        d[f"ref_target_{tag}"], d[f"ref_weight_{tag}"] = np.stack(tg), np.stack(tw)
+    hm, _ = synth.blob_heatmaps(N, K, H, W, seed=seed + 1)
+    d["hm"] = hm.numpy()
+    HL = ref.loss.heatmapLoss
+    d["ref_loss_bal_s2"] = np.float32(HL.DistanceLoss(loss_type="L2", balance=True)(
+        hm, torch.from_numpy(d["ref_target_s2"]), torch.from_numpy(d["ref_weight_s2"])).item())
+    np.savez_compressed(os.path.join(OUT, name), **d)
+
+
 def backward_case(ref, name, seed):
     """Gradients of the reference losses by torch autograd on the CPU: the explicit-target
     heatmap losses on a rendered target, and KLDiscretLoss on SimDR vectors."""
@@ -217,6 +240,7 @@ def main():
     render_loss_case(ref, "render_loss_56.npz", N=2, K=6, H=56, W=56, seed=22, image_size=(224, 224), hm=hm56)
     metrics_case(ref, "metrics_16.npz", N=48, K=16, seed=31)
     backward_case(ref, "loss_backward.npz", seed=41)
+    udp_case(ref, "render_udp.npz", seed=51)
     # the reference's only hand-derivable known answer (utils/SPheatmapParser.py:221-233)
     kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
     k, _ = ref.SPheatmapParser.HeatmapParser_SH().parse(kpt_hm.clone(), image_size=(256, 256))

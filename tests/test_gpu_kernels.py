@@ -347,6 +347,33 @@ def test_render_multi_sigma_and_edges(ops, L):
 
 
 # ---- SimDR -----------------------------------------------------------------------------------------
+def test_udp_render_loss_and_backward(ops, L):
+    """UDP encoding (render side): lhn_render_targets, the fused loss on UDP targets and its
+    backward against the executed reference (tests/golden/render_udp.npz) and the oracle."""
+    g = load_golden("render_udp.npz")
+    isz, hsz = tuple(int(v) for v in g["image_size"]), tuple(int(v) for v in g["heatmap_size"])
+    j, v = cu(g["joints_3d"]), cu(g["joints_3d_visible"])
+    for sg, tag in ((2, "s2"), (1.5, "s15"), ([2, 3], "list")):
+        t, w = ops.render_targets(j, v, isz, hsz, sg, "udp")
+        assert np.array_equal(nump(w), g[f"ref_weight_{tag}"])
+        assert np.abs(nump(t) - g[f"ref_target_{tag}"]).max() <= 1.2e-7
+    # non-integer 3*sigma in the MSRA integer-centre branch as well (patch centre != rounded joint)
+    t, w = ops.render_targets(j, v, isz, hsz, 1.5, False)
+    rt, rw = O.render_targets(g["joints_3d"], g["joints_3d_visible"], isz, hsz, 1.5, False)
+    assert np.array_equal(nump(w), rw) and np.abs(nump(t) - rt).max() <= 1.2e-7
+    for sg, tag, mode in ((2, "s2", "udp"), (1.5, "s15", "udp"), (1.5, None, False)):
+        render = dict(loss_mode=L.LOSS_DISTANCE_BALANCE, image_size=isz, sigma=sg, unbiased=mode)
+        r = ops.fused_render_loss_decode(cu(g["hm"]), L.MASK_NEG1, L.REFINE_NONE, L.XFORM_NONE, None, None, render, j, v)
+        tg, tw = O.render_targets(g["joints_3d"], g["joints_3d_visible"], isz, hsz, sg, mode)
+        want = O.distance_loss_l2(g["hm"], tg, tw, True)
+        np.testing.assert_allclose(nump(r["loss"])[0], want, rtol=1e-5)
+        if tag == "s2":
+            np.testing.assert_allclose(nump(r["loss"])[0], g["ref_loss_bal_s2"], rtol=1e-5)
+        grad = ops.render_loss_backward(cu(g["hm"]), j, v, render, r["sums"])
+        ref = O.distance_loss_l2_grad(g["hm"], tg, tw, True)
+        assert np.abs(nump(grad) - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 def test_simdr_decode_and_loss(ops, L):
     g = load_golden("render_loss_64.npz")
     xv, yv = g["simdr_xv"], g["simdr_yv"]
