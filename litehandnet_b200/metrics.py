@@ -19,7 +19,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .decode import _up
+from .decode import _device, _up
 
 
 def _counters(pred, gt, mask, thr, normalize=None, norm_const=1.0, counters=None):
@@ -145,6 +145,40 @@ def report_metric(outputs, gts, masks, bbox_wh=None, head_size=None, metrics=("P
     if 'EPE' in metrics:
         info_str.append(('EPE', keypoint_epe(outputs, gts, masks)))
     return info_str
+
+
+def evaluate_results(results, db, metric='PCK', pck_thr=0.2, pckh_thr=0.5, auc_nor=30):
+    """dataset.evaluate(results, res_folder, metric) without the JSON detour:
+    datasets/datasets/hand/freihand_dataset.py:111-183 + base_dataset.py:193-284.
+
+    results: list of TopDownDecoder.decode() dicts (preds [N,K,3], boxes [N,6], image_paths, bbox_ids) — NumPy
+    arrays or CUDA tensors; db: the dataset's list of annotation dicts ('joints_3d' [K,3], 'joints_3d_visible'
+    [K,3], 'bbox' [x,y,w,h], optional 'head_size'), sorted by bbox_id as the reference's _get_db leaves it.
+    The predictions are sorted by bbox_id and de-duplicated (_sort_and_unique_bboxes keeps the first of equal
+    ids), the distances are taken in float64 (the reference reads the points back from JSON) and the hit
+    counts come from lhn_pck_accumulate.  Returns an OrderedDict like the reference."""
+    metrics = metric if isinstance(metric, (list, tuple)) else [metric]
+    for m in metrics:
+        if m not in ('PCK', 'PCKh', 'AUC', 'EPE'):
+            raise KeyError(f'metric {m} is not supported')
+    dev = _device()
+    preds = torch.cat([_up(r['preds'], torch.float32)[0] for r in results], 0)
+    ids = torch.as_tensor(np.concatenate([np.asarray(r['bbox_ids']).reshape(-1) for r in results])).to(dev)
+    order = torch.sort(ids, stable=True).indices                  # stable: the first of equal ids stays first
+    ids_s = ids[order]
+    keep = torch.ones_like(ids_s, dtype=torch.bool)
+    keep[1:] = ids_s[1:] != ids_s[:-1]
+    preds = preds[order][keep]
+    assert preds.shape[0] == len(db), (preds.shape[0], len(db))
+    gts = torch.as_tensor(np.stack([np.asarray(it['joints_3d'], dtype=np.float32)[:, :2] for it in db])).to(dev)
+    masks = torch.as_tensor(np.stack([np.asarray(it['joints_3d_visible'])[:, 0] > 0 for it in db])).to(dev)
+    bbox_wh = head = None
+    if 'PCK' in metrics:
+        bbox_wh = np.stack([np.asarray(it['bbox'], dtype=np.float64)[2:] for it in db])
+    if 'PCKh' in metrics:
+        head = np.asarray([it['head_size'] for it in db], dtype=np.float64)
+    return OrderedDict(report_metric(preds[..., :2].double(), gts, masks, bbox_wh, head, metrics, pck_thr, pckh_thr,
+                                     auc_nor))
 
 
 def evaluate_pck(pred_keypoints_hm, gt_keypoints_hm, bbox, image_size=256, target_weight=None, thr=0.2):

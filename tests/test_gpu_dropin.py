@@ -341,6 +341,38 @@ def test_full_size_config2_properties():
     assert_coords_close(a["preds"][:n, :, :2].cpu().numpy(), ref["preds"], what="config-2 preds")
 
 
+def test_evaluate_results_like_dataset_evaluate():
+    """test.py:114-135: results.append(decoder.decode(meta, outputs)); dataset.evaluate(results, out, metric) —
+    on shuffled, partly duplicated batches (the last batch of a DistributedSampler repeats samples), against
+    the reference's _report_metric arithmetic (oracle) on the de-duplicated, id-sorted predictions."""
+    from litehandnet_b200 import decode as D, metrics as M
+    N, K = 96, 21
+    hm, cen = synth.blob_heatmaps(N, K, 64, 64, seed=91)
+    c, s = synth.bbox_center_scale(N, seed=92)
+    gt, mask, wh = synth.pck_inputs(cen, seed=93)
+    db = [dict(joints_3d=np.concatenate([gt[i].numpy(), np.zeros((K, 1), np.float32)], 1),
+               joints_3d_visible=np.repeat(mask[i].numpy().astype(np.float32)[:, None], 3, 1),
+               bbox=np.array([10.0, 20.0, float(wh[i, 0]), float(wh[i, 1])]), bbox_id=i) for i in range(N)]
+    dec = D.TopDownDecoder(make_cfg(K=K, unbiased=False))             # post_process='default'
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(0))
+    perm = torch.cat([perm, perm[:16]])                               # 16 duplicates at the end
+    results = []
+    for b in range(0, len(perm), 32):
+        idx = perm[b:b + 32]
+        meta = dict(center=c[idx], scale=s[idx], image_file=[f"img{int(i)}.jpg" for i in idx],
+                    bbox_score=torch.ones(len(idx)), bbox_id=[int(i) for i in idx])
+        results.append(dec.decode(meta, hm[idx].to(DEV)))
+    got = M.evaluate_results(results, db, ["PCK", "AUC", "EPE"])
+    _, preds, _ = O.keypoints_from_heatmaps(hm.numpy(), c.numpy(), s.numpy(), "default", 11)
+    p64 = preds.astype(np.float64)
+    t = wh.max(1).values.double().numpy()
+    _, pck, _ = O.keypoint_pck_accuracy(p64, gt.numpy(), mask.numpy(), 0.2, np.stack([t, t], 1))
+    assert list(got.keys()) == ["PCK", "AUC", "EPE"]
+    np.testing.assert_allclose(got["PCK"], pck, rtol=1e-12)
+    np.testing.assert_allclose(got["AUC"], O.keypoint_auc(p64, gt.numpy(), mask.numpy(), 30), rtol=1e-12)
+    np.testing.assert_allclose(got["EPE"], O.keypoint_epe(p64, gt.numpy(), mask.numpy()), rtol=1e-5)
+
+
 def test_udp_target_transform_dict_in_dict_out():
     """TopDownGenerateTarget(encoding='UDP') as the dataset pipeline calls it (generateTarget.py:245-300)."""
     from litehandnet_b200 import render as R
