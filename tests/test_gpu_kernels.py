@@ -374,6 +374,30 @@ def test_udp_render_loss_and_backward(ops, L):
         assert np.abs(nump(grad) - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("shape", [(5, 21, 64, 64), (4, 6, 56, 56), (3, 4, 28, 28)])
+def test_misaligned_base_pointer_takes_the_non_tma_path(ops, L, shape):
+    """A heatmap tensor whose base address is only 4-byte aligned cannot be fetched with TMA bulk copies: the
+    kernel stages the plane with plain loads instead.  Same results as the aligned tensor, bit for bit."""
+    N, K, H, W = shape
+    hm, cen, center, scale = synth_case(N, K, H, W, seed=61)
+    hf = synth.flipped_blob_heatmaps(cen, H, W, seed=62).numpy()
+    j, v = synth.hand_joints(N, K, (4 * W, 4 * H), seed=63)
+    render = dict(loss_mode=L.LOSS_DISTANCE_BALANCE, image_size=(4 * W, 4 * H), sigma=2, unbiased=True)
+
+    def shifted(a):                      # the same values at a base address that is 4 (mod 16)
+        buf = torch.empty(a.size + 1, dtype=torch.float32, device=DEV)
+        view = buf[1:].view(a.shape)
+        view.copy_(cu(a))
+        assert view.data_ptr() % 16 == 4
+        return view
+
+    args = (L.MASK_NEG1, L.REFINE_DARK, L.XFORM_CENTER_SCALE, cu(center), cu(scale))
+    a = ops.decode_heatmap(cu(hm), *args, hm_flip=cu(hf), render=render, joints=cu(j.numpy()), vis=cu(v.numpy()))
+    b = ops.decode_heatmap(shifted(hm), *args, hm_flip=shifted(hf), render=render, joints=cu(j.numpy()), vis=cu(v.numpy()))
+    for k in ("hm_kpts", "kpts", "idx", "weight", "partials"):
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_simdr_decode_and_loss(ops, L):
     g = load_golden("render_loss_64.npz")
     xv, yv = g["simdr_xv"], g["simdr_yv"]
