@@ -55,6 +55,7 @@ struct HmArgs {
   int warp_smem;                   // bytes of shared memory owned by one team (stage + aux)
   int team_warps;                  // warps per team
   int stage_bytes;                 // bytes of one TMA stage (plane0 [+ plane1])
+  int stagger_ns;                  // delay between the first loads of consecutive teams of a CTA (0 = none)
   int sweeper_tables;              // the sweepers (not the epilogue warp) evaluate each plane's Gaussian tables
   int stages;                      // stages per team (1, 2 or 4), at the start of the team's shared memory
   int tile_dim;                    // DARK window side = blur_ksize + 4 (0 when DARK is off)

@@ -689,6 +689,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   if (sl == 0) {
     policy = policy_evict_first();
     if (a.use_tma) {
+      // Stagger the first loads of the CTA's teams: issued all at once they also all land at once (~5 us for
+      // the 29 MB first wave) and the teams then sweep in lockstep while HBM idles.
+      if (a.stagger_ns > 0 && team > 0) __nanosleep((unsigned)(team * a.stagger_ns));
       uint32_t ib = pb, ic = pc, ip = p;
       for (int i = 0; i < nstg && ip < n_planes; ++i, ip += total_teams, advance(ib, ic)) issue(ib, ic, i);
     }
@@ -1066,6 +1069,12 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   const char* env = getenv("LHN_TEAM_STAGES");
   if (env && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4) && atoi(env) <= nstg) nstg = atoi(env);
   a.stages = nstg;
+  {
+    // measured (profiles/probes/stagger_sweep.sh): 600 ns between teams buys ~1.3 % on a cold launch of the
+    // headline shape; pointless (and a visible delay) when a team only has a few planes
+    const char* sg = getenv("LHN_STAGGER_NS");
+    a.stagger_ns = sg ? atoi(sg) : ((a.n_planes >= (int64_t)8 * nteams * sm_count()) ? 600 : 0);
+  }
   a.sweeper_tables = (nstg >= 2 && tw >= 4) ? 1 : 0;
   a.team_warps = tw;
   a.warp_smem = (int)((size_t)nstg * a.stage_bytes + aux_al);
