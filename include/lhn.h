@@ -59,6 +59,9 @@ typedef void* lhn_stream_t; /* cudaStream_t */
 #define LHN_REFINE_SIGN_ROUND 4  /* D4: transforms.py:18-44 (px=floor(x+0.5)) */
 #define LHN_REFINE_DARK 5        /* D5: top_down_eval.py:233-272,338-372,433-439 (f32 blur) */
 #define LHN_REFINE_DARK_LEGACY 6 /* D6: heatmap_post_processing.py:35-91 (f64 blur, +1e-6) */
+#define LHN_REFINE_DARK_UDP 7    /* D7: post_dark_udp, top_down_eval.py:274-335 (reflect-101 blur of the whole plane,
+                                    clip [0.001, 50], log, edge-padded 3x3 stencil, (H + eps I)^-1 in f64); use with
+                                    use_udp = 1 and LHN_MASK_NEG1 as keypoints_from_heatmaps(use_udp=True) does */
 
 /* heatmap -> image coordinates */
 #define LHN_XFORM_NONE 0

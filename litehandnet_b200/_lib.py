@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("LHN_LIB", os.path.join(_HERE, "lib", "liblhn.so"))
 F32, BF16, F16, F64 = 0, 1, 2, 3
 MASK_NONE, MASK_ZERO, MASK_NEG1 = 0, 1, 2
 REFINE_NONE, REFINE_OFFSET_HALF, REFINE_OFFSET, REFINE_SIGN, REFINE_SIGN_ROUND, REFINE_DARK, \
-    REFINE_DARK_LEGACY = range(7)
+    REFINE_DARK_LEGACY, REFINE_DARK_UDP = range(8)
 XFORM_NONE, XFORM_CENTER_SCALE, XFORM_SCALE = 0, 1, 2
 LOSS_NONE, LOSS_DISTANCE, LOSS_DISTANCE_BALANCE, LOSS_JOINTS_MSE = 0, 1, 2, 3
 FLAG_OVERLAP_PREVIOUS = 1

@@ -460,9 +460,15 @@ static int run_heatmap(HmArgs& a, int dtype, cudaStream_t st, int* used_team_ker
     const char* f = getenv("LHN_FORCE_CTA_KERNEL");
     a.force_cta_kernel = (f && f[0] == '1') ? 1 : 0;
   }
+  if (a.refine == LHN_REFINE_DARK_UDP) {
+    // one mirror reflection per side (cv2 BORDER_REFLECT_101 over a (k-1)/2 + 2 margin); team kernel only
+    const int margin = ((a.ksize - 1) >> 1) + 2;
+    if (a.H <= margin || a.W <= margin || a.force_cta_kernel) return LHN_EINVAL;
+  }
   if (!a.force_cta_kernel) {
     const int rc = launch_heatmap_warp_kernel(a, dtype, st);
     if (rc <= 0) { if (used_team_kernel) *used_team_kernel = 1; return rc; }
+    if (a.refine == LHN_REFINE_DARK_UDP) return LHN_EINVAL;      // the CTA-per-plane fallback has no UDP decode
   }
   if (a.fallback_partials) a.partials = a.fallback_partials;   // the CTA-per-plane kernel needs per-plane sums
   switch (dtype) {
@@ -475,7 +481,7 @@ static int run_heatmap(HmArgs& a, int dtype, cudaStream_t st, int* used_team_ker
 
 static int fill_decode(HmArgs& a, const lhn_decode_params* dp) {
   if (!dp) return LHN_EINVAL;
-  if (dp->mask_mode < 0 || dp->mask_mode > 2 || dp->refine < 0 || dp->refine > 6 ||
+  if (dp->mask_mode < 0 || dp->mask_mode > 2 || dp->refine < 0 || dp->refine > 7 ||
       dp->transform < 0 || dp->transform > 2)
     return LHN_EINVAL;
   a.mask_mode = dp->mask_mode; a.refine = dp->refine; a.transform = dp->transform;
@@ -484,7 +490,7 @@ static int fill_decode(HmArgs& a, const lhn_decode_params* dp) {
   a.overlap_previous = (dp->flags & LHN_FLAG_OVERLAP_PREVIOUS) ? 1 : 0;
   a.spare_sms = (dp->flags >> 8) & 0xff;
   a.loss_accumulate = (dp->flags & LHN_FLAG_ACCUMULATE_LOSS) ? 1 : 0;
-  if (dp->refine == LHN_REFINE_DARK || dp->refine == LHN_REFINE_DARK_LEGACY) {
+  if (dp->refine == LHN_REFINE_DARK || dp->refine == LHN_REFINE_DARK_LEGACY || dp->refine == LHN_REFINE_DARK_UDP) {
     if (a.ksize < 3 || a.ksize > LHN_MAX_TAPS || (a.ksize & 1) == 0) return LHN_EINVAL;
     for (int i = 0; i < a.ksize; ++i) { a.tapsd[i] = dp->taps[i]; a.tapsf[i] = (float)dp->taps[i]; }
   }

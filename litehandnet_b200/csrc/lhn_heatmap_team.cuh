@@ -191,6 +191,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   };
   const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
   const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
+  const bool udp = a.refine == LHN_REFINE_DARK_UDP;       // post_dark_udp (top_down_eval.py:274-335)
 
   // Side inputs of plane (b, c) -> ring slot `slot` (lanes 0..SD_N-1 of one warp; asynchronous).
   auto side_fetch = [&](uint32_t b, uint32_t c, int slot) {
@@ -401,6 +402,15 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           }
         }
         __syncwarp();
+        if (udp) {
+          // np.clip(., 0.001, 50) (NaN stays NaN), np.log
+          float v = lane < 25 ? hout[lane] : 1.f;
+          v = (v != v) ? v : fminf(fmaxf(v, 0.001f), 50.f);
+          const float lv = logf(v);
+          __syncwarp();
+          if (lane < 25) hout[lane] = lv;
+          __syncwarp();
+        } else {
         // can the 1e-10 clamp of log() (or a non-finite value) touch the 13 stencil points?
         const float hv = lane < 25 ? hout[lane] : CUDART_INF_F;
         const int dr = lane / 5 - 2, dc = lane % 5 - 2;
@@ -471,11 +481,78 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         __syncwarp();
         if (lane < 25) hout[lane] = hval;
         __syncwarp();
+        }
+      }
+      // UDP, plane without a positive maximum (coordinates (-1, -1)): the reference's flat indexing into the
+      // edge-padded batch reads i_, ix1, iy1, ix1y1 from this plane's pixel (0, 0) and ix1_, ix1_y1_, iy1_ from the
+      // PREVIOUS plane's last row (the last plane's for plane 0).  Those three blurred values are computed here
+      // from global memory (rare path); udp_deg = (own(0,0), prev(H-1,W-1), prev(H-1,0)).
+      float udp_deg0 = 0.f, udp_deg1 = 0.f, udp_deg2 = 0.f;
+      const bool udp_degenerate = udp && !dark_guard;
+      if (udp_degenerate) {
+        uint32_t qb2, qc2;
+        if (p == 0) { qb2 = (uint32_t)((n_planes - 1) / C); qc2 = (n_planes - 1) - qb2 * C; }
+        else if (pc == 0) { qb2 = pb - 1; qc2 = C - 1; }
+        else { qb2 = pb; qc2 = pc - 1; }
+        auto blur_at = [&](uint32_t bq, uint32_t cq, int y, int x) -> float {
+          const T* g0 = gptr0(bq, cq);
+          const T* g1 = FLIP ? gptr1(bq, cq) : nullptr;
+          auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+          // lanes 0..ksize-1: one window row each (sequential FMA over the taps), then the column pass on lane 0
+          float rowv = 0.f;
+          if (lane < ksize) {
+            const int yy = refl(y + lane - bb, H);
+            for (int j = 0; j < ksize; ++j) {
+              const int xx = refl(x + j - bb, W);
+              float o = elem_f32<T>(g0, yy * W + xx);
+              if (FLIP) o = __fmul_rn(__fadd_rn(o, elem_f32<T>(g1, yy * W + (W - 1 - xx))), 0.5f);
+              rowv = __fmaf_rn(a.tapsf[j], o, rowv);
+            }
+          }
+          float acc = __fmul_rn(a.tapsf[bb], __shfl_sync(0xffffffffu, rowv, bb));
+          for (int j = 1; j <= bb; ++j)
+            acc = __fmaf_rn(a.tapsf[bb + j], __fadd_rn(__shfl_sync(0xffffffffu, rowv, bb + j),
+                                                       __shfl_sync(0xffffffffu, rowv, bb - j)), acc);
+          float v = (acc != acc) ? acc : fminf(fmaxf(acc, 0.001f), 50.f);
+          return logf(v);
+        };
+        udp_deg0 = blur_at(pb, pc, 0, 0);
+        udp_deg1 = blur_at(qb2, qc2, H - 1, W - 1);
+        udp_deg2 = blur_at(qb2, qc2, H - 1, 0);
       }
       TRE(9);
 
       if (lane == 0) {
-        if (dark_guard) {
+        if (udp) {
+          // 3x3 stencil on the edge-padded log map: a neighbour beyond the plane is the border pixel itself
+          const int px = (int)rx, py = (int)ry;
+          auto LL = [&](int dy, int dx) -> float {
+            const int yy = min(max(py + dy, 0), H - 1) - py, xx = min(max(px + dx, 0), W - 1) - px;
+            return hout[(yy + 2) * 5 + xx + 2];
+          };
+          float i_, ix1, iy1, ix1y1, ix1_y1_, ix1_, iy1_;
+          if (udp_degenerate) {
+            i_ = ix1 = iy1 = ix1y1 = udp_deg0; ix1_y1_ = ix1_ = udp_deg1; iy1_ = udp_deg2;
+          } else {
+            i_ = LL(0, 0); ix1 = LL(0, 1); iy1 = LL(1, 0); ix1y1 = LL(1, 1);
+            ix1_y1_ = LL(-1, -1); ix1_ = LL(0, -1); iy1_ = LL(-1, 0);
+          }
+          const float ddx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_));
+          const float ddy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
+          const float dxx = __fadd_rn(__fsub_rn(ix1, __fmul_rn(2.f, i_)), ix1_);
+          const float dyy = __fadd_rn(__fsub_rn(iy1, __fmul_rn(2.f, i_)), iy1_);
+          float t = __fsub_rn(ix1y1, ix1);
+          t = __fsub_rn(t, iy1); t = __fadd_rn(t, i_); t = __fadd_rn(t, i_);
+          t = __fsub_rn(t, ix1_); t = __fsub_rn(t, iy1_); t = __fadd_rn(t, ix1_y1_);
+          const float dxy = __fmul_rn(0.5f, t);
+          // (H + eps I)^-1 d in f64 (np.linalg.inv of the f64 matrix), coords (f32) -= that, rounded once
+          const double eps = 1.1920928955078125e-07;
+          const double ha = (double)dxx + eps, hd = (double)dyy + eps, hb = (double)dxy;
+          const double det = __dsub_rn(__dmul_rn(ha, hd), __dmul_rn(hb, hb));
+          const double ox = __dadd_rn(__dmul_rn(hd / det, (double)ddx), __dmul_rn(-hb / det, (double)ddy));
+          const double oy = __dadd_rn(__dmul_rn(-hb / det, (double)ddx), __dmul_rn(ha / det, (double)ddy));
+          rx = (float)((double)rx - ox); ry = (float)((double)ry - oy);
+        } else if (dark_guard) {
 #define HH(dy, dx) hout[((dy) + 2) * 5 + (dx) + 2]
           const float h00 = HH(0, 0);
           const float ddx = __fmul_rn(0.5f, __fsub_rn(HH(0, 1), HH(0, -1)));
@@ -867,14 +944,23 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     if (a.mask_mode == LHN_MASK_ZERO && !positive) { cx = 0.f; cy = 0.f; }
     if (a.mask_mode == LHN_MASK_NEG1 && !positive) { cx = -1.f; cy = -1.f; }
     const int px = (int)cx, py = (int)cy;
-    const bool dark_guard = is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2);
+    // DARK: the reference's interior guard; UDP: every plane with a positive maximum (coordinates >= 0)
+    const bool dark_guard = (is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2)) || (udp && px >= 0 && py >= 0);
 
     PlaneRec* rec = &th->rec[buf];
     const int wx0 = px - 2 - bb;                      // first window column (may be negative)
     const int c0 = wx0 & ~3, xo = wx0 & 3;            // its quad-aligned start and the offset inside it
 
     // ---- stage the DARK window: zero-padded (ksize+4) rows x NQ quads of the decoded plane -----------------
-    if (dark_guard) {
+    if (dark_guard && udp) {
+      // UDP blurs the plane with cv2's default BORDER_REFLECT_101: the window is addressed through the mirror
+      float* tile = reinterpret_cast<float*>(tile0 + (size_t)buf * tile_bytes);
+      auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+      for (int e = sl; e < TD * TD; e += ST) {
+        const int r = e / TD, c = e - r * TD;
+        tile[r * TCW + c] = val(refl(py - 2 - bb + r, H), refl(px - 2 - bb + c, W));
+      }
+    } else if (dark_guard) {
       float* tile = reinterpret_cast<float*>(tile0 + (size_t)buf * tile_bytes);
       for (int e = sl; e < TD * NQ; e += ST) {
         const int r = e / NQ, cq = e - r * NQ;          // compile-time divisor when KS > 0
@@ -944,7 +1030,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       if (LOSS) for (int i = 0; i < NS; ++i) S += th->red_s[i];
       rec->idx = idx; rec->maxval = maxval; rec->rx = rx; rec->ry = ry;
       rec->ssum = S;
-      rec->flags = (dark_guard ? 1 : 0) | (any_nan ? 2 : 0) | (xo << 8);
+      rec->flags = (dark_guard ? 1 : 0) | (any_nan ? 2 : 0) | ((udp ? 0 : xo) << 8);
     }
     TRS(4);
     // S3: everything the epilogue needs is out of the stage — nobody reads it again
@@ -1043,7 +1129,8 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   if (plane_bytes % 16) return 1;
   const size_t plane_al = align_up(plane_bytes, 128);
   a.stage_bytes = (int)(flip ? 2 * plane_al : plane_al);
-  const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY;
+  const bool is_dark = a.refine == LHN_REFINE_DARK || a.refine == LHN_REFINE_DARK_LEGACY ||
+                       a.refine == LHN_REFINE_DARK_UDP;
   a.tile_dim = is_dark ? a.ksize + 4 : 0;
   const size_t aux = align_up(sizeof(TeamHeader), 16) + 3 * align_up((size_t)(a.W + a.H) * 4, 16) +
                      2 * align_up((size_t)a.tile_dim * 4 * tile_quads(a.tile_dim) * 4, 16) +

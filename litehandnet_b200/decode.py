@@ -83,8 +83,9 @@ def keypoints_from_heatmaps(heatmaps, center, scale, post_process='default', ker
 
     Additive: ``heatmaps_flipped`` (+ ``flip_pairs``) fuses the flip-test average
     (heatmaps + flip_back(heatmaps_flipped, flip_pairs)) * 0.5 into the same pass."""
-    if use_udp:
-        raise NotImplementedError("UDP decoding (post_dark_udp) is SURVEY §8f 'next' (rank 3)")
+    if use_udp and target_type.lower() != 'gaussianheatmap':
+        raise NotImplementedError("UDP 'CombinedTarget' decoding: the reference's keypoints_from_heatmaps leaves "
+                                  "hm_preds undefined for it (top_down_eval.py:427-431)")
     if post_process == 'unbiased':
         assert kernel > 0
     if post_process == 'megvii':
@@ -93,6 +94,8 @@ def keypoints_from_heatmaps(heatmaps, center, scale, post_process='default', ker
     c, _ = _up(center, torch.float32)
     s, _ = _up(scale, torch.float32)
     refine = L.REFINE_DARK if post_process == 'unbiased' else (L.REFINE_SIGN if post_process is not None else L.REFINE_NONE)
+    if use_udp:
+        refine = L.REFINE_DARK_UDP            # top_down_eval.py:427-431: post_dark_udp whatever post_process says
     hf = fi = None
     if heatmaps_flipped is not None:
         hf, _ = _hm(heatmaps_flipped)
@@ -100,7 +103,7 @@ def keypoints_from_heatmaps(heatmaps, center, scale, post_process='default', ker
         if flip_pairs:
             fi = flip_index_from_pairs(t.shape[1], flip_pairs, t.device)
     r = ops.decode_heatmap(t, L.MASK_NEG1, refine, L.XFORM_CENTER_SCALE, c, s, hm_flip=hf, flip_index=fi,
-                           blur_ksize=kernel, want_idx=False)
+                           blur_ksize=kernel, use_udp=bool(use_udp), want_idx=False)
     hm_preds, preds, maxvals = r["hm_kpts"][..., :2], r["kpts"][..., :2], r["kpts"][..., 2:]
     if not was:
         hm_preds, preds, maxvals = _np(hm_preds), _np(preds), _np(maxvals)

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib as L
 
-_REFINE_KSIZE = {L.REFINE_DARK: 11, L.REFINE_DARK_LEGACY: 19}
+_REFINE_KSIZE = {L.REFINE_DARK: 11, L.REFINE_DARK_LEGACY: 19, L.REFINE_DARK_UDP: 11}
 
 
 def _decode_params(mask_mode, refine, transform, scale_xy=(1.0, 1.0), blur_ksize=None, use_udp=False, flags=0):

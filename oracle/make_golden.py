@@ -188,6 +188,31 @@ def udp_case(ref, name, seed):
     np.savez_compressed(os.path.join(OUT, name), **d)
 
 
+def udp_decode_case(ref, name, seed):
+    """keypoints_from_heatmaps(use_udp=True) = _get_max_preds + post_dark_udp + transform_preds(use_udp)
+    (top_down_eval.py:274-335, 427-431): blobs + noise, all-zero and negative planes (incl. the first and the last
+    plane of the batch: the reference then indexes the previous / the last plane's padding), border maxima, ties."""
+    T = ref.top_down_eval
+    N, K, H, W = 3, 7, 56, 56
+    hm, _ = synth.blob_heatmaps(N, K, H, W, seed=seed, zero_frac=0.1, tie_frac=0.1)
+    hm = hm.numpy()
+    hm[0, 0] = 0.0                                    # first plane of the batch without a positive maximum
+    hm[N - 1, K - 1] = -0.25                          # and the last one
+    hm[1, 0] = 0.0; hm[1, 1] = 0.0                    # two degenerate planes in a row
+    hm[0, 1] = 0.0; hm[0, 1, 0, 0] = 1.0              # maxima on the corners / edges
+    hm[0, 2] = 0.0; hm[0, 2, H - 1, W - 1] = 0.7
+    hm[0, 3] = 0.0; hm[0, 3, 0, 20] = 0.5
+    hm[0, 4] = 0.0; hm[0, 4, 30, W - 1] = 0.9
+    hm[0, 1:5] += np.random.default_rng(seed).random((4, H, W)).astype(np.float32) * 0.01
+    center, scale = [t.numpy() for t in synth.bbox_center_scale(N, seed=seed + 1)]
+    d = dict(hm=hm, center=center, scale=scale)
+    for k in (11, 17):                                # k=17 is the reference's "sigma=3" setting
+        with np.errstate(all="ignore"):
+            hp, p, mv = T.keypoints_from_heatmaps(hm.copy(), center, scale, post_process="default", kernel=k, use_udp=True)
+        d[f"ref_udp_hm_preds_k{k}"], d[f"ref_udp_preds_k{k}"], d["ref_udp_maxvals"] = hp, p, mv
+    np.savez_compressed(os.path.join(OUT, name), **d)
+
+
 def backward_case(ref, name, seed):
     """Gradients of the reference losses by torch autograd on the CPU: the explicit-target
     heatmap losses on a rendered target, and KLDiscretLoss on SimDR vectors."""
@@ -241,6 +266,7 @@ def main():
     metrics_case(ref, "metrics_16.npz", N=48, K=16, seed=31)
     backward_case(ref, "loss_backward.npz", seed=41)
     udp_case(ref, "render_udp.npz", seed=51)
+    udp_decode_case(ref, "decode_udp.npz", seed=61)
     # the reference's only hand-derivable known answer (utils/SPheatmapParser.py:221-233)
     kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
     k, _ = ref.SPheatmapParser.HeatmapParser_SH().parse(kpt_hm.clone(), image_size=(256, 256))

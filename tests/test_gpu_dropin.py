@@ -373,6 +373,29 @@ def test_evaluate_results_like_dataset_evaluate():
     np.testing.assert_allclose(got["EPE"], O.keypoint_epe(p64, gt.numpy(), mask.numpy()), rtol=1e-5)
 
 
+def test_udp_decode_golden_and_oracle():
+    """keypoints_from_heatmaps(..., use_udp=True) (top_down_eval.py:427-431 -> post_dark_udp) against the executed
+    reference and, on a larger random batch and with the flip average, against the oracle."""
+    from litehandnet_b200 import decode as D
+    g = load_golden("decode_udp.npz")
+    for k in (11, 17):
+        hp, p, mv = D.keypoints_from_heatmaps(g["hm"], g["center"], g["scale"], post_process="default", kernel=k, use_udp=True)
+        assert np.array_equal(mv, g["ref_udp_maxvals"])
+        assert_coords_close(hp, g[f"ref_udp_hm_preds_k{k}"], what=f"udp hm k={k}")
+        assert_coords_close(p, g[f"ref_udp_preds_k{k}"], what=f"udp img k={k}")
+    for shape in ((40, 21, 64, 64), (9, 16, 56, 56), (6, 5, 28, 28)):
+        hm, cen = synth.blob_heatmaps(*shape, seed=101, zero_frac=0.05, tie_frac=0.03)
+        hf = synth.flipped_blob_heatmaps(cen, shape[2], shape[3], seed=102)
+        c, s = synth.bbox_center_scale(shape[0], seed=103)
+        hp, p, mv = D.keypoints_from_heatmaps(hm.to(DEV), c, s, kernel=11, use_udp=True, heatmaps_flipped=hf.to(DEV))
+        avg = O.flip_average(hm.numpy(), hf.numpy(), ())
+        with np.errstate(all="ignore"):
+            rhp, rp_, rmv = O.keypoints_from_heatmaps_udp(avg, c.numpy(), s.numpy(), 11)
+        assert np.array_equal(mv.cpu().numpy(), rmv)
+        assert_coords_close(hp.cpu().numpy(), rhp, what="udp hm vs oracle")
+        assert_coords_close(p.cpu().numpy(), rp_, what="udp img vs oracle")
+
+
 def test_udp_target_transform_dict_in_dict_out():
     """TopDownGenerateTarget(encoding='UDP') as the dataset pipeline calls it (generateTarget.py:245-300)."""
     from litehandnet_b200 import render as R
