@@ -306,6 +306,16 @@ LHN_API int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_stride
                                int K, const float* thr /* host, T floats */, int T,
                                int64_t* counters, lhn_stream_t stream);
 
+/* MPII PCKh counters (datasets/datasets/body/topdown_mpii_dataset.py:186-214, duplicate in
+ * topdown_mpii_action_dataset.py:176-204): pred f32 [N,K,pred_stride] 0-based (the kernel adds the reference's
+ * +1.0 in f32), gt f64 [N,K,2] (pos_gt_src transposed), head f64 [N,4] = (x1,y1,x2,y2) of headboxes_src,
+ * visible uint8 [N,K] = 1 - jnt_missing.  err / (|head box| * sc_bias) <= thr[t] in f64 (thr: host, T <= 64
+ * doubles).  counters int64 [(T+1)*K]: hits[t][k], count[k]; ADDS (shardable). */
+LHN_API int lhn_mpii_pckh_accumulate(const float* pred, int pred_stride, const double* gt,
+                                     const double* head, const uint8_t* visible, int64_t N, int K,
+                                     const double* thr /* host */, int T, double sc_bias,
+                                     int64_t* counters, lhn_stream_t stream);
+
 /* Fused decode + metrics counters for the sharded evaluation (BASELINE config 4): as
  * lhn_decode_heatmap (decode only) and, per plane, the three _report_metric accumulations
  * (base_dataset.py:193-261): PCK@pck_thr / max(bbox w,h), AUC thresholds i/auc_steps / auc_nor,

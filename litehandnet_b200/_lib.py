@@ -34,7 +34,7 @@ EXPORTS = [
     "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
-    "lhn_simdr_smoothl1_backward",
+    "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate",
 ]
 
 
@@ -77,6 +77,7 @@ def _declare(lib):
     lib.lhn_simdr_backward_workspace_bytes.restype = i64
     lib.lhn_simdr_smoothl1_backward.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, i64,
                                                 vp, vp, vp]
+    lib.lhn_mpii_pckh_accumulate.argtypes = [vp, i32, vp, vp, vp, i64, i32, C.POINTER(C.c_double), i32, f64, vp, vp]
     lib.lhn_decode_heatmap_pck.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp,
                                            C.POINTER(DecodeParams), vp, vp, vp, vp, vp, vp, f32, f32,
                                            i32, vp, vp]

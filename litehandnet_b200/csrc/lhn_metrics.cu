@@ -68,6 +68,45 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
     if (sc[i]) atomicAdd(a.counters + i, sc[i]);
 }
 
+// ---- MPII PCKh counters (topdown_mpii_dataset.py:186-214): f64 throughout, `<=`, head-box norm * sc_bias ------
+struct MpiiArgs {
+  const float* pred; int pred_stride;
+  const double* gt;        // [N,K,2] 1-based ground truth (pos_gt_src transposed)
+  const double* head;      // [N,4] head box (x1, y1, x2, y2) (headboxes_src transposed)
+  const uint8_t* visible;  // [N,K] 1 - jnt_missing
+  int64_t N; int K, T;
+  double sc_bias;
+  double thr[kMaxThr];
+  unsigned long long* counters;   // hits[T][K], count[K]
+};
+
+__global__ void __launch_bounds__(256) mpii_pckh_kernel(const __grid_constant__ MpiiArgs a) {
+  extern __shared__ unsigned long long sc[];   // (T+1)*K
+  const int K = a.K, T = a.T;
+  const int ncnt = (T + 1) * K;
+  for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sc[i] = 0ull;
+  __syncthreads();
+  const int64_t total = a.N * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    if (!a.visible[e]) continue;
+    const int64_t n = e / K;
+    const int k = (int)(e - n * K);
+    // preds[..., :2] + 1.0 stays f32 (NumPy keeps the array dtype), the difference with the f64 ground truth is f64
+    const double dx = __dsub_rn((double)__fadd_rn(a.pred[e * a.pred_stride], 1.0f), a.gt[2 * e]);
+    const double dy = __dsub_rn((double)__fadd_rn(a.pred[e * a.pred_stride + 1], 1.0f), a.gt[2 * e + 1]);
+    const double err = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    const double hx = __dsub_rn(a.head[4 * n + 2], a.head[4 * n]), hy = __dsub_rn(a.head[4 * n + 3], a.head[4 * n + 1]);
+    const double hs = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(hx, hx), __dmul_rn(hy, hy))), a.sc_bias);
+    const double v = __ddiv_rn(err, hs);
+    atomicAdd(&sc[T * K + k], 1ull);
+    for (int t = 0; t < T; ++t)
+      if (v <= a.thr[t]) atomicAdd(&sc[t * K + k], 1ull);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncnt; i += blockDim.x)
+    if (sc[i]) atomicAdd(a.counters + i, sc[i]);
+}
+
 // ---- legacy evaluate_pck (evaluation.py:10-59): per-image reduction over the decoded joints -----
 // pk/gk: [B*K,3] (x*fx, y*fy, maxval) already scaled (A1 + T2 from the heatmap kernel).
 __global__ void __launch_bounds__(128) evaluate_pck_image_kernel(const float* __restrict__ pk,
@@ -182,5 +221,26 @@ extern "C" int lhn_evaluate_pck(const void* pred_hm, const void* gt_hm, int dtyp
   rc = check_launch();
   if (rc) return rc;
   mean_f32_to_f64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pck_per_image, B, mean_out);
+  return check_launch();
+}
+
+extern "C" int lhn_mpii_pckh_accumulate(const float* pred, int pred_stride, const double* gt, const double* head,
+                                        const uint8_t* visible, int64_t N, int K, const double* thr, int T,
+                                        double sc_bias, int64_t* counters, lhn_stream_t stream) {
+  if (!pred || !gt || !head || !visible || !thr || !counters || N < 0 || K <= 0 || T <= 0 || T > kMaxThr ||
+      pred_stride < 2 || !(sc_bias > 0.0))
+    return LHN_EINVAL;
+  if (N == 0) return LHN_OK;
+  MpiiArgs a{};
+  a.pred = pred; a.pred_stride = pred_stride; a.gt = gt; a.head = head; a.visible = visible;
+  a.N = N; a.K = K; a.T = T; a.sc_bias = sc_bias;
+  for (int t = 0; t < T; ++t) a.thr[t] = thr[t];
+  a.counters = reinterpret_cast<unsigned long long*>(counters);
+  const size_t smem = (size_t)(T + 1) * K * sizeof(unsigned long long);
+  if (smem > 48 * 1024) return LHN_EINVAL;
+  int64_t blocks = (N * K + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  mpii_pckh_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch();
 }

@@ -181,6 +181,63 @@ def evaluate_results(results, db, metric='PCK', pck_thr=0.2, pckh_thr=0.5, auc_n
                                      auc_nor))
 
 
+def mpii_pckh_counters(preds, gt_dict, thresholds, counters=None, sc_bias=0.6):
+    """Shardable int64 counters of the MPII PCKh arithmetic (lhn_mpii_pckh_accumulate): hits[T][K], count[K].
+    preds [N,K,>=2] 0-based (CUDA or NumPy); gt_dict arrays cover the same N samples (or a shard of them)."""
+    import ctypes as C
+    dev = _device()
+    p, _ = _up(preds, torch.float32)
+    p = p.contiguous()
+    N, K = p.shape[0], p.shape[1]
+    gt = torch.as_tensor(np.ascontiguousarray(np.transpose(np.asarray(gt_dict['pos_gt_src'], dtype=np.float64), (2, 0, 1)))).to(dev)
+    hb = np.asarray(gt_dict['headboxes_src'], dtype=np.float64)                       # [corner, xy, N]
+    head = torch.as_tensor(np.ascontiguousarray(np.concatenate([hb[0].T, hb[1].T], axis=1))).to(dev)   # [N,4]
+    vis = torch.as_tensor(np.ascontiguousarray((1 - np.asarray(gt_dict['jnt_missing'])).T != 0)).to(dev).to(torch.uint8)
+    T = len(thresholds)
+    if counters is None:
+        counters = torch.zeros((T + 1) * K, dtype=torch.int64, device=dev)
+    thr = (C.c_double * T)(*[float(t) for t in thresholds])
+    L.check(L.lib().lhn_mpii_pckh_accumulate(L.ptr(p), p.shape[2], L.ptr(gt), L.ptr(head), L.ptr(vis), N, K, thr, T,
+                                             float(sc_bias), L.ptr(counters), L.stream()), "lhn_mpii_pckh_accumulate")
+    return counters
+
+
+def mpii_evaluate(results, gt_dict, metric='PCKh'):
+    """TopDownMpiiDataset.evaluate (datasets/datasets/body/topdown_mpii_dataset.py:126-249) with the contents of
+    mpii_gt_val.mat handed in as ``gt_dict`` (dataset_joints, jnt_missing, pos_gt_src, headboxes_src): results are
+    sorted / de-duplicated by bbox_id, the hit counts come from the GPU, the name/value table is the reference's."""
+    metrics = metric if isinstance(metric, (list, tuple)) else [metric]
+    for m in metrics:
+        if m not in ('PCKh',):
+            raise KeyError(f'metric {m} is not supported')
+    dev = _device()
+    preds = torch.cat([_up(r['preds'], torch.float32)[0] for r in results], 0)
+    ids = torch.as_tensor(np.concatenate([np.asarray(r['bbox_ids']).reshape(-1) for r in results])).to(dev)
+    order = torch.sort(ids, stable=True).indices
+    ids_s = ids[order]
+    keep = torch.ones_like(ids_s, dtype=torch.bool)
+    keep[1:] = ids_s[1:] != ids_s[:-1]
+    preds = preds[order][keep].contiguous()
+    rng = np.arange(0, 0.5 + 0.01, 0.01)
+    thr = [0.5] + [float(t) for t in rng]
+    K = preds.shape[1]
+    c = mpii_pckh_counters(preds, gt_dict, thr).cpu().numpy().reshape(len(thr) + 1, K).astype(np.float64)
+    jnt_count = c[-1]
+    PCKh = 100. * c[0] / jnt_count
+    pck10 = (100. * c[1 + 10] / jnt_count).astype(np.float32)                  # pckAll is a float32 table
+    names = np.asarray(gt_dict['dataset_joints'])
+    J = {n: np.where(names == n)[1][0] for n in ('head', 'lsho', 'lelb', 'lwri', 'lhip', 'lkne', 'lank', 'rsho',
+                                                 'relb', 'rwri', 'rkne', 'rank', 'rhip')}
+    PCKh = np.ma.array(PCKh, mask=False); PCKh.mask[6:8] = True
+    jc = np.ma.array(jnt_count, mask=False); jc.mask[6:8] = True
+    ratio = jc / np.sum(jc).astype(np.float64)
+    return OrderedDict([('Head', PCKh[J['head']]), ('Shoulder', 0.5 * (PCKh[J['lsho']] + PCKh[J['rsho']])),
+                        ('Elbow', 0.5 * (PCKh[J['lelb']] + PCKh[J['relb']])), ('Wrist', 0.5 * (PCKh[J['lwri']] + PCKh[J['rwri']])),
+                        ('Hip', 0.5 * (PCKh[J['lhip']] + PCKh[J['rhip']])), ('Knee', 0.5 * (PCKh[J['lkne']] + PCKh[J['rkne']])),
+                        ('Ankle', 0.5 * (PCKh[J['lank']] + PCKh[J['rank']])), ('PCKh', np.sum(PCKh * ratio)),
+                        ('PCKh@0.1', np.sum(pck10 * ratio))])
+
+
 def evaluate_pck(pred_keypoints_hm, gt_keypoints_hm, bbox, image_size=256, target_weight=None, thr=0.2):
     """utils/evaluation.py:10-59 -> python float (NaN if an image has zero total weight, as the
     reference).  bbox [B, n_hand, 4] (cx, cy, w, h); only hand 0 is used (:23)."""

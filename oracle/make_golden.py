@@ -213,6 +213,54 @@ def udp_decode_case(ref, name, seed):
     np.savez_compressed(os.path.join(OUT, name), **d)
 
 
+def mpii_case(name, seed):
+    """MPII PCKh (datasets/datasets/body/topdown_mpii_dataset.py:126-249).  The dataset class cannot be imported
+    (xtcocotools, json_tricks) and its mpii_gt_val.mat is not in the tree, so the method's own source is compiled
+    from the reference file and executed on a fake `self` with a synthetic gt_dict standing in for loadmat()."""
+    import ast
+    import textwrap
+    from collections import OrderedDict
+    path = os.path.join(ref_loader.REF_ROOT, "datasets/datasets/body/topdown_mpii_dataset.py")
+    src = open(path).read()
+    fn = None
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name == "evaluate":
+            fn = textwrap.dedent(ast.get_source_segment(src, node))
+    rng = np.random.default_rng(seed)
+    N, K = 40, 16
+    names = np.array([["rank", "rkne", "rhip", "lhip", "lkne", "lank", "pelv", "thor", "neck", "head", "rwri", "relb", "rsho",
+                       "lsho", "lelb", "lwri"]], dtype=object)
+    pos_gt = rng.uniform(20, 400, (K, 2, N))
+    head = np.zeros((2, 2, N)); head[0] = rng.uniform(50, 200, (2, N)); head[1] = head[0] + rng.uniform(15, 60, (2, N))
+    missing = (rng.random((K, N)) < 0.15).astype(np.float64)
+    gt_dict = dict(dataset_joints=names, jnt_missing=missing, pos_gt_src=pos_gt, headboxes_src=head)
+    preds = (np.transpose(pos_gt, (2, 0, 1)) - 1.0 + rng.normal(0, 8, (N, K, 2))).astype(np.float32)
+    preds = np.concatenate([preds, rng.random((N, K, 1)).astype(np.float32)], axis=2)
+    ids = list(rng.permutation(N)) + [3, 7]           # shuffled, two duplicates
+    order = [int(i) for i in ids]
+    results = [dict(preds=preds[order[a:a + 16]], bbox_ids=order[a:a + 16]) for a in range(0, len(order), 16)]
+
+    class _Self:
+        ann_file = "/nonexistent/mpii_val.json"
+
+        @staticmethod
+        def _sort_and_unique_bboxes(kpts, key="bbox_id"):
+            kpts = sorted(kpts, key=lambda x: x[key])
+            for i in range(len(kpts) - 1, 0, -1):
+                if kpts[i][key] == kpts[i - 1][key]:
+                    del kpts[i]
+            return kpts
+
+    ns = dict(np=np, OrderedDict=OrderedDict, osp=os.path, loadmat=lambda f: gt_dict, savemat=lambda *a, **k: None)
+    exec(fn, ns)
+    out = ns["evaluate"](_Self(), results, None, "PCKh")
+    d = dict(preds=preds, bbox_ids=np.array(order), dataset_joints=names.astype(str), jnt_missing=missing,
+             pos_gt_src=pos_gt, headboxes_src=head,
+             ref_names=np.array(list(out.keys())), ref_values=np.array([float(v) for v in out.values()], dtype=np.float64))
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    return out
+
+
 def backward_case(ref, name, seed):
     """Gradients of the reference losses by torch autograd on the CPU: the explicit-target
     heatmap losses on a rendered target, and KLDiscretLoss on SimDR vectors."""
@@ -267,6 +315,7 @@ def main():
     backward_case(ref, "loss_backward.npz", seed=41)
     udp_case(ref, "render_udp.npz", seed=51)
     udp_decode_case(ref, "decode_udp.npz", seed=61)
+    mpii_case("mpii_pckh.npz", seed=71)
     # the reference's only hand-derivable known answer (utils/SPheatmapParser.py:221-233)
     kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
     k, _ = ref.SPheatmapParser.HeatmapParser_SH().parse(kpt_hm.clone(), image_size=(256, 256))

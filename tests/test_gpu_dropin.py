@@ -373,6 +373,28 @@ def test_evaluate_results_like_dataset_evaluate():
     np.testing.assert_allclose(got["EPE"], O.keypoint_epe(p64, gt.numpy(), mask.numpy()), rtol=1e-5)
 
 
+def test_mpii_evaluate_golden_and_sharded():
+    """TopDownMpiiDataset.evaluate arithmetic (topdown_mpii_dataset.py:126-249) from shuffled, partly duplicated
+    result batches; counters of two shards add up to the monolithic ones."""
+    from litehandnet_b200 import metrics as M
+    g = load_golden("mpii_pckh.npz")
+    gt = dict(dataset_joints=g["dataset_joints"], jnt_missing=g["jnt_missing"], pos_gt_src=g["pos_gt_src"],
+              headboxes_src=g["headboxes_src"])
+    ids = [int(i) for i in g["bbox_ids"]]
+    results = [dict(preds=g["preds"][ids[a:a + 16]], bbox_ids=ids[a:a + 16]) for a in range(0, len(ids), 16)]
+    out = M.mpii_evaluate(results, gt)
+    assert list(out.keys()) == list(g["ref_names"])
+    np.testing.assert_allclose(np.array([float(v) for v in out.values()]), g["ref_values"], rtol=1e-12)
+    thr = [0.5, 0.1]
+    mono = M.mpii_pckh_counters(g["preds"], gt, thr)
+    parts = None
+    for sl in (slice(0, 17), slice(17, 40)):
+        sub = dict(dataset_joints=g["dataset_joints"], jnt_missing=g["jnt_missing"][:, sl],
+                   pos_gt_src=g["pos_gt_src"][:, :, sl], headboxes_src=g["headboxes_src"][:, :, sl])
+        parts = M.mpii_pckh_counters(g["preds"][sl], sub, thr, counters=parts)
+    assert torch.equal(mono, parts)
+
+
 def test_udp_decode_golden_and_oracle():
     """keypoints_from_heatmaps(..., use_udp=True) (top_down_eval.py:427-431 -> post_dark_udp) against the executed
     reference and, on a larger random batch and with the flip average, against the oracle."""
