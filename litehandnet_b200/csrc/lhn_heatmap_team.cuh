@@ -189,9 +189,13 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     const uint32_t kf = a.flip_index ? (uint32_t)fidx[k] : k;
     return reinterpret_cast<const T*>(a.hm_flip) + (int64_t)b * a.fstride_b + (int64_t)(s * K + kf) * a.fstride_c;
   };
-  const bool is_dark = (a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY);
-  const bool legacy = a.refine == LHN_REFINE_DARK_LEGACY;
-  const bool udp = a.refine == LHN_REFINE_DARK_UDP;       // post_dark_udp (top_down_eval.py:274-335)
+  // KS > 0 is only instantiated for LHN_REFINE_DARK (the Gen-2 decoder): the other refinements, and the fused
+  // metrics when a loss is fused (never together through the C ABI), are compiled out of those kernels — the
+  // instruction footprint matters: 24 warps in different phases share a 32 KB L1.5 instruction cache.
+  const bool is_dark = KS > 0 ? true : ((a.refine == LHN_REFINE_DARK) || (a.refine == LHN_REFINE_DARK_LEGACY));
+  const bool legacy = KS > 0 ? false : (a.refine == LHN_REFINE_DARK_LEGACY);
+  const bool udp = KS > 0 ? false : (a.refine == LHN_REFINE_DARK_UDP);   // post_dark_udp (top_down_eval.py:274-335)
+  const bool has_counters = LOSS ? false : (a.counters != nullptr);
 
   // Side inputs of plane (b, c) -> ring slot `slot` (lanes 0..SD_N-1 of one warp; asynchronous).
   auto side_fetch = [&](uint32_t b, uint32_t c, int slot) {
@@ -204,8 +208,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       case SD_VIS: if (LOSS) src = a.vis + bk * a.vis_stride; break;
       case SD_CX: case SD_CY: if (a.center) src = a.center + 2 * (int64_t)b + (lane - SD_CX); break;
       case SD_SX: case SD_SY: if (a.scale) src = a.scale + 2 * (int64_t)b + (lane - SD_SX); break;
-      case SD_GX: case SD_GY: if (a.counters) src = a.gt + 2 * bk + (lane - SD_GX); break;
-      case SD_BW: case SD_BH: if (a.counters) src = a.bbox_wh + 2 * (int64_t)b + (lane - SD_BW); break;
+      case SD_GX: case SD_GY: if (has_counters) src = a.gt + 2 * bk + (lane - SD_GX); break;
+      case SD_BW: case SD_BH: if (has_counters) src = a.bbox_wh + 2 * (int64_t)b + (lane - SD_BW); break;
       default: break;
     }
     if (src) cp_async_4(&th->side[slot][lane], src);
@@ -228,10 +232,10 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   // Fused metrics: one CTA-shared set of u64 counters in shared memory (same layout as the global ones, with
   // the AUC rows holding a histogram of "thresholds passed"), flushed once by the last epilogue warp of the CTA.
   unsigned long long* cta_cnt = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)nteams * a.warp_smem);
-  const int n_cnt = a.counters ? (a.auc_steps + 5) * (int)K : 0;
+  const int n_cnt = (!LOSS && a.counters) ? (a.auc_steps + 5) * (int)K : 0;
   unsigned int* cta_done = reinterpret_cast<unsigned int*>(cta_cnt + n_cnt);
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cta_cnt[i] = 0ull;
-  if (threadIdx.x == 0 && a.counters) *cta_done = 0u;
+  if (threadIdx.x == 0 && !LOSS && a.counters) *cta_done = 0u;
 
   // Let the next launch on the stream (if it was launched with LHN_FLAG_OVERLAP_PREVIOUS) take over SMs as
   // this grid's CTAs retire; a no-op otherwise.
@@ -293,7 +297,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     // side-input ring (kSideAhead planes ahead) and the tables of the first two planes; the sweepers start
     // on plane 0 as soon as its tables exist
     int mask_cur = 1, mask_nxt = 1;                  // fused-metrics mask bytes of planes n, n+1 (lane 0)
-    if (lane == 0 && a.counters) {
+    if (lane == 0 && has_counters) {
       mask_cur = a.mask[(int64_t)pb * K + (C == K ? pc : pc % K)];
       if (p + total_teams < n_planes) {
         uint32_t mb = pb, mc = pc;
@@ -601,7 +605,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         }
         keepX = X; keepY = Y;
       }
-      if (a.counters) {
+      if (has_counters) {
         // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32): lanes 0..2 take one
         // normaliser each (bbox, AUC constant, 1) so the three divide / sqrt chains run side by side
         const float Xb = __shfl_sync(0xffffffffu, keepX, 0), Yb = __shfl_sync(0xffffffffu, keepY, 0);
@@ -641,7 +645,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       }
       TRE(11);
       // ---- side-input ring + the tables of plane n+2; then plane n+2 may start ------------------------------
-      if (lane == 0 && a.counters) {
+      if (lane == 0 && has_counters) {
         mask_cur = mask_nxt;
         mask_nxt = 1;
         if (p + 2 * total_teams < n_planes) {
@@ -665,7 +669,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       if (lane == 0) mbar_arrive(&th->empty[buf]);   // release: record/tile buffer free, tables of n+2 ready
     }
 
-    if (a.counters) {
+    if (has_counters) {
       // the last epilogue warp of the CTA to finish adds the CTA's counters to the global ones
       __syncwarp();
       unsigned int last = 0;
@@ -1009,7 +1013,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     // ---- the first sweeper warp: +-0.25 rules (neighbours read while the plane is resident) + the record ----
     if (role == 1 && lane == 0) {
       float rx = cx, ry = cy;
-      if (a.refine == LHN_REFINE_OFFSET_HALF || a.refine == LHN_REFINE_OFFSET) {
+      if (KS > 0) {
+        // DARK: no quarter offset
+      } else if (a.refine == LHN_REFINE_OFFSET_HALF || a.refine == LHN_REFINE_OFFSET) {
         const int xx = min(max(px, 0), W - 1), yy = min(max(py, 0), H - 1);
         // clamped neighbours; `>` false (equality, NaN) -> -0.25
         rx += (val(yy, min(xx + 1, W - 1)) > val(yy, max(xx - 1, 0))) ? 0.25f : -0.25f;
