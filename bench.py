@@ -77,7 +77,8 @@ def recorded_traffic(batch):
 class ClockSampler:
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, interval_s=0.0005):
+        self.interval_s = interval_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -105,7 +106,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.0002)
+            time.sleep(self.interval_s)
 
     def start(self):
         if self.nv is not None:
@@ -227,6 +228,20 @@ def run_gpu_arm(args, rank, local_rank, world):
     if use_graph:
         for b in bound:
             b.capture()
+    # N > 1 (per-rank loss): the K steps of the timed region are ONE CUDA graph of K kernel launches, so the result
+    # does not depend on how fast N Python processes sharing the host's cores can issue launches.
+    graph_all = None
+    if world > 1 and not global_loss and not args.no_graph_all:
+        for i in range(3):
+            bound[i % R].launch_kernel(fused.L.stream())
+        torch.cuda.synchronize()
+        graph_all = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_all):
+            for i in range(args.steps):
+                bound[i % R].launch_kernel(fused.L.stream())
+        if epoch_loss is not None:
+            torch.cuda.synchronize()
+            epoch_loss.zero_()
 
     pending = []                                          # (async all-reduce, step) awaiting finalisation
 
@@ -263,16 +278,24 @@ def run_gpu_arm(args, rank, local_rank, world):
     for i in range(args.warmup):
         one_step(i)
     end_of_epoch()
+    # NVML is initialised and the sampler thread started BEFORE the barrier: nvmlInit from N processes at once takes
+    # milliseconds and would otherwise skew the ranks' entry into the timed region (the final all-reduce then waits
+    # for the last rank).  Sampling period: 0.5 ms at N = 1, 2 ms at N > 1.
+    sampler = ClockSampler(physical_gpu_index(local_rank), args.clock_interval_ms * 1e-3 if args.clock_interval_ms > 0
+                           else (0.0005 if world == 1 else 0.002))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     if epoch_loss is not None:
         epoch_loss.zero_()
         fence()
-    sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.samples.clear()
     e0.record()
-    for i in range(args.steps):
-        one_step(i)
+    if graph_all is not None:
+        graph_all.replay()
+    else:
+        for i in range(args.steps):
+            one_step(i)
     end_of_epoch()
     e1.record()
     fence()
@@ -340,7 +363,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                             "; per-rank loss (reference DDP semantics), ONE NCCL all-reduce of the epoch loss sum per timed region")),
                        "l2_policy": f"inputs {2 * B * K_JOINTS * H * W * 4 / 1e6:.0f} MB/step > 126 MB L2, "
                                     f"{R} rotating input sets, L2 evict_first loads",
-                       "launch": ("CUDA graph replay" if use_graph else "eager C-ABI launches, one per step") +
+                       "launch": ("one CUDA graph of all K launches" if graph_all is not None else
+                                  "CUDA graph replay" if use_graph else "eager C-ABI launches, one per step") +
                                  ("" if args.no_overlap or R < 2 else
                                   "; LHN_FLAG_OVERLAP_PREVIOUS (programmatic dependent launch over rotating buffer sets)"),
                        "loss_check": loss_val},
@@ -389,6 +413,9 @@ def main():
     ap.add_argument("--spare-sms", type=int, default=4,
                     help="N > 1: SMs the persistent kernel leaves free so the NCCL all-reduce of the previous step "
                          "can run beside it")
+    ap.add_argument("--clock-interval-ms", type=float, default=0.0, help="NVML sampling period (0 = automatic)")
+    ap.add_argument("--no-graph-all", action="store_true",
+                    help="N > 1: issue the timed steps eagerly instead of as one CUDA graph of K launches")
     ap.add_argument("--no-overlap", action="store_true", help="do not let a launch overlap the previous one's tail")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
