@@ -370,10 +370,15 @@ def get_coordinates_from_heatmap(batch_heatmaps):
 
 def get_final_preds(batch_heatmaps, center, scale):
     """utils/transforms.py:18-44 (A3 -> floor(x+0.5) guarded quarter shift -> back-transform).  The
-    reference's cv2-affine transform (rot = 0) is evaluated in closed form."""
+    reference's cv2-affine transform_preds (utils/transforms.py:112-152) is, for rot = 0, the similarity
+    X = (x - W/2) f + cx, Y = (y - H/2) f + cy with f = 200 scale[0] / W — scale[1] is never used — which is
+    T1 with scale_y := scale[0] * H / W."""
     t, was = _hm(batch_heatmaps)
     c, _ = _up(center, torch.float32)
     s, _ = _up(scale, torch.float32)
+    H, W = t.shape[-2:]
+    # tensor / tensor: torch turns division by a Python scalar on CUDA into a multiplication by its reciprocal
+    s = torch.stack([s[:, 0], (s[:, 0] * float(H)) / torch.full_like(s[:, 0], float(W))], dim=1).contiguous()
     r = ops.decode_heatmap(t, L.MASK_ZERO, L.REFINE_SIGN_ROUND, L.XFORM_CENTER_SCALE, c, s, want_idx=False)
     preds = r["kpts"][..., :2]
     return preds if was else _np(preds)

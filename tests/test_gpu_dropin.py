@@ -373,6 +373,19 @@ def test_evaluate_results_like_dataset_evaluate():
     np.testing.assert_allclose(got["EPE"], O.keypoint_epe(p64, gt.numpy(), mask.numpy()), rtol=1e-5)
 
 
+def test_get_final_preds_uses_scale0_only():
+    """utils/transforms.py:18-44,112-152: the cv2-affine back-transform of the legacy path is a similarity built
+    from scale[0] alone; anisotropic scales and a non-square heatmap (oracle checked live against the reference)."""
+    from litehandnet_b200.decode import get_final_preds
+    for shape, seed in (((5, 16, 64, 64), 150), ((4, 16, 64, 48), 151)):
+        hm, _ = synth.blob_heatmaps(*shape, seed=seed, zero_frac=0.1, tie_frac=0.1)
+        rng = np.random.default_rng(seed)
+        c = rng.uniform(60, 200, (shape[0], 2)).astype(np.float32)
+        s = np.stack([rng.uniform(0.6, 1.6, shape[0]), rng.uniform(0.6, 1.6, shape[0])], 1).astype(np.float32)
+        got = get_final_preds(hm.to(DEV), cu(c), cu(s)).cpu().numpy()
+        assert np.array_equal(got, O.get_final_preds(hm.numpy(), c, s))
+
+
 def test_mpii_evaluate_golden_and_sharded():
     """TopDownMpiiDataset.evaluate arithmetic (topdown_mpii_dataset.py:126-249) from shuffled, partly duplicated
     result batches; counters of two shards add up to the monolithic ones."""

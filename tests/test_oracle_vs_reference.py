@@ -105,3 +105,15 @@ def test_simdr_live(ref):
     r = ref.top_down_eval.keypoints_from_simdr(xv.numpy(), yv.numpy(), c.numpy(), s.numpy(), k=2)
     o = O.keypoints_from_simdr(xv.numpy(), yv.numpy(), c.numpy(), s.numpy(), 2)
     assert np.array_equal(o, r)
+
+
+def test_get_final_preds_anisotropic_live(ref):
+    """utils/transforms.py:18-44 with the cv2-affine transform_preds: only scale[0] enters."""
+    for shape, seed in (((3, 16, 64, 64), 150), ((2, 16, 64, 48), 151)):
+        hm, _ = _hm(*shape, seed)
+        rng = np.random.default_rng(seed)
+        c = rng.uniform(60, 200, (shape[0], 2)).astype(np.float32)
+        s = np.stack([rng.uniform(0.6, 1.6, shape[0]), rng.uniform(0.6, 1.6, shape[0])], 1).astype(np.float32)
+        r = ref.transforms.get_final_preds(torch.from_numpy(hm.copy()), c, s)
+        o = O.get_final_preds(hm, c, s)
+        assert_coords_close(o, r, rtol=1e-5, atol=1e-4, what="final_preds (anisotropic scale)")
