@@ -39,6 +39,7 @@ for case in range(n_cases):
     hm, cen = synth.blob_heatmaps(N, K, H, W, seed=seed, zero_frac=0.05, tie_frac=0.05, sigma=max(1.0, 2.0 * W / 64), dtype=dt)
     hf = synth.flipped_blob_heatmaps(cen, H, W, seed=seed + 1, flip_pairs=pairs, dtype=dt) if flip else None
     c, s = synth.bbox_center_scale(N, seed=seed + 2)
+    s = s * torch.tensor([1.0, 0.6 + 0.1 * (seed % 9)])                 # anisotropic boxes
     j, v = synth.hand_joints(N, K, (4 * W, 4 * H), seed=seed + 3, vis_prob=0.9, outside_frac=0.05)
     hm32 = hm.float().numpy()
     hf32 = None if hf is None else hf.float().numpy()
@@ -83,6 +84,14 @@ for case in range(n_cases):
             for b_, k_, _ in w[:4]:
                 print(' plane', b_, k_, 'got', got[b_, k_], 'want', want[b_, k_], 'p0', p0[b_, k_], 'max', mv[b_, k_])
                 np.save('/root/repo/gpurun_out/fuzz_plane.npy', avg[b_, k_])
+    # image-space coordinates: transform_preds of the oracle's heatmap coordinates (T1, both scale components)
+    gi = r['kpts'].cpu().numpy()[..., :2]
+    wi = np.stack([O.transform_preds(want[i], c.numpy()[i], s.numpy()[i], [W, H], use_udp=(refine == L.REFINE_DARK_UDP))[:, :2]
+                   for i in range(N)])
+    ei = np.abs(gi - wi)
+    toli = (1e-5 * np.maximum(np.abs(wi), 1.0) + 2e-4) * (50 if refine in (L.REFINE_DARK, L.REFINE_DARK_LEGACY, L.REFINE_DARK_UDP) else 1)
+    if not np.all((ei <= toli) | ~np.isfinite(wi)):
+        ok = False; print(case, 'IMAGE-COORD mismatch', float(np.nanmax(ei)), (N, K, H, W), dt, refine, mm)
     if render is not None:
         tg, tw = O.render_targets(j.numpy(), v.numpy(), (4 * W, 4 * H), (W, H), sig, enc)
         if mode == L.LOSS_JOINTS_MSE: wl = O.joints_distance_loss_mse(hm32, tg, tw)

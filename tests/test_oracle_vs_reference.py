@@ -117,3 +117,25 @@ def test_get_final_preds_anisotropic_live(ref):
         r = ref.transforms.get_final_preds(torch.from_numpy(hm.copy()), c, s)
         o = O.get_final_preds(hm, c, s)
         assert_coords_close(o, r, rtol=1e-5, atol=1e-4, what="final_preds (anisotropic scale)")
+
+
+def test_anisotropic_scales_live(ref):
+    """transform_preds (post_transforms.py:6-48) uses both scale components; the synthetic boxes elsewhere are
+    square, so pin the anisotropic case for the Gen-2 heatmap / SimDR / UDP decoders here."""
+    rng = np.random.default_rng(160)
+    N = 4
+    hm, _ = _hm(N, 21, 64, 48, 161)
+    c = rng.uniform(60, 200, (N, 2)).astype(np.float32)
+    s = np.stack([rng.uniform(0.6, 1.6, N), rng.uniform(0.6, 1.6, N)], 1).astype(np.float32)
+    T = ref.top_down_eval
+    with np.errstate(all="ignore"):
+        for pp in ("default", "unbiased"):
+            r = T.keypoints_from_heatmaps(hm.copy(), c, s, post_process=pp, kernel=11)
+            o = O.keypoints_from_heatmaps(hm, c, s, pp, 11)
+            assert_coords_close(o[1], r[1], what=f"preds {pp}")
+        r = T.keypoints_from_heatmaps(hm.copy(), c, s, kernel=11, use_udp=True)
+        o = O.keypoints_from_heatmaps_udp(hm, c, s, 11)
+        assert np.array_equal(o[0], r[0], equal_nan=True) and np.array_equal(o[1], r[1], equal_nan=True)
+    xv, yv = synth.simdr_vectors(N, 21, 448, seed=162)
+    assert np.array_equal(O.keypoints_from_simdr(xv.numpy(), yv.numpy(), c, s, 2),
+                          T.keypoints_from_simdr(xv.numpy(), yv.numpy(), c, s, k=2))
