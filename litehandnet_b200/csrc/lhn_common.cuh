@@ -206,11 +206,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "LHN_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // suspend-time hint: fewer polling retries
       "@p bra LHN_DONE;\n"
       "bra LHN_WAIT;\n"
       "LHN_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(2000u)
       : "memory");
 }
 // L2 eviction policy for read-once streams
