@@ -30,6 +30,7 @@ constexpr int kMaxWarpsPerCta = 24;
 constexpr int kMaxTeams = kMaxTeamsPerCta;
 
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
+  if (nthreads == 32) { __syncwarp(); return; }      // a one-warp team needs no barrier unit
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
