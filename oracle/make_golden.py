@@ -301,6 +301,110 @@ def backward_case(ref, name, seed):
     np.savez_compressed(os.path.join(OUT, name), **d)
 
 
+def region_maps(B, seed, H=64, W=64, npk=3):
+    """Centre map = noise U(0,0.3) + npk Gaussian blobs (sigma 2) per image; size maps U(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(B, 1, H, W, generator=g) * 0.3
+    ys, xs = torch.meshgrid(torch.arange(float(H)), torch.arange(float(W)), indexing="ij")
+    for i in range(B):
+        for _ in range(npk):
+            cx = torch.rand(1, generator=g).item() * W
+            cy = torch.rand(1, generator=g).item() * H
+            a = 0.4 + torch.rand(1, generator=g).item()
+            c[i, 0] += a * torch.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / 8)
+    s = torch.rand(B, 2, H, W, generator=g)
+    return c, s
+
+
+def _boxes_to_arrays(lists, max_num):
+    """list over images of None | [[x,y,w,h,conf], ...] -> (boxes f32 [B,max_num,5] zero-filled, counts int32 [B])."""
+    B = len(lists)
+    boxes = np.zeros((B, max_num, 5), np.float32)
+    counts = np.zeros(B, np.int32)
+    for i, l in enumerate(lists):
+        if l is not None:
+            counts[i] = len(l)
+            boxes[i, :len(l)] = np.asarray(l, np.float32)
+    return boxes, counts
+
+
+FIRST_RESULT_BOXES = [[80., 124., 58.02, 102.15, 1.3], [10., 250., 30., 40., 1.], [300., 300., 10., 10., 1.],
+                      [128., 128., 400., 400., 1.], [5.0, 5.0, 3., 3., 1.], [200.5, 31.25, 77.7, 20.1, 0.4]]
+
+
+def region_case(ref, name, seed):
+    """the bbox branch of the legacy parsers executed on seeded region maps.
+    HeatmapParser_SH (utils/SPheatmapParser.py:32-138,169-206), ResultParser with cfg['DARK'] = True
+    (utils/result_parser.py:50-59,131-229,288-306), cs_from_region_map / non_max_suppression
+    (utils/evaluation.py:94-212)."""
+    B = 6
+    c, s = region_maps(B, seed)
+    c[1, 0, 10, 10:13] = 2.0                       # a plateau: three equal maxima inside one window all survive the NMS
+    c[2] = 0                                       # an empty centre map: no candidate passes the threshold
+    c[2, 0, 40, 20] = 0.05
+    s40 = s * 40
+    d = dict(center=c.numpy().copy(), size=s.numpy().copy())
+    SH = ref.SPheatmapParser.HeatmapParser_SH()
+    cn = SH.heatmap_nms(c.clone())
+    d["ref_nms"] = cn.numpy().copy()
+    cand = SH.candidate_bbox(cn.clone(), s.clone(), (256, 256))
+    d["ref_sh_cand"] = cand.numpy().copy()
+    d["ref_sh_boxes"], d["ref_sh_counts"] = _boxes_to_arrays(SH.non_max_suppression(cand), 1)
+    SH.max_num_bbox = 10
+    for thr in (0.6, 0.3, 0.1):
+        SH.iou_threshold = thr
+        bx, ct = _boxes_to_arrays(SH.non_max_suppression(cand), 10)
+        d[f"ref_sh_boxes10_iou{int(thr * 10)}"], d[f"ref_sh_counts10_iou{int(thr * 10)}"] = bx, ct
+    # the whole parse() call, centre maps mutated in place by the reference
+    hm = torch.rand(B, 5, 64, 64, generator=torch.Generator().manual_seed(seed + 1))
+    d["kpt_hm"] = hm.numpy().copy()
+    SH = ref.SPheatmapParser.HeatmapParser_SH()
+    c_in = c.clone()
+    kpt, boxes = SH.parse(hm.clone(), c_in, s.clone(), (256, 256))
+    d["ref_parse_kpt"] = kpt.numpy().copy()
+    d["ref_parse_boxes"], d["ref_parse_counts"] = _boxes_to_arrays(boxes, 1)
+    d["ref_parse_center_after"] = c_in.numpy().copy()
+    # ResultParser, DARK = True.  One candidate: the executed method as is.  Ten candidates: on CPU tensors the
+    # reference's blur aliases the centre map and re-blurs it once per candidate; the CUDA semantics (a fresh copy
+    # each time) are obtained by executing its own adjust_keypoints_by_DARK per candidate on un-aliased inputs.
+    RP = ref_loader.make_result_parser(ref, dark=True)
+    cn2 = RP.heatmap_nms(c.clone())
+    RP.num_candidates = 1
+    d["ref_rp_cand1"] = RP.candidate_bbox(cn2.clone(), s40.clone()).numpy().copy()
+    d["ref_rp_boxes1"], d["ref_rp_counts1"] = _boxes_to_arrays(
+        RP.non_max_suppression(torch.from_numpy(d["ref_rp_cand1"])), 1)
+    tv, ti = torch.topk(cn2.reshape(B, -1), 10)
+    xy = np.zeros((B, 10, 2), np.float32)
+    for i in range(10):
+        kp = torch.stack([(ti[:, i] % 64).float(), torch.div(ti[:, i], 64, rounding_mode="trunc").float()], 1)[:, None, :]
+        xy[:, i] = ref.heatmap_post_processing.adjust_keypoints_by_DARK(kp.clone(), cn2.clone())[:, 0, :]
+    d["ref_rp_xy10"] = xy * 4
+    d["ref_rp_topk_idx"] = ti.numpy().copy()
+    d["ref_rp_topk_val"] = tv.numpy().copy()
+    # cs_from_region_map + non_max_suppression (evaluation.py)
+    ev = ref.evaluation
+    region = torch.cat([c, s40], 1)
+    for K, thr in ((20, 0.1), (5, 0.5)):
+        cc = ev.cs_from_region_map(region.clone(), 256, K, thr)
+        d[f"ref_cs_cand_k{K}"] = cc.numpy().copy()
+        d[f"ref_cs_boxes_k{K}"], d[f"ref_cs_counts_k{K}"] = _boxes_to_arrays(ev.non_max_suppression(cc, 0.6, 0.1, 3), 3)
+    # bbox-restricted keypoint decode
+    RPn = ref_loader.make_result_parser(ref, dark=False)
+    for dark, P in ((False, RPn), (True, RP)):
+        out = np.zeros((len(FIRST_RESULT_BOXES), 5, 3), np.float32)
+        for j, bb in enumerate(FIRST_RESULT_BOXES):
+            out[j] = P._get_first_result(list(bb), hm.clone(), j % B).numpy()[0]
+        d[f"ref_first_result_dark{int(dark)}"] = out
+    d["first_result_boxes"] = np.asarray(FIRST_RESULT_BOXES, np.float64)
+    # the reference's own fixture (utils/SPheatmapParser.py:221-233)
+    c_hm = torch.zeros(2, 1, 64, 64); c_hm[..., 3, 3] = 1
+    s_hm = torch.zeros(2, 2, 64, 64); s_hm[..., 0:7, 0:7] = 1.
+    k_hm = torch.zeros((2, 4, 64, 64)); k_hm[..., 3, 3] = 1; k_hm[..., 3, 2] = 0.5; k_hm[..., 2, 3] = 0.5
+    _, b = ref.SPheatmapParser.HeatmapParser_SH().parse(k_hm, c_hm, s_hm, (256, 256))
+    d["ref_main_boxes"], _ = _boxes_to_arrays(b, 1)
+    np.savez_compressed(os.path.join(OUT, name), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -316,6 +420,7 @@ def main():
     udp_case(ref, "render_udp.npz", seed=51)
     udp_decode_case(ref, "decode_udp.npz", seed=61)
     mpii_case("mpii_pckh.npz", seed=71)
+    region_case(ref, "region_bbox.npz", seed=81)
     # the reference's only hand-derivable known answer (utils/SPheatmapParser.py:221-233)
     kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
     k, _ = ref.SPheatmapParser.HeatmapParser_SH().parse(kpt_hm.clone(), image_size=(256, 256))

@@ -34,3 +34,17 @@ def assert_coords_close(a, b, rtol=1e-5, atol=2e-5, what=""):
     ok = np.abs(a - b) <= atol + rtol * np.abs(b)
     ok |= nan_a
     assert ok.all(), f"{what}: max abs diff {np.nanmax(np.abs(a - b))} at {np.argwhere(~ok)[:5]}"
+
+
+def canon_candidates(c):
+    """torch.topk leaves the order of EQUAL values unspecified (and, when the k-th value is tied with values that
+    did not make the cut, which of them it returns).  Canonical form for comparing candidate lists [B,N,5]: rows
+    sorted by (-confidence, y, x) per image, and a mask of the rows whose confidence is strictly above the k-th
+    value — those are the rows every correct top-k must return."""
+    c = np.asarray(c).copy()
+    det = np.zeros(c.shape[:2], bool)
+    for b in range(c.shape[0]):
+        order = np.lexsort((c[b, :, 0], c[b, :, 1], -c[b, :, 4].astype(np.float64)))
+        c[b] = c[b][order]
+        det[b] = c[b, :, 4] > c[b, -1, 4]
+    return c, det
