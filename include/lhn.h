@@ -345,6 +345,92 @@ LHN_API int lhn_evaluate_pck(const void* pred_hm, const void* gt_hm, int dtype, 
 LHN_API int lhn_flip_back(const void* in, void* out, int dtype, int64_t B, int K, int H, int W,
                           const int32_t* flip_index, lhn_stream_t stream);
 
+/* ---- region-map bbox decode -------------------------------------------------
+ * The bbox branch of the legacy parsers: centre-map NMS -> top-k candidate centres -> size lookup ->
+ * (centre refinement) -> box filter + IoU NMS, one CTA per image, everything on the device.
+ *   LHN_REGION_SH  HeatmapParser_SH.heatmap_nms / candidate_bbox / non_max_suppression
+ *                  (utils/SPheatmapParser.py:32-41,58-99,101-138): size = clip(avgpool(size)[y,x], 0, 0.99) *
+ *                  image_size, centre = (idx % W, idx // W) * (image_size / [W, H]);
+ *   LHN_REGION_RP  ResultParser.heatmap_nms / candidate_bbox / non_max_suppression
+ *                  (utils/result_parser.py:50-59,131-175,177-215) with cfg['DARK'] = True: candidate centres
+ *                  refined by the legacy DARK (blur_ksize = 19, f64 blur) on the NMS'd centre map — every
+ *                  candidate on the same un-blurred map, the reference's CUDA semantics — then centre and
+ *                  avgpool size both * (stride_x, stride_y).  refine = LHN_REFINE_NONE skips the refinement;
+ *   LHN_REGION_CS  cs_from_region_map + non_max_suppression (utils/evaluation.py:94-212): no centre NMS
+ *                  (nms_kernel = 0), size = mean of the size maps over the clipped window [c-6, c+7) *
+ *                  image_w / W, only candidates with confidence > cand_thr get centre and size.
+ * top-k follows torch.topk: descending, NaN greatest; EQUAL values (whose order torch leaves unspecified) come
+ * lowest index first.  The IoU NMS is torchvision.ops.nms: f32 arithmetic, IoU compared with the double
+ * threshold, candidates already in descending score order. */
+#define LHN_REGION_SH 0
+#define LHN_REGION_RP 1
+#define LHN_REGION_CS 2
+#define LHN_MAX_CANDIDATES 32
+
+typedef struct {
+  int32_t mode;            /* LHN_REGION_* */
+  int32_t nms_kernel;      /* centre-map MaxPool2d window (odd, stride 1, padding (k-1)/2; pcfg nms_kernel = 11);
+                              0 = use the centre map as it is */
+  int32_t num_candidates;  /* top-k size N <= LHN_MAX_CANDIDATES (pcfg num_candidates = 10; evaluate_ap k = 20) */
+  int32_t max_num_bbox;    /* boxes kept per image <= N (pcfg max_num_bbox = 1) */
+  int32_t avg_kernel;      /* SH / RP: AvgPool2d window of the size maps (pcfg region_avg_kernel = 3) */
+  int32_t refine;          /* RP: LHN_REFINE_NONE or LHN_REFINE_DARK_LEGACY */
+  int32_t blur_ksize;      /* RP + DARK: 19 (pcfg blue_kernel) */
+  int32_t reserved;
+  float image_w, image_h;  /* SH, CS */
+  float stride_x, stride_y;/* RP: feature_stride */
+  float cand_thr;          /* CS: detection threshold inside cs_from_region_map */
+  float det_thr;           /* box filter: confidence > det_thr (pcfg detection_threshold = 0.1) */
+  float min_wh, max_wh;    /* box filter: min_wh < w, h < max_wh (2, 4096) */
+  double iou_thr;          /* pcfg iou_threshold = 0.6 */
+  double taps[LHN_MAX_TAPS]; /* lhn_gaussian_taps(blur_ksize) */
+} lhn_region_params;
+
+/* center [B,1,H,W] (batch stride center_stride_b elements, plane contiguous), size [B,2,H,W] (strides
+ * size_stride_b / size_stride_c) — e.g. the two channel slices of one region map [B,3,H,W].
+ * nms_out    NULL, or a tensor like `center` (same dtype and batch stride) that receives the NMS'd centre map;
+ *            it MAY be `center` itself: the reference masks its argument in place (heatmaps *= mask).
+ * candidates f32 [B, N, 5] (x, y, w, h, confidence) or NULL.
+ * boxes      f32 [B, max_num_bbox, 5], zero-filled past counts[b]; counts int32 [B]. */
+LHN_API int lhn_region_bbox_decode(const void* center, const void* size, int dtype, int64_t B, int H, int W,
+                                   int64_t center_stride_b, int64_t size_stride_b, int64_t size_stride_c,
+                                   const lhn_region_params* rp, void* nms_out, float* candidates,
+                                   float* boxes, int32_t* counts, lhn_stream_t stream);
+
+/* non_max_suppression alone (utils/result_parser.py:177-215, utils/SPheatmapParser.py:101-138,
+ * utils/evaluation.py:170-212) on given candidates f32 [B, N, 5] (x, y, w, h, confidence), N <= LHN_MAX_CANDIDATES:
+ * confidence > det_thr, min_wh < w, h < max_wh, torchvision.ops.nms with iou_thr, first max_num kept.
+ * boxes f32 [B, max_num, 5] zero-filled past counts[b]; counts int32 [B]. */
+LHN_API int lhn_box_nms(const float* candidates, int64_t B, int N, float det_thr, float min_wh, float max_wh,
+                        double iou_thr, int max_num, float* boxes, int32_t* counts, lhn_stream_t stream);
+
+/* heatmap_nms alone (utils/result_parser.py:50-59, utils/SPheatmapParser.py:32-41) on [B, C, H, W] planes:
+ * out = hm * eq(maxpool_k(hm), hm).  out has the same dtype and strides as hm and may alias it. */
+LHN_API int lhn_heatmap_nms(const void* hm, void* out, int dtype, int64_t B, int C, int H, int W,
+                            int64_t stride_b, int64_t stride_c, int nms_kernel, lhn_stream_t stream);
+
+/* ResultParser.vector_nms (utils/result_parser.py:61-74): out = v * eq(max_pool1d(v, 3, 1, 1), v) on n_rows
+ * contiguous rows of length L.  out must NOT alias v. */
+LHN_API int lhn_vector_nms(const void* v, void* out, int dtype, int64_t n_rows, int L, lhn_stream_t stream);
+
+/* The +-0.25 rule at GIVEN integer positions (HeatmapParser.adjust_keypoints, utils/HeatmapParser.py:197-223,
+ * whose grouped candidates are not plane argmaxima): for point i on plane (bc[2i], bc[2i+1]) of hm [B,C,H,W],
+ * xx = int(x), yy = int(y); x += 0.25 if hm[yy, min(xx+1, W-1)] > hm[yy, max(xx-1, 0)] else -0.25, likewise y;
+ * refine = LHN_REFINE_OFFSET, or LHN_REFINE_OFFSET_HALF (then + 0.5).  xy f32 [n, xy_stride] updated in place. */
+LHN_API int lhn_refine_points(const void* hm, int dtype, int64_t B, int C, int H, int W, int64_t stride_b,
+                              int64_t stride_c, const int32_t* bc, float* xy, int xy_stride, int64_t n,
+                              int refine, lhn_stream_t stream);
+
+/* Bbox-restricted keypoint decode (ResultParser._get_first_result, utils/result_parser.py:288-306):
+ * for image b only the window roi[b] = (x0, y0, x1, y1) (int32 [B,4], 0 <= x0 < x1 <= W) of each plane takes
+ * part: first-index argmax of the cropped plane (A4), then LHN_REFINE_NONE / _OFFSET / _OFFSET_HALF /
+ * _DARK_LEGACY evaluated ON THE CROP (neighbours clamp, and the blur zero-pads, at the window's border), then
+ * (x + x0, y + y0) * (scale_x, scale_y).  dp: refine, blur_ksize, taps, scale_x/scale_y are read.
+ * out f32 [B*K, 3] (X, Y, score); out_idx int32 [B*K] flat index inside the crop, or NULL. */
+LHN_API int lhn_decode_heatmap_roi(const void* hm, int dtype, int64_t B, int K, int H, int W, int64_t stride_b,
+                                   int64_t stride_c, const int32_t* roi, const lhn_decode_params* dp,
+                                   float* out, int32_t* out_idx, lhn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

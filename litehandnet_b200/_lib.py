@@ -22,6 +22,8 @@ LOSS_NONE, LOSS_DISTANCE, LOSS_DISTANCE_BALANCE, LOSS_JOINTS_MSE = 0, 1, 2, 3
 FLAG_OVERLAP_PREVIOUS = 1
 FLAG_ACCUMULATE_LOSS = 2
 MAX_TAPS, MAX_STACKS = 31, 8
+REGION_SH, REGION_RP, REGION_CS = 0, 1, 2
+MAX_CANDIDATES = 32
 
 ERRORS = {-1: "LHN_EINVAL (bad shape / null pointer / bad enum)", -2: "LHN_EDTYPE (unsupported dtype)",
           -3: "LHN_EALIGN (misaligned pointer)", -4: "LHN_EWORKSPACE (workspace too small)",
@@ -34,7 +36,8 @@ EXPORTS = [
     "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
-    "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate",
+    "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate", "lhn_region_bbox_decode", "lhn_heatmap_nms",
+    "lhn_vector_nms", "lhn_refine_points", "lhn_decode_heatmap_roi", "lhn_box_nms",
 ]
 
 
@@ -48,6 +51,15 @@ class RenderParams(C.Structure):
     _fields_ = [("loss_mode", C.c_int32), ("unbiased", C.c_int32), ("num_stacks", C.c_int32),
                 ("reserved", C.c_int32), ("image_w", C.c_float), ("image_h", C.c_float),
                 ("pos_value", C.c_float), ("sigma", C.c_float * MAX_STACKS)]
+
+
+class RegionParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("nms_kernel", C.c_int32), ("num_candidates", C.c_int32),
+                ("max_num_bbox", C.c_int32), ("avg_kernel", C.c_int32), ("refine", C.c_int32),
+                ("blur_ksize", C.c_int32), ("reserved", C.c_int32), ("image_w", C.c_float), ("image_h", C.c_float),
+                ("stride_x", C.c_float), ("stride_y", C.c_float), ("cand_thr", C.c_float), ("det_thr", C.c_float),
+                ("min_wh", C.c_float), ("max_wh", C.c_float), ("iou_thr", C.c_double),
+                ("taps", C.c_double * MAX_TAPS)]
 
 
 class LhnError(RuntimeError):
@@ -98,6 +110,14 @@ def _declare(lib):
     lib.lhn_evaluate_pck.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, f32, f32, f32, vp, i64,
                                      vp, vp, vp]
     lib.lhn_flip_back.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp]
+    lib.lhn_region_bbox_decode.argtypes = [vp, vp, i32, i64, i32, i32, i64, i64, i64, C.POINTER(RegionParams),
+                                           vp, vp, vp, vp, vp]
+    lib.lhn_box_nms.argtypes = [vp, i64, i32, f32, f32, f32, f64, i32, vp, vp, vp]
+    lib.lhn_heatmap_nms.argtypes = [vp, vp, i32, i64, i32, i32, i32, i64, i64, i32, vp]
+    lib.lhn_vector_nms.argtypes = [vp, vp, i32, i64, i32, vp]
+    lib.lhn_refine_points.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp, i32, i64, i32, vp]
+    lib.lhn_decode_heatmap_roi.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, C.POINTER(DecodeParams),
+                                           vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("lhn_version",):

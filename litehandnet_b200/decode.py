@@ -9,8 +9,12 @@ Mirrored (file:line relative to the reference root):
   utils/post_processing/decoder.py:9                     TopDownDecoder (.decode / .decode_simdr)
   utils/heatmap_post_processing.py:6,35                  adjust_keypoints_by_offset / _by_DARK
   utils/result_parser.py:14                              ResultParser (.get_coordinates_from_heatmaps,
-                                                         .get_pred_kpt, .vector_nms, .get_coordinates_from_vectors)
-  utils/SPheatmapParser.py:12                            HeatmapParser_SH (.get_coordinates, .adjust_keypoints, .parse)
+                                                         .get_pred_kpt, .vector_nms, .get_coordinates_from_vectors,
+                                                         .heatmap_nms, .candidate_bbox, .non_max_suppression,
+                                                         .get_pred_bbox, ._get_first_result, .get_group_keypoints)
+  utils/SPheatmapParser.py:12                            HeatmapParser_SH (.get_coordinates, .adjust_keypoints, .parse,
+                                                         .heatmap_nms, .candidate_bbox, .non_max_suppression)
+  utils/evaluation.py:94,170                             cs_from_region_map, non_max_suppression
   utils/HeatmapParser.py:197                             HeatmapParser.adjust_keypoints (list-of-lists form)
   utils/transforms.py:18,47,78                           get_final_preds, get_max_preds, flip_back
   utils/evaluation.py:62                                 get_coordinates_from_heatmap
@@ -192,6 +196,31 @@ class TopDownDecoder:
 
 
 # ---- legacy (Gen-1) ---------------------------------------------------------------------------------
+# config/__init__.py:4-24 (the post-processing constants the legacy parsers read at construction)
+pcfg = {
+    "num_candidates": 10, "max_num_bbox": 1, "nms_kernel": 11, "nms_stride": 1, "nms_padding": 5,
+    "detection_threshold": 0.1, "iou_threshold": 0.6, "bbox_factor": 1.3, "region_avg_kernel": 3,
+    "region_avg_stride": 1, "blue_kernel": 19, "cd_iou": 0.3, "cd_ratio": 0,
+}
+
+
+def _boxes_to_lists(boxes, counts):
+    """(boxes [B,M,5], counts [B]) on the device -> the reference's list over images: None or
+    [[x, y, w, h, conf], ...] (x[index].tolist())."""
+    bx = boxes.cpu().tolist()
+    ct = counts.cpu().tolist()
+    return [bx[i][:n] if n > 0 else None for i, n in enumerate(ct)]
+
+
+def _region_inplace(center_maps):
+    """The reference's heatmap_nms masks its argument in place; do the same when the argument is a CUDA tensor
+    with contiguous planes (a channel slice of a region map qualifies).  -> (cuda tensor, inplace)"""
+    t, was = _hm(center_maps)
+    ok = was and t is not None and t.dim() == 4 and t.stride(3) == 1 and t.stride(2) == t.shape[3] \
+        and isinstance(center_maps, torch.Tensor) and t.data_ptr() == center_maps.data_ptr()
+    return t, ok
+
+
 def adjust_keypoints_by_offset(keypoints, heatmaps):
     """utils/heatmap_post_processing.py:6-33: keypoints [B,K,3] (x,y,conf) from the argmax ->
     +-0.25 towards the higher clamped neighbour, then +0.5.  Returns a new tensor (callers pass
@@ -228,12 +257,26 @@ def adjust_keypoints_by_DARK(keypoints, heatmaps):
 
 
 class ResultParser:
-    """utils/result_parser.py:14 — keypoint branch only (get_coordinates_from_heatmaps, get_pred_kpt,
-    vector_nms, get_coordinates_from_vectors).  The bbox/NMS/cycle-detection branch is out of scope."""
+    """utils/result_parser.py:14 — keypoint branch (get_coordinates_from_heatmaps, get_pred_kpt, vector_nms,
+    get_coordinates_from_vectors) and bbox branch (heatmap_nms, candidate_bbox, non_max_suppression,
+    get_pred_bbox, _get_first_result, get_group_keypoints without cycle detection — the second pass re-runs the
+    model, which is outside the path)."""
 
     def __init__(self, cfg):
         self.cfg = cfg
-        self.max_num_bbox = 1                                        # pcfg["max_num_bbox"]
+        self.nms_kernel = pcfg["nms_kernel"]
+        if pcfg["nms_stride"] != 1 or 2 * pcfg["nms_padding"] + 1 != pcfg["nms_kernel"]:
+            raise L.LhnError("only the size-preserving centre-map max-pool (stride 1, kernel = 2 padding + 1) is supported")
+        self.avg_kernel = pcfg["region_avg_kernel"]
+        self.num_candidates = pcfg["num_candidates"]
+        self.max_num_bbox = pcfg["max_num_bbox"]
+        self.detection_threshold = pcfg["detection_threshold"]
+        self.iou_threshold = pcfg["iou_threshold"]
+        self.bbox_factor = pcfg["bbox_factor"]
+        self.image_area = cfg['image_size'][0] * cfg['image_size'][1]
+        self.bbox_alpha = cfg.get('bbox_alpha')
+        self.cd_enabled = cfg.get('with_region_map', False)
+        self.cd_reduction = cfg.get('cycle_detection_reduction')
         self.image_size = torch.tensor(cfg['image_size'])
         if cfg['model'] == 'srhandnet':
             self.heatmap_size = torch.tensor([cfg['hm_size'][-1], cfg['hm_size'][-1]])
@@ -259,10 +302,97 @@ class ResultParser:
 
     def vector_nms(self, vector):
         """result_parser.py:61-74 (returns a new tensor; the reference masks its argument in place)."""
-        v, was = _up(vector, torch.float32)
-        vmax = torch.max_pool1d(v, 3, 1, 1)
-        out = v * torch.eq(vmax, v).float()
+        v, was = _hm(vector)
+        out = ops.vector_nms(v)
         return out if was else out.cpu()
+
+    # ---- bbox branch (SURVEY §8f rank 4) ----
+    def heatmap_nms(self, heatmaps):
+        """result_parser.py:50-59: hm * eq(maxpool11(hm), hm), in place on a CUDA tensor like the reference."""
+        t, inplace = _region_inplace(heatmaps)
+        out = ops.heatmap_nms(t, self.nms_kernel, inplace=inplace)
+        return heatmaps if inplace else (out if isinstance(heatmaps, torch.Tensor) and heatmaps.is_cuda else out.cpu())
+
+    def _region(self, center_maps, size_maps, nms_kernel, inplace):
+        if not self.cfg['DARK']:
+            # result_parser.py:161-166: with DARK off the reference passes the tensor adjust_keypoints_by_offset
+            # returned to torch.from_numpy and raises — same error here
+            raise TypeError("expected np.ndarray (got Tensor)")
+        fs = self.feature_stride.tolist()
+        return ops.region_bbox_decode(center_maps, size_maps, L.REGION_RP, nms_kernel=nms_kernel,
+                                      num_candidates=self.num_candidates, max_num_bbox=self.max_num_bbox,
+                                      avg_kernel=self.avg_kernel, refine=L.REFINE_DARK_LEGACY,
+                                      blur_ksize=pcfg['blue_kernel'], stride=(float(fs[0]), float(fs[1])),
+                                      det_thr=self.detection_threshold, iou_thr=self.iou_threshold,
+                                      nms_inplace=inplace)
+
+    def candidate_bbox(self, center_maps, size_maps):
+        """result_parser.py:131-175 on an already NMS'd centre map -> candidates [B, k, 5] (a CPU tensor, as the
+        reference allocates it).  Every candidate is refined on the same map (the reference's CUDA semantics)."""
+        c, _ = _hm(center_maps)
+        sm, _ = _hm(size_maps)
+        return self._region(c, sm.to(c.dtype), 0, False)["candidates"].cpu()
+
+    def non_max_suppression(self, candidates):
+        """result_parser.py:177-215 -> list over images: None or [[x, y, w, h, conf], ...]."""
+        c, _ = _up(candidates, torch.float32)
+        return _boxes_to_lists(*ops.box_nms(c, self.detection_threshold, self.iou_threshold, self.max_num_bbox))
+
+    def get_pred_bbox(self, region_map):
+        """result_parser.py:217-229: region_map [B,3,H,W] -> list of bboxes; ONE launch (NMS + top-k + size
+        lookup + DARK refinement + box NMS); channel 0 of a CUDA region_map is masked in place as in the reference."""
+        t, _ = _hm(region_map)
+        c, inplace = _region_inplace(region_map[:, 0:1]) if isinstance(region_map, torch.Tensor) else (t[:, 0:1], False)
+        if not inplace:
+            c = t[:, 0:1]
+        r = self._region(c, t[:, 1:3], self.nms_kernel, inplace)
+        return _boxes_to_lists(r["boxes"], r["counts"])
+
+    def _first_result_roi(self, bbox, H, W):
+        """result_parser.py:290-303: the enlarged bbox as a heatmap window, in f32 like the reference's 0-dim tensors."""
+        f32 = np.float32
+        stride = f32(int(self.feature_stride[0]))
+        xc, yc, wb, hb = [f32(f32(v) / stride) for v in bbox[:4]]
+        wb = int(f32(wb * f32(self.bbox_factor)))
+        hb = int(f32(hb * f32(self.bbox_factor)))
+        ul_x = max(0, int(f32(f32(xc - f32(wb / 2)) + f32(0.5))))
+        ul_y = max(0, int(f32(f32(yc - f32(hb / 2)) + f32(0.5))))
+        br_x, br_y = min(ul_x + wb, W), min(ul_y + hb, H)
+        if br_x <= ul_x or br_y <= ul_y:
+            return 0, 0, W, H
+        return ul_x, ul_y, br_x, br_y
+
+    def _decode_rois(self, heatmaps, rois):
+        refine = L.REFINE_DARK_LEGACY if self.cfg['DARK'] else L.REFINE_OFFSET_HALF
+        fs = self.feature_stride.tolist()
+        roi = torch.tensor(rois, dtype=torch.int32).to(heatmaps.device)
+        return ops.decode_heatmap_roi(heatmaps, roi, refine, scale_xy=(float(fs[0]), float(fs[1])),
+                                      blur_ksize=pcfg['blue_kernel'] if self.cfg['DARK'] else None)
+
+    def _get_first_result(self, bbox, heatmaps, img_idx: int):
+        """result_parser.py:288-306: keypoints of image img_idx decoded inside the enlarged bbox only -> [1,K,3]."""
+        t, was = _hm(heatmaps)
+        H, W = t.shape[2:]
+        out = self._decode_rois(t[img_idx:img_idx + 1], [self._first_result_roi(bbox, H, W)])
+        return out if was else out.cpu()
+
+    def get_group_keypoints(self, model, img, bbox_list, heatmaps):
+        """result_parser.py:251-273 without cycle detection: one launch per bbox slot over the whole batch
+        -> [B, max_num_bbox, K, 3] (zeros where an image has no such bbox; a CPU tensor, as the reference's)."""
+        if self.cd_enabled:
+            raise NotImplementedError("cycle detection re-runs the model on a crop (result_parser.py:308-352): "
+                                      "outside the heatmap decode path")
+        t, _ = _hm(heatmaps)
+        B, K, H, W = t.shape
+        pred = torch.zeros((B, self.max_num_bbox, K, 3), device=t.device)
+        for j in range(self.max_num_bbox):
+            has = [bl is not None and len(bl) > j for bl in bbox_list]
+            if not any(has):
+                continue
+            rois = [self._first_result_roi(bl[j], H, W) if h else (0, 0, W, H) for bl, h in zip(bbox_list, has)]
+            out = self._decode_rois(t, rois)
+            pred[:, j] = out * torch.tensor(has, device=t.device)[:, None, None]
+        return pred.cpu()
 
     def get_coordinates_from_vectors(self, x_vectors, y_vectors, pred_bboxes):
         """result_parser.py:92-129 with max_num_bbox = 1: vector_nms, bbox-masked first-max argmax, /k,
@@ -288,8 +418,8 @@ class ResultParser:
 
 
 class HeatmapParser_SH:
-    """utils/SPheatmapParser.py:12 — keypoint branch (get_coordinates, adjust_keypoints, parse with
-    center_maps=None)."""
+    """utils/SPheatmapParser.py:12 — keypoint branch (get_coordinates, adjust_keypoints) and bbox branch
+    (heatmap_nms, candidate_bbox, non_max_suppression), both behind parse()."""
 
     @staticmethod
     def get_coordinates(heatmaps):
@@ -305,17 +435,53 @@ class HeatmapParser_SH:
         out[..., :2] = _refine_from(kp, r["hm_kpts"], t)
         return out.cpu() if not (isinstance(keypoints, torch.Tensor) and keypoints.is_cuda) else out
 
+    def __init__(self):
+        self.nms_kernel = pcfg["nms_kernel"]
+        self.avg_kernel = pcfg["region_avg_kernel"]
+        self.num_candidates = pcfg["num_candidates"]
+        self.max_num_bbox = pcfg["max_num_bbox"]
+        self.detection_threshold = pcfg["detection_threshold"]
+        self.iou_threshold = pcfg["iou_threshold"]
+
+    def heatmap_nms(self, heatmaps):
+        """SPheatmapParser.py:32-41 (in place on a CUDA tensor, like the reference)."""
+        t, inplace = _region_inplace(heatmaps)
+        out = ops.heatmap_nms(t, self.nms_kernel, inplace=inplace)
+        return heatmaps if inplace else (out if isinstance(heatmaps, torch.Tensor) and heatmaps.is_cuda else out.cpu())
+
+    def _region(self, c, sm, image_size, nms_kernel, inplace):
+        isz = [float(v) for v in (image_size.tolist() if isinstance(image_size, torch.Tensor) else image_size)]
+        return ops.region_bbox_decode(c, sm.to(c.dtype), L.REGION_SH, nms_kernel=nms_kernel,
+                                      num_candidates=self.num_candidates, max_num_bbox=self.max_num_bbox,
+                                      avg_kernel=self.avg_kernel, image_size=isz, det_thr=self.detection_threshold,
+                                      iou_thr=self.iou_threshold, nms_inplace=inplace)
+
+    def candidate_bbox(self, center_maps, size_maps, image_size=(352, 352)):
+        """SPheatmapParser.py:58-99 on an already NMS'd centre map -> candidates [B, k, 5] (CPU tensor)."""
+        c, _ = _hm(center_maps)
+        sm, _ = _hm(size_maps)
+        return self._region(c, sm, image_size, 0, False)["candidates"].cpu()
+
+    def non_max_suppression(self, candidates):
+        """SPheatmapParser.py:101-138 -> list over images: None or [[x, y, w, h, conf], ...]."""
+        c, _ = _up(candidates, torch.float32)
+        return _boxes_to_lists(*ops.box_nms(c, self.detection_threshold, self.iou_threshold, self.max_num_bbox))
+
     def parse(self, heatmaps, center_maps=None, size_maps=None, image_size=(256, 256), scale_factor=1):
-        """SPheatmapParser.py:169-206 -> (kpt [B,K,3] on CPU, pred_bboxes).  With center/size maps the
-        bbox branch would run — out of scope: raises."""
+        """SPheatmapParser.py:169-206 -> (kpt [B,K,3] on CPU, pred_bboxes).  With centre/size maps the bbox
+        branch runs as ONE launch (centre NMS in place on a CUDA centre map, top-k, avg-pool size lookup, box NMS)."""
+        pred_bboxes = None
         if center_maps is not None and size_maps is not None:
-            raise NotImplementedError("bbox decoding from centre/size maps is SURVEY §8f 'next' (rank 4)")
+            c, inplace = _region_inplace(center_maps)
+            sm, _ = _hm(size_maps)
+            r = self._region(c, sm, image_size, self.nms_kernel, inplace)
+            pred_bboxes = _boxes_to_lists(r["boxes"], r["counts"])
         t, _ = _hm(heatmaps)
         H, W = t.shape[2:]
         isz = torch.tensor(image_size, dtype=torch.float32)
         f = (isz / torch.tensor([W, H], dtype=torch.float32)).tolist()
         r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_OFFSET, L.XFORM_SCALE, scale_xy=(f[0], f[1]), want_idx=False)
-        return r["kpts"].cpu(), None
+        return r["kpts"].cpu(), pred_bboxes
 
 
 class HeatmapParser:
@@ -327,24 +493,40 @@ class HeatmapParser:
         self.channel_offset = channel_offset
 
     def adjust_keypoints(self, keypoints, heatmaps):
+        """keypoints[batch][bbox] = list of [x, y, ...] per joint (grouped candidates, not plane argmaxima): all
+        points are refined in ONE launch (lhn_refine_points) and written back into the lists."""
         t, _ = _hm(heatmaps)
-        hm_cpu = None
+        bc, xy, where = [], [], []
         for batch_id, kpt_list in enumerate(keypoints):
             for bbox_id, kpt in enumerate(kpt_list):
-                if not len(kpt):
-                    continue
-                # grouped candidates are not plane argmaxima: refine at the given integer positions
-                if hm_cpu is None:
-                    hm_cpu = t.float().cpu()
                 for joint_id, joint in enumerate(kpt):
-                    x, y = joint[:2]
-                    xx, yy = int(x), int(y)
-                    tmp = hm_cpu[batch_id, joint_id + self.channel_offset]
-                    x += 0.25 if tmp[yy, min(xx + 1, tmp.shape[1] - 1)] > tmp[yy, max(xx - 1, 0)] else -0.25
-                    y += 0.25 if tmp[min(yy + 1, tmp.shape[0] - 1), xx] > tmp[max(yy - 1, 0), xx] else -0.25
-                    keypoints[batch_id][bbox_id][joint_id][0] = x
-                    keypoints[batch_id][bbox_id][joint_id][1] = y
+                    bc.append((batch_id, joint_id + self.channel_offset))
+                    xy.append((float(joint[0]), float(joint[1])))
+                    where.append((batch_id, bbox_id, joint_id))
+        if not xy:
+            return keypoints
+        out = ops.refine_points(t, torch.tensor(bc, dtype=torch.int32).to(t.device),
+                                torch.tensor(xy, dtype=torch.float32).to(t.device), plus_half=False).cpu().tolist()
+        for (b, g, j), (x, y) in zip(where, out):
+            keypoints[b][g][j][0] = x
+            keypoints[b][g][j][1] = y
         return keypoints
+
+
+# ---- region maps (utils/evaluation.py) ------------------------------------------------------------------
+def cs_from_region_map(batch_region_maps, image_size=256, k=20, thr=0.8):
+    """utils/evaluation.py:94-138: top-k of the (un-suppressed) centre map, size = mean of the size maps over the
+    clipped window around each centre; candidates [B, k, 5] (a CPU tensor, as the reference allocates it)."""
+    t, _ = _hm(batch_region_maps)
+    r = ops.region_bbox_decode(t[:, 0:1], t[:, 1:3], L.REGION_CS, nms_kernel=0, num_candidates=k, max_num_bbox=1,
+                               image_size=(float(image_size), float(image_size)), cand_thr=thr)
+    return r["candidates"].cpu()
+
+
+def non_max_suppression(prediction, iou_threshold=0.8, conf_threshold=0.8, max_num=100):
+    """utils/evaluation.py:170-212 -> list over images: None or [[x, y, w, h, conf], ...]."""
+    c, _ = _up(prediction, torch.float32)
+    return _boxes_to_lists(*ops.box_nms(c, conf_threshold, iou_threshold, max_num))
 
 
 # ---- HRNet-style helpers (utils/transforms.py) ---------------------------------------------------------

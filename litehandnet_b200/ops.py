@@ -483,3 +483,130 @@ def flip_back(x, flip_index=None):
     L.check(L.lib().lhn_flip_back(L.ptr(x), L.ptr(out), L.dtype_code(x), B, K, H, W, L.ptr(flip_index),
                                   L.stream()), "lhn_flip_back")
     return out
+
+
+# ---- region-map bbox decode and point / window restricted refinements --------------------
+def region_bbox_decode(center, size, mode, nms_kernel=11, num_candidates=10, max_num_bbox=1, avg_kernel=3,
+                       refine=L.REFINE_NONE, blur_ksize=19, image_size=(256, 256), stride=(4.0, 4.0), cand_thr=0.1,
+                       det_thr=0.1, iou_thr=0.6, min_wh=2.0, max_wh=4096.0, nms_inplace=False, want_nms=False):
+    """lhn_region_bbox_decode.  center [B,1,H,W] and size [B,2,H,W] may be channel slices of one region map
+    (no copy).  Returns dict(candidates [B,N,5], boxes [B,max_num_bbox,5], counts [B] int32[, nms [B,1,H,W]]).
+    nms_inplace: write the NMS'd centre map over `center` (the reference's in-place heatmaps *= mask)."""
+    L.require_cuda(center, "center_maps")
+    L.require_cuda(size, "size_maps")
+    if center.dim() != 4 or center.shape[1] != 1 or size.dim() != 4 or size.shape[1] != 2:
+        raise L.LhnError("center_maps must be [B,1,H,W] and size_maps [B,2,H,W]")
+    B, _, H, W = center.shape
+    if size.shape[0] != B or tuple(size.shape[2:]) != (H, W) or size.dtype != center.dtype:
+        raise L.LhnError("size_maps must match center_maps in batch, plane size and dtype")
+
+    def planes_ok(t):
+        return t.stride(3) == 1 and t.stride(2) == W
+
+    if not planes_ok(center):
+        if nms_inplace:
+            raise L.LhnError("in-place NMS needs contiguous centre planes")
+        center = center.contiguous()
+    if not planes_ok(size) or size.stride(1) < H * W:
+        size = size.contiguous()
+    rp = L.RegionParams()
+    rp.mode, rp.nms_kernel, rp.num_candidates, rp.max_num_bbox = int(mode), int(nms_kernel), int(num_candidates), int(max_num_bbox)
+    rp.avg_kernel, rp.refine, rp.blur_ksize = int(avg_kernel), int(refine), int(blur_ksize)
+    rp.image_w, rp.image_h = float(image_size[0]), float(image_size[1])
+    rp.stride_x, rp.stride_y = float(stride[0]), float(stride[1])
+    rp.cand_thr, rp.det_thr, rp.min_wh, rp.max_wh, rp.iou_thr = float(cand_thr), float(det_thr), float(min_wh), float(max_wh), float(iou_thr)
+    if refine == L.REFINE_DARK_LEGACY:
+        for i, t in enumerate(L.gaussian_taps(int(blur_ksize))):
+            rp.taps[i] = t
+    dev = center.device
+    nms = None
+    if nms_inplace:
+        nms = center
+    elif want_nms:
+        nms = torch.empty((B, 1, H, W), dtype=center.dtype, device=dev)
+        if nms.stride(0) != center.stride(0):
+            center = center.contiguous()
+    cand = torch.empty((B, int(num_candidates), 5), dtype=torch.float32, device=dev)
+    boxes = torch.empty((B, int(max_num_bbox), 5), dtype=torch.float32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    L.check(L.lib().lhn_region_bbox_decode(L.ptr(center), L.ptr(size), L.dtype_code(center), B, H, W,
+                                           center.stride(0), size.stride(0), size.stride(1), C.byref(rp),
+                                           L.ptr(nms), L.ptr(cand), L.ptr(boxes), L.ptr(counts), L.stream()),
+            "lhn_region_bbox_decode")
+    r = dict(candidates=cand, boxes=boxes, counts=counts)
+    if nms is not None:
+        r["nms"] = nms
+    return r
+
+
+def box_nms(candidates, det_thr=0.1, iou_thr=0.6, max_num=1, min_wh=2.0, max_wh=4096.0):
+    """lhn_box_nms on candidates [B,N,5] -> (boxes [B,max_num,5], counts [B] int32)."""
+    c = _f32c(candidates, "candidates")
+    if c.dim() != 3 or c.shape[2] != 5 or c.shape[1] > L.MAX_CANDIDATES:
+        raise L.LhnError(f"candidates must be [B, N <= {L.MAX_CANDIDATES}, 5]")
+    B, N = c.shape[:2]
+    max_num = min(int(max_num), N)
+    boxes = torch.empty((B, max_num, 5), dtype=torch.float32, device=c.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=c.device)
+    L.check(L.lib().lhn_box_nms(L.ptr(c), B, N, float(det_thr), float(min_wh), float(max_wh), float(iou_thr), max_num,
+                                L.ptr(boxes), L.ptr(counts), L.stream()), "lhn_box_nms")
+    return boxes, counts
+
+
+def heatmap_nms(hm, nms_kernel=11, inplace=False):
+    """lhn_heatmap_nms: hm * eq(maxpool_k(hm), hm) on [B,C,H,W]; inplace=True overwrites hm as the reference does."""
+    L.require_cuda(hm, "heatmaps")
+    if hm.dim() != 4:
+        raise L.LhnError("heatmaps must be [B,C,H,W]")
+    B, Cc, H, W = hm.shape
+    ok = hm.stride(3) == 1 and hm.stride(2) == W and (Cc == 1 or hm.stride(1) >= H * W)
+    if not ok:
+        if inplace:
+            raise L.LhnError("in-place NMS needs contiguous planes")
+        hm = hm.contiguous()
+    out = hm if inplace else torch.empty_strided(hm.shape, hm.stride(), dtype=hm.dtype, device=hm.device)
+    L.check(L.lib().lhn_heatmap_nms(L.ptr(hm), L.ptr(out), L.dtype_code(hm), B, Cc, H, W, hm.stride(0),
+                                    hm.stride(1) if Cc > 1 else H * W, int(nms_kernel), L.stream()), "lhn_heatmap_nms")
+    return out
+
+
+def vector_nms(v):
+    """lhn_vector_nms on [..., L] (returns a new tensor)."""
+    L.require_cuda(v, "vector")
+    v = v.contiguous()
+    out = torch.empty_like(v)
+    Ln = v.shape[-1]
+    L.check(L.lib().lhn_vector_nms(L.ptr(v), L.ptr(out), L.dtype_code(v), v.numel() // max(Ln, 1), Ln, L.stream()),
+            "lhn_vector_nms")
+    return out
+
+
+def refine_points(hm, bc, xy, plus_half=False):
+    """lhn_refine_points: the +-0.25 rule at given positions.  bc int32 [n,2] (image, channel), xy f32 [n,>=2]
+    (updated in place and returned)."""
+    hm, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
+    bc = L.require_cuda(bc, "bc").to(torch.int32).contiguous()
+    L.require_cuda(xy, "xy")
+    if xy.dtype != torch.float32 or not xy.is_contiguous() or xy.dim() != 2 or xy.shape[1] < 2:
+        raise L.LhnError("xy must be a contiguous f32 [n,>=2] tensor")
+    n = xy.shape[0]
+    if bc.shape != (n, 2):
+        raise L.LhnError("bc must be [n,2]")
+    L.check(L.lib().lhn_refine_points(L.ptr(hm), L.dtype_code(hm), B, Cc, H, W, sb, sc, L.ptr(bc), L.ptr(xy),
+                                      xy.shape[1], n, L.REFINE_OFFSET_HALF if plus_half else L.REFINE_OFFSET,
+                                      L.stream()), "lhn_refine_points")
+    return xy
+
+
+def decode_heatmap_roi(hm, roi, refine, scale_xy=(1.0, 1.0), blur_ksize=None, want_idx=False):
+    """lhn_decode_heatmap_roi: per-image window roi int32 [B,4] = (x0, y0, x1, y1) -> [B,K,3] (X, Y, score)."""
+    hm, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
+    roi = L.require_cuda(roi, "roi").to(torch.int32).contiguous()
+    if roi.shape != (B, 4):
+        raise L.LhnError("roi must be [B,4]")
+    dp = _decode_params(L.MASK_NONE, refine, L.XFORM_SCALE, scale_xy, blur_ksize)
+    out = torch.empty((B, Cc, 3), dtype=torch.float32, device=hm.device)
+    idx = torch.empty((B, Cc), dtype=torch.int32, device=hm.device) if want_idx else None
+    L.check(L.lib().lhn_decode_heatmap_roi(L.ptr(hm), L.dtype_code(hm), B, Cc, H, W, sb, sc, L.ptr(roi), C.byref(dp),
+                                           L.ptr(out), L.ptr(idx), L.stream()), "lhn_decode_heatmap_roi")
+    return (out, idx) if want_idx else out

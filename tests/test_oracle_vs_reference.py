@@ -139,3 +139,45 @@ def test_anisotropic_scales_live(ref):
     xv, yv = synth.simdr_vectors(N, 21, 448, seed=162)
     assert np.array_equal(O.keypoints_from_simdr(xv.numpy(), yv.numpy(), c, s, 2),
                           T.keypoints_from_simdr(xv.numpy(), yv.numpy(), c, s, k=2))
+
+
+def test_region_bbox_decode_live(ref):
+    """SURVEY §8f rank 4, live: the oracle against the executed bbox branch of HeatmapParser_SH, ResultParser (DARK)
+    and utils/evaluation.py on freshly seeded region maps (other seeds than the golden fixture)."""
+    import torch
+    from oracle import make_golden as M
+    from conftest import canon_candidates
+    for seed in (5, 6):
+        c, s = M.region_maps(4, seed)
+        SH = ref.SPheatmapParser.HeatmapParser_SH()
+        cn = SH.heatmap_nms(c.clone())
+        on = O.heatmap_nms(c.numpy())
+        assert np.array_equal(cn.numpy(), on)
+        cand = SH.candidate_bbox(cn.clone(), s.clone(), (256, 256))
+        oc = O.candidate_bbox(on, s.numpy(), "sh", (256, 256))
+        (a, da), (b, db) = canon_candidates(oc), canon_candidates(cand.numpy())
+        assert np.array_equal(da, db) and np.array_equal(a[da], b[db])
+        SH.max_num_bbox = 10
+        for thr in (0.6, 0.2):
+            SH.iou_threshold = thr
+            assert SH.non_max_suppression(cand) == O.box_nms(cand.numpy(), 0.1, thr, 10)
+        RP = ref_loader.make_result_parser(ref, dark=True)
+        RP.num_candidates = 1
+        s40 = s * 40
+        c1 = RP.candidate_bbox(RP.heatmap_nms(c.clone()), s40.clone())
+        with np.errstate(all="ignore"):
+            o1 = O.candidate_bbox(on, s40.numpy(), "rp", num_candidates=1)
+        assert_coords_close(o1, c1.numpy(), what="rp cand1")
+        ev = ref.evaluation
+        cc = ev.cs_from_region_map(torch.cat([c, s40], 1), 256, 20, 0.1)
+        oc2 = O.candidate_bbox(c.numpy(), s40.numpy(), "cs", (256, 256), num_candidates=20, thr=0.1)
+        (a, da), (b, db) = canon_candidates(oc2), canon_candidates(cc.numpy())
+        assert np.array_equal(da, db)
+        assert_coords_close(a[da], b[db], what="cs cand")
+        hm = torch.rand(4, 5, 64, 64, generator=torch.Generator().manual_seed(seed))
+        for dark, P in ((False, ref_loader.make_result_parser(ref, dark=False)), (True, RP)):
+            for j, bb in enumerate(M.FIRST_RESULT_BOXES):
+                r = P._get_first_result(list(bb), hm.clone(), j % 4)
+                with np.errstate(all="ignore"):
+                    o = O.get_first_result(list(bb), hm.numpy(), j % 4, dark=dark)
+                assert_coords_close(o, r.numpy(), what=f"first_result dark={dark} box {j}")
