@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kNT) decode_roi_kernel(const __grid_constant__
 
 template <typename K> int set_smem(K kernel, size_t bytes) {
   if (bytes > 227 * 1024) return LHN_EINVAL;
-  if (bytes > 48 * 1024) {
+  if (bytes > 40 * 1024) {                                  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
   }

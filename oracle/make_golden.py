@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
+from oracle import np_oracle as O  # noqa: E402  (only to place the synthetic blobs inside the decoded windows)
 from litehandnet_b200 import synth  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -356,8 +357,17 @@ def region_case(ref, name, seed):
         bx, ct = _boxes_to_arrays(SH.non_max_suppression(cand), 10)
         d[f"ref_sh_boxes10_iou{int(thr * 10)}"], d[f"ref_sh_counts10_iou{int(thr * 10)}"] = bx, ct
     # the whole parse() call, centre maps mutated in place by the reference
-    hm = torch.rand(B, 5, 64, 64, generator=torch.Generator().manual_seed(seed + 1))
+    # keypoint heatmaps: blobs + noise whose centres lie inside the bbox window that image j is decoded in below
+    # (a window holding only noise makes the DARK Taylor step ill-conditioned: no parity to speak of)
+    rng = np.random.default_rng(seed + 1)
+    centers = np.zeros((B, 5, 2), np.float32)
+    for j in range(B):
+        x0, y0, x1, y1 = O.first_result_roi(FIRST_RESULT_BOXES[j], (64, 64), 4, 1.3)
+        centers[j, :, 0] = (x0 + x1) / 2 + (rng.random(5) - 0.5) * 0.5 * (x1 - x0)
+        centers[j, :, 1] = (y0 + y1) / 2 + (rng.random(5) - 0.5) * 0.5 * (y1 - y0)
+    hm, _ = synth.blob_heatmaps(B, 5, 64, 64, seed=seed + 1, centers=torch.from_numpy(centers))
     d["kpt_hm"] = hm.numpy().copy()
+    d["kpt_centers"] = centers
     SH = ref.SPheatmapParser.HeatmapParser_SH()
     c_in = c.clone()
     kpt, boxes = SH.parse(hm.clone(), c_in, s.clone(), (256, 256))
