@@ -3,6 +3,7 @@
 // coalesced loads, reduced with redux/shuffles; nothing is staged in shared memory because every
 // element is used exactly once (the 3-tap NMS neighbourhood comes from warp shuffles).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "lhn_common.cuh"
 
@@ -127,6 +128,30 @@ __device__ __forceinline__ void warp_pair_argmax(const T* __restrict__ xv, const
   warp_finish<T>(yv, nqy, lane, sy, iy, my);
 }
 
+// lane 0 of the warp that owns pair bk: preds = idx / k (int64 / int -> f64 -> f32: one rounding of the exact quotient,
+// which is what the correctly rounded f32 division of the exactly representable operands gives),
+// score = (max_x + max_y) / 2, transform_preds with output_size [Lx // k, Ly // k].
+__device__ __forceinline__ void simdr_store(uint32_t ix, uint32_t iy, float mx, float my, int k, int Lx, int Ly,
+                                            bool xform, float cx, float cy, float sc0, float sc1, float* __restrict__ out,
+                                            int32_t* __restrict__ out_idx, int64_t bk) {
+  float px, py;
+  if (ix < (1u << 24) && iy < (1u << 24) && k < (1 << 24)) {
+    px = __fdiv_rn((float)ix, (float)k); py = __fdiv_rn((float)iy, (float)k);
+  } else {
+    px = (float)((double)ix / (double)k); py = (float)((double)iy / (double)k);
+  }
+  const float score = __fdiv_rn(__fadd_rn(mx, my), 2.f);
+  if (xform) {
+    const float s0 = __fmul_rn(sc0, 200.f), s1 = __fmul_rn(sc1, 200.f);
+    const float fx = __fdiv_rn(s0, (float)(Lx / k)), fy = __fdiv_rn(s1, (float)(Ly / k));
+    px = __fsub_rn(__fadd_rn(__fmul_rn(px, fx), cx), __fmul_rn(s0, 0.5f));
+    py = __fsub_rn(__fadd_rn(__fmul_rn(py, fy), cy), __fmul_rn(s1, 0.5f));
+  }
+  float* o = out + 3 * bk;
+  o[0] = px; o[1] = py; o[2] = score;
+  if (out_idx) { out_idx[2 * bk] = (int32_t)ix; out_idx[2 * bk + 1] = (int32_t)iy; }
+}
+
 template <typename T, bool NMS>
 __global__ void __launch_bounds__(256, 6) decode_simdr_kernel(const T* __restrict__ xv, const T* __restrict__ yv,
                                                            int64_t n_bk, int K, int Lx, int Ly, int k,
@@ -156,26 +181,86 @@ __global__ void __launch_bounds__(256, 6) decode_simdr_kernel(const T* __restric
       warp_vec_argmax<T, NMS>(xp, Lx, x1, x2, lane, ix, mx);
       warp_vec_argmax<T, NMS>(yp, Ly, y1, y2, lane, iy, my);
     }
-    if (lane == 0) {
-      // preds = idx / k (int64 / int -> f64 -> f32: one rounding of the exact quotient, which is what the
-      // correctly rounded f32 division of the exactly representable operands gives), score = (max_x + max_y) / 2
-      float px, py;
-      if (ix < (1u << 24) && iy < (1u << 24) && k < (1 << 24)) {
-        px = __fdiv_rn((float)ix, (float)k); py = __fdiv_rn((float)iy, (float)k);
-      } else {
-        px = (float)((double)ix / (double)k); py = (float)((double)iy / (double)k);
-      }
-      const float score = __fdiv_rn(__fadd_rn(mx, my), 2.f);
-      if (center) {
-        const float s0 = __fmul_rn(sc0, 200.f), s1 = __fmul_rn(sc1, 200.f);
-        const float fx = __fdiv_rn(s0, (float)(Lx / k)), fy = __fdiv_rn(s1, (float)(Ly / k));
-        px = __fsub_rn(__fadd_rn(__fmul_rn(px, fx), cx), __fmul_rn(s0, 0.5f));
-        py = __fsub_rn(__fadd_rn(__fmul_rn(py, fy), cy), __fmul_rn(s1, 0.5f));
-      }
-      float* o = out + 3 * bk;
-      o[0] = px; o[1] = py; o[2] = score;
-      if (out_idx) { out_idx[2 * bk] = (int32_t)ix; out_idx[2 * bk + 1] = (int32_t)iy; }
+    if (lane == 0) simdr_store(ix, iy, mx, my, k, Lx, Ly, center != nullptr, cx, cy, sc0, sc1, out, out_idx, bk);
+  }
+}
+
+// ---- persistent ring variant (the fast path at scale) ------------------------------------------------------------
+// The grid-stride kernel above has no load in flight while a warp reduces, re-reads the winning quad (two L2 round
+// trips) and stores: at 48 warps x 4 KB per SM that duty cycle leaves ~100 KB in flight, marginal for 7 TB/s at the
+// loaded latency.  Here every warp owns a private ring of `nstg` stages filled by TMA bulk copies (cp.async.bulk +
+// mbarrier, L2 evict_first): while it scans one (b, k) pair out of shared memory the next nstg - 1 pairs are already
+// in flight, and the winning quad is re-read from shared memory.  One CTA of 16 warps per SM, 3 stages of 4 KB at
+// 2 x 512 f32 (16 warps x 3 stages x 4 KB = 192 KB per SM).  No CTA-wide barrier after set-up.
+// Measured (profiles/r01_simdr_ring_sweep.txt): throughput follows the number of warps, not the number of stages —
+// a pair costs a warp ~2.2k cycles of serial work (scan, two warp reductions, re-arm, five IEEE divisions in the
+// epilogue; ~2.5k before the per-pair 64-bit index division was made incremental), so 8 warps run at 59 % of the HBM
+// peak and 16 or 24 warps at 90 % (the grid-stride kernel: 82 %).
+constexpr int kRingWarps = 16;
+constexpr int kRingMaxStages = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int64_t n_bk, int K, int Lx, int Ly, int k,
+                         const float* __restrict__ center, const float* __restrict__ scale, float* __restrict__ out,
+                         int32_t* __restrict__ out_idx, int nstg, int pair_al) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned char* wbase = smem_raw + (size_t)warp * nstg * pair_al;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * nstg * pair_al) + warp * kRingMaxStages;
+  const uint32_t xbytes = (uint32_t)Lx * sizeof(T), ybytes = (uint32_t)Ly * sizeof(T);
+  if (lane == 0) {
+    for (int s = 0; s < nstg; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint64_t pol = policy_evict_first();
+  const int64_t total = (int64_t)gridDim.x * nwarps;
+  const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;   // warp-major: the leftover pairs spread over all SMs
+  auto issue = [&](int s, int64_t pair) {
+    unsigned char* dst = wbase + (size_t)s * pair_al;
+    mbar_arrive_expect_tx(&bars[s], xbytes + ybytes);
+    tma_load_1d(dst, xv + pair * Lx, xbytes, &bars[s], pol);
+    tma_load_1d(dst + xbytes, yv + pair * Ly, ybytes, &bars[s], pol);
+  };
+  if (lane == 0)
+    for (int s = 0; s < nstg; ++s) {
+      const int64_t pair = gw + (int64_t)s * total;
+      if (pair < n_bk) issue(s, pair);
     }
+  const int nqx = Lx >> 2, nqy = Ly >> 2, nq = nqx > nqy ? nqx : nqy;
+  int s = 0;
+  uint32_t ph = 0;
+  // b = bk / K advanced incrementally (the only 64-bit divisions: once per warp)
+  int64_t b = gw / K;
+  int kk = (int)(gw - b * K);
+  const int64_t step_b = total / K;
+  const int step_k = (int)(total - step_b * K);
+  for (int64_t bk = gw; bk < n_bk; bk += total) {
+    // per-sample side inputs: requested by lane 0 before the wait, consumed after the scan
+    float cx = 0.f, cy = 0.f, sc0 = 0.f, sc1 = 0.f;
+    if (center && lane == 0) { cx = center[2 * b]; cy = center[2 * b + 1]; sc0 = scale[2 * b]; sc1 = scale[2 * b + 1]; }
+    b += step_b; kk += step_k;
+    if (kk >= K) { kk -= K; ++b; }
+    mbar_wait(&bars[s], ph);
+    const T* xs = reinterpret_cast<const T*>(wbase + (size_t)s * pair_al);
+    const T* ys = xs + Lx;
+    LaneBest sx{-CUDART_INF_F, 0xffffffffu}, sy = sx;
+#pragma unroll 4
+    for (int q = lane; q < nq; q += 32) {
+      if (q < nqx) lane_scan4(load4<T>(xs + 4 * q), (uint32_t)q, sx);
+      if (q < nqy) lane_scan4(load4<T>(ys + 4 * q), (uint32_t)q, sy);
+    }
+    uint32_t ix, iy; float mx, my;
+    warp_finish<T>(xs, nqx, lane, sx, ix, mx);
+    warp_finish<T>(ys, nqy, lane, sy, iy, my);
+    __syncwarp();                                             // every lane is done with stage s
+    if (lane == 0) {
+      const int64_t next = bk + (int64_t)nstg * total;
+      if (next < n_bk) { fence_proxy_async(); issue(s, next); }
+      simdr_store(ix, iy, mx, my, k, Lx, Ly, center != nullptr, cx, cy, sc0, sc1, out, out_idx, bk);
+    }
+    if (++s == nstg) { s = 0; ph ^= 1u; }
   }
 }
 
@@ -248,6 +333,35 @@ template <typename T>
 static int launch_simdr(const void* xv, const void* yv, int64_t n_bk, int K, int Lx, int Ly, int k,
                         const float* center, const float* scale, int nms, const int32_t* ranges,
                         float* out, int32_t* out_idx, cudaStream_t st) {
+  // Ring kernel: no NMS, TMA-able vectors (16-byte multiples, 16-byte aligned bases), at least two stages per warp,
+  // and enough pairs to give every warp of the persistent grid a few (below that the launch is latency-bound anyway).
+  {
+    const size_t xb = (size_t)Lx * sizeof(T), yb = (size_t)Ly * sizeof(T);
+    const size_t pair_al = (xb + yb + 127) / 128 * 128;
+    int warps = kRingWarps;
+    if (const char* e = getenv("LHN_SIMDR_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 32) warps = w; }
+    const size_t bar_bytes = (size_t)warps * kRingMaxStages * 8;
+    int nstg = (int)((227 * 1024 - bar_bytes) / (warps * pair_al));
+    if (nstg > kRingMaxStages) nstg = kRingMaxStages;
+    if (const char* e = getenv("LHN_SIMDR_STAGES")) { const int g = atoi(e); if (g >= 2 && g <= nstg) nstg = g; }
+    const char* env = getenv("LHN_SIMDR_RING");
+    const bool ring_ok = !nms && !(env && env[0] == '0') && xb % 16 == 0 && yb % 16 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(xv) | reinterpret_cast<uintptr_t>(yv)) & 15) == 0 && nstg >= 2 &&
+                         n_bk >= (int64_t)num_sms() * warps * 4;
+    if (ring_ok) {
+      const size_t smem = (size_t)warps * nstg * pair_al + bar_bytes;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(decode_simdr_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
+        if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
+        attr_set = true;
+      }
+      decode_simdr_ring_kernel<T><<<num_sms(), warps * 32, smem, st>>>((const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k,
+                                                                            center, scale, out, out_idx, nstg, (int)pair_al);
+      return check_launch();
+    }
+  }
   const int threads = 256;
   // grid-stride over (b, k) pairs: exactly the resident CTAs (6 per SM at 40 registers), so there is no second wave
   int64_t need = (n_bk * 32 + threads - 1) / threads, cap = (int64_t)num_sms() * 6;

@@ -83,21 +83,24 @@ def simdr_case(name, B, K, Lv, k=2):
 
 
 def main():
-    rows = [
-        heatmap_case("cfg1 decode argmax + quarter offset, 64x21x64x64 f32 (22 MB/launch: launch-bound)", 64, 21, 64, 64,
-                     refine=L.REFINE_SIGN, loss=False, sets=32),
-        heatmap_case("cfg1 shape at batch 1024", 1024, 21, 64, 64, refine=L.REFINE_SIGN, loss=False),
-        heatmap_case("cfg2 without flip (render + loss + DARK), 1024x21x64x64 f32", 1024, 21, 64, 64),
-        heatmap_case("cfg2 headline (flip), 1024x21x64x64 f32", 1024, 21, 64, 64, flip=True),
-        heatmap_case("cfg2 headline, bf16 inputs", 1024, 21, 64, 64, dtype=torch.bfloat16, flip=True),
-        simdr_case("cfg3 SimDR decode k=2, 2 x 4096x21x512 f32", 4096, 21, 512),
-        heatmap_case("cfg4 MPII 16x64x64 decode + fused PCK/AUC/EPE counters, batch 1024/GPU", 1024, 16, 64, 64,
-                     refine=L.REFINE_SIGN, pck=True),
-        heatmap_case("      the same decode without the fused counters (16x64x64, batch 1024)", 1024, 16, 64, 64,
-                     refine=L.REFINE_SIGN, loss=False),
-        heatmap_case("cfg5 21x128x128 render + loss + DARK, batch 1024/GPU f32", 1024, 21, 128, 128),
-        heatmap_case("56x56 (33 reference configs), render + loss + DARK, 1024x21 f32", 1024, 21, 56, 56),
+    H = heatmap_case
+    cases = [
+        lambda: H("cfg1 decode argmax + quarter offset, 64x21x64x64 f32 (22 MB/launch: launch-bound)", 64, 21, 64, 64,
+                  refine=L.REFINE_SIGN, loss=False, sets=32),
+        lambda: H("cfg1 shape at batch 1024", 1024, 21, 64, 64, refine=L.REFINE_SIGN, loss=False),
+        lambda: H("cfg2 without flip (render + loss + DARK), 1024x21x64x64 f32", 1024, 21, 64, 64),
+        lambda: H("cfg2 headline (flip), 1024x21x64x64 f32", 1024, 21, 64, 64, flip=True),
+        lambda: H("cfg2 headline, bf16 inputs", 1024, 21, 64, 64, dtype=torch.bfloat16, flip=True),
+        lambda: simdr_case("cfg3 SimDR decode k=2, 2 x 4096x21x512 f32", 4096, 21, 512),
+        lambda: H("cfg4 MPII 16x64x64 decode + fused PCK/AUC/EPE counters, batch 1024/GPU", 1024, 16, 64, 64,
+                  refine=L.REFINE_SIGN, pck=True),
+        lambda: H("      the same decode without the fused counters (16x64x64, batch 1024)", 1024, 16, 64, 64,
+                  refine=L.REFINE_SIGN, loss=False),
+        lambda: H("cfg5 21x128x128 render + loss + DARK, batch 1024/GPU f32", 1024, 21, 128, 128),
+        lambda: H("56x56 (33 reference configs), render + loss + DARK, 1024x21 f32", 1024, 21, 56, 56),
     ]
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None   # e.g. --only 5 (cfg3)
+    rows = [c() for i, c in enumerate(cases) if only is None or str(i) in only]
     print("launch overlap (LHN_FLAG_OVERLAP_PREVIOUS over rotating buffer sets):", "on" if OVERLAP else "off")
     for r in rows:
         print(f"{r['config']:95s} {r['ms'] * 1e3:9.1f} us  {r['gbs']:8.1f} GB/s  {r['frac'] * 100:5.1f}% of {PEAK:.0f}  "

@@ -430,6 +430,43 @@ def test_simdr_vs_oracle(ops, L, B, K, Lx, Ly):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("B,K,Lx,Ly,dtype", [(512, 21, 512, 512, "f32"), (700, 16, 448, 448, "f32"), (600, 21, 256, 512, "f32"),
+                                             (1024, 21, 512, 512, "bf16"), (1030, 21, 64, 32, "f16")])
+def test_simdr_ring_kernel_vs_oracle(ops, L, B, K, Lx, Ly, dtype, monkeypatch):
+    """Batches large enough for the persistent TMA-ring kernel (>= 148 * 16 * 4 pairs): exact equality with the
+    oracle incl. NaN / all-zero / tied / -inf vectors and a ragged pair count, and with the grid-stride kernel
+    (LHN_SIMDR_RING=0) on the same inputs."""
+    assert B * K >= 148 * 16 * 4
+    xv, _ = synth.simdr_vectors(B, K, Lx, seed=71)
+    _, yv = synth.simdr_vectors(B, K, Ly, seed=72)
+    td = dict(f32=torch.float32, bf16=torch.bfloat16, f16=torch.float16)[dtype]
+    xv, yv = xv.to(td).float().numpy(), yv.to(td).float().numpy()      # values exactly representable in `dtype`
+    xv[0, 0, 7] = np.nan; yv[0, 0] = 0.0
+    xv[1, 1, 3] = xv[1, 1].max(); xv[1, 1, 9] = xv[1, 1, 3]
+    yv[2, 2] = -np.inf
+    xv[-1, -1, Lx - 1] = 9.0; yv[-1, -1, 0] = 9.0; yv[-1, -1, Ly - 1] = 9.0
+    xv[3, 0, 5] = np.nan; xv[3, 0, 2] = np.nan
+    xv[4, 0] = -0.0; xv[4, 0, 17] = 0.0
+    center, scale = [t.numpy() for t in synth.bbox_center_scale(B, seed=73)]
+    with np.errstate(all="ignore"):
+        want = O.keypoints_from_simdr(xv, yv, center, scale, 2)
+    xt, yt = cu(xv).to(td), cu(yv).to(td)
+    got, idx = ops.decode_simdr(xt, yt, 2, cu(center), cu(scale), want_idx=True)
+    assert np.array_equal(nump(got), want, equal_nan=True)
+    assert np.array_equal(nump(idx)[..., 0], np.argmax(xv, -1)) and np.array_equal(nump(idx)[..., 1], np.argmax(yv, -1))
+    monkeypatch.setenv("LHN_SIMDR_RING", "0")
+    got0, idx0 = ops.decode_simdr(xt, yt, 2, cu(center), cu(scale), want_idx=True)
+    monkeypatch.delenv("LHN_SIMDR_RING")
+    assert torch.equal(idx, idx0) and np.array_equal(nump(got), nump(got0), equal_nan=True)
+    # no transform
+    got2 = ops.decode_simdr(xt, yt, 2)
+    with np.errstate(all="ignore"):
+        want2 = np.concatenate([np.stack([np.argmax(xv, -1), np.argmax(yv, -1)], -1).astype(np.float32) / 2,
+                                ((xv.max(-1) + yv.max(-1)) / 2)[..., None]], -1)
+    want2[..., 2] = want[..., 2]
+    assert np.array_equal(nump(got2), want2.astype(np.float32), equal_nan=True)
+
+
 # ---- metrics ---------------------------------------------------------------------------------------
 def _counters_to_pck(cnt, T, K):
     cnt = cnt.reshape(T + 2, K)
