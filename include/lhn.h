@@ -397,6 +397,15 @@ LHN_API int lhn_region_bbox_decode(const void* center, const void* size, int dty
                                    const lhn_region_params* rp, void* nms_out, float* candidates,
                                    float* boxes, int32_t* counts, lhn_stream_t stream);
 
+/* The width / height planes of SRHandNet's region-map target (SRHandNetGenerateTarget._region_generate_target,
+ * datasets/data_pipeline/generateTarget.py:350-365): out[b, c, y, x] = gamma[b, c] inside the window
+ * rect[b] = (x1, x2, y1, y2) (int32, half-open, already clipped to the plane), else 0; c = 0 width ratio,
+ * 1 height ratio.  out f32, plane contiguous, out_stride_b elements between images (>= 2*H*W, so the two planes
+ * can be written straight into channels K+1, K+2 of a [B, K+3, H, W] target).  The centre plane (channel K) is
+ * lhn_render_targets on the box centre. */
+LHN_API int lhn_render_region_wh(const int32_t* rect, const float* gamma, int64_t B, int H, int W, float* out,
+                                 int64_t out_stride_b, lhn_stream_t stream);
+
 /* non_max_suppression alone (utils/result_parser.py:177-215, utils/SPheatmapParser.py:101-138,
  * utils/evaluation.py:170-212) on given candidates f32 [B, N, 5] (x, y, w, h, confidence), N <= LHN_MAX_CANDIDATES:
  * confidence > det_thr, min_wh < w, h < max_wh, torchvision.ops.nms with iou_thr, first max_num kept.

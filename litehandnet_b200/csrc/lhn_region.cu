@@ -463,6 +463,21 @@ __global__ void __launch_bounds__(kNT) decode_roi_kernel(const __grid_constant__
   if (a.out_idx) a.out_idx[p] = idx;
 }
 
+// ==========================================================================================================
+// lhn_render_region_wh: the width/height planes of SRHandNet's region map (generateTarget.py:350-365)
+// ==========================================================================================================
+__global__ void render_region_wh_kernel(const int32_t* __restrict__ rect, const float* __restrict__ gamma, int H, int W,
+                                        float* __restrict__ out, int64_t out_stride_b, int64_t n) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int HW = H * W;
+  const int64_t b = e / (2 * HW);
+  const int r = (int)(e - b * 2 * HW), c = r / HW, q = r - c * HW, y = q / W, x = q - y * W;
+  const int32_t* rc = rect + 4 * b;
+  const bool in = x >= rc[0] && x < rc[1] && y >= rc[2] && y < rc[3];
+  out[b * out_stride_b + (int64_t)c * HW + q] = in ? gamma[2 * b + c] : 0.f;
+}
+
 template <typename K> int set_smem(K kernel, size_t bytes) {
   if (bytes > 227 * 1024) return LHN_EINVAL;
   if (bytes > 40 * 1024) {                                  // static shared memory counts against the 48 KB default too
@@ -590,5 +605,15 @@ extern "C" int lhn_box_nms(const float* candidates, int64_t B, int N, float det_
   if (B == 0) return LHN_OK;
   box_nms_kernel<<<(unsigned)((B + 31) / 32), 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       candidates, B, N, det_thr, min_wh, max_wh, iou_thr, max_num, boxes, counts);
+  return check_launch();
+}
+
+extern "C" int lhn_render_region_wh(const int32_t* rect, const float* gamma, int64_t B, int H, int W, float* out,
+                                    int64_t out_stride_b, lhn_stream_t stream) {
+  if (!rect || !gamma || !out || B < 0 || H < 1 || W < 1 || out_stride_b < (int64_t)2 * H * W) return LHN_EINVAL;
+  const int64_t n = B * 2 * H * W;
+  if (n == 0) return LHN_OK;
+  render_region_wh_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      rect, gamma, H, W, out, out_stride_b, n);
   return check_launch();
 }

@@ -610,3 +610,21 @@ def decode_heatmap_roi(hm, roi, refine, scale_xy=(1.0, 1.0), blur_ksize=None, wa
     L.check(L.lib().lhn_decode_heatmap_roi(L.ptr(hm), L.dtype_code(hm), B, Cc, H, W, sb, sc, L.ptr(roi), C.byref(dp),
                                            L.ptr(out), L.ptr(idx), L.stream()), "lhn_decode_heatmap_roi")
     return (out, idx) if want_idx else out
+
+
+def render_region_wh(rect, gamma, H, W, out=None):
+    """lhn_render_region_wh: rect int32 [B,4] = (x1, x2, y1, y2), gamma f32 [B,2] -> [B,2,H,W] f32; `out` may be a
+    two-channel slice of a larger contiguous [B,C,H,W] target."""
+    rect = L.require_cuda(rect, "rect").to(torch.int32).contiguous()
+    gamma = _f32c(gamma, "gamma")
+    B = rect.shape[0]
+    if rect.shape != (B, 4) or gamma.shape != (B, 2):
+        raise L.LhnError("rect must be [B,4] and gamma [B,2]")
+    if out is None:
+        out = torch.empty((B, 2, H, W), dtype=torch.float32, device=rect.device)
+    if out.dtype != torch.float32 or tuple(out.shape) != (B, 2, H, W) or out.stride(3) != 1 or out.stride(2) != W \
+            or out.stride(1) != H * W:
+        raise L.LhnError("out must be an f32 [B,2,H,W] view with contiguous planes")
+    L.check(L.lib().lhn_render_region_wh(L.ptr(rect), L.ptr(gamma), B, H, W, L.ptr(out), out.stride(0) if B > 1 else 2 * H * W,
+                                         L.stream()), "lhn_render_region_wh")
+    return out

@@ -415,6 +415,38 @@ def region_case(ref, name, seed):
     np.savez_compressed(os.path.join(OUT, name), **d)
 
 
+def srhandnet_case(ref, name, seed):
+    """R3b: SRHandNetGenerateTarget (generateTarget.py:303-426) executed per sample: four scales, region map on/off,
+    integer-centre and sub-pixel encodings, boxes inside, across and outside the image."""
+    rng = np.random.default_rng(seed)
+    N, K = 4, 5
+    hs = [[16, 16], [16, 16], [32, 32], [64, 64]]
+    j = np.zeros((N, K, 3), np.float32); j[..., :2] = rng.uniform(-30, 290, (N, K, 2))
+    v = np.zeros((N, K, 3), np.float32); v[..., :2] = (rng.random((N, K, 1)) < 0.85)
+    bbox = np.stack([rng.uniform(0, 200, N), rng.uniform(0, 200, N), rng.uniform(10, 200, N), rng.uniform(10, 200, N)], 1).astype(np.float32)
+    bbox[1] = (-150.0, 40.0, 60.0, 60.0)          # centre left of the image: the slice's upper bound goes negative
+    bbox[2] = (250.0, 250.0, 30.0, 500.0)         # height ratio clipped to 1, window cut by the border
+    bbox[3] = (400.0, 10.0, 20.0, 20.0)           # outside on the right: empty window
+    d = dict(joints_3d=j, joints_3d_visible=v, bbox=bbox, heatmap_sizes=np.asarray(hs), sigmas=np.asarray([2, 2, 2, 2]))
+    G = ref.generateTarget
+    for pred_bbox in (True, False):
+        for unb in (False, True):
+            T = G.SRHandNetGenerateTarget(pred_bbox=pred_bbox, sigma=[2, 2, 2, 2], unbiased_encoding=unb)
+            for i in range(len(hs)):
+                d[f"ref_t_bbox{int(pred_bbox)}_unb{int(unb)}_s{i}"] = []
+                d[f"ref_w_bbox{int(pred_bbox)}_unb{int(unb)}_s{i}"] = []
+            for n in range(N):
+                res = dict(joints_3d=j[n].copy(), joints_3d_visible=v[n].copy(), bbox=bbox[n].copy(),
+                           ann_info=dict(image_size=np.array([256, 256]), heatmap_size=np.array(hs), num_joints=K,
+                                         joint_weights=np.ones((K, 1), np.float32), use_different_joint_weights=False))
+                out = T(res)
+                for i in range(len(hs)):
+                    d[f"ref_t_bbox{int(pred_bbox)}_unb{int(unb)}_s{i}"].append(out["target"][i])
+                    d[f"ref_w_bbox{int(pred_bbox)}_unb{int(unb)}_s{i}"].append(out["target_weight"][i])
+    d = {k: np.asarray(x) for k, x in d.items()}
+    np.savez_compressed(os.path.join(OUT, name), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -431,6 +463,7 @@ def main():
     udp_decode_case(ref, "decode_udp.npz", seed=61)
     mpii_case("mpii_pckh.npz", seed=71)
     region_case(ref, "region_bbox.npz", seed=81)
+    srhandnet_case(ref, "render_srhandnet.npz", seed=91)
     # the reference's only hand-derivable known answer (utils/SPheatmapParser.py:221-233)
     kpt_hm = torch.zeros((2, 4, 64, 64)); kpt_hm[..., 3, 3] = 1; kpt_hm[..., 3, 2] = 0.5; kpt_hm[..., 2, 3] = 0.5
     k, _ = ref.SPheatmapParser.HeatmapParser_SH().parse(kpt_hm.clone(), image_size=(256, 256))

@@ -345,3 +345,36 @@ def test_heatmap_parser_adjust_keypoints_points():
                     ey = y + (0.25 if t[min(yy + 1, H - 1), xx] > t[max(yy - 1, 0), xx] else -0.25)
                     assert mine[b][g_][j][0] == ex and mine[b][g_][j][1] == ey and mine[b][g_][j][2] == 0.5
         assert mine[1][1] == []
+
+
+# ---- SRHandNet multi-scale targets with the region map (R3b) --------------------------------------------------
+def test_srhandnet_generate_target_golden():
+    """datasets/data_pipeline/generateTarget.py:303-426 — dict in, lists of NumPy arrays out, as the pipeline calls it."""
+    from litehandnet_b200.render import SRHandNetGenerateTarget, render_srhandnet_targets
+    g = load_golden("render_srhandnet.npz")
+    hs = [list(x) for x in g["heatmap_sizes"]]
+    N, K = g["joints_3d"].shape[:2]
+    for pred_bbox in (1, 0):
+        for unb in (0, 1):
+            T = SRHandNetGenerateTarget(pred_bbox=bool(pred_bbox), sigma=[2, 2, 2, 2], unbiased_encoding=bool(unb))
+            for n in range(N):
+                res = dict(joints_3d=g["joints_3d"][n].copy(), joints_3d_visible=g["joints_3d_visible"][n].copy(),
+                           bbox=g["bbox"][n].copy(),
+                           ann_info=dict(image_size=np.array([256, 256]), heatmap_size=np.array(hs), num_joints=K,
+                                         use_different_joint_weights=False))
+                out = T(res)
+                assert isinstance(out["target"], list) and len(out["target"]) == 4
+                for i in range(4):
+                    rt = g[f"ref_t_bbox{pred_bbox}_unb{unb}_s{i}"][n]
+                    t = out["target"][i]
+                    assert isinstance(t, np.ndarray) and t.shape == rt.shape and t.dtype == np.float32
+                    np.testing.assert_allclose(t, rt, rtol=1e-5, atol=2e-7)
+                    assert np.array_equal(out["target_weight"][i], g[f"ref_w_bbox{pred_bbox}_unb{unb}_s{i}"][n])
+                    if pred_bbox:       # the width / height planes are exact (one f32 constant inside the window)
+                        assert np.array_equal(t[K + 1:], rt[K + 1:])
+            # the batched entry: every sample in one go
+            t, w = render_srhandnet_targets(cu(g["joints_3d"]), cu(g["joints_3d_visible"]), g["bbox"], (256, 256), hs,
+                                            [2, 2, 2, 2], bool(pred_bbox), bool(unb))
+            for i in range(4):
+                np.testing.assert_allclose(t[i].cpu().numpy(), g[f"ref_t_bbox{pred_bbox}_unb{unb}_s{i}"], rtol=1e-5, atol=2e-7)
+                assert np.array_equal(w[i].cpu().numpy(), g[f"ref_w_bbox{pred_bbox}_unb{unb}_s{i}"])
