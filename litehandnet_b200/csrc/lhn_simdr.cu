@@ -128,22 +128,44 @@ __device__ __forceinline__ void warp_pair_argmax(const T* __restrict__ xv, const
   warp_finish<T>(yv, nqy, lane, sy, iy, my);
 }
 
+// Loop-invariant divisors of the epilogue.  k, Lx / k and Ly / k are powers of two in every reference config
+// (k = 2, 256- or 512-bin vectors), and dividing by a power of two is the same correctly rounded result as
+// multiplying by its exact reciprocal — so the five IEEE divisions per pair (a fifth of the ring kernel's
+// instructions, profiles/r01_simdr_ring_ncu_summary.txt) become multiplications; other sizes keep the divisions.
+struct SimdrDiv {
+  float fk, fxo, fyo;      // (float)k, (float)(Lx / k), (float)(Ly / k)
+  float rk, rxo, ryo;      // their reciprocals (exact when pow2)
+  bool pow2;
+};
+__device__ __forceinline__ bool is_pow2f(float v) { return v > 0.f && (__float_as_uint(v) & 0x007fffffu) == 0u && v < 1e30f && v > 1e-30f; }
+__device__ __forceinline__ SimdrDiv simdr_div(int k, int Lx, int Ly) {
+  SimdrDiv d;
+  d.fk = (float)k; d.fxo = (float)(Lx / k); d.fyo = (float)(Ly / k);
+  d.pow2 = is_pow2f(d.fk) && is_pow2f(d.fxo) && is_pow2f(d.fyo) && k < (1 << 24);
+  d.rk = d.pow2 ? 1.f / d.fk : 0.f; d.rxo = d.pow2 ? 1.f / d.fxo : 0.f; d.ryo = d.pow2 ? 1.f / d.fyo : 0.f;
+  return d;
+}
+
 // lane 0 of the warp that owns pair bk: preds = idx / k (int64 / int -> f64 -> f32: one rounding of the exact quotient,
 // which is what the correctly rounded f32 division of the exactly representable operands gives),
 // score = (max_x + max_y) / 2, transform_preds with output_size [Lx // k, Ly // k].
-__device__ __forceinline__ void simdr_store(uint32_t ix, uint32_t iy, float mx, float my, int k, int Lx, int Ly,
+__device__ __forceinline__ void simdr_store(uint32_t ix, uint32_t iy, float mx, float my, int k, const SimdrDiv& dv,
                                             bool xform, float cx, float cy, float sc0, float sc1, float* __restrict__ out,
                                             int32_t* __restrict__ out_idx, int64_t bk) {
   float px, py;
-  if (ix < (1u << 24) && iy < (1u << 24) && k < (1 << 24)) {
-    px = __fdiv_rn((float)ix, (float)k); py = __fdiv_rn((float)iy, (float)k);
+  const bool small = ix < (1u << 24) && iy < (1u << 24) && k < (1 << 24);
+  if (small && dv.pow2) {
+    px = __fmul_rn((float)ix, dv.rk); py = __fmul_rn((float)iy, dv.rk);
+  } else if (small) {
+    px = __fdiv_rn((float)ix, dv.fk); py = __fdiv_rn((float)iy, dv.fk);
   } else {
     px = (float)((double)ix / (double)k); py = (float)((double)iy / (double)k);
   }
-  const float score = __fdiv_rn(__fadd_rn(mx, my), 2.f);
+  const float score = __fmul_rn(__fadd_rn(mx, my), 0.5f);
   if (xform) {
     const float s0 = __fmul_rn(sc0, 200.f), s1 = __fmul_rn(sc1, 200.f);
-    const float fx = __fdiv_rn(s0, (float)(Lx / k)), fy = __fdiv_rn(s1, (float)(Ly / k));
+    const float fx = dv.pow2 ? __fmul_rn(s0, dv.rxo) : __fdiv_rn(s0, dv.fxo);
+    const float fy = dv.pow2 ? __fmul_rn(s1, dv.ryo) : __fdiv_rn(s1, dv.fyo);
     px = __fsub_rn(__fadd_rn(__fmul_rn(px, fx), cx), __fmul_rn(s0, 0.5f));
     py = __fsub_rn(__fadd_rn(__fmul_rn(py, fy), cy), __fmul_rn(s1, 0.5f));
   }
@@ -163,6 +185,7 @@ __global__ void __launch_bounds__(256, 6) decode_simdr_kernel(const T* __restric
   const int lane = threadIdx.x & 31;
   const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const SimdrDiv dv = simdr_div(k, Lx, Ly);
   for (int64_t bk = wg; bk < n_bk; bk += nw) {
     const int64_t b = bk / K;
     int x1 = 0, x2 = Lx, y1 = 0, y2 = Ly;
@@ -181,7 +204,7 @@ __global__ void __launch_bounds__(256, 6) decode_simdr_kernel(const T* __restric
       warp_vec_argmax<T, NMS>(xp, Lx, x1, x2, lane, ix, mx);
       warp_vec_argmax<T, NMS>(yp, Ly, y1, y2, lane, iy, my);
     }
-    if (lane == 0) simdr_store(ix, iy, mx, my, k, Lx, Ly, center != nullptr, cx, cy, sc0, sc1, out, out_idx, bk);
+    if (lane == 0) simdr_store(ix, iy, mx, my, k, dv, center != nullptr, cx, cy, sc0, sc1, out, out_idx, bk);
   }
 }
 
@@ -215,6 +238,7 @@ decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int
   }
   __syncthreads();
   const uint64_t pol = policy_evict_first();
+  const SimdrDiv dv = simdr_div(k, Lx, Ly);
   const int64_t total = (int64_t)gridDim.x * nwarps;
   const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;   // warp-major: the leftover pairs spread over all SMs
   auto issue = [&](int s, int64_t pair) {
@@ -258,7 +282,7 @@ decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int
     if (lane == 0) {
       const int64_t next = bk + (int64_t)nstg * total;
       if (next < n_bk) { fence_proxy_async(); issue(s, next); }
-      simdr_store(ix, iy, mx, my, k, Lx, Ly, center != nullptr, cx, cy, sc0, sc1, out, out_idx, bk);
+      simdr_store(ix, iy, mx, my, k, dv, center != nullptr, cx, cy, sc0, sc1, out, out_idx, bk);
     }
     if (++s == nstg) { s = 0; ph ^= 1u; }
   }
