@@ -430,6 +430,16 @@ LHN_API int lhn_refine_points(const void* hm, int dtype, int64_t B, int C, int H
                               int64_t stride_c, const int32_t* bc, float* xy, int xy_stride, int64_t n,
                               int refine, lhn_stream_t stream);
 
+/* The legacy DARK at GIVEN positions (adjust_keypoints_by_DARK, utils/heatmap_post_processing.py:35-76, which
+ * refines around int(keypoints) wherever the caller puts them — e.g. the top-k candidates of
+ * ResultParser.candidate_bbox): per point the plane (bc[2i], bc[2i+1]) is blurred (f64, zero-padded, dp->blur_ksize =
+ * 19), scaled by max / (max(blurred) + 1e-6), log, Taylor step under the 1 < p < size - 2 guard.  One CTA per point;
+ * two points on the same plane may run concurrently (the plane is only read).  xy f32 [n, xy_stride] updated in
+ * place.  dp->refine must be LHN_REFINE_DARK_LEGACY. */
+LHN_API int lhn_dark_refine_points(const void* hm, int dtype, int64_t B, int C, int H, int W, int64_t stride_b,
+                                   int64_t stride_c, const int32_t* bc, float* xy, int xy_stride, int64_t n,
+                                   const lhn_decode_params* dp, lhn_stream_t stream);
+
 /* Bbox-restricted keypoint decode (ResultParser._get_first_result, utils/result_parser.py:288-306):
  * for image b only the window roi[b] = (x0, y0, x1, y1) (int32 [B,4], 0 <= x0 < x1 <= W) of each plane takes
  * part: first-index argmax of the cropped plane (A4), then LHN_REFINE_NONE / _OFFSET / _OFFSET_HALF /

@@ -37,7 +37,7 @@ EXPORTS = [
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
     "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate", "lhn_region_bbox_decode", "lhn_heatmap_nms",
-    "lhn_vector_nms", "lhn_refine_points", "lhn_decode_heatmap_roi", "lhn_box_nms", "lhn_render_region_wh",
+    "lhn_vector_nms", "lhn_refine_points", "lhn_decode_heatmap_roi", "lhn_box_nms", "lhn_render_region_wh", "lhn_dark_refine_points",
 ]
 
 
@@ -113,6 +113,8 @@ def _declare(lib):
     lib.lhn_region_bbox_decode.argtypes = [vp, vp, i32, i64, i32, i32, i64, i64, i64, C.POINTER(RegionParams),
                                            vp, vp, vp, vp, vp]
     lib.lhn_render_region_wh.argtypes = [vp, vp, i64, i32, i32, vp, i64, vp]
+    lib.lhn_dark_refine_points.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp, i32, i64,
+                                           C.POINTER(DecodeParams), vp]
     lib.lhn_box_nms.argtypes = [vp, i64, i32, f32, f32, f32, f64, i32, vp, vp, vp]
     lib.lhn_heatmap_nms.argtypes = [vp, vp, i32, i64, i32, i32, i32, i64, i64, i32, vp]
     lib.lhn_vector_nms.argtypes = [vp, vp, i32, i64, i32, vp]

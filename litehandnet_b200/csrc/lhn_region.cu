@@ -478,6 +478,50 @@ __global__ void render_region_wh_kernel(const int32_t* __restrict__ rect, const 
   out[b * out_stride_b + (int64_t)c * HW + q] = in ? gamma[2 * b + c] : 0.f;
 }
 
+// ==========================================================================================================
+// lhn_dark_refine_points: the legacy DARK at GIVEN positions, one CTA per point
+// ==========================================================================================================
+struct DarkPointsArgs {
+  const void* hm; const int32_t* bc; float* xy;
+  int64_t stride_b, stride_c, B;
+  int C, H, W, xy_stride, ksize;
+  double taps[LHN_MAX_TAPS];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kNT) dark_points_kernel(const __grid_constant__ DarkPointsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float redf[kNW];
+  __shared__ float win[25];
+  const int tid = threadIdx.x, HW = a.H * a.W;
+  const int64_t i = blockIdx.x;
+  const int b = a.bc[2 * i], c = a.bc[2 * i + 1];
+  if (b < 0 || b >= a.B || c < 0 || c >= a.C) return;
+  float* xyp = a.xy + i * a.xy_stride;
+  float rx = xyp[0], ry = xyp[1];
+  const int px = (int)rx, py = (int)ry;                      // int() truncates
+  if (!(1 < px && px < a.W - 2 && 1 < py && py < a.H - 2)) return;   // taylor()'s guard: coordinates unchanged
+  float* sP = reinterpret_cast<float*>(smem_raw);
+  double* sD = reinterpret_cast<double*>(smem_raw + align_up((size_t)HW * 4, 16));
+  const T* src = reinterpret_cast<const T*>(a.hm) + (int64_t)b * a.stride_b + (int64_t)c * a.stride_c;
+  float m = -CUDART_INF_F;
+  bool first = true;
+  for (int e = tid; e < HW; e += kNT) {
+    const float v = Elem<T>::to_f32(src[e]);
+    sP[e] = v;
+    m = first ? v : nanmax(m, v);
+    first = false;
+  }
+  const float origin_max = block_nanmax(m, redf);            // np.max of the plane (ends with a CTA barrier)
+  blur_rows_f64(sP, sD, a.H, a.W, a.ksize, a.taps);
+  const float bmax = blurred_plane_max(sD, a.H, a.W, a.ksize, a.taps, redf);
+  const float sc = __fdiv_rn(origin_max, __fadd_rn(bmax, 1e-6f));
+  if (tid < 32) {
+    dark_legacy_at(sD, a.H, a.W, a.ksize, a.taps, px, py, sc, win, rx, ry);
+    if (tid == 0) { xyp[0] = rx; xyp[1] = ry; }
+  }
+}
+
 template <typename K> int set_smem(K kernel, size_t bytes) {
   if (bytes > 227 * 1024) return LHN_EINVAL;
   if (bytes > 40 * 1024) {                                  // static shared memory counts against the 48 KB default too
@@ -615,5 +659,27 @@ extern "C" int lhn_render_region_wh(const int32_t* rect, const float* gamma, int
   if (n == 0) return LHN_OK;
   render_region_wh_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       rect, gamma, H, W, out, out_stride_b, n);
+  return check_launch();
+}
+
+extern "C" int lhn_dark_refine_points(const void* hm, int dtype, int64_t B, int C, int H, int W, int64_t stride_b,
+                                      int64_t stride_c, const int32_t* bc, float* xy, int xy_stride, int64_t n,
+                                      const lhn_decode_params* dp, lhn_stream_t stream) {
+  if (!hm || !bc || !xy || !dp || B < 1 || C < 1 || H < 1 || W < 1 || xy_stride < 2 || n < 0) return LHN_EINVAL;
+  if (dp->refine != LHN_REFINE_DARK_LEGACY) return LHN_EINVAL;
+  if (dp->blur_ksize < 3 || dp->blur_ksize > LHN_MAX_TAPS || (dp->blur_ksize & 1) == 0) return LHN_EINVAL;
+  if (n == 0) return LHN_OK;
+  DarkPointsArgs a;
+  a.hm = hm; a.bc = bc; a.xy = xy; a.stride_b = stride_b; a.stride_c = stride_c; a.B = B; a.C = C; a.H = H; a.W = W;
+  a.xy_stride = xy_stride; a.ksize = dp->blur_ksize;
+  for (int i = 0; i < LHN_MAX_TAPS; ++i) a.taps[i] = dp->taps[i];
+  const size_t HW = (size_t)H * W;
+  const size_t smem = align_up(HW * 4, 16) + HW * 8;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LHN_DISPATCH_DTYPE(dtype, {
+    int rc = set_smem(dark_points_kernel<T>, smem);
+    if (rc) return rc;
+    dark_points_kernel<T><<<(unsigned)n, kNT, smem, st>>>(a);
+  });
   return check_launch();
 }

@@ -222,37 +222,52 @@ def _region_inplace(center_maps):
 
 
 def adjust_keypoints_by_offset(keypoints, heatmaps):
-    """utils/heatmap_post_processing.py:6-33: keypoints [B,K,3] (x,y,conf) from the argmax ->
-    +-0.25 towards the higher clamped neighbour, then +0.5.  Returns a new tensor (callers pass
-    .clone() to the reference); the confidence column is preserved."""
+    """utils/heatmap_post_processing.py:6-33: keypoints [B,K,3] (x,y,conf) -> +-0.25 towards the higher clamped
+    neighbour, then +0.5.  Returns a new tensor (callers pass .clone() to the reference); the confidence column is
+    preserved.  Keypoints that are the per-plane argmax (every call site of the reference) take the fused decode
+    kernel; any other positions are refined where they are (lhn_refine_points)."""
     kp, was = _up(keypoints, torch.float32)
     t, _ = _hm(heatmaps)
-    r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_OFFSET_HALF, want_idx=False)
     out = kp.clone()
-    out[..., :2] = _refine_from(kp, r["hm_kpts"], t)
-    return out if (was or isinstance(keypoints, torch.Tensor) and was) else (out.cpu() if isinstance(keypoints, torch.Tensor) else _np(out))
+    out[..., :2] = _refine_offset(kp, t, L.REFINE_OFFSET_HALF)
+    return out if was else (out.cpu() if isinstance(keypoints, torch.Tensor) else _np(out))
 
 
-def _refine_from(kp, decoded, hm):
-    """The reference refines around int(keypoints[..., :2]); every caller passes the plane argmax, for
-    which the kernel's own argmax is identical.  Reject anything else loudly instead of guessing."""
+def _refine_offset(kp, hm, refine):
+    """The +-0.25 rule of D1 / D2 around int(kp[..., :2]): the decode kernel's own result when kp is the plane
+    argmax, else the rule evaluated at the given positions."""
+    r = ops.decode_heatmap(hm, L.MASK_NONE, refine, want_idx=False)["hm_kpts"][..., :2]
     r0 = ops.decode_heatmap(hm, L.MASK_NONE, L.REFINE_NONE, want_idx=False)["hm_kpts"][..., :2]
-    same = torch.equal(kp[..., :2].to(torch.float32), r0)
-    if not same:
-        raise L.LhnError("adjust_keypoints_*: keypoints are not the per-plane argmax of `heatmaps`; "
-                         "only the reference's call pattern (argmax -> adjust) is supported")
-    return decoded[..., :2]
+    if torch.equal(kp[..., :2], r0):
+        return r
+    B, K = kp.shape[:2]
+    xy = kp[..., :2].reshape(-1, 2).contiguous().clone()
+    ops.refine_points(hm, _plane_index(B, K, kp.device), xy, plus_half=(refine == L.REFINE_OFFSET_HALF))
+    return xy.reshape(B, K, 2)
+
+
+def _plane_index(B, K, device):
+    return torch.stack(torch.meshgrid(torch.arange(B, device=device, dtype=torch.int32),
+                                      torch.arange(K, device=device, dtype=torch.int32), indexing="ij"), -1).reshape(-1, 2)
 
 
 def adjust_keypoints_by_DARK(keypoints, heatmaps):
-    """utils/heatmap_post_processing.py:35-54: blur k=pcfg['blue_kernel']=19 (f64), log, Taylor.
-    Returns a NumPy array like the reference; the input heatmap is left untouched (the reference's CUDA
-    semantics — on CPU inputs the reference blurs the caller's array in place)."""
+    """utils/heatmap_post_processing.py:35-54: blur k=pcfg['blue_kernel']=19 (f64), log, Taylor around
+    int(keypoints).  Returns a NumPy array like the reference; the input heatmap is left untouched (the reference's
+    CUDA semantics — on CPU inputs the reference blurs the caller's array in place).  Keypoints that are the
+    per-plane argmax (get_pred_kpt's call pattern) take the fused decode kernel; any other positions — e.g.
+    candidate_bbox's top-k candidates — are refined where they are (lhn_dark_refine_points)."""
     kp, _ = _up(keypoints, torch.float32)
     t, _ = _hm(heatmaps)
-    r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_DARK_LEGACY, want_idx=False)
     out = kp.clone()
-    out[..., :2] = _refine_from(kp, r["hm_kpts"], t)
+    r0 = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_NONE, want_idx=False)["hm_kpts"][..., :2]
+    if torch.equal(kp[..., :2], r0):
+        out[..., :2] = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_DARK_LEGACY, want_idx=False)["hm_kpts"][..., :2]
+    else:
+        B, K = kp.shape[:2]
+        xy = kp[..., :2].reshape(-1, 2).contiguous().clone()
+        ops.dark_refine_points(t, _plane_index(B, K, kp.device), xy, pcfg['blue_kernel'])
+        out[..., :2] = xy.reshape(B, K, 2)
     return _np(out)
 
 
@@ -430,9 +445,8 @@ class HeatmapParser_SH:
     def adjust_keypoints(keypoints, heatmaps):
         kp, _ = _up(keypoints, torch.float32)
         t, _ = _hm(heatmaps)
-        r = ops.decode_heatmap(t, L.MASK_NONE, L.REFINE_OFFSET, want_idx=False)
         out = kp.clone()
-        out[..., :2] = _refine_from(kp, r["hm_kpts"], t)
+        out[..., :2] = _refine_offset(kp, t, L.REFINE_OFFSET)
         return out.cpu() if not (isinstance(keypoints, torch.Tensor) and keypoints.is_cuda) else out
 
     def __init__(self):

@@ -628,3 +628,20 @@ def render_region_wh(rect, gamma, H, W, out=None):
     L.check(L.lib().lhn_render_region_wh(L.ptr(rect), L.ptr(gamma), B, H, W, L.ptr(out), out.stride(0) if B > 1 else 2 * H * W,
                                          L.stream()), "lhn_render_region_wh")
     return out
+
+
+def dark_refine_points(hm, bc, xy, blur_ksize=19):
+    """lhn_dark_refine_points: the legacy DARK at given positions.  bc int32 [n,2] (image, channel), xy f32 [n,>=2]
+    (updated in place and returned)."""
+    hm, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
+    bc = L.require_cuda(bc, "bc").to(torch.int32).contiguous()
+    L.require_cuda(xy, "xy")
+    if xy.dtype != torch.float32 or not xy.is_contiguous() or xy.dim() != 2 or xy.shape[1] < 2:
+        raise L.LhnError("xy must be a contiguous f32 [n,>=2] tensor")
+    n = xy.shape[0]
+    if bc.shape != (n, 2):
+        raise L.LhnError("bc must be [n,2]")
+    dp = _decode_params(L.MASK_NONE, L.REFINE_DARK_LEGACY, L.XFORM_NONE, blur_ksize=blur_ksize)
+    L.check(L.lib().lhn_dark_refine_points(L.ptr(hm), L.dtype_code(hm), B, Cc, H, W, sb, sc, L.ptr(bc), L.ptr(xy),
+                                           xy.shape[1], n, C.byref(dp), L.stream()), "lhn_dark_refine_points")
+    return xy

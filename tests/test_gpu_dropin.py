@@ -127,8 +127,12 @@ def test_legacy_parsers(case):
                         rtol=1e-5, atol=1e-4, what="final preds")
     pairs = [tuple(int(v) for v in pr) for pr in g["flip_pairs"]]
     assert np.array_equal(flip_back(g["hm"], pairs), g["ref_flip_back"], equal_nan=True)
-    with pytest.raises(Exception):
-        adjust_keypoints_by_offset(kpts + 1.0, hm)          # not the argmax: rejected loudly
+    # positions that are not the plane argmax are refined where they are (lhn_refine_points), as the reference does
+    moved = kpts.clone()
+    moved[..., :2] = torch.clamp(moved[..., :2] + 1.0, 0, min(H, W) - 1)
+    with np.errstate(all="ignore"):
+        want = O.refine_offset_clamped(moved.cpu().numpy(), g["hm"], plus_half=True)
+    assert np.array_equal(adjust_keypoints_by_offset(moved, hm).cpu().numpy(), want, equal_nan=True)
 
 
 def test_sp_parser_main_fixture():

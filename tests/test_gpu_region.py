@@ -378,3 +378,54 @@ def test_srhandnet_generate_target_golden():
             for i in range(4):
                 np.testing.assert_allclose(t[i].cpu().numpy(), g[f"ref_t_bbox{pred_bbox}_unb{unb}_s{i}"], rtol=1e-5, atol=2e-7)
                 assert np.array_equal(w[i].cpu().numpy(), g[f"ref_w_bbox{pred_bbox}_unb{unb}_s{i}"])
+
+
+def test_adjust_keypoints_by_offset_at_arbitrary_positions():
+    """utils/heatmap_post_processing.py:6-33 / SPheatmapParser.py:140-167 refine around int(keypoints) wherever the
+    caller puts them; positions that are not the plane argmax go through lhn_refine_points."""
+    from litehandnet_b200.decode import HeatmapParser_SH, adjust_keypoints_by_offset
+    rng = np.random.default_rng(21)
+    B, K, H, W = 4, 6, 64, 64
+    hm = rng.random((B, K, H, W)).astype(F32)
+    kp = np.zeros((B, K, 3), F32)
+    kp[..., 0] = rng.integers(0, W, (B, K)); kp[..., 1] = rng.integers(0, H, (B, K)); kp[..., 2] = rng.random((B, K))
+    kp[0, 0, :2] = (0, 0); kp[0, 1, :2] = (W - 1, H - 1)
+    got = adjust_keypoints_by_offset(cu(kp), cu(hm))
+    assert np.array_equal(got.cpu().numpy(), O.refine_offset_clamped(kp, hm, plus_half=True))
+    got2 = HeatmapParser_SH.adjust_keypoints(cu(kp), cu(hm))
+    assert np.array_equal(got2.cpu().numpy(), O.refine_offset_clamped(kp, hm, plus_half=False))
+    # and the argmax call pattern still takes the fused kernel with the same answer
+    p, mv, _ = O.max_preds(hm, "none")
+    ka = np.concatenate([p, mv], 2)
+    assert np.array_equal(adjust_keypoints_by_offset(cu(ka), cu(hm)).cpu().numpy(), O.refine_offset_clamped(ka, hm, plus_half=True))
+
+
+def test_adjust_keypoints_by_dark_at_arbitrary_positions():
+    """utils/heatmap_post_processing.py:35-76 refines around int(keypoints) wherever the caller puts them
+    (ResultParser.candidate_bbox passes top-k candidates): positions one or two pixels off the blob maximum, on the
+    border (guard fails: unchanged) and the exact argmax (fused-kernel path) — against the oracle."""
+    from litehandnet_b200 import synth
+    from litehandnet_b200.decode import adjust_keypoints_by_DARK
+    B, K, H, W = 3, 5, 64, 64
+    hm, centers = synth.blob_heatmaps(B, K, H, W, seed=31)
+    hm = hm.numpy()
+    p, mv, _ = O.max_preds(hm, "none")
+    rng = np.random.default_rng(32)
+    kp = np.concatenate([p + rng.integers(-2, 3, p.shape).astype(F32), mv], 2)
+    kp[..., :2] = np.clip(kp[..., :2], 0, 63)
+    kp[0, 0, :2] = (1, 30); kp[0, 1, :2] = (30, 62)                      # guard fails
+    with np.errstate(all="ignore"):
+        want = O.refine_dark(kp, hm, 19, legacy=True)
+    got = adjust_keypoints_by_DARK(cu(kp), cu(hm))
+    assert isinstance(got, np.ndarray) and got.shape == kp.shape
+    assert_coords_close(got, want, what="dark at points")
+    assert np.array_equal(got[0, :2], kp[0, :2]) and np.array_equal(got[..., 2], kp[..., 2])
+    ka = np.concatenate([p, mv], 2)
+    with np.errstate(all="ignore"):
+        assert_coords_close(adjust_keypoints_by_DARK(cu(ka), cu(hm)), O.refine_dark(ka, hm, 19, legacy=True), what="dark at argmax")
+    # bf16 planes, strided channel view
+    big = torch.cat([cu(hm), torch.rand(B, 2, H, W, device=DEV)], 1).to(torch.bfloat16)
+    hb = big[:, :K]
+    with np.errstate(all="ignore"):
+        want_b = O.refine_dark(kp, hb.float().cpu().numpy(), 19, legacy=True)
+    assert_coords_close(adjust_keypoints_by_DARK(cu(kp), hb), want_b, rtol=1e-5, atol=5e-5, what="dark at points, bf16")
