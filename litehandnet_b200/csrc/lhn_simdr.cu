@@ -374,13 +374,10 @@ static int launch_simdr(const void* xv, const void* yv, int64_t n_bk, int K, int
                          n_bk >= (int64_t)num_sms() * warps * 4;
     if (ring_ok) {
       const size_t smem = (size_t)warps * nstg * pair_al + bar_bytes;
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(decode_simdr_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
-        if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
-        attr_set = true;
-      }
+      // per launch (the attribute is per device; a host call of ~1 us), as the team kernel does
+      cudaError_t e = cudaFuncSetAttribute(decode_simdr_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
       decode_simdr_ring_kernel<T><<<num_sms(), warps * 32, smem, st>>>((const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k,
                                                                             center, scale, out, out_idx, nstg, (int)pair_al);
       return check_launch();
