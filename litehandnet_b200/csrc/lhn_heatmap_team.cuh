@@ -632,14 +632,18 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             const int t = t0 + lane;
             nh += __popc(__ballot_sync(0xffffffffu, t < a.auc_steps && d_auc < a.auc_thr[t]));
           }
+          // Plane counts of one CTA stay far below 2^32: they are bumped with the native 32-bit shared-memory
+          // atomic on the low word of the 64-bit slot (a 64-bit shared atomicAdd is a compare-and-swap loop);
+          // only the fixed-point EPE sum needs the 64-bit add.
+          auto bump = [&](unsigned long long* slot) { atomicAdd(reinterpret_cast<unsigned int*>(slot), 1u); };
           if (lane == 0 && counted) {
-            atomicAdd(cta_cnt + Ki + k, 1ull);
-            if (d < a.pck_thr) atomicAdd(cta_cnt + k, 1ull);
+            bump(cta_cnt + Ki + k);
+            if (d < a.pck_thr) bump(cta_cnt + k);
           } else if (lane == 1) {
-            atomicAdd(cta_cnt + (int64_t)(2 + nh) * Ki + k, 1ull);
+            bump(cta_cnt + (int64_t)(2 + nh) * Ki + k);
           } else if (lane == 2) {
             unsigned long long* epe = cta_cnt + (int64_t)(3 + a.auc_steps) * Ki;
-            atomicAdd(epe + k, 1ull);
+            bump(epe + k);
             atomicAdd(epe + Ki + k, (unsigned long long)llrint((double)d * 1048576.0));
           }
         }
