@@ -956,6 +956,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     // DARK: the reference's interior guard; UDP: every plane with a positive maximum (coordinates >= 0)
     const bool dark_guard = (is_dark && (1 < px) && (px < W - 2) && (1 < py) && (py < H - 2)) || (udp && px >= 0 && py >= 0);
 
+    TRS(6);
     PlaneRec* rec = &th->rec[buf];
     const int wx0 = px - 2 - bb;                      // first window column (may be negative)
     const int c0 = wx0 & ~3, xo = wx0 & 3;            // its quad-aligned start and the offset inside it
@@ -979,6 +980,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         *reinterpret_cast<float4*>(tile + r * TCW + 4 * cq) = v;
       }
     }
+    TRS(7);
     // ---- positives of the balanced loss: a small window around the joint, by the last sweeper warp ---------
     if (LOSS && role == TW - 1) {
       float Spos = 0.f;

@@ -30,7 +30,8 @@ def stat(name, x):
 # sweepers (first sweeper warp, lane 0): 0 = S1 passed, 1 = plane landed, 2 = sweep done, 3 = S2 passed,
 # 4 = row sums / positives / record staged, 5 = S3 passed + stage re-armed
 for a_, b_, n in [(0, 1, 'sweeper wait for plane (mbar)'), (1, 2, 'sweep'), (2, 3, 'warp reduce + S2'),
-                  (3, 4, 'resolve + window + positives'), (4, 5, 'S3 + re-arm TMA')]:
+                  (3, 4, 'resolve + window + positives'), (3, 6, '  resolve argmax'), (6, 7, '  window staging'),
+                  (7, 4, '  positives + record'), (4, 5, 'S3 + re-arm TMA')]:
     stat(n, T[:, its, b_] - T[:, its, a_])
 stat('wait for tables/empty (next plane)', T[:, 4:15, 0] - T[:, 3:14, 5])
 stat('sweeper cycle per plane', T[:, 4:15, 0] - T[:, 3:14, 0])
