@@ -101,7 +101,9 @@ struct TeamHeader {
   uint64_t bar[4];            // TMA completion barriers of the stages
   uint64_t full[2];           // record n is complete          (sweepers -> epilogue warp)
   uint64_t empty[2];          // record/row-sum buffer is free (epilogue warp -> sweepers)
-  uint64_t pad;
+  uint32_t cta_done;          // team 0's header only: teams of this CTA that have published `tsum`
+  uint32_t pad;
+  double tsum[4];             // one-launch loss: this team's (S_pos, S_neg, N_pos, numel)
   float red_max[8];           // per-warp sweep partials: max (NaN-propagating), first quad holding it, sum
   uint32_t red_q[8];
   float red_s[8];
@@ -117,7 +119,8 @@ struct TeamHeader {
   float side[8][12];
 };
 constexpr int kSideAhead = 4;
-enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_N };
+// SD_MASK: the aligned 32-bit word that holds the plane's fused-metrics mask byte (cp.async moves >= 4 bytes)
+enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_MASK, SD_N };
 
 template <typename T>
 __device__ __forceinline__ float elem_f32(const T* p, int i) { return Elem<T>::to_f32(p[i]); }
@@ -211,6 +214,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       case SD_SX: case SD_SY: if (a.scale) src = a.scale + 2 * (int64_t)b + (lane - SD_SX); break;
       case SD_GX: case SD_GY: if (has_counters) src = a.gt + 2 * bk + (lane - SD_GX); break;
       case SD_BW: case SD_BH: if (has_counters) src = a.bbox_wh + 2 * (int64_t)b + (lane - SD_BW); break;
+      case SD_MASK:
+        if (has_counters) src = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(a.mask + bk) & ~(uintptr_t)3);
+        break;
       default: break;
     }
     if (src) cp_async_4(&th->side[slot][lane], src);
@@ -247,6 +253,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     for (int i = 0; i < nstg; ++i) mbar_init(&th->bar[i], 1);
     mbar_init(&th->full[0], 1); mbar_init(&th->full[1], 1);
     mbar_init(&th->empty[0], 1); mbar_init(&th->empty[1], 1);
+    th->cta_done = 0u;
     fence_mbar_init();
   }
   __syncthreads();
@@ -297,15 +304,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     double acc_sp = 0.0, acc_sn = 0.0, acc_np = 0.0, acc_ne = 0.0;   // this team's loss sums (lane 0)
     // side-input ring (kSideAhead planes ahead) and the tables of the first two planes; the sweepers start
     // on plane 0 as soon as its tables exist
-    int mask_cur = 1, mask_nxt = 1;                  // fused-metrics mask bytes of planes n, n+1 (lane 0)
-    if (lane == 0 && has_counters) {
-      mask_cur = a.mask[(int64_t)pb * K + (C == K ? pc : pc % K)];
-      if (p + total_teams < n_planes) {
-        uint32_t mb = pb, mc = pc;
-        advance(mb, mc);
-        mask_nxt = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];
-      }
-    }
 #pragma unroll
     for (int i = 2; i < kSideAhead; ++i) {
       if (pq < n_planes) side_fetch(qb, qc, i);
@@ -610,12 +608,15 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         // fused PCK / AUC / EPE counters (_calc_distances in f64, compared in f32): lanes 0..2 take one
         // normaliser each (bbox, AUC constant, 1) so the three divide / sqrt chains run side by side
         const float Xb = __shfl_sync(0xffffffffu, keepX, 0), Yb = __shfl_sync(0xffffffffu, keepY, 0);
-        const int mk = __shfl_sync(0xffffffffu, mask_cur, 0);
+        uint32_t s_, k;
+        split_channel(pc, s_, k);
+        const float* sd = th->side[n_it & 7];
+        // the mask byte came with the side inputs (four planes ahead): a plain load here waits microseconds behind
+        // the plane traffic, once per plane, on the epilogue warp's critical path
+        const uintptr_t maddr = reinterpret_cast<uintptr_t>(a.mask + ((int64_t)pb * K + k));
+        const uint32_t mk = (__float_as_uint(sd[SD_MASK]) >> (8u * (uint32_t)(maddr & 3))) & 0xffu;
         if (mk) {
-          uint32_t s_, k;
-          split_channel(pc, s_, k);
           const int Ki = (int)K;
-          const float* sd = th->side[n_it & 7];
           const double ddx = (double)Xb - (double)sd[SD_GX], ddy = (double)Yb - (double)sd[SD_GY];
           double nb = lane == 0 ? (double)fmaxf(sd[SD_BW], sd[SD_BH]) : (lane == 1 ? (double)a.auc_nor : 1.0);
           const bool counted = nb != 0.0;                   // normalize == 0 masks the sample out (PCK only)
@@ -650,15 +651,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       }
       TRE(11);
       // ---- side-input ring + the tables of plane n+2; then plane n+2 may start ------------------------------
-      if (lane == 0 && has_counters) {
-        mask_cur = mask_nxt;
-        mask_nxt = 1;
-        if (p + 2 * total_teams < n_planes) {
-          uint32_t mb = pb, mc = pc;
-          advance(mb, mc); advance(mb, mc);
-          mask_nxt = a.mask[(int64_t)mb * K + (C == K ? mc : mc % K)];   // consumed two planes from now
-        }
-      }
       if (pq < n_planes) side_fetch(qb, qc, (n_it + kSideAhead) & 7);
       cp_async_commit();
       pq += total_teams; advance(qb, qc);
@@ -715,28 +707,57 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       g_trace[((blockIdx.x * 12 + team) * 16 + 1) * 16 + 13] = (long long)gt;
     }
 #endif
-    // ---- one-launch loss: publish this team's sums; the last team reduces all of them in a fixed order ----
+    // ---- one-launch loss: two fixed-order levels.  A team leaves its sums in shared memory; the last team of the
+    // CTA to finish adds the CTA's teams (team order) and publishes ONE row; the last CTA adds the rows (lane-strided,
+    // then a fixed tree) and finalises.  The whole grid waits for that last warp: 148 rows are one L2 round trip
+    // (a row per team was ~47 dependent round trips, 4-5 us per launch: profiles/r01_batch_scaling.txt).
     if (LOSS && a.team_sums) {
       // the workspace is shared with the previous launch on the stream: it must have completed (it has, long
       // ago; this only orders the memory operations when the launches overlap)
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      const uint32_t active = n_planes < total_teams ? n_planes : total_teams;
+      TeamHeader* th0 = reinterpret_cast<TeamHeader*>(smem_raw + (size_t)nstg * a.stage_bytes);   // team 0's header
+      unsigned int last = 0;
+      if (lane == 0) {
+        th->tsum[0] = acc_sp; th->tsum[1] = acc_sn; th->tsum[2] = acc_np; th->tsum[3] = acc_ne;
+        unsigned int cta_teams = 0;
+        for (int t = 0; t < nteams; ++t) cta_teams += ((uint64_t)t * gridDim.x + blockIdx.x < n_planes) ? 1u : 0u;
+        __threadfence_block();
+        last = (atomicAdd(&th0->cta_done, 1u) == cta_teams - 1u) ? 1u : 0u;
+      }
+      if (!__shfl_sync(0xffffffffu, last, 0)) return;
       unsigned int ticket = 0;
       if (lane == 0) {
-        double* dst = a.team_sums + 4 * (size_t)gteam;
-        __stcg(reinterpret_cast<double2*>(dst), make_double2(acc_sp, acc_sn));
-        __stcg(reinterpret_cast<double2*>(dst) + 1, make_double2(acc_np, acc_ne));
+        __threadfence_block();
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        for (int t = 0; t < nteams; ++t) {
+          if ((uint64_t)t * gridDim.x + blockIdx.x >= n_planes) break;
+          const TeamHeader* tt = reinterpret_cast<const TeamHeader*>(reinterpret_cast<const unsigned char*>(th0) +
+                                                                     (size_t)t * a.warp_smem);
+          c0 += tt->tsum[0]; c1 += tt->tsum[1]; c2 += tt->tsum[2]; c3 += tt->tsum[3];
+        }
+        double* dst = a.team_sums + 4 * (size_t)blockIdx.x;
+        __stcg(reinterpret_cast<double2*>(dst), make_double2(c0, c1));
+        __stcg(reinterpret_cast<double2*>(dst) + 1, make_double2(c2, c3));
         __threadfence();
         ticket = atomicAdd(a.ticket, 1u);
       }
       ticket = __shfl_sync(0xffffffffu, ticket, 0);
-      if (ticket == active - 1) {
+      if (ticket == gridDim.x - 1) {                            // every CTA of the grid owns at least one plane
         __threadfence();
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        for (uint32_t t = lane; t < active; t += 32) {          // fixed order: lane-strided, then a fixed tree
-          const double2 x = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t));
-          const double2 y = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t) + 1);
-          v0 += x.x; v1 += x.y; v2 += y.x; v3 += y.y;
+        for (uint32_t t0 = lane; t0 < gridDim.x; t0 += 160) {   // five rows per lane in flight: 148 SMs in one trip
+          double2 x[5], y[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const uint32_t t = t0 + 32u * u;
+            x[u] = y[u] = make_double2(0.0, 0.0);               // rows past the end add +0.0
+            if (t < gridDim.x) {
+              x[u] = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t));
+              y[u] = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t) + 1);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { v0 += x[u].x; v1 += x[u].y; v2 += y[u].x; v3 += y[u].y; }
         }
         v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
         if (lane == 0) {

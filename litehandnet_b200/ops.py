@@ -225,6 +225,18 @@ def fused_render_loss_decode(hm, mask_mode, refine, transform, center, scale, re
     return res
 
 
+def _mask_u8(mask):
+    """Boolean joint mask as the uint8 bytes the kernels read: a bool tensor is reinterpreted in place (no
+    conversion kernel in front of every launch — it cost ~15 us per call and broke the launch overlap); anything
+    else is `!= 0`."""
+    mask = L.require_cuda(mask, "mask")
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    if mask.dtype == torch.uint8:
+        return mask.contiguous()
+    return (mask != 0).contiguous().view(torch.uint8)
+
+
 def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, counters,
                        pck_thr=0.2, auc_nor=30.0, auc_steps=20, blur_ksize=None, overlap_previous=False):
     """K1 + fused PCK/AUC/EPE counters (BASELINE config 4).  `counters` int64 [(auc_steps+5)*K] is
@@ -236,7 +248,7 @@ def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, 
     center, scale = _f32c(center, "center"), _f32c(scale, "scale")
     gt = _f32c(gt, "gt")
     bbox_wh = _f32c(bbox_wh, "bbox_wh")
-    mask = L.require_cuda(mask, "mask").to(torch.uint8).contiguous()
+    mask = _mask_u8(mask)
     if counters.dtype != torch.int64 or counters.numel() != (auc_steps + 5) * K or not counters.is_contiguous():
         raise L.LhnError("counters must be a contiguous int64 tensor of (auc_steps+5)*K entries")
     out_hm = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
@@ -435,7 +447,7 @@ def pck_accumulate(pred, gt, mask, thr, normalize=None, norm_const=1.0, counters
         gt = gt.float()
     pred, gt = pred.contiguous(), gt.contiguous()
     N, K = pred.shape[:2]
-    mask = L.require_cuda(mask, "mask").to(torch.uint8).contiguous()
+    mask = _mask_u8(mask)
     if normalize is not None:
         L.require_cuda(normalize, "normalize")
         if normalize.dtype not in (torch.float32, torch.float64):
