@@ -171,8 +171,9 @@ LHN_API int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int32_
 /* ---- the headline step in ONE launch ------------------------------------------------------------
  * lhn_decode_heatmap (with the fused render + loss) followed by lhn_loss_reduce and
  * lhn_loss_finalize, as a single kernel: every team of the persistent kernel keeps its own f64
- * loss sums and the last team to finish reduces them in a fixed order (bitwise reproducible for a
- * given shape) and finalises the loss.  Replaces the same reference calls as lhn_decode_heatmap +
+ * loss sums; the last team of a CTA adds the CTA's teams in team order and publishes one row, the
+ * last CTA adds the rows in a fixed order (bitwise reproducible for a given shape and device) and
+ * finalises the loss.  Replaces the same reference calls as lhn_decode_heatmap +
  * DistanceLoss.forward / JointsDistanceLoss.forward (heatmapLoss.py:242-265, :195-225).
  *
  * workspace  device buffer of lhn_fused_workspace_bytes(B, K, num_stacks) bytes; zero it ONCE
@@ -280,6 +281,13 @@ LHN_API int lhn_decode_simdr(const void* x_vec, const void* y_vec, int dtype, in
                              int Lx, int Ly, int split_ratio, const float* center,
                              const float* scale, int nms, const int32_t* ranges, float* out,
                              int32_t* out_idx, lhn_stream_t stream);
+/* The same with `flags` (LHN_FLAG_OVERLAP_PREVIOUS: this launch shares no buffer with the previous launch on the
+ * stream — e.g. a loop over rotating batches — and may start while that one drains; honoured by the
+ * persistent ring kernel, ignored by the small-batch / NMS path). */
+LHN_API int lhn_decode_simdr_flags(const void* x_vec, const void* y_vec, int dtype, int64_t B, int K,
+                                   int Lx, int Ly, int split_ratio, const float* center,
+                                   const float* scale, int nms, const int32_t* ranges, float* out,
+                                   int32_t* out_idx, int flags, lhn_stream_t stream);
 
 /* KLDiscretLoss.forward (centernet_simdr_loss.py:27-39): per-joint SmoothL1(beta=1) sums.
  * out/target [B,K,L*]; weight f32 [B,K]; joint_sums f64 [K,3] = (sum_x, sum_y, sum_w) must be

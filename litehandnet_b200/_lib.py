@@ -32,7 +32,7 @@ ERRORS = {-1: "LHN_EINVAL (bad shape / null pointer / bad enum)", -2: "LHN_EDTYP
 EXPORTS = [
     "lhn_version", "lhn_last_cuda_error", "lhn_gaussian_taps", "lhn_decode_heatmap",
     "lhn_decode_heatmap_pck", "lhn_loss_partials", "lhn_loss_reduce", "lhn_loss_finalize",
-    "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_simdr_loss_workspace_bytes",
+    "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_decode_simdr_flags", "lhn_simdr_loss_workspace_bytes",
     "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
@@ -100,6 +100,7 @@ def _declare(lib):
                                        vp, vp, vp]
     lib.lhn_render_simdr.argtypes = [vp, i32, vp, i32, i64, i32, i32, i32, f32, f32, vp, vp, vp]
     lib.lhn_decode_simdr.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]
+    lib.lhn_decode_simdr_flags.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, vp]
     lib.lhn_simdr_loss_workspace_bytes.argtypes = [i64, i32]
     lib.lhn_simdr_loss_workspace_bytes.restype = i64
     lib.lhn_simdr_smoothl1.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, vp, i64, vp, vp]

@@ -504,8 +504,8 @@ using namespace lhn;
 
 namespace lhn { int num_sms(); }
 
-// workspace layout of the one-launch step: [ticket u32 | pad to 256 B][team sums: teams x 4 f64][partials of
-// the three-launch fallback: n_planes x 4 f64]
+// workspace layout of the one-launch step: [ticket u32 | pad to 256 B][loss-sum rows x 4 f64: one per CTA is used,
+// the region keeps its older size of one per team][partials of the three-launch fallback: n_planes x 4 f64]
 static const int64_t kWsHeader = 256;
 static int64_t ws_team_bytes() { return (int64_t)lhn::num_sms() * lhn::kMaxTeamsPerCta * 32; }
 

@@ -232,6 +232,8 @@ decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int
   unsigned char* wbase = smem_raw + (size_t)warp * nstg * pair_al;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * nstg * pair_al) + warp * kRingMaxStages;
   const uint32_t xbytes = (uint32_t)Lx * sizeof(T), ybytes = (uint32_t)Ly * sizeof(T);
+  // the next launch on the stream, if it carries LHN_FLAG_OVERLAP_PREVIOUS, takes over SMs as these CTAs retire
+  asm volatile("griddepcontrol.launch_dependents;");
   if (lane == 0) {
     for (int s = 0; s < nstg; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(1024) simdr_loss_finalize_kernel(const double*
 template <typename T>
 static int launch_simdr(const void* xv, const void* yv, int64_t n_bk, int K, int Lx, int Ly, int k,
                         const float* center, const float* scale, int nms, const int32_t* ranges,
-                        float* out, int32_t* out_idx, cudaStream_t st) {
+                        float* out, int32_t* out_idx, int flags, cudaStream_t st) {
   // Ring kernel: no NMS, TMA-able vectors (16-byte multiples, 16-byte aligned bases), at least two stages per warp,
   // and enough pairs to give every warp of the persistent grid a few (below that the launch is latency-bound anyway).
   {
@@ -378,8 +380,16 @@ static int launch_simdr(const void* xv, const void* yv, int64_t n_bk, int K, int
       cudaError_t e = cudaFuncSetAttribute(decode_simdr_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
       if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
-      decode_simdr_ring_kernel<T><<<num_sms(), warps * 32, smem, st>>>((const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k,
-                                                                            center, scale, out, out_idx, nstg, (int)pair_al);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)num_sms()); cfg.blockDim = dim3((unsigned)(warps * 32));
+      cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = (flags & LHN_FLAG_OVERLAP_PREVIOUS) ? 1 : 0;
+      e = cudaLaunchKernelEx(&cfg, decode_simdr_ring_kernel<T>, (const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k, center, scale,
+                             out, out_idx, nstg, (int)pair_al);
+      if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
       return check_launch();
     }
   }
@@ -404,6 +414,14 @@ extern "C" int lhn_decode_simdr(const void* x_vec, const void* y_vec, int dtype,
                                 int Lx, int Ly, int split_ratio, const float* center,
                                 const float* scale, int nms, const int32_t* ranges, float* out,
                                 int32_t* out_idx, lhn_stream_t stream) {
+  return lhn_decode_simdr_flags(x_vec, y_vec, dtype, B, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out,
+                                out_idx, 0, stream);
+}
+
+extern "C" int lhn_decode_simdr_flags(const void* x_vec, const void* y_vec, int dtype, int64_t B, int K,
+                                      int Lx, int Ly, int split_ratio, const float* center,
+                                      const float* scale, int nms, const int32_t* ranges, float* out,
+                                      int32_t* out_idx, int flags, lhn_stream_t stream) {
   if (!x_vec || !y_vec || !out || B < 0 || K <= 0 || Lx <= 0 || Ly <= 0 || split_ratio <= 0 ||
       ((center == nullptr) != (scale == nullptr)))
     return LHN_EINVAL;
@@ -411,9 +429,9 @@ extern "C" int lhn_decode_simdr(const void* x_vec, const void* y_vec, int dtype,
   if (n == 0) return LHN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case LHN_F32: return launch_simdr<float>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, st);
-    case LHN_BF16: return launch_simdr<__nv_bfloat16>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, st);
-    case LHN_F16: return launch_simdr<__half>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, st);
+    case LHN_F32: return launch_simdr<float>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, flags, st);
+    case LHN_BF16: return launch_simdr<__nv_bfloat16>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, flags, st);
+    case LHN_F16: return launch_simdr<__half>(x_vec, y_vec, n, K, Lx, Ly, split_ratio, center, scale, nms, ranges, out, out_idx, flags, st);
     default: return LHN_EDTYPE;
   }
 }

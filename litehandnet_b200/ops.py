@@ -398,7 +398,9 @@ def render_simdr(joints, vis, image_size, k=2, sigma=2):
     return sx, sy
 
 
-def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=None, want_idx=False):
+def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=None, want_idx=False,
+                 overlap_previous=False):
+    """K2.  overlap_previous: as in decode_heatmap (rotating buffers; honoured by the ring kernel)."""
     L.require_cuda(x_vec, "x_vectors")
     L.require_cuda(y_vec, "y_vectors")
     if y_vec.dtype != x_vec.dtype:
@@ -411,9 +413,9 @@ def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=N
         ranges = L.require_cuda(ranges, "ranges").to(torch.int32).contiguous()
     out = torch.empty((B, K, 3), dtype=torch.float32, device=x_vec.device)
     idx = torch.empty((B, K, 2), dtype=torch.int32, device=x_vec.device) if want_idx else None
-    rc = L.lib().lhn_decode_simdr(L.ptr(x_vec), L.ptr(y_vec), L.dtype_code(x_vec), B, K, Lx, Ly, int(k),
-                                  L.ptr(center), L.ptr(scale), int(bool(nms)), L.ptr(ranges), L.ptr(out),
-                                  L.ptr(idx), L.stream())
+    rc = L.lib().lhn_decode_simdr_flags(L.ptr(x_vec), L.ptr(y_vec), L.dtype_code(x_vec), B, K, Lx, Ly, int(k),
+                                        L.ptr(center), L.ptr(scale), int(bool(nms)), L.ptr(ranges), L.ptr(out),
+                                        L.ptr(idx), L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0, L.stream())
     L.check(rc, "lhn_decode_simdr")
     return (out, idx) if want_idx else out
 

@@ -76,7 +76,7 @@ def simdr_case(name, B, K, Lv, k=2):
     for r in range(3):
         xv, yv = synth.simdr_vectors(B, K, Lv, seed=r, device=DEV, k=k)
         c, s = synth.bbox_center_scale(B, seed=3, device=DEV)
-        fns.append(lambda xv=xv, yv=yv, c=c, s=s: ops.decode_simdr(xv, yv, k, c, s))
+        fns.append(lambda xv=xv, yv=yv, c=c, s=s: ops.decode_simdr(xv, yv, k, c, s, overlap_previous=OVERLAP))
     ms = timed(fns)
     return dict(config=name, bytes=nbytes, ms=ms, gbs=nbytes / ms / 1e6, frac=nbytes / ms / 1e6 / PEAK,
                 samples_per_s=B / ms * 1e3)

@@ -458,6 +458,10 @@ def test_simdr_ring_kernel_vs_oracle(ops, L, B, K, Lx, Ly, dtype, monkeypatch):
     got0, idx0 = ops.decode_simdr(xt, yt, 2, cu(center), cu(scale), want_idx=True)
     monkeypatch.delenv("LHN_SIMDR_RING")
     assert torch.equal(idx, idx0) and np.array_equal(nump(got), nump(got0), equal_nan=True)
+    # lhn_decode_simdr_flags: back-to-back launches on disjoint outputs that may overlap (LHN_FLAG_OVERLAP_PREVIOUS)
+    outs = [ops.decode_simdr(xt, yt, 2, cu(center), cu(scale), want_idx=True, overlap_previous=True) for _ in range(4)]
+    for g_, i_ in outs:
+        assert torch.equal(i_, idx) and np.array_equal(nump(g_), nump(got), equal_nan=True)
     # no transform
     got2 = ops.decode_simdr(xt, yt, 2)
     with np.errstate(all="ignore"):
