@@ -10,7 +10,23 @@ from . import _lib as L
 _REFINE_KSIZE = {L.REFINE_DARK: 11, L.REFINE_DARK_LEGACY: 19, L.REFINE_DARK_UDP: 11}
 
 
+_DP_CACHE = {}
+
+
 def _decode_params(mask_mode, refine, transform, scale_xy=(1.0, 1.0), blur_ksize=None, use_udp=False, flags=0):
+    """lhn_decode_params for one call; the library only reads it, so equal arguments share one cached struct (building
+    it costs ~4 us of host time per launch otherwise)."""
+    key = (int(mask_mode), int(refine), int(transform), float(scale_xy[0]), float(scale_xy[1]),
+           int(blur_ksize) if blur_ksize else 0, bool(use_udp), int(flags))
+    dp = _DP_CACHE.get(key)
+    if dp is None:
+        if len(_DP_CACHE) > 256:
+            _DP_CACHE.clear()
+        dp = _DP_CACHE[key] = _build_decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp, flags)
+    return dp
+
+
+def _build_decode_params(mask_mode, refine, transform, scale_xy, blur_ksize, use_udp, flags):
     dp = L.DecodeParams()
     dp.mask_mode, dp.refine, dp.transform, dp.use_udp = int(mask_mode), int(refine), int(transform), int(bool(use_udp))
     dp.scale_x, dp.scale_y = float(scale_xy[0]), float(scale_xy[1])
@@ -58,6 +74,8 @@ def _f32c(t, name):
     if t is None:
         return None
     L.require_cuda(t, name)
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
     return t.to(torch.float32).contiguous()
 
 

@@ -37,8 +37,23 @@ def timed(fns, reps=20, warm=3):
 OVERLAP = "--overlap" in sys.argv     # consecutive launches work on disjoint buffer sets: LHN_FLAG_OVERLAP_PREVIOUS
 
 
+def as_graphs(fns):
+    """Each launch captured once into a CUDA graph and replayed: takes the Python ops layer (20-35 us of host time per
+    call, profiles/r01_configs.txt note) out of a launch-bound measurement."""
+    reps = []
+    side = torch.cuda.Stream()
+    for f in fns:
+        f()                                      # allocations + cudaFuncSetAttribute outside the capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            f()
+        reps.append(g.replay)
+    return reps
+
+
 def heatmap_case(name, B, K, H, W, dtype=torch.float32, flip=False, refine=L.REFINE_DARK, loss=True, pck=False,
-                 sets=None):
+                 sets=None, graph=False):
     esz = torch.empty((), dtype=dtype).element_size()
     nbytes = B * K * H * W * esz * (2 if flip else 1)
     sets = sets or max(2, int(600e6 // nbytes) + 1)
@@ -65,7 +80,7 @@ def heatmap_case(name, B, K, H, W, dtype=torch.float32, flip=False, refine=L.REF
             fns.append(lambda hm=hm, hf=hf, c=c, s=s, out=out:
                        out.update(ops.decode_heatmap(hm, L.MASK_NEG1, refine, L.XFORM_CENTER_SCALE, c, s, hm_flip=hf,
                                                      blur_ksize=11, out=out or None, overlap_previous=OVERLAP)))
-    ms = timed(fns)
+    ms = timed(as_graphs(fns) if graph else fns)
     return dict(config=name, bytes=nbytes, ms=ms, gbs=nbytes / ms / 1e6, frac=nbytes / ms / 1e6 / PEAK,
                 samples_per_s=B / ms * 1e3)
 
@@ -98,6 +113,9 @@ def main():
                   refine=L.REFINE_SIGN, loss=False),
         lambda: H("cfg5 21x128x128 render + loss + DARK, batch 1024/GPU f32", 1024, 21, 128, 128),
         lambda: H("56x56 (33 reference configs), render + loss + DARK, 1024x21 f32", 1024, 21, 56, 56),
+        # appended (the --only indices of the rows above are used by the probe scripts)
+        lambda: H("cfg1, the same launches replayed as CUDA graphs (no Python between launches)", 64, 21, 64, 64,
+                  refine=L.REFINE_SIGN, loss=False, sets=32, graph=True),
     ]
     only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None   # e.g. --only 5 (cfg3)
     rows = [c() for i, c in enumerate(cases) if only is None or str(i) in only]

@@ -24,6 +24,7 @@ SHAPES = [
     ("56x56 f32 (render + loss + DARK)", dict(K=21, H=56, W=56), 21 * 56 * 56 * 4),
     ("cfg4 16x64x64 decode + fused counters", dict(K=16, H=64, W=64, refine=L.REFINE_SIGN, pck=True), 262144),
     ("cfg4 shape without counters", dict(K=16, H=64, W=64, refine=L.REFINE_SIGN, loss=False), 262144),
+    ("cfg5 128x128 f32 (render + loss + DARK)", dict(K=21, H=128, W=128), 21 * 128 * 128 * 4),
 ]
 
 
@@ -35,6 +36,7 @@ def main():
         if only is not None and str(i) not in only:
             continue
         ts = []
+        batches = [256, 512, 1024] if kw["H"] >= 128 else [1024, 2048, 4096]
         for B in batches:
             r = H(name, B, sets=2 if B * bps > 300e6 else 3, **kw)
             ts.append(r["ms"] * 1e3)

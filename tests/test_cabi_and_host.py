@@ -145,12 +145,15 @@ def test_sharded_counters_and_loss_sums_over_gloo(tmp_path):
     import socket
     script = tmp_path / "gloo_worker.py"
     script.write_text(_GLOO_WORKER % {"root": ROOT})
-    with socket.socket() as sk:                       # a free rendezvous port (a fixed one can be in TIME_WAIT)
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
-                       cwd=ROOT, capture_output=True, text=True, timeout=240)
+    for attempt in range(2):                          # the port can be taken between the probe and the rendezvous
+        with socket.socket() as sk:                   # a free rendezvous port (a fixed one can be in TIME_WAIT)
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                           cwd=ROOT, capture_output=True, text=True, timeout=240)
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
 
