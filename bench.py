@@ -228,10 +228,12 @@ def run_gpu_arm(args, rank, local_rank, world):
     if use_graph:
         for b in bound:
             b.capture()
-    # N > 1 (per-rank loss): the K steps of the timed region are ONE CUDA graph of K kernel launches, so the result
-    # does not depend on how fast N Python processes sharing the host's cores can issue launches.
+    # --graph-all: the K steps of the timed region as ONE CUDA graph of K kernel launches (no Python between launches).
+    # It was the N > 1 default until the A/B of profiles/r01_graph_vs_eager.txt: a replayed graph keeps almost none of
+    # the launch overlap (N = 1: 109.0 us per step against 103.0 eager; N = 8: 108.3 against 104.8), and eight
+    # Python processes issuing one launch per 100 us do not starve anything once NVML is initialised before the barrier.
     graph_all = None
-    if world > 1 and not global_loss and not args.no_graph_all:
+    if args.graph_all and not global_loss and not args.no_graph_all:
         for i in range(3):
             bound[i % R].launch_kernel(fused.L.stream())
         torch.cuda.synchronize()
@@ -414,8 +416,10 @@ def main():
                     help="N > 1: SMs the persistent kernel leaves free so the NCCL all-reduce of the previous step "
                          "can run beside it")
     ap.add_argument("--clock-interval-ms", type=float, default=0.0, help="NVML sampling period (0 = automatic)")
+    ap.add_argument("--graph-all", action="store_true",
+                    help="run the timed steps as one CUDA graph of K launches instead of eager launches (A/B runs)")
     ap.add_argument("--no-graph-all", action="store_true",
-                    help="N > 1: issue the timed steps eagerly instead of as one CUDA graph of K launches")
+                    help="(default now: eager launches at every N; kept for old command lines)")
     ap.add_argument("--no-overlap", action="store_true", help="do not let a launch overlap the previous one's tail")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
