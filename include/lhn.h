@@ -327,7 +327,8 @@ LHN_API int lhn_mpii_pckh_accumulate(const float* pred, int pred_stride, const d
 /* Fused decode + metrics counters for the sharded evaluation (BASELINE config 4): as
  * lhn_decode_heatmap (decode only) and, per plane, the three _report_metric accumulations
  * (base_dataset.py:193-261): PCK@pck_thr / max(bbox w,h), AUC thresholds i/auc_steps / auc_nor,
- * EPE.  gt f32 [B,K,2], mask uint8 [B,K], bbox_wh f32 [B,2].
+ * EPE.  gt f32 [B,K,2], mask uint8 [B,K] (fetched as the aligned 32-bit words that hold its bytes: the
+ * buffer must be readable up to the next 4-byte boundary, which every cudaMalloc'd block is), bbox_wh f32 [B,2].
  * counters int64 [(1 + auc_steps + 4) * K] laid out as
  *   pck_hits[K], pck_valid[K], auc_hits[auc_steps][K], auc_valid[K], epe_valid[K], epe_fix[K]. */
 LHN_API int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, int H, int W,
