@@ -1,3 +1,5 @@
+# A/B script of the dropped experiment profiles/probes/r01_early_rearm_chunked_loads.patch (apply the patch first:
+# LHN_TEAM_CHUNKS only exists with it).  Output of the round-1 run: profiles/r01_early_rearm_chunked_loads.txt
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/ch_tests.log; cat gpurun_out/ch_tests.log
 echo "== chunks on (default), overlap" > gpurun_out/ch_scaling.txt
 python profiles/probes/batch_scaling.py --overlap >> gpurun_out/ch_scaling.txt 2>&1
