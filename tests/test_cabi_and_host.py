@@ -168,3 +168,18 @@ def test_bench_reference_arm_prints_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_decode_params_cache_is_keyed_on_every_field(lib_path):
+    """ops._decode_params shares one read-only struct between calls with equal arguments (host time per launch);
+    any differing field — flags included — must give a different struct."""
+    from litehandnet_b200 import _lib as L, ops
+    a = ops._decode_params(L.MASK_NEG1, L.REFINE_DARK, L.XFORM_CENTER_SCALE, blur_ksize=11)
+    b = ops._decode_params(L.MASK_NEG1, L.REFINE_DARK, L.XFORM_CENTER_SCALE, blur_ksize=11)
+    assert a is b and a.blur_ksize == 11 and abs(sum(a.taps[i] for i in range(11)) - 1.0) < 1e-12
+    c = ops._decode_params(L.MASK_NEG1, L.REFINE_DARK, L.XFORM_CENTER_SCALE, blur_ksize=11, flags=L.FLAG_OVERLAP_PREVIOUS)
+    assert c is not a and c.flags == L.FLAG_OVERLAP_PREVIOUS and a.flags == 0
+    d = ops._decode_params(L.MASK_NEG1, L.REFINE_DARK, L.XFORM_SCALE, scale_xy=(4.0, 2.0), blur_ksize=11)
+    assert d is not a and (d.scale_x, d.scale_y, d.transform) == (4.0, 2.0, L.XFORM_SCALE)
+    e = ops._decode_params(L.MASK_ZERO, L.REFINE_SIGN, L.XFORM_NONE, use_udp=True)
+    assert e.use_udp == 1 and e.mask_mode == L.MASK_ZERO and e.blur_ksize == 0
