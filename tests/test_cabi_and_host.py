@@ -137,7 +137,8 @@ assert abs(v.item() - (world + 1) / 2) < 1e-6
 s = D.all_reduce([1.0, float(rank)], device="cpu")
 assert s.tolist() == [float(world), float(sum(range(world)))]
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\n" % rank)      # ONE write: the two ranks share the pipe and print() writes piecewise
+sys.stdout.flush()
 '''
 
 
