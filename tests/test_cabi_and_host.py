@@ -137,7 +137,7 @@ assert abs(v.item() - (world + 1) / 2) < 1e-6
 s = D.all_reduce([1.0, float(rank)], device="cpu")
 assert s.tolist() == [float(world), float(sum(range(world)))]
 dist.destroy_process_group()
-sys.stdout.write("rank %d ok\n" % rank)      # ONE write: the two ranks share the pipe and print() writes piecewise
+sys.stdout.write("rank " + str(rank) + " ok\n")      # ONE write: the two ranks share the pipe and print() writes piecewise
 sys.stdout.flush()
 '''
 
