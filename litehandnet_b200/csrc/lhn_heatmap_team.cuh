@@ -1121,6 +1121,12 @@ static int dispatch_variant(HmArgs& a, int wc, int nteams, size_t smem, cudaStre
   // compile-time team size of the fixed-size paths (64x64, 56x56): stage > 16 KB (f32 + flip) -> 4 warps, else 2
   constexpr int TWF = (sizeof(T) == 4 && FLIP) ? 4 : 2;
   const bool ks11 = a.refine == LHN_REFINE_DARK && a.ksize == 11;
+  // 128x128 (hourglass / srhandnet high-resolution maps): always 8-warp teams (7 sweepers), one 64 KB stage each.
+  // On the run-time-size path this shape streamed at 85 % of the peak (profiles/r01_batch_scaling_cfg5.txt).
+  if (wc == 128 && a.team_warps == 8) {
+    if (ks11) return launch_one<T, 128, 8, FLIP, LOSS, 11>(a, nteams, smem, st);
+    return launch_one<T, 128, 8, FLIP, LOSS, 0>(a, nteams, smem, st);
+  }
   if (wc == 64 && a.team_warps == TWF) {
     if (ks11) return launch_one<T, 64, TWF, FLIP, LOSS, 11>(a, nteams, smem, st);
     return launch_one<T, 64, TWF, FLIP, LOSS, 0>(a, nteams, smem, st);
@@ -1212,7 +1218,7 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
     a.pos_radius[i] = (a.pos_value > 0.f && a.pos_value < 1.f && sg > 0)
                           ? (float)(sg * sqrt(-2.0 * log((double)a.pos_value)) * 1.001 + 0.01) : 0.f;
   }
-  const int wc = (a.W == 64 && a.H == 64) ? 64 : ((a.W == 56 && a.H == 56) ? 56 : 0);
+  const int wc = (a.W == 64 && a.H == 64) ? 64 : ((a.W == 56 && a.H == 56) ? 56 : ((a.W == 128 && a.H == 128) ? 128 : 0));
   size_t smem = (size_t)nteams * a.warp_smem;
   if (a.counters) {
     // CTA-shared metric counters after the teams' regions; drop a team if they do not fit
