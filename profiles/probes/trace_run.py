@@ -2,16 +2,16 @@ import ctypes, sys, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from litehandnet_b200 import fused, synth, _lib as L
 dev = torch.device('cuda', 0)
-B, K, H, W = 1024, 21, 64, 64
-MODE = sys.argv[1] if len(sys.argv) > 1 else 'headline'      # headline | noflip | bf16
+MODE = sys.argv[1] if len(sys.argv) > 1 else 'headline'      # headline | noflip | bf16 | p56 | cfg5 (last two: no flip)
+B, K, H, W = {'p56': (1024, 21, 56, 56), 'cfg5': (256, 21, 128, 128)}.get(MODE, (1024, 21, 64, 64))
 DT = torch.bfloat16 if MODE == 'bf16' else torch.float32
 print('mode', MODE)
-step = fused.FusedHeatmapStep((256, 256), sigma=2, unbiased_encoding=True, balance=True, post_process='unbiased', kernel=11)
+step = fused.FusedHeatmapStep((4 * W, 4 * H), sigma=2.0 * W / 64, unbiased_encoding=True, balance=True, post_process='unbiased', kernel=11)
 sets = []
 for r in range(2):
     hm, cen = synth.blob_heatmaps(B, K, H, W, seed=10 * r, device=dev, dtype=DT)
-    hf = None if MODE == 'noflip' else synth.flipped_blob_heatmaps(cen, H, W, seed=10 * r + 1, device=dev, dtype=DT)
-    j, v = synth.hand_joints(B, K, (256, 256), seed=10 * r + 2, device=dev)
+    hf = None if MODE in ('noflip', 'p56', 'cfg5') else synth.flipped_blob_heatmaps(cen, H, W, seed=10 * r + 1, device=dev, dtype=DT)
+    j, v = synth.hand_joints(B, K, (4 * W, 4 * H), seed=10 * r + 2, device=dev)
     c, s = synth.bbox_center_scale(B, seed=10 * r + 3, device=dev)
     sets.append(fused.BoundFusedStep(step, hm, j, v, c, s, hm_flip=hf))
 for i in range(6):
