@@ -187,6 +187,44 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def parity_block(bound, sets, epoch_local, steps, R):
+    """Outputs of the MEASURED path (the bound steps' buffers as the timed loop left them) against the reference's
+    CPU pipeline (oracle.cpu_path.FusedCpuRunner: TopDownGenerateTarget -> DistanceLoss(balance) -> flip average ->
+    keypoints_from_heatmaps('unbiased')) on every sample of every rotating set: argmax indices bit-exact,
+    coordinates |a-b| <= 2e-5 + 1e-5 |b| element-wise, loss 1e-5 relative (north_star)."""
+    import numpy as np
+    from oracle import cpu_path
+    idx_equal, coord_ok, max_rel, loss_rel, n = True, True, 0.0, 0.0, 0
+    ref_losses = []
+    for r in range(R):
+        b = bound[r]
+        runner = cpu_path.FusedCpuRunner(*[t.cpu().numpy() for t in sets[r]], image_size=IMAGE_SIZE, sigma=2, kernel=11)
+        try:
+            with np.errstate(all="ignore"):
+                preds, loss, _ = runner.run()
+            ridx = runner.last_idx
+        finally:
+            runner.close()
+        ref_losses.append(float(loss))
+        got = b.preds.cpu().numpy()
+        idx_equal &= bool(np.array_equal(b.idx.cpu().numpy(), ridx))
+        d = np.abs(got[..., :2].astype(np.float64) - preds[..., :2])
+        coord_ok &= bool((d <= 2e-5 + 1e-5 * np.abs(preds[..., :2])).all())
+        coord_ok &= bool(np.array_equal(got[..., 2], preds[..., 2], equal_nan=True))
+        max_rel = max(max_rel, float((d / np.maximum(np.abs(preds[..., :2]), 1.0)).max()))
+        n += preds.shape[0]
+        if epoch_local is None:
+            loss_rel = max(loss_rel, abs(float(b.loss.item()) - float(loss)) / abs(float(loss)))
+    if epoch_local is not None:       # accumulated over the timed steps: sum of the per-step reference losses
+        want = sum(ref_losses[i % R] for i in range(steps))
+        loss_rel = abs(epoch_local - want) / abs(want)
+    ok = idx_equal and coord_ok and loss_rel <= (1e-5 if epoch_local is None else 5e-5)
+    return {"ok": ok, "idx_equal": idx_equal, "coord_max_rel": max_rel, "coord_within_1e-5": coord_ok,
+            "loss_rel": loss_rel, "samples": n,
+            "against": "oracle.cpu_path.FusedCpuRunner (reference CPU pipeline restated) on every sample of the "
+                       "rotating sets, outputs as left by the timed loop, rank 0"}
+
+
 # ---- GPU arm -----------------------------------------------------------------------------------------
 def run_gpu_arm(args, rank, local_rank, world):
     import torch

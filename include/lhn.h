@@ -314,6 +314,15 @@ LHN_API int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_stride
                                int K, const float* thr /* host, T floats */, int T,
                                int64_t* counters, lhn_stream_t stream);
 
+/* Kpt2dDataset._report_metric's final ratios (datasets/base_dataset.py:193-261) from the fused counter block of
+ * lhn_decode_heatmap_pck / MetricAccumulator, on the device: no device->host copy or sync per metric call.
+ * counters int64 [(auc_steps+5)*K] (after the cross-rank ncclSum, if sharded).
+ * out f64 [3 + K]: out[0] = PCK = keypoint_pck_accuracy's avg_acc (top_down_eval.py:65-101: mean of the per-joint
+ * hits/valid that are >= 0, numpy's pairwise summation order), out[1] = keypoint_auc (:167-196: sum_t avg_acc_t /
+ * auc_steps), out[2] = EPE (:104-126, from the 2^-20 px fixed-point sum), out[3..3+K) = the per-joint PCK
+ * accuracies (-1 where a joint has no valid sample).  K <= 128.  f64 results equal the host expressions exactly. */
+LHN_API int lhn_metrics_finalize(const int64_t* counters, int K, int auc_steps, double* out, lhn_stream_t stream);
+
 /* MPII PCKh counters (datasets/datasets/body/topdown_mpii_dataset.py:186-214, duplicate in
  * topdown_mpii_action_dataset.py:176-204): pred f32 [N,K,pred_stride] 0-based (the kernel adds the reference's
  * +1.0 in f32), gt f64 [N,K,2] (pos_gt_src transposed), head f64 [N,4] = (x1,y1,x2,y2) of headboxes_src,

@@ -33,7 +33,7 @@ EXPORTS = [
     "lhn_version", "lhn_last_cuda_error", "lhn_gaussian_taps", "lhn_decode_heatmap",
     "lhn_decode_heatmap_pck", "lhn_loss_partials", "lhn_loss_reduce", "lhn_loss_finalize",
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_decode_simdr_flags", "lhn_simdr_loss_workspace_bytes",
-    "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_evaluate_pck_workspace_bytes",
+    "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
     "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate", "lhn_region_bbox_decode", "lhn_heatmap_nms",
@@ -106,6 +106,7 @@ def _declare(lib):
     lib.lhn_simdr_smoothl1.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, vp, i64, vp, vp]
     lib.lhn_pck_accumulate.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, i32, f64, i64, i32,
                                        C.POINTER(C.c_float), i32, vp, vp]
+    lib.lhn_metrics_finalize.argtypes = [vp, i32, i32, vp, vp]
     lib.lhn_evaluate_pck_workspace_bytes.argtypes = [i64, i32]
     lib.lhn_evaluate_pck_workspace_bytes.restype = i64
     lib.lhn_evaluate_pck.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, f32, f32, f32, vp, i64,
@@ -159,8 +160,31 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    """Raw handle of torch's current stream on `device` (default: the current device; ops wrappers run under a
+    guard for their tensors' device, so the default is that device)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class on_device:
+    """`with on_device(dev):` — no-op when `dev` is already current, else torch.cuda.device(dev).  The library
+    launches on the CURRENT device, so every launch on tensors of another device must run under this."""
+    __slots__ = ("dev", "ctx")
+
+    def __init__(self, dev):
+        self.dev, self.ctx = dev, None
+
+    def __enter__(self):
+        if self.dev.index is not None and self.dev.index != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(self.dev)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+        return False
 
 
 def dtype_code(t):

@@ -119,6 +119,8 @@ struct TeamHeader {
   float side[8][12];
 };
 constexpr int kSideAhead = 4;
+// overlapped launches: team 0's epilogue warp lets the successor grid in after this many of its planes (see the kernel)
+constexpr int kTriggerPlane = 2;
 // SD_MASK: the aligned 32-bit word that holds the plane's fused-metrics mask byte (cp.async moves >= 4 bytes)
 enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_MASK, SD_N };
 
@@ -244,9 +246,16 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cta_cnt[i] = 0ull;
   if (threadIdx.x == 0 && !LOSS && a.counters) *cta_done = 0u;
 
-  // Let the next launch on the stream (if it was launched with LHN_FLAG_OVERLAP_PREVIOUS) take over SMs as
-  // this grid's CTAs retire; a no-op otherwise.
-  asm volatile("griddepcontrol.launch_dependents;");
+  // Programmatic dependent launch.  A launch WITHOUT the overlap flag is ordered after everything before it on
+  // the stream (a normal launch), so it lets its successor in at once.  A launch WITH the flag (promise: it
+  // shares no buffer with the launch just before it) must not let ITS successor in before the launch two back
+  // has completed: with two rotating buffer sets that one writes the successor's outputs, and small grids
+  // (n_planes < SMs, spare SMs, little shared memory) could otherwise be co-resident three deep.  So in an
+  // overlapped launch only the epilogue warp of team 0 triggers, after griddepcontrol.wait (= the predecessor
+  // grid has completed and its writes are visible), a few planes into its loop — by then the predecessor is
+  // long gone, and with one CTA per SM the successor cannot get an SM before this CTA retires anyway, so the
+  // late trigger costs nothing.  Net contract: an overlapped launch runs after everything but its predecessor.
+  if (!a.overlap_previous) asm volatile("griddepcontrol.launch_dependents;");
 
   // ---- one-time setup: barriers visible to the whole CTA before anybody waits on them ------------------
   if (wt == 0 && lane == 0) {
@@ -664,6 +673,14 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       TRE(12);
       __syncwarp();
       if (lane == 0) mbar_arrive(&th->empty[buf]);   // release: record/tile buffer free, tables of n+2 ready
+      if (a.overlap_previous && team == 0 && n_it == kTriggerPlane) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+      }
+    }
+    if (a.overlap_previous && team == 0 && n_it <= kTriggerPlane) {   // fewer planes than that: trigger at the end
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("griddepcontrol.launch_dependents;");
     }
 
     if (has_counters) {
@@ -1085,15 +1102,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-static int g_sm_count = 0;
-static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    g_sm_count = n > 0 ? n : 148;
-  }
-  return g_sm_count;
-}
+int num_sms();                       // lhn_loss_render.cu: SM count of the current device, cached per device
+static int sm_count() { return num_sms(); }
 
 template <typename T, int WC, int TWC, bool FLIP, bool LOSS, int KS>
 static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {

@@ -10,14 +10,17 @@
 
 namespace lhn {
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device, cached per device (a process may drive several GPUs)
+static int g_num_sms[64] = {0};
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    g_num_sms = n > 0 ? n : 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (g_num_sms[dev] == 0) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms[dev] = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return g_num_sms[dev];
 }
 
 // ---- loss partials against an explicit target (heatmapLoss.py:242-265, :195-225) -------------

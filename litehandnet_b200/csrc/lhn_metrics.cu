@@ -186,6 +186,59 @@ extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_str
   return check_launch();
 }
 
+// ---- _report_metric's final ratios on the device (no host round trip) ---------------------------------------
+// One warp.  np.mean of the valid per-joint accuracies is numpy's pairwise sum (n < 8: sequential; n <= 128:
+// eight strided accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail sequentially)
+// divided by the count — restated literally so the f64 results equal the host expressions bit for bit.
+__device__ double np_mean_valid(const double* acc, int n) {
+  if (n <= 0) return 0.0;                       // keypoint_pck_accuracy: avg_acc = 0 when no joint is valid
+  double res;
+  if (n < 8) {
+    res = 0.0;
+    for (int i = 0; i < n; ++i) res += acc[i];
+  } else {
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = acc[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += acc[i + j];
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += acc[i];
+  }
+  return res / (double)n;
+}
+
+constexpr int kMaxFinalizeJoints = 128;         // numpy's pairwise block: above it the summation tree changes
+
+__global__ void metrics_finalize_kernel(const long long* __restrict__ c, int K, int T, double* __restrict__ out) {
+  // counters: pck_hits[K], pck_valid[K], auc_hits[T][K], auc_valid[K], epe_valid[K], epe_fix[K]
+  __shared__ double acc[kMaxFinalizeJoints];
+  if (threadIdx.x != 0) return;
+  auto avg_acc = [&](const long long* hits, const long long* valid, double* per_joint) {
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+      const double a = valid[k] > 0 ? (double)hits[k] / (double)valid[k] : -1.0;     // _distance_acc
+      if (per_joint) per_joint[k] = a;
+      if (a >= 0.0) acc[n++] = a;
+    }
+    return np_mean_valid(acc, n);
+  };
+  out[0] = avg_acc(c, c + K, out + 3);                                                 // PCK (+ acc[K])
+  double auc = 0.0;
+  for (int t = 0; t < T; ++t) auc += 1.0 / (double)T * avg_acc(c + (int64_t)(2 + t) * K, c + (int64_t)(2 + T) * K, nullptr);
+  out[1] = auc;                                                                        // keypoint_auc
+  long long cnt = 0, fix = 0;
+  for (int k = 0; k < K; ++k) { cnt += c[(int64_t)(3 + T) * K + k]; fix += c[(int64_t)(4 + T) * K + k]; }
+  out[2] = ((double)fix / 1048576.0) / (double)(cnt > 1 ? cnt : 1);                    // EPE from the fixed-point sum
+}
+
+extern "C" int lhn_metrics_finalize(const int64_t* counters, int K, int auc_steps, double* out, lhn_stream_t stream) {
+  if (!counters || !out || K <= 0 || K > kMaxFinalizeJoints || auc_steps < 0) return LHN_EINVAL;
+  metrics_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(counters), K,
+                                                             auc_steps, out);
+  return check_launch();
+}
+
 extern "C" int64_t lhn_evaluate_pck_workspace_bytes(int64_t B, int K) {
   if (B < 0 || K <= 0) return LHN_EINVAL;
   return 2 * B * K * 3 * (int64_t)sizeof(float);

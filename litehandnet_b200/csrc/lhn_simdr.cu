@@ -221,19 +221,23 @@ __global__ void __launch_bounds__(256, 6) decode_simdr_kernel(const T* __restric
 // peak and 16 or 24 warps at 90 % (the grid-stride kernel: 82 %).
 constexpr int kRingWarps = 16;
 constexpr int kRingMaxStages = 4;
+constexpr int kRingTriggerPair = 8;   // overlapped launches: warp 0 lets the successor grid in after this many pairs
 
 template <typename T>
 __global__ void __launch_bounds__(1024, 1)
 decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int64_t n_bk, int K, int Lx, int Ly, int k,
                          const float* __restrict__ center, const float* __restrict__ scale, float* __restrict__ out,
-                         int32_t* __restrict__ out_idx, int nstg, int pair_al) {
+                         int32_t* __restrict__ out_idx, int nstg, int pair_al, int overlap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * nstg * pair_al;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * nstg * pair_al) + warp * kRingMaxStages;
   const uint32_t xbytes = (uint32_t)Lx * sizeof(T), ybytes = (uint32_t)Ly * sizeof(T);
-  // the next launch on the stream, if it carries LHN_FLAG_OVERLAP_PREVIOUS, takes over SMs as these CTAs retire
-  asm volatile("griddepcontrol.launch_dependents;");
+  // The next launch on the stream, if it carries LHN_FLAG_OVERLAP_PREVIOUS, takes over SMs as these CTAs retire.
+  // A launch that itself overlaps its predecessor lets its successor in only after the predecessor has completed
+  // (warp 0: griddepcontrol.wait, then the trigger, a few pairs into its loop), so launch i + 2 never runs beside
+  // launch i — the rule that makes two rotating buffer sets sufficient (same scheme as lhn_heatmap_team.cuh).
+  if (!overlap) asm volatile("griddepcontrol.launch_dependents;");
   if (lane == 0) {
     for (int s = 0; s < nstg; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
@@ -255,7 +259,7 @@ decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int
       if (pair < n_bk) issue(s, pair);
     }
   const int nqx = Lx >> 2, nqy = Ly >> 2, nq = nqx > nqy ? nqx : nqy;
-  int s = 0;
+  int s = 0, n_done = 0;
   uint32_t ph = 0;
   // b = bk / K advanced incrementally (the only 64-bit divisions: once per warp)
   int64_t b = gw / K;
@@ -287,6 +291,14 @@ decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int
       simdr_store(ix, iy, mx, my, k, dv, center != nullptr, cx, cy, sc0, sc1, out, out_idx, bk);
     }
     if (++s == nstg) { s = 0; ph ^= 1u; }
+    if (overlap && warp == 0 && ++n_done == kRingTriggerPair) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("griddepcontrol.launch_dependents;");
+    }
+  }
+  if (overlap && warp == 0 && n_done < kRingTriggerPair) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
   }
 }
 
@@ -386,9 +398,10 @@ static int launch_simdr(const void* xv, const void* yv, int64_t n_bk, int K, int
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = (flags & LHN_FLAG_OVERLAP_PREVIOUS) ? 1 : 0;
+      const int overlap = (flags & LHN_FLAG_OVERLAP_PREVIOUS) ? 1 : 0;
+      cfg.attrs = at; cfg.numAttrs = overlap;
       e = cudaLaunchKernelEx(&cfg, decode_simdr_ring_kernel<T>, (const T*)xv, (const T*)yv, n_bk, K, Lx, Ly, k, center, scale,
-                             out, out_idx, nstg, (int)pair_al);
+                             out, out_idx, nstg, (int)pair_al, overlap);
       if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
       return check_launch();
     }

@@ -91,9 +91,11 @@ class HostPipeline:
     land in one buffer so the balanced loss still uses batch-global counts; the [B,K,3] predictions and
     the loss scalar are copied back device->host at the end.
 
-    h2d_bytes / d2h_bytes report what one call moves."""
+    h2d_bytes / d2h_bytes report what one call moves.  Inputs may be pinned host tensors (fastest: truly
+    asynchronous copies), pageable host tensors or NumPy arrays (what a reference caller holds; the driver then
+    stages each copy itself).  want_idx adds the int32 argmax indices to the device->host read."""
 
-    def __init__(self, step, B, K, H, W, dtype=torch.float32, flip=True, chunks=8, device="cuda"):
+    def __init__(self, step, B, K, H, W, dtype=torch.float32, flip=True, chunks=8, device="cuda", want_idx=False):
         self.step, self.B, self.K, self.H, self.W = step, B, K, H, W
         self.flip = flip
         self.dev = torch.device(device)
@@ -114,29 +116,45 @@ class HostPipeline:
         self.d_hmk = torch.empty((B, K, 3), device=self.dev)
         self.d_weight = torch.empty((B, K), device=self.dev)
         self.d_loss = torch.empty(1, device=self.dev)
+        self.flip_index = flip_index_from_pairs(K, step.flip_pairs, self.dev) if (flip and step.flip_pairs) else None
+        self.want_idx = bool(want_idx)
+        self.d_idx = torch.empty((B, K), dtype=torch.int32, device=self.dev) if want_idx else None
+        self.h_idx = torch.empty((B, K), dtype=torch.int32, pin_memory=True) if want_idx else None
+        self.has_loss = step.loss_mode != L.LOSS_NONE
         self.h_preds = torch.empty((B, K, 3), pin_memory=True)
         self.h_loss = torch.empty(1, pin_memory=True)
         self.copied = [torch.cuda.Event() for _ in self.bounds]
         self.freed = [torch.cuda.Event() for _ in range(2)]
         esz = torch.empty((), dtype=dtype).element_size()
         self.h2d_bytes = B * K * H * W * esz * (2 if flip else 1) + B * (K * 3 * 4 * 2 + 16)
-        self.d2h_bytes = B * K * 3 * 4 + 4
+        if not self.has_loss:
+            self.h2d_bytes = B * K * H * W * esz * (2 if flip else 1) + B * 16
+        self.d2h_bytes = B * K * 3 * 4 + (4 if self.has_loss else 0) + (B * K * 4 if want_idx else 0)
         self.launches = 0
 
     def __call__(self, hm, hm_flip, joints, vis, center, scale):
-        """All arguments are pinned HOST tensors.  Returns (h_preds [B,K,3], h_loss [1]) host tensors,
-        valid after the call returns (it synchronises on the final device->host copy)."""
+        """All arguments are HOST tensors / arrays (hm_flip None when flip=False; joints and vis may be None for a
+        decode-only step).  Returns (h_preds [B,K,3], h_loss [1] or None) host tensors — and h_idx in `self.h_idx`
+        when want_idx — valid after the call returns (it synchronises on the final device->host copy)."""
         step = self.step
+
+        def host(t):
+            return t if (t is None or isinstance(t, torch.Tensor)) else torch.as_tensor(t)
+
+        hm, hm_flip, joints, vis, center, scale = (host(t) for t in (hm, hm_flip, joints, vis, center, scale))
+        if hm.shape[0] != self.B or (self.flip and (hm_flip is None or hm_flip.shape != hm.shape)):
+            raise L.LhnError("HostPipeline: heatmap batch does not match the bound shape")
         comp = torch.cuda.current_stream(self.dev)
         cs = self.copy_stream
         cs.wait_stream(comp)
         with torch.cuda.stream(cs):
-            self.d_joints.copy_(joints, non_blocking=True)
-            self.d_vis.copy_(vis, non_blocking=True)
+            if self.has_loss:
+                self.d_joints.copy_(joints, non_blocking=True)
+                self.d_vis.copy_(vis, non_blocking=True)
             self.d_center.copy_(center, non_blocking=True)
             self.d_scale.copy_(scale, non_blocking=True)
         render = dict(loss_mode=step.loss_mode, image_size=step.image_size, sigma=step.sigma,
-                      unbiased=step.unbiased, pos_value=step.pos_value)
+                      unbiased=step.unbiased, pos_value=step.pos_value) if self.has_loss else None
         self.launches = 0
         for i, (a, b) in enumerate(self.bounds):
             slot = i & 1
@@ -149,22 +167,29 @@ class HostPipeline:
                     self.d_hf[slot][:n].copy_(hm_flip[a:b], non_blocking=True)
                 self.copied[i].record(cs)
             comp.wait_event(self.copied[i])
+            out = dict(kpts=self.d_preds[a:b], hm_kpts=self.d_hmk[a:b])
+            if self.has_loss:
+                out.update(partials=self.d_partials[a * self.K:b * self.K], weight=self.d_weight[a:b])
+            if self.want_idx:
+                out["idx"] = self.d_idx[a:b]
             ops.decode_heatmap(self.d_hm[slot][:n], L.MASK_NEG1, step.refine, L.XFORM_CENTER_SCALE,
                                self.d_center[a:b], self.d_scale[a:b],
-                               hm_flip=self.d_hf[slot][:n] if self.flip else None,
-                               blur_ksize=step.kernel, want_idx=False, render=render,
-                               joints=self.d_joints[a:b], vis=self.d_vis[a:b],
-                               out=dict(partials=self.d_partials[a * self.K:b * self.K], kpts=self.d_preds[a:b],
-                                        hm_kpts=self.d_hmk[a:b], weight=self.d_weight[a:b]))
+                               hm_flip=self.d_hf[slot][:n] if self.flip else None, flip_index=self.flip_index,
+                               blur_ksize=step.kernel, want_idx=self.want_idx, render=render,
+                               joints=self.d_joints[a:b] if self.has_loss else None,
+                               vis=self.d_vis[a:b] if self.has_loss else None, out=out)
             self.freed[slot].record(comp)
             self.launches += 1
-        sums = ops.loss_reduce(self.d_partials)
-        ops.loss_finalize(sums, step.loss_mode, "mean", step.loss_weight, out=self.d_loss)
-        self.launches += 2
+        if self.has_loss:
+            sums = ops.loss_reduce(self.d_partials)
+            ops.loss_finalize(sums, step.loss_mode, "mean", step.loss_weight, out=self.d_loss)
+            self.launches += 2
+            self.h_loss.copy_(self.d_loss, non_blocking=True)
         self.h_preds.copy_(self.d_preds, non_blocking=True)
-        self.h_loss.copy_(self.d_loss, non_blocking=True)
+        if self.want_idx:
+            self.h_idx.copy_(self.d_idx, non_blocking=True)
         comp.synchronize()
-        return self.h_preds, self.h_loss
+        return self.h_preds, (self.h_loss if self.has_loss else None)
 
 
 class BoundFusedStep:
@@ -174,17 +199,26 @@ class BoundFusedStep:
     launch-bound at ~0.1 ms of GPU work per step)."""
 
     def __init__(self, step, hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None,
-                 finalize=True, overlap_previous=False, spare_sms=0, accumulate_into=None):
+                 finalize=True, overlap_previous=False, spare_sms=0, accumulate_into=None, outputs=None):
         """overlap_previous: this step shares no buffer with the step launched just before it on the stream
-        (rotating input/output sets), so its kernel may start while that one drains (LHN_FLAG_OVERLAP_PREVIOUS).
+        (rotating input/output sets), so its kernel may start while that one drains (LHN_FLAG_OVERLAP_PREVIOUS);
+        it is still ordered after every EARLIER launch, so two rotating sets are enough.
         accumulate_into: f32 [1] device tensor that receives ``+= loss`` of every step (the epoch sum that
-        train_one_epoch keeps in loss_dict['sum'], left on the device; LHN_FLAG_ACCUMULATE_LOSS)."""
+        train_one_epoch keeps in loss_dict['sum'], left on the device; LHN_FLAG_ACCUMULATE_LOSS).
+        outputs: optional dict of caller-owned contiguous output tensors (hm_preds / preds f32 [B,K,3], idx int32
+        [B,K], weight f32 [B,K], sums f64 [4], loss f32 [1]; larger leading sizes are fine) — e.g. the other
+        output set of a rotation whose steps have different batch sizes."""
         import ctypes as C
         self.step = step
         lib = L.lib()
         self._lib = lib
         hm, B, Cc, H, W, sb, sc = ops._plane_view(hm, "heatmaps")
         dev = hm.device
+        self.dev = dev
+        for name, t in (("hm_flip", hm_flip), ("joints_3d", joints_3d), ("joints_3d_visible", joints_3d_visible),
+                        ("center", center), ("scale", scale), ("accumulate_into", accumulate_into)):
+            if t is not None and t.device != dev:
+                raise L.LhnError(f"{name} is on {t.device}, the heatmaps on {dev}")
         self.B, self.K, self.H, self.W = B, Cc, H, W
         fb = fc = 0
         if hm_flip is not None:
@@ -204,18 +238,32 @@ class BoundFusedStep:
                                      (L.FLAG_ACCUMULATE_LOSS if accumulate_into is not None else 0) |
                                      ((int(spare_sms) & 0xff) << 8))
         self.rp = ops._render_params(step.loss_mode, step.image_size, step.sigma, step.unbiased, step.pos_value)
-        self.hm_preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
-        self.preds = torch.empty((B, Cc, 3), dtype=torch.float32, device=dev)
-        self.idx = torch.empty((B, Cc), dtype=torch.int32, device=dev)
-        self.weight = torch.empty((B, Cc), dtype=torch.float32, device=dev)
+        outputs = outputs or {}
+
+        def _out(name, shape, dtype):
+            t = outputs.get(name)
+            if t is None:
+                return torch.empty(shape, dtype=dtype, device=dev)
+            n = 1
+            for d in shape:
+                n *= d
+            if t.dtype != dtype or t.device != dev or not t.is_contiguous() or t.numel() < n:
+                raise L.LhnError(f"output '{name}' has the wrong dtype/device/layout or is too small")
+            return t
+
+        self.hm_preds = _out("hm_preds", (B, Cc, 3), torch.float32)
+        self.preds = _out("preds", (B, Cc, 3), torch.float32)
+        self.idx = _out("idx", (B, Cc), torch.int32)
+        self.weight = _out("weight", (B, Cc), torch.float32)
         self.partials = torch.empty((B * Cc, 4), dtype=torch.float64, device=dev)
-        self.sums = torch.empty(4, dtype=torch.float64, device=dev)
-        self.loss = torch.empty(1, dtype=torch.float32, device=dev) if accumulate_into is None else accumulate_into
+        self.sums = _out("sums", (4,), torch.float64)
+        self.loss = _out("loss", (1,), torch.float32) if accumulate_into is None else accumulate_into
         self.finalize = finalize
         # one-launch step: the kernel reduces the loss sums itself; `finalize=False` (multi-GPU) leaves the
         # f64 sums for the cross-rank all-reduce and finalises afterwards with launch_finalize()
-        self.workspace = torch.zeros(int(lib.lhn_fused_workspace_bytes(B, Cc // self.rp.num_stacks, self.rp.num_stacks)),
-                                     dtype=torch.uint8, device=dev)
+        with L.on_device(dev):       # the workspace size depends on the device's SM count
+            nbytes = int(lib.lhn_fused_workspace_bytes(B, Cc // self.rp.num_stacks, self.rp.num_stacks))
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self._fused_args = (
             L.ptr(hm), L.ptr(hm_flip), L.ptr(fi), L.dtype_code(hm), B, Cc // self.rp.num_stacks, H, W, sb, sc, fb, fc,
             L.ptr(center), L.ptr(scale), C.byref(self.dp), L.ptr(self.hm_preds), L.ptr(self.preds),
@@ -246,14 +294,19 @@ class BoundFusedStep:
         L.check(self._lib.lhn_loss_finalize(self._p_sums, self.step.loss_mode, 0, self.step.loss_weight,
                                             self._p_loss, 0, stream), "lhn_loss_finalize")
 
+    def stream(self):
+        """torch's current stream on this step's device, as the raw handle the C ABI takes."""
+        return L.stream(self.dev)
+
     def launch(self, events=None):
-        """Issue the step on the current stream.  events=(before, after) brackets the fused kernel."""
-        st = L.stream()
-        if events is not None:
-            events[0].record()
-        self.launch_kernel(st)
-        if events is not None:
-            events[1].record()
+        """Issue the step on the current stream of the step's device.  events=(before, after) brackets the kernel."""
+        with L.on_device(self.dev):
+            st = L.stream(self.dev)
+            if events is not None:
+                events[0].record()
+            self.launch_kernel(st)
+            if events is not None:
+                events[1].record()
 
     def capture(self):
         """Record the step into a CUDA graph (warm-up launch first so attributes are set eagerly)."""

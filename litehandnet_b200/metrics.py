@@ -111,8 +111,18 @@ class MetricAccumulator:
             dist.all_reduce(self.counters, op=dist.ReduceOp.SUM, group=group)
         return self.counters
 
-    def compute(self, metrics=("PCK", "AUC", "EPE")):
-        """-> OrderedDict like dataset.evaluate() (freihand_dataset.py:177-178)."""
+    def compute_device(self):
+        """f64 [3 + K] device tensor (PCK, AUC, EPE, per-joint PCK accuracies): lhn_metrics_finalize, no sync and
+        no device->host copy — for loops that log or all-gather the metrics without leaving the stream."""
+        return ops.metrics_finalize(self.counters, self.K, self.steps)
+
+    def compute(self, metrics=("PCK", "AUC", "EPE"), on_device=False):
+        """-> OrderedDict like dataset.evaluate() (freihand_dataset.py:177-178).  on_device=True takes the ratios
+        from lhn_metrics_finalize (one 24-byte device->host read) instead of finishing the counters in NumPy;
+        the two are bit-identical."""
+        if on_device:
+            v = self.compute_device()[:3].cpu().numpy()
+            return OrderedDict((m, float(v[i])) for i, m in enumerate(("PCK", "AUC", "EPE")) if m in metrics)
         K, T = self.K, self.steps
         c = self.counters.cpu().numpy().reshape(T + 5, K)
         out = OrderedDict()

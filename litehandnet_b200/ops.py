@@ -2,10 +2,46 @@
 on ``torch.cuda.current_stream()`` and returns CUDA tensors; nothing here synchronises or falls back.
 """
 import ctypes as C
+import functools
 
 import torch
 
 from . import _lib as L
+
+
+def _cuda_tensors(values):
+    for v in values:
+        if isinstance(v, torch.Tensor):
+            if v.is_cuda:
+                yield v
+        elif isinstance(v, dict):
+            yield from _cuda_tensors(v.values())
+
+
+def _on_device(fn):
+    """Run the wrapped launch on the device of its tensors: all CUDA tensor arguments must live on ONE device;
+    if that is not the current device the call runs under ``torch.cuda.device(dev)``, so the library's launch,
+    ``torch.cuda.current_stream()`` (L.stream()) and every output allocation refer to the tensors' device — the
+    reference calls set_device only in its DDP entry points, a single process may well drive several GPUs."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = None
+        for t in _cuda_tensors(args):
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise L.LhnError(f"{fn.__name__}: tensors on different devices ({dev} and {t.device})")
+        for t in _cuda_tensors(kw.values()):
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise L.LhnError(f"{fn.__name__}: tensors on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
+
 
 _REFINE_KSIZE = {L.REFINE_DARK: 11, L.REFINE_DARK_LEGACY: 19, L.REFINE_DARK_UDP: 11}
 
@@ -79,6 +115,7 @@ def _f32c(t, name):
     return t.to(torch.float32).contiguous()
 
 
+@_on_device
 def decode_heatmap(hm, mask_mode, refine, transform=L.XFORM_NONE, center=None, scale=None,
                    scale_xy=(1.0, 1.0), hm_flip=None, flip_index=None, blur_ksize=None, use_udp=False,
                    want_idx=True, render=None, joints=None, vis=None, out=None, overlap_previous=False):
@@ -174,6 +211,7 @@ def fused_workspace(device, B, K, S=1, stream_key=None):
     return ws
 
 
+@_on_device
 def fused_render_loss_decode(hm, mask_mode, refine, transform, center, scale, render, joints, vis,
                              hm_flip=None, flip_index=None, blur_ksize=None, use_udp=False, scale_xy=(1.0, 1.0),
                              want_idx=True, want_partials=False, reduction="mean", loss_scale=1.0,
@@ -255,6 +293,7 @@ def _mask_u8(mask):
     return (mask != 0).contiguous().view(torch.uint8)
 
 
+@_on_device
 def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, counters,
                        pck_thr=0.2, auc_nor=30.0, auc_steps=20, blur_ksize=None, overlap_previous=False):
     """K1 + fused PCK/AUC/EPE counters (BASELINE config 4).  `counters` int64 [(auc_steps+5)*K] is
@@ -280,6 +319,7 @@ def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, 
     return dict(hm_kpts=out_hm, kpts=out_k, idx=out_idx)
 
 
+@_on_device
 def loss_partials(output, target, weight, loss_mode, pos_value=0.5):
     """Per-plane sums of DistanceLoss / JointsDistanceLoss against an explicit target tensor."""
     L.require_cuda(output, "output")
@@ -308,6 +348,7 @@ def _grad_out_ptr(grad_out, device):
     return g, L.ptr(g)
 
 
+@_on_device
 def loss_backward(output, target, weight, loss_mode, sums, pos_value=0.5, reduction="mean", scale=1.0,
                   grad_out=None):
     """d loss / d output for the explicit-target losses (lhn_loss_backward); returns a tensor like output."""
@@ -328,6 +369,7 @@ def loss_backward(output, target, weight, loss_mode, sums, pos_value=0.5, reduct
     return grad
 
 
+@_on_device
 def render_loss_backward(hm, joints, vis, render, sums, reduction="mean", scale=1.0, grad_out=None):
     """d loss / d hm for the fused (render-in-kernel) losses (lhn_render_loss_backward)."""
     hm_v, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
@@ -347,6 +389,7 @@ def render_loss_backward(hm, joints, vis, render, sums, reduction="mean", scale=
     return grad
 
 
+@_on_device
 def simdr_smoothl1_backward(out_x, out_y, tgt_x, tgt_y, weight, scale=1.0, grad_out=None):
     dt = out_x.dtype
     out_x, out_y = out_x.contiguous(), out_y.to(dt).contiguous()
@@ -365,6 +408,7 @@ def simdr_smoothl1_backward(out_x, out_y, tgt_x, tgt_y, weight, scale=1.0, grad_
     return gx, gy
 
 
+@_on_device
 def loss_reduce(partials, sums=None, accumulate=False):
     if sums is None:
         sums = torch.empty(4, dtype=torch.float64, device=partials.device)
@@ -373,6 +417,7 @@ def loss_reduce(partials, sums=None, accumulate=False):
     return sums
 
 
+@_on_device
 def loss_finalize(sums, loss_mode, reduction="mean", scale=1.0, out=None, accumulate=False):
     if out is None:
         out = torch.empty(1, dtype=torch.float32, device=sums.device)
@@ -381,6 +426,7 @@ def loss_finalize(sums, loss_mode, reduction="mean", scale=1.0, out=None, accumu
     return out
 
 
+@_on_device
 def render_targets(joints, vis, image_size, heatmap_size, sigma, unbiased=True):
     """Batched TopDownGenerateTarget: target [B,(S,)K,H,W] f32, target_weight [B,(S,)K,1] f32."""
     joints = _f32c(joints, "joints")
@@ -401,6 +447,7 @@ def render_targets(joints, vis, image_size, heatmap_size, sigma, unbiased=True):
     return target, tw
 
 
+@_on_device
 def render_simdr(joints, vis, image_size, k=2, sigma=2):
     joints = _f32c(joints, "joints")
     vis = _f32c(vis, "vis")
@@ -416,6 +463,7 @@ def render_simdr(joints, vis, image_size, k=2, sigma=2):
     return sx, sy
 
 
+@_on_device
 def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=None, want_idx=False,
                  overlap_previous=False):
     """K2.  overlap_previous: as in decode_heatmap (rotating buffers; honoured by the ring kernel)."""
@@ -438,6 +486,7 @@ def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=N
     return (out, idx) if want_idx else out
 
 
+@_on_device
 def simdr_smoothl1(out_x, out_y, tgt_x, tgt_y, weight):
     for n, t in (("output_x", out_x), ("output_y", out_y), ("target_x", tgt_x), ("target_y", tgt_y)):
         L.require_cuda(t, n)
@@ -457,6 +506,7 @@ def simdr_smoothl1(out_x, out_y, tgt_x, tgt_y, weight):
     return loss
 
 
+@_on_device
 def pck_accumulate(pred, gt, mask, thr, normalize=None, norm_const=1.0, counters=None):
     """Adds hits[T,K], valid[K], dist_fix[K] (int64, [(T+2)*K]) for one shard of samples."""
     L.require_cuda(pred, "pred")
@@ -485,6 +535,21 @@ def pck_accumulate(pred, gt, mask, thr, normalize=None, norm_const=1.0, counters
     return counters
 
 
+@_on_device
+def metrics_finalize(counters, K, auc_steps=20, out=None):
+    """lhn_metrics_finalize: f64 [3 + K] = (PCK, AUC, EPE, per-joint PCK accuracies) from the fused counter block,
+    computed on the device (no sync, no device->host copy)."""
+    L.require_cuda(counters, "counters")
+    if counters.dtype != torch.int64 or not counters.is_contiguous() or counters.numel() != (auc_steps + 5) * K:
+        raise L.LhnError("counters must be a contiguous int64 tensor of (auc_steps+5)*K entries")
+    if out is None:
+        out = torch.empty(3 + K, dtype=torch.float64, device=counters.device)
+    L.check(L.lib().lhn_metrics_finalize(L.ptr(counters), int(K), int(auc_steps), L.ptr(out), L.stream()),
+            "lhn_metrics_finalize")
+    return out
+
+
+@_on_device
 def evaluate_pck(pred_hm, gt_hm, bbox_wh, weight, image_size, thr):
     L.require_cuda(pred_hm, "pred_keypoints_hm")
     L.require_cuda(gt_hm, "gt_keypoints_hm")
@@ -505,6 +570,7 @@ def evaluate_pck(pred_hm, gt_hm, bbox_wh, weight, image_size, thr):
     return pck, mean
 
 
+@_on_device
 def flip_back(x, flip_index=None):
     L.require_cuda(x, "output_flipped")
     x = x.contiguous()
@@ -571,6 +637,7 @@ def region_bbox_decode(center, size, mode, nms_kernel=11, num_candidates=10, max
     return r
 
 
+@_on_device
 def box_nms(candidates, det_thr=0.1, iou_thr=0.6, max_num=1, min_wh=2.0, max_wh=4096.0):
     """lhn_box_nms on candidates [B,N,5] -> (boxes [B,max_num,5], counts [B] int32)."""
     c = _f32c(candidates, "candidates")
@@ -585,6 +652,7 @@ def box_nms(candidates, det_thr=0.1, iou_thr=0.6, max_num=1, min_wh=2.0, max_wh=
     return boxes, counts
 
 
+@_on_device
 def heatmap_nms(hm, nms_kernel=11, inplace=False):
     """lhn_heatmap_nms: hm * eq(maxpool_k(hm), hm) on [B,C,H,W]; inplace=True overwrites hm as the reference does."""
     L.require_cuda(hm, "heatmaps")
@@ -602,6 +670,7 @@ def heatmap_nms(hm, nms_kernel=11, inplace=False):
     return out
 
 
+@_on_device
 def vector_nms(v):
     """lhn_vector_nms on [..., L] (returns a new tensor)."""
     L.require_cuda(v, "vector")
@@ -613,6 +682,7 @@ def vector_nms(v):
     return out
 
 
+@_on_device
 def refine_points(hm, bc, xy, plus_half=False):
     """lhn_refine_points: the +-0.25 rule at given positions.  bc int32 [n,2] (image, channel), xy f32 [n,>=2]
     (updated in place and returned)."""
@@ -630,6 +700,7 @@ def refine_points(hm, bc, xy, plus_half=False):
     return xy
 
 
+@_on_device
 def decode_heatmap_roi(hm, roi, refine, scale_xy=(1.0, 1.0), blur_ksize=None, want_idx=False):
     """lhn_decode_heatmap_roi: per-image window roi int32 [B,4] = (x0, y0, x1, y1) -> [B,K,3] (X, Y, score)."""
     hm, B, Cc, H, W, sb, sc = _plane_view(hm, "heatmaps")
@@ -644,6 +715,7 @@ def decode_heatmap_roi(hm, roi, refine, scale_xy=(1.0, 1.0), blur_ksize=None, wa
     return (out, idx) if want_idx else out
 
 
+@_on_device
 def render_region_wh(rect, gamma, H, W, out=None):
     """lhn_render_region_wh: rect int32 [B,4] = (x1, x2, y1, y2), gamma f32 [B,2] -> [B,2,H,W] f32; `out` may be a
     two-channel slice of a larger contiguous [B,C,H,W] target."""
@@ -662,6 +734,7 @@ def render_region_wh(rect, gamma, H, W, out=None):
     return out
 
 
+@_on_device
 def dark_refine_points(hm, bc, xy, blur_ksize=19):
     """lhn_dark_refine_points: the legacy DARK at given positions.  bc int32 [n,2] (image, channel), xy f32 [n,>=2]
     (updated in place and returned)."""

@@ -37,7 +37,8 @@ def _shard(bounds):
         sums = O.distance_loss_l2_sums(hm, tg, tw)
         avg = hm if g["hf"] is None else O.flip_average(hm, g["hf"][a:b], g["pairs"])
         hm_preds, preds, maxvals = O.keypoints_from_heatmaps(avg, g["center"][a:b], g["scale"][a:b], "unbiased", g["kernel"])
-    return a, b, np.concatenate([preds, maxvals], axis=2), sums
+        idx = avg.reshape(avg.shape[0], avg.shape[1], -1).argmax(-1).astype(np.int32)   # _get_max_preds' np.argmax
+    return a, b, np.concatenate([preds, maxvals], axis=2), sums, idx
 
 
 class FusedCpuRunner:
@@ -62,10 +63,13 @@ class FusedCpuRunner:
         t0 = time.perf_counter()
         results = self.pool.map(_shard, bounds, chunksize=1) if self.pool else [_shard(bd) for bd in bounds]
         preds = np.zeros((n, self.K, 3), np.float32)
+        idx = np.zeros((n, self.K), np.int32)
         sums = np.zeros(4, np.float64)
-        for a, b, p, s in results:
+        for a, b, p, s, ix in results:
             preds[a:b] = p
+            idx[a:b] = ix
             sums += s
+        self.last_idx, self.last_sums = idx, sums       # argmax indices / f64 loss sums of the last run (parity checks)
         loss = O.distance_loss_from_sums(sums, True)
         return preds, loss, time.perf_counter() - t0
 
