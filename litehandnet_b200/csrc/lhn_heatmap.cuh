@@ -175,7 +175,7 @@ __device__ __forceinline__ float nanmax(float a, float b) {  // np.max: NaN prop
 }
 
 
-// persistent warp-per-plane kernel (lhn_heatmap_warp.cu): returns LHN_OK after launching, or
+// persistent team kernel (lhn_heatmap_team.cuh, launched from lhn_heatmap_team_launch.cu): returns LHN_OK after launching, or
 // +1 when the shape/alignment is outside its envelope (caller falls back to the CTA-per-plane kernel)
 int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st);
 

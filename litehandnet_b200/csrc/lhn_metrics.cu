@@ -225,7 +225,9 @@ __global__ void metrics_finalize_kernel(const long long* __restrict__ c, int K, 
   };
   out[0] = avg_acc(c, c + K, out + 3);                                                 // PCK (+ acc[K])
   double auc = 0.0;
-  for (int t = 0; t < T; ++t) auc += 1.0 / (double)T * avg_acc(c + (int64_t)(2 + t) * K, c + (int64_t)(2 + T) * K, nullptr);
+  // auc += 1.0 / num_step * avg_acc: a rounded product, then a rounded sum (no FMA contraction)
+  for (int t = 0; t < T; ++t)
+    auc = __dadd_rn(auc, __dmul_rn(1.0 / (double)T, avg_acc(c + (int64_t)(2 + t) * K, c + (int64_t)(2 + T) * K, nullptr)));
   out[1] = auc;                                                                        // keypoint_auc
   long long cnt = 0, fix = 0;
   for (int k = 0; k < K; ++k) { cnt += c[(int64_t)(3 + T) * K + k]; fix += c[(int64_t)(4 + T) * K + k]; }

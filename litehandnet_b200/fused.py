@@ -95,8 +95,27 @@ class HostPipeline:
     asynchronous copies), pageable host tensors or NumPy arrays (what a reference caller holds; the driver then
     stages each copy itself).  want_idx adds the int32 argmax indices to the device->host read."""
 
-    def __init__(self, step, B, K, H, W, dtype=torch.float32, flip=True, chunks=8, device="cuda", want_idx=False):
+    def __init__(self, step, B, K, H, W, dtype=torch.float32, flip=True, chunks=8, device="cuda", want_idx=False,
+                 metrics=None):
+        """metrics: None or dict(pck_thr=0.2, auc_nor=30.0, auc_steps=20) — decode-only steps then also accumulate
+        the PCK/AUC/EPE counters per chunk (lhn_decode_heatmap_pck; __call__ takes gt, mask, bbox_wh) and the call
+        returns the finalised (PCK, AUC, EPE) from lhn_metrics_finalize in `self.h_metrics` (BASELINE config 4)."""
         self.step, self.B, self.K, self.H, self.W = step, B, K, H, W
+        self.metrics = None
+        if metrics is not None:
+            if step.loss_mode != L.LOSS_NONE or flip:
+                raise L.LhnError("HostPipeline: fused metrics go with a decode-only step without a flip plane")
+            self.metrics = dict(pck_thr=0.2, auc_nor=30.0, auc_steps=20)
+            self.metrics.update(metrics)
+            T = int(self.metrics["auc_steps"])
+            dev_ = torch.device(device)
+            self.d_counters = torch.zeros((T + 5) * K, dtype=torch.int64, device=dev_)
+            self.d_gt = torch.empty((B, K, 2), device=dev_)
+            self.d_mask = torch.empty((B, K), dtype=torch.uint8, device=dev_)
+            self.d_wh = torch.empty((B, 2), device=dev_)
+            self.d_metrics = torch.empty(3 + K, dtype=torch.float64, device=dev_)
+            self.h_metrics = torch.empty(3 + K, dtype=torch.float64, pin_memory=True)
+            self.h_counters = torch.empty((T + 5) * K, dtype=torch.int64, pin_memory=True)
         self.flip = flip
         self.dev = torch.device(device)
         chunks = max(1, min(chunks, B))
@@ -129,10 +148,14 @@ class HostPipeline:
         self.h2d_bytes = B * K * H * W * esz * (2 if flip else 1) + B * (K * 3 * 4 * 2 + 16)
         if not self.has_loss:
             self.h2d_bytes = B * K * H * W * esz * (2 if flip else 1) + B * 16
+        if self.metrics is not None:
+            self.h2d_bytes += B * K * 8 + B * K + B * 8
         self.d2h_bytes = B * K * 3 * 4 + (4 if self.has_loss else 0) + (B * K * 4 if want_idx else 0)
+        if self.metrics is not None:
+            self.d2h_bytes += (3 + K) * 8 + self.d_counters.numel() * 8
         self.launches = 0
 
-    def __call__(self, hm, hm_flip, joints, vis, center, scale):
+    def __call__(self, hm, hm_flip, joints, vis, center, scale, gt=None, mask=None, bbox_wh=None):
         """All arguments are HOST tensors / arrays (hm_flip None when flip=False; joints and vis may be None for a
         decode-only step).  Returns (h_preds [B,K,3], h_loss [1] or None) host tensors — and h_idx in `self.h_idx`
         when want_idx — valid after the call returns (it synchronises on the final device->host copy)."""
@@ -142,6 +165,9 @@ class HostPipeline:
             return t if (t is None or isinstance(t, torch.Tensor)) else torch.as_tensor(t)
 
         hm, hm_flip, joints, vis, center, scale = (host(t) for t in (hm, hm_flip, joints, vis, center, scale))
+        gt, mask, bbox_wh = host(gt), host(mask), host(bbox_wh)
+        if mask is not None and mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
         if hm.shape[0] != self.B or (self.flip and (hm_flip is None or hm_flip.shape != hm.shape)):
             raise L.LhnError("HostPipeline: heatmap batch does not match the bound shape")
         comp = torch.cuda.current_stream(self.dev)
@@ -153,9 +179,15 @@ class HostPipeline:
                 self.d_vis.copy_(vis, non_blocking=True)
             self.d_center.copy_(center, non_blocking=True)
             self.d_scale.copy_(scale, non_blocking=True)
+            if self.metrics is not None:
+                self.d_gt.copy_(gt, non_blocking=True)
+                self.d_mask.copy_(mask, non_blocking=True)
+                self.d_wh.copy_(bbox_wh, non_blocking=True)
+        if self.metrics is not None:
+            self.d_counters.zero_()
         render = dict(loss_mode=step.loss_mode, image_size=step.image_size, sigma=step.sigma,
                       unbiased=step.unbiased, pos_value=step.pos_value) if self.has_loss else None
-        self.launches = 0
+        self.launches = 1 if self.metrics is not None else 0
         for i, (a, b) in enumerate(self.bounds):
             slot = i & 1
             n = b - a
@@ -172,6 +204,14 @@ class HostPipeline:
                 out.update(partials=self.d_partials[a * self.K:b * self.K], weight=self.d_weight[a:b])
             if self.want_idx:
                 out["idx"] = self.d_idx[a:b]
+            if self.metrics is not None:
+                m = self.metrics
+                ops.decode_heatmap_pck(self.d_hm[slot][:n], L.MASK_NEG1, step.refine, self.d_center[a:b], self.d_scale[a:b],
+                                       self.d_gt[a:b], self.d_mask[a:b], self.d_wh[a:b], self.d_counters, m["pck_thr"],
+                                       m["auc_nor"], m["auc_steps"], step.kernel, out=out)
+                self.freed[slot].record(comp)
+                self.launches += 1
+                continue
             ops.decode_heatmap(self.d_hm[slot][:n], L.MASK_NEG1, step.refine, L.XFORM_CENTER_SCALE,
                                self.d_center[a:b], self.d_scale[a:b],
                                hm_flip=self.d_hf[slot][:n] if self.flip else None, flip_index=self.flip_index,
@@ -188,6 +228,11 @@ class HostPipeline:
         self.h_preds.copy_(self.d_preds, non_blocking=True)
         if self.want_idx:
             self.h_idx.copy_(self.d_idx, non_blocking=True)
+        if self.metrics is not None:
+            ops.metrics_finalize(self.d_counters, self.K, self.metrics["auc_steps"], out=self.d_metrics)
+            self.launches += 1
+            self.h_metrics.copy_(self.d_metrics, non_blocking=True)
+            self.h_counters.copy_(self.d_counters, non_blocking=True)
         comp.synchronize()
         return self.h_preds, (self.h_loss if self.has_loss else None)
 
@@ -320,3 +365,178 @@ class BoundFusedStep:
 
     def replay(self):
         self.graph.replay()
+
+
+class SimdrHostPipeline:
+    """End-to-end SimDR decode for HOST vectors (keypoints_from_simdr, top_down_eval.py:466-500, which takes NumPy
+    arrays): chunked host->device copies on a copy stream overlapped with the decode kernel, [B,K,3] read back."""
+
+    def __init__(self, B, K, Lx, Ly, k=2, dtype=torch.float32, chunks=8, device="cuda"):
+        self.B, self.K, self.Lx, self.Ly, self.k = B, K, Lx, Ly, int(k)
+        self.dev = torch.device(device)
+        chunks = max(1, min(chunks, B))
+        edges = [round(i * B / chunks) for i in range(chunks + 1)]
+        self.bounds = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        cb = max(b - a for a, b in self.bounds)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.d_x = [torch.empty((cb, K, Lx), dtype=dtype, device=self.dev) for _ in range(2)]
+        self.d_y = [torch.empty((cb, K, Ly), dtype=dtype, device=self.dev) for _ in range(2)]
+        self.d_center = torch.empty((B, 2), device=self.dev)
+        self.d_scale = torch.empty((B, 2), device=self.dev)
+        self.d_out = torch.empty((B, K, 3), device=self.dev)
+        self.h_out = torch.empty((B, K, 3), pin_memory=True)
+        self.copied = [torch.cuda.Event() for _ in self.bounds]
+        self.freed = [torch.cuda.Event() for _ in range(2)]
+        esz = torch.empty((), dtype=dtype).element_size()
+        self.h2d_bytes = B * K * (Lx + Ly) * esz + B * 16
+        self.d2h_bytes = B * K * 3 * 4
+        self.launches = 0
+
+    def __call__(self, x_vec, y_vec, center, scale):
+        def host(t):
+            return t if isinstance(t, torch.Tensor) else torch.as_tensor(t)
+
+        x_vec, y_vec, center, scale = host(x_vec), host(y_vec), host(center), host(scale)
+        comp = torch.cuda.current_stream(self.dev)
+        cs = self.copy_stream
+        cs.wait_stream(comp)
+        with torch.cuda.stream(cs):
+            self.d_center.copy_(center, non_blocking=True)
+            self.d_scale.copy_(scale, non_blocking=True)
+        self.launches = 0
+        for i, (a, b) in enumerate(self.bounds):
+            slot, n = i & 1, b - a
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(self.freed[slot])
+                self.d_x[slot][:n].copy_(x_vec[a:b], non_blocking=True)
+                self.d_y[slot][:n].copy_(y_vec[a:b], non_blocking=True)
+                self.copied[i].record(cs)
+            comp.wait_event(self.copied[i])
+            ops.decode_simdr(self.d_x[slot][:n], self.d_y[slot][:n], self.k, self.d_center[a:b], self.d_scale[a:b],
+                             out=self.d_out[a:b])
+            self.freed[slot].record(comp)
+            self.launches += 1
+        self.h_out.copy_(self.d_out, non_blocking=True)
+        comp.synchronize()
+        return self.h_out
+
+
+class BoundDecodeStep:
+    """A decode-only launch (argmax + refinement + back-transform[, fused PCK/AUC/EPE counters]) bound to fixed
+    device buffers: every ctypes argument is built once, a step is ONE raw C-ABI launch (lhn_decode_heatmap, or
+    lhn_decode_heatmap_pck when `metrics` is given).  The eager ops wrappers cost 20-30 us of Python per call,
+    which is more than the kernel at the reference's batch sizes (BASELINE config 1: batch 64)."""
+
+    def __init__(self, hm, center, scale, mask_mode=L.MASK_NEG1, refine=L.REFINE_SIGN, transform=L.XFORM_CENTER_SCALE,
+                 hm_flip=None, flip_pairs=(), kernel=11, scale_xy=(1.0, 1.0), overlap_previous=False, metrics=None,
+                 outputs=None):
+        """metrics: None or dict(gt [B,K,2] f32, mask [B,K] bool/u8, bbox_wh [B,2] f32, counters int64
+        [(auc_steps+5)*K], pck_thr=0.2, auc_nor=30.0, auc_steps=20)."""
+        import ctypes as C
+        lib = L.lib()
+        self._lib = lib
+        hm, B, Cc, H, W, sb, sc = ops._plane_view(hm, "heatmaps")
+        dev = hm.device
+        self.dev, self.B, self.K, self.H, self.W = dev, B, Cc, H, W
+        fb = fc = 0
+        fi = None
+        if hm_flip is not None:
+            hm_flip, _, _, _, _, fb, fc = ops._plane_view(hm_flip, "flipped heatmaps")
+            if flip_pairs:
+                fi = flip_index_from_pairs(Cc, flip_pairs, dev)
+        center, scale = ops._f32c(center, "center"), ops._f32c(scale, "scale")
+        self.dp = ops._decode_params(mask_mode, refine, transform, scale_xy, kernel,
+                                     flags=L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0)
+        outputs = outputs or {}
+
+        def _out(name, shape, dtype):
+            t = outputs.get(name)
+            if t is None:
+                return torch.empty(shape, dtype=dtype, device=dev)
+            n = 1
+            for d in shape:
+                n *= d
+            if t.dtype != dtype or t.device != dev or not t.is_contiguous() or t.numel() < n:
+                raise L.LhnError(f"output '{name}' has the wrong dtype/device/layout or is too small")
+            return t
+
+        self.hm_preds = _out("hm_preds", (B, Cc, 3), torch.float32)
+        self.preds = _out("preds", (B, Cc, 3), torch.float32)
+        self.idx = _out("idx", (B, Cc), torch.int32)
+        self._keep = [hm, hm_flip, fi, center, scale]
+        self.counters = None
+        if metrics is None:
+            self._fn, self._name = lib.lhn_decode_heatmap, "lhn_decode_heatmap"
+            self._args = (L.ptr(hm), L.ptr(hm_flip), L.ptr(fi), L.dtype_code(hm), B, Cc, H, W, sb, sc, fb, fc,
+                          L.ptr(center), L.ptr(scale), C.byref(self.dp), L.ptr(self.hm_preds), L.ptr(self.preds),
+                          L.ptr(self.idx), None, None, 0, None, 0, None, None)
+        else:
+            if hm_flip is not None:
+                raise L.LhnError("the fused-metrics decode takes no flip plane")
+            gt = ops._f32c(metrics["gt"], "gt")
+            mask = ops._mask_u8(metrics["mask"])
+            wh = ops._f32c(metrics["bbox_wh"], "bbox_wh")
+            steps = int(metrics.get("auc_steps", 20))
+            self.counters = metrics["counters"]
+            if self.counters.dtype != torch.int64 or self.counters.numel() != (steps + 5) * Cc or \
+                    not self.counters.is_contiguous() or self.counters.device != dev:
+                raise L.LhnError("counters must be a contiguous int64 tensor of (auc_steps+5)*K entries on the heatmaps' device")
+            self._keep += [gt, mask, wh, self.counters]
+            self._fn, self._name = lib.lhn_decode_heatmap_pck, "lhn_decode_heatmap_pck"
+            self._args = (L.ptr(hm), L.dtype_code(hm), B, Cc, H, W, sb, sc, L.ptr(center), L.ptr(scale), C.byref(self.dp),
+                          L.ptr(self.hm_preds), L.ptr(self.preds), L.ptr(self.idx), L.ptr(gt), L.ptr(mask), L.ptr(wh),
+                          float(metrics.get("pck_thr", 0.2)), float(metrics.get("auc_nor", 30.0)), steps,
+                          L.ptr(self.counters))
+        self.graph = None
+
+    def stream(self):
+        return L.stream(self.dev)
+
+    def launch_kernel(self, stream):
+        L.check(self._fn(*self._args, stream), self._name)
+
+    def launch(self):
+        with L.on_device(self.dev):
+            self.launch_kernel(L.stream(self.dev))
+
+    def capture(self):
+        self.launch()
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.launch()
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
+
+
+class BoundSimdrStep:
+    """lhn_decode_simdr_flags bound to fixed buffers (one raw C-ABI launch per step; BASELINE config 3)."""
+
+    def __init__(self, x_vec, y_vec, k=2, center=None, scale=None, overlap_previous=False, out=None):
+        L.require_cuda(x_vec, "x_vectors")
+        L.require_cuda(y_vec, "y_vectors")
+        x_vec, y_vec = x_vec.contiguous(), y_vec.to(x_vec.dtype).contiguous()
+        B, K, Lx = x_vec.shape
+        Ly = y_vec.shape[2]
+        self.dev, self.B, self.K = x_vec.device, B, K
+        center, scale = ops._f32c(center, "center"), ops._f32c(scale, "scale")
+        self.out = out if out is not None else torch.empty((B, K, 3), dtype=torch.float32, device=self.dev)
+        self.idx = torch.empty((B, K, 2), dtype=torch.int32, device=self.dev)
+        self._keep = [x_vec, y_vec, center, scale]
+        self._lib = L.lib()
+        self._args = (L.ptr(x_vec), L.ptr(y_vec), L.dtype_code(x_vec), B, K, Lx, Ly, int(k), L.ptr(center), L.ptr(scale),
+                      0, None, L.ptr(self.out), L.ptr(self.idx), L.FLAG_OVERLAP_PREVIOUS if overlap_previous else 0)
+
+    def stream(self):
+        return L.stream(self.dev)
+
+    def launch_kernel(self, stream):
+        L.check(self._lib.lhn_decode_simdr_flags(*self._args, stream), "lhn_decode_simdr_flags")
+
+    def launch(self):
+        with L.on_device(self.dev):
+            self.launch_kernel(L.stream(self.dev))

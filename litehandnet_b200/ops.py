@@ -295,9 +295,10 @@ def _mask_u8(mask):
 
 @_on_device
 def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, counters,
-                       pck_thr=0.2, auc_nor=30.0, auc_steps=20, blur_ksize=None, overlap_previous=False):
+                       pck_thr=0.2, auc_nor=30.0, auc_steps=20, blur_ksize=None, overlap_previous=False, out=None):
     """K1 + fused PCK/AUC/EPE counters (BASELINE config 4).  `counters` int64 [(auc_steps+5)*K] is
-    ADDED to.  Returns dict(hm_kpts, kpts, idx)."""
+    ADDED to.  Returns dict(hm_kpts, kpts, idx).  out: optional preallocated hm_kpts / kpts / idx."""
+    out = out or {}
     hm, B, K, H, W, sb, sc = _plane_view(hm, "heatmaps")
     dev = hm.device
     dp = _decode_params(mask_mode, refine, L.XFORM_CENTER_SCALE, (1, 1), blur_ksize,
@@ -308,9 +309,17 @@ def decode_heatmap_pck(hm, mask_mode, refine, center, scale, gt, mask, bbox_wh, 
     mask = _mask_u8(mask)
     if counters.dtype != torch.int64 or counters.numel() != (auc_steps + 5) * K or not counters.is_contiguous():
         raise L.LhnError("counters must be a contiguous int64 tensor of (auc_steps+5)*K entries")
-    out_hm = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
-    out_k = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
-    out_idx = torch.empty((B, K), dtype=torch.int32, device=dev)
+    out_hm, out_k, out_idx = out.get("hm_kpts"), out.get("kpts"), out.get("idx")
+    if out_hm is None:
+        out_hm = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
+    if out_k is None:
+        out_k = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
+    if out_idx is None:
+        out_idx = torch.empty((B, K), dtype=torch.int32, device=dev)
+    for name, t, dt, n in (("hm_kpts", out_hm, torch.float32, B * K * 3), ("kpts", out_k, torch.float32, B * K * 3),
+                           ("idx", out_idx, torch.int32, B * K)):
+        if t.dtype != dt or t.numel() != n or not t.is_contiguous() or t.device != dev:
+            raise L.LhnError(f"preallocated output '{name}' has the wrong dtype/size/layout/device")
     rc = L.lib().lhn_decode_heatmap_pck(
         L.ptr(hm), L.dtype_code(hm), B, K, H, W, sb, sc, L.ptr(center), L.ptr(scale), C.byref(dp),
         L.ptr(out_hm), L.ptr(out_k), L.ptr(out_idx), L.ptr(gt), L.ptr(mask), L.ptr(bbox_wh),
@@ -465,8 +474,9 @@ def render_simdr(joints, vis, image_size, k=2, sigma=2):
 
 @_on_device
 def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=None, want_idx=False,
-                 overlap_previous=False):
-    """K2.  overlap_previous: as in decode_heatmap (rotating buffers; honoured by the ring kernel)."""
+                 overlap_previous=False, out=None):
+    """K2.  overlap_previous: as in decode_heatmap (rotating buffers; honoured by the ring kernel).
+    out: optional preallocated contiguous f32 [B,K,3]."""
     L.require_cuda(x_vec, "x_vectors")
     L.require_cuda(y_vec, "y_vectors")
     if y_vec.dtype != x_vec.dtype:
@@ -477,7 +487,10 @@ def decode_simdr(x_vec, y_vec, k=2, center=None, scale=None, nms=False, ranges=N
     center, scale = _f32c(center, "center"), _f32c(scale, "scale")
     if ranges is not None:
         ranges = L.require_cuda(ranges, "ranges").to(torch.int32).contiguous()
-    out = torch.empty((B, K, 3), dtype=torch.float32, device=x_vec.device)
+    if out is None:
+        out = torch.empty((B, K, 3), dtype=torch.float32, device=x_vec.device)
+    elif out.dtype != torch.float32 or out.numel() != B * K * 3 or not out.is_contiguous() or out.device != x_vec.device:
+        raise L.LhnError("preallocated output has the wrong dtype/size/layout/device")
     idx = torch.empty((B, K, 2), dtype=torch.int32, device=x_vec.device) if want_idx else None
     rc = L.lib().lhn_decode_simdr_flags(L.ptr(x_vec), L.ptr(y_vec), L.dtype_code(x_vec), B, K, Lx, Ly, int(k),
                                         L.ptr(center), L.ptr(scale), int(bool(nms)), L.ptr(ranges), L.ptr(out),

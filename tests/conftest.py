@@ -24,14 +24,25 @@ def golden():
     return load_golden
 
 
-def assert_coords_close(a, b, rtol=1e-5, atol=2e-5, what=""):
+def xform_magnitude(center, scale):
+    """Magnitude of the terms of transform_preds (x * s/W + c - s/2, post_transforms.py:6-48) per sample, [N,1,2]:
+    |c| + |s * 100|.  Image-space coordinates near 0 are a difference of terms this large, so their f32 rounding
+    (one ulp of ~130 is 1.5e-5) is the floor of any element-wise comparison."""
+    c = np.abs(np.asarray(center, np.float64)); s = np.abs(np.asarray(scale, np.float64)) * 100.0
+    return (c + s)[:, None, :]
+
+
+def assert_coords_close(a, b, rtol=1e-5, atol=2e-5, what="", mag=None):
     """Float coordinates: 1e-5 relative (north_star) with a 2e-5 px absolute floor for values
-    near zero; NaNs must coincide."""
+    near zero; NaNs must coincide.  mag (optional, broadcastable): magnitude of the terms the coordinate was
+    computed from (xform_magnitude for image-space coordinates) — the relative bound is taken against
+    max(|b|, mag), element-wise."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     assert a.shape == b.shape, (what, a.shape, b.shape)
     nan_a, nan_b = np.isnan(a), np.isnan(b)
     assert np.array_equal(nan_a, nan_b), f"{what}: NaN pattern differs"
-    ok = np.abs(a - b) <= atol + rtol * np.abs(b)
+    ref_mag = np.abs(b) if mag is None else np.maximum(np.abs(b), np.broadcast_to(np.asarray(mag, np.float64), b.shape))
+    ok = np.abs(a - b) <= atol + rtol * ref_mag
     ok |= nan_a
     assert ok.all(), f"{what}: max abs diff {np.nanmax(np.abs(a - b))} at {np.argwhere(~ok)[:5]}"
 

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_coords_close
+from conftest import assert_coords_close, xform_magnitude
 from oracle import cpu_path
 from oracle import np_oracle as O
 from litehandnet_b200 import _lib as L
@@ -42,18 +42,19 @@ def oracle_of(s, key):
         try:
             with np.errstate(all="ignore"):
                 preds, loss, _ = r.run()
-            _ORACLE_CACHE[key] = (preds, r.last_idx.copy(), float(loss), r.last_sums.copy())
+            mag = xform_magnitude(s[4].cpu().numpy(), s[5].cpu().numpy())
+            _ORACLE_CACHE[key] = (preds, r.last_idx.copy(), float(loss), r.last_sums.copy(), mag)
         finally:
             r.close()
     return _ORACLE_CACHE[key]
 
 
 def check_step(bound, ref, what, loss=True):
-    preds, idx, rloss, _ = ref
+    preds, idx, rloss, _, mag = ref
     B = preds.shape[0]
     assert np.array_equal(bound.idx[:B].cpu().numpy(), idx), f"{what}: argmax indices differ"
     got = bound.preds[:B].cpu().numpy()
-    assert_coords_close(got[..., :2], preds[..., :2], what=f"{what}: coordinates")
+    assert_coords_close(got[..., :2], preds[..., :2], what=f"{what}: coordinates", mag=mag)
     assert np.array_equal(got[..., 2], preds[..., 2], equal_nan=True), f"{what}: maxvals differ"
     if loss:
         np.testing.assert_allclose(float(bound.loss.item()), rloss, rtol=1e-5, err_msg=f"{what}: loss")
@@ -212,7 +213,7 @@ def test_host_pipeline_vs_oracle(B, chunks):
     for rep in range(2):                                         # the second call reuses the staging buffers
         preds, loss = pipe(*pinned)
         assert np.array_equal(pipe.h_idx.numpy(), ref[1]), "argmax indices differ"
-        assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what=f"host pipeline B={B} chunks={chunks}")
+        assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what=f"host pipeline B={B} chunks={chunks}", mag=ref[4])
         assert np.array_equal(preds.numpy()[..., 2], ref[0][..., 2], equal_nan=True)
         np.testing.assert_allclose(float(loss.item()), ref[2], rtol=1e-5)
     assert pipe.h2d_bytes == sum(t.numel() * t.element_size() for t in s)
@@ -226,10 +227,10 @@ def test_host_pipeline_accepts_numpy_and_pageable_inputs():
     ref = oracle_of(s, ("host-np", B))
     pipe = fused.HostPipeline(step_cfg(), B, K, H, W, flip=True, chunks=4, device=DEV)
     preds, loss = pipe(*[t.numpy() for t in s])
-    assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what="numpy inputs")
+    assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what="numpy inputs", mag=ref[4])
     np.testing.assert_allclose(float(loss.item()), ref[2], rtol=1e-5)
     preds, loss = pipe(*s)                                                    # pageable torch tensors
-    assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what="pageable inputs")
+    assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what="pageable inputs", mag=ref[4])
 
 
 def test_host_pipeline_decode_only():
@@ -242,7 +243,7 @@ def test_host_pipeline_decode_only():
     assert loss is None and pipe.launches == len(pipe.bounds)
     ref = oracle_of(s, ("host-dec", B))
     assert np.array_equal(pipe.h_idx.numpy(), ref[1])
-    assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what="decode-only host pipeline")
+    assert_coords_close(preds.numpy()[..., :2], ref[0][..., :2], what="decode-only host pipeline", mag=ref[4])
 
 
 def test_ops_follow_the_tensors_device():
