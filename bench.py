@@ -427,7 +427,14 @@ class DecodeWorkload(Workload):
         hm, cen = synth.blob_heatmaps(B, self.K, self.H, self.W, seed=seed, device=dev, zero_frac=0.02, tie_frac=0.01)
         if self.metrics:
             center, scale = synth.bbox_center_scale(B, seed=seed + 3, device=dev)
-            gt, mask, wh = synth.pck_inputs(cen, seed=seed + 5, device=dev)
+            gt, mask, wh = synth.pck_inputs(cen, seed=seed + 5, device=dev, stride=1.0, gt_noise=0.0)
+            # ground truth in the IMAGE frame the decoder maps to (transform_preds), + N(0, 6 px) annotation noise
+            import torch
+            g = torch.Generator(device=dev)
+            g.manual_seed(seed + 6)
+            s200 = scale * 200.0
+            gt = gt * (s200 / float(self.W))[:, None, :] + center[:, None, :] - 0.5 * s200[:, None, :]
+            gt = (gt + torch.randn(gt.shape, generator=g, device=dev) * 6.0).float().contiguous()
             return hm, center, scale, gt, mask, wh
         center, scale = synth.bbox_center_scale(B, seed=seed + 3, device=dev, fixed=True)
         return hm, center, scale
@@ -782,8 +789,12 @@ def cpu_only_inputs(cfg_id, batch):
         return [t.numpy() for t in (xv, yv, center, scale)], (256, 256), 2
     hm, cen = synth.blob_heatmaps(B, sh["K"], 64, 64, seed=0, zero_frac=0.02, tie_frac=0.01)
     if cfg_id == 4:
+        import torch
         center, scale = synth.bbox_center_scale(B, seed=3)
-        gt, mask, wh = synth.pck_inputs(cen, seed=5)
+        gt, mask, wh = synth.pck_inputs(cen, seed=5, stride=1.0, gt_noise=0.0)
+        s200 = scale * 200.0
+        gt = gt * (s200 / 64.0)[:, None, :] + center[:, None, :] - 0.5 * s200[:, None, :]
+        gt = (gt + torch.randn(gt.shape, generator=torch.Generator().manual_seed(6)) * 6.0).float().contiguous()
         return [t.numpy() for t in (hm, center, scale, gt, mask, wh)], (256, 256), 2
     center, scale = synth.bbox_center_scale(B, seed=3, fixed=True)
     return [t.numpy() for t in (hm, center, scale)], (256, 256), 2
