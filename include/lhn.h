@@ -299,6 +299,26 @@ LHN_API int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const void*
                                int Lx, int Ly, void* workspace, int64_t workspace_bytes, float* loss,
                                lhn_stream_t stream);
 
+/* ---- SimDRLoss with its two nn.Linear heads fused (centernet_simdr_loss.py:42-69) -------------------------------
+ * pred_x | pred_y = heatmap.flatten(2) @ [Wx ; Wy]^T + [bx ; by], then KLDiscretLoss (:27-39) — ONE tcgen05 kernel:
+ * the predictions stay in tensor memory, the epilogue takes SmoothL1 against the targets and row-reduces it; a
+ * second tiny launch adds the partial sums in a fixed order and applies the joint weights.
+ *
+ * fp32 parity: operands are passed as bf16 pairs x = hi + lo made by lhn_split_bf16 (x f32 [n], n % 4 == 0,
+ * 16-byte aligned; hi / lo bf16 [n]); the kernel issues lo*hi + hi*lo + hi*hi into one fp32 accumulator.
+ *   a_hi / a_lo  bf16 [B*K, Kd]   the heatmaps flattened (Kd = H*W, a multiple of 64)
+ *   w_hi / w_lo  bf16 [Lx+Ly, Kd] rows 0..Lx-1 = x_shared_decoder.weight, then y_shared_decoder.weight
+ *   bias f32 [Lx+Ly]; target_x f32 [B,K,Lx], target_y f32 [B,K,Ly]; weight f32 [B,K]; (Lx+Ly) % 64 == 0, Lx % 4 == 0
+ *   loss f32 [1];  dpred (optional) f32 [B*K, Lx+Ly] = clamp(pred - target, -1, 1) = d SmoothL1 / d pred for the
+ *   backward;  pred (optional) f32 [B*K, Lx+Ly] = the predictions (inference).  All pointers 16-byte aligned. */
+LHN_API int lhn_split_bf16(const float* x, int64_t n, void* hi, void* lo, lhn_stream_t stream);
+LHN_API int64_t lhn_simdr_heads_workspace_bytes(int64_t B, int K, int Lx, int Ly);
+LHN_API int lhn_simdr_heads_loss(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                                 const float* bias, const float* target_x, const float* target_y,
+                                 const float* weight, int64_t B, int K, int Kd, int Lx, int Ly, void* workspace,
+                                 int64_t workspace_bytes, float* loss, float* dpred, float* pred,
+                                 lhn_stream_t stream);
+
 /* ---- K3: metrics ------------------------------------------------------------------------------
  * _calc_distances + _distance_acc (top_down_eval.py:12-62) as shardable counters.
  * pred [N,K,pred_stride] / gt [N,K,gt_stride] (x,y in columns 0,1), dtype f32 or f64 each;

@@ -33,7 +33,7 @@ EXPORTS = [
     "lhn_version", "lhn_last_cuda_error", "lhn_gaussian_taps", "lhn_decode_heatmap",
     "lhn_decode_heatmap_pck", "lhn_loss_partials", "lhn_loss_reduce", "lhn_loss_finalize",
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_decode_simdr_flags", "lhn_simdr_loss_workspace_bytes",
-    "lhn_simdr_smoothl1", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
+    "lhn_simdr_smoothl1", "lhn_split_bf16", "lhn_simdr_heads_workspace_bytes", "lhn_simdr_heads_loss", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
     "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate", "lhn_region_bbox_decode", "lhn_heatmap_nms",
@@ -107,6 +107,10 @@ def _declare(lib):
     lib.lhn_pck_accumulate.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, i32, f64, i64, i32,
                                        C.POINTER(C.c_float), i32, vp, vp]
     lib.lhn_metrics_finalize.argtypes = [vp, i32, i32, vp, vp]
+    lib.lhn_split_bf16.argtypes = [vp, i64, vp, vp, vp]
+    lib.lhn_simdr_heads_workspace_bytes.argtypes = [i64, i32, i32, i32]
+    lib.lhn_simdr_heads_workspace_bytes.restype = i64
+    lib.lhn_simdr_heads_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.lhn_evaluate_pck_workspace_bytes.argtypes = [i64, i32]
     lib.lhn_evaluate_pck_workspace_bytes.restype = i64
     lib.lhn_evaluate_pck.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, f32, f32, f32, vp, i64,

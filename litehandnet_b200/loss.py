@@ -75,6 +75,46 @@ class _SimDRLossFn(torch.autograd.Function):
         return gx, gy.to(out_y.dtype), None, None, None
 
 
+class _SimDRHeadsLossFn(torch.autograd.Function):
+    """SimDRLoss.forward with the two linear heads fused into the loss kernel (lhn_simdr_heads_loss).  When a
+    gradient is needed the kernel's epilogue also stores g = d SmoothL1 / d pred = clamp(pred - target, -1, 1); the
+    backward scales its rows by grad * mean_b(w[b, j]) / (B * L * K) and takes the three plain GEMMs of a linear layer
+    (d heatmap = G W, d W = G^T A, d b = column sums of G) from the library."""
+
+    @staticmethod
+    def forward(ctx, heatmap, wx, bx, wy, by, tgt_x, tgt_y, weight, w_split):
+        need = any(ctx.needs_input_grad[:5])
+        bias = torch.cat([bx.detach(), by.detach()])
+        loss, dpred, _ = ops.simdr_heads_loss(heatmap.detach(), w_split, bias, tgt_x, tgt_y, weight, want_dpred=need)
+        if need:
+            ctx.save_for_backward(heatmap.detach(), wx.detach(), wy.detach(), weight, dpred)
+            ctx.Lx, ctx.Ly = tgt_x.shape[-1], tgt_y.shape[-1]
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        heatmap, wx, wy, weight, g = ctx.saved_tensors
+        B, K = heatmap.shape[:2]
+        Lx, Ly = ctx.Lx, ctx.Ly
+        A = heatmap.reshape(B * K, -1).float()
+        mw = weight.reshape(B, K).float().mean(0)                          # mean_b w[b, j]
+        row = (grad_out.float() * mw / float(K * B)).repeat(B)              # coefficient of row b*K + j, without 1/L
+        g = g * row[:, None]
+        gx, gy = g[:, :Lx] * (1.0 / Lx), g[:, Lx:] * (1.0 / Ly)
+        d_hm = d_wx = d_bx = d_wy = d_by = None
+        if ctx.needs_input_grad[0]:
+            d_hm = (gx @ wx.float() + gy @ wy.float()).reshape(heatmap.shape).to(heatmap.dtype)
+        if ctx.needs_input_grad[1]:
+            d_wx = gx.t() @ A
+        if ctx.needs_input_grad[2]:
+            d_bx = gx.sum(0)
+        if ctx.needs_input_grad[3]:
+            d_wy = gy.t() @ A
+        if ctx.needs_input_grad[4]:
+            d_by = gy.sum(0)
+        return d_hm, d_wx, d_bx, d_wy, d_by, None, None, None, None
+
+
 class DistanceLoss(nn.Module):
     """loss/heatmapLoss.py:228-265.  Only loss_type 'L2' is on the path (every config uses it)."""
 
@@ -146,8 +186,11 @@ class KLDiscretLoss(nn.Module):
 
 
 class SimDRLoss(nn.Module):
-    """loss/centernet_simdr_loss.py:42-69.  The two nn.Linear heads are the criterion's own dense
-    contraction and stay in torch/cuBLAS; the SmoothL1 reduction is ours."""
+    """loss/centernet_simdr_loss.py:42-69.  Same parameters as the reference (two nn.Linear heads, so checkpoints
+    load unchanged); the forward is ONE tcgen05 kernel that multiplies the flattened heatmaps with both heads and
+    takes KLDiscretLoss in its epilogue (lhn_simdr_heads_loss: the [B*K, k*W_img] predictions never reach HBM).
+    ``fused=False`` keeps the reference's structure (cuBLAS heads, then lhn_simdr_smoothl1); shapes outside the
+    fused kernel's envelope (H*W not a multiple of 64, non-f32 heatmaps) take that route too."""
 
     def __init__(self, cfg=None):
         super().__init__()
@@ -160,8 +203,29 @@ class SimDRLoss(nn.Module):
         self.x_shared_decoder = nn.Linear(in_features, self.simdr_width)
         self.y_shared_decoder = nn.Linear(in_features, self.simdr_height)
         self.loss = KLDiscretLoss()
+        self.fused = True
+        self._split = None                   # (key, (w_hi, w_lo)): bf16 pair of cat([Wx, Wy]), rebuilt when the weights change
+
+    def _weight_split(self):
+        wx, wy = self.x_shared_decoder.weight, self.y_shared_decoder.weight
+        key = (wx.data_ptr(), wx._version, wy.data_ptr(), wy._version, wx.device)
+        if self._split is None or self._split[0] != key:
+            self._split = (key, ops.split_bf16(torch.cat([wx.detach(), wy.detach()]).float().contiguous()))
+        return self._split[1]
+
+    def _fusable(self, heatmap):
+        n = self.simdr_width + self.simdr_height
+        return (self.fused and heatmap.is_cuda and heatmap.dtype == torch.float32 and heatmap.dim() == 4 and
+                heatmap[0, 0].numel() % 64 == 0 and n % 64 == 0 and self.simdr_width % 4 == 0 and self.simdr_height % 4 == 0
+                and self.x_shared_decoder.weight.dtype == torch.float32)
 
     def forward(self, heatmap, simdr_x, simdr_y, target_weight):
+        if self._fusable(heatmap):
+            dev = heatmap.device
+            return _SimDRHeadsLossFn.apply(heatmap, self.x_shared_decoder.weight, self.x_shared_decoder.bias,
+                                           self.y_shared_decoder.weight, self.y_shared_decoder.bias,
+                                           _as_cuda(simdr_x, dev), _as_cuda(simdr_y, dev), _as_cuda(target_weight, dev),
+                                           self._weight_split())
         pred_x = self.x_shared_decoder(heatmap.flatten(start_dim=2))
         pred_y = self.y_shared_decoder(heatmap.flatten(start_dim=2))
         return self.loss(pred_x, pred_y, simdr_x, simdr_y, target_weight)

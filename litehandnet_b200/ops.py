@@ -520,6 +520,50 @@ def simdr_smoothl1(out_x, out_y, tgt_x, tgt_y, weight):
 
 
 @_on_device
+def split_bf16(x):
+    """lhn_split_bf16: f32 tensor -> (hi, lo) bf16 tensors of the same shape with x = hi + lo + O(2^-17 |x|)."""
+    L.require_cuda(x, "x")
+    x = x.detach()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.to(torch.float32).contiguous()
+    if x.numel() % 4:
+        raise L.LhnError("split_bf16 needs a multiple of 4 elements")
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().lhn_split_bf16(L.ptr(x), x.numel(), L.ptr(hi), L.ptr(lo), L.stream()), "lhn_split_bf16")
+    return hi, lo
+
+
+@_on_device
+def simdr_heads_loss(heatmap, w_split, bias, tgt_x, tgt_y, weight, want_dpred=False, want_pred=False):
+    """lhn_simdr_heads_loss: SimDRLoss.forward with both linear heads in ONE tcgen05 kernel (the predictions stay in
+    tensor memory).  heatmap f32 [B,K,H,W]; w_split = split_bf16(cat([Wx, Wy])) ([Lx+Ly, H*W] each); bias f32 [Lx+Ly];
+    tgt_x [B,K,Lx], tgt_y [B,K,Ly], weight [B,K(,1)].  Returns (loss f32[1], dpred or None, pred or None)."""
+    L.require_cuda(heatmap, "heatmap")
+    B, K = heatmap.shape[:2]
+    Kd = heatmap[0, 0].numel()
+    w_hi, w_lo = w_split
+    N = w_hi.shape[0]
+    tgt_x, tgt_y = _f32c(tgt_x, "simdr_x"), _f32c(tgt_y, "simdr_y")
+    Lx, Ly = tgt_x.shape[-1], tgt_y.shape[-1]
+    if Lx + Ly != N or w_hi.shape[1] != Kd or tgt_x.shape[:2] != (B, K) or tgt_y.shape[:2] != (B, K):
+        raise L.LhnError("simdr_heads_loss: shapes of the heads, the heatmap and the targets do not agree")
+    a_hi, a_lo = split_bf16(heatmap.reshape(B * K, Kd))
+    bias = _f32c(bias, "bias")
+    weight = _f32c(weight, "target_weight").reshape(B, K)
+    dev = heatmap.device
+    nbytes = int(L.lib().lhn_simdr_heads_workspace_bytes(B, K, Lx, Ly))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dpred = torch.empty((B * K, N), dtype=torch.float32, device=dev) if want_dpred else None
+    pred = torch.empty((B * K, N), dtype=torch.float32, device=dev) if want_pred else None
+    L.check(L.lib().lhn_simdr_heads_loss(L.ptr(a_hi), L.ptr(a_lo), L.ptr(w_hi), L.ptr(w_lo), L.ptr(bias), L.ptr(tgt_x),
+                                         L.ptr(tgt_y), L.ptr(weight), B, K, Kd, Lx, Ly, L.ptr(ws), nbytes, L.ptr(loss),
+                                         L.ptr(dpred), L.ptr(pred), L.stream()), "lhn_simdr_heads_loss")
+    return loss, dpred, pred
+
+
+@_on_device
 def pck_accumulate(pred, gt, mask, thr, normalize=None, norm_const=1.0, counters=None):
     """Adds hits[T,K], valid[K], dist_fix[K] (int64, [(T+2)*K]) for one shard of samples."""
     L.require_cuda(pred, "pred")

@@ -47,3 +47,120 @@ def test_metrics_finalize_rejects_bad_arguments():
         ops.metrics_finalize(cnt, 15)
     with pytest.raises(L.LhnError):
         ops.metrics_finalize(cnt.int(), 16)
+
+
+# ---- SimDRLoss heads fused into one tcgen05 kernel (centernet_simdr_loss.py:42-69) ---------------------------
+def _heads_case(B, K, HW, Lx, Ly, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    side = int(round(HW ** 0.5))
+    hm, _ = synth.blob_heatmaps(B, K, side, side, seed=seed, device=DEV)
+    wx = (torch.rand(Lx, HW, generator=g, device=DEV) * 2 - 1) * HW ** -0.5       # nn.Linear's default init range
+    wy = (torch.rand(Ly, HW, generator=g, device=DEV) * 2 - 1) * HW ** -0.5
+    bx = (torch.rand(Lx, generator=g, device=DEV) * 2 - 1) * HW ** -0.5
+    by = (torch.rand(Ly, generator=g, device=DEV) * 2 - 1) * HW ** -0.5
+    j, v = synth.hand_joints(B, K, (Lx // 2, Ly // 2), seed=seed + 1, device=DEV)
+    tx, ty = ops.render_simdr(j, v, (Lx // 2, Ly // 2), 2, 2)
+    w = v[..., :1].contiguous()
+    return hm, wx, bx, wy, by, tx, ty, w
+
+
+def _heads_reference(hm, wx, bx, wy, by, tx, ty, w):
+    """SimDRLoss.forward literally, in float64 (the fp32 reference's own rounding is ~1e-7 of this)."""
+    A = hm.flatten(2).double()
+    px = A @ wx.double().t() + bx.double()
+    py = A @ wy.double().t() + by.double()
+    sl1 = torch.nn.SmoothL1Loss(reduction="mean")
+    K = hm.shape[1]
+    loss = 0
+    for k in range(K):
+        loss = loss + (sl1(px[:, k], tx[:, k].double()) * w[:, k].squeeze().double()).mean()
+        loss = loss + (sl1(py[:, k], ty[:, k].double()) * w[:, k].squeeze().double()).mean()
+    return loss / K, torch.cat([px, py], -1)
+
+
+@pytest.mark.parametrize("B,K,HW,Lx,Ly", [(64, 21, 4096, 512, 512), (5, 21, 4096, 512, 512), (8, 16, 3136, 448, 448),
+                                          (3, 2, 256, 64, 192)])
+def test_simdr_heads_fused_forward(B, K, HW, Lx, Ly):
+    hm, wx, bx, wy, by, tx, ty, w = _heads_case(B, K, HW, Lx, Ly, seed=40 + B)
+    ref_loss, ref_pred = _heads_reference(hm, wx, bx, wy, by, tx, ty, w)
+    split = ops.split_bf16(torch.cat([wx, wy]).contiguous())
+    loss, dpred, pred = ops.simdr_heads_loss(hm, split, torch.cat([bx, by]), tx, ty, w, want_dpred=True, want_pred=True)
+    np.testing.assert_allclose(float(loss.item()), float(ref_loss.item()), rtol=1e-5)
+    # predictions: bf16x3 leaves ~2^-17 per product; bound relative to the magnitude of the summed terms
+    mag = (hm.flatten(2).double().abs() @ torch.cat([wx, wy]).double().abs().t()).reshape(B * K, -1)
+    err = (pred.double() - ref_pred.reshape(B * K, -1)).abs()
+    assert float((err / mag).max()) < 2e-5, float((err / mag).max())
+    want_g = (ref_pred.reshape(B * K, -1) - torch.cat([tx, ty], -1).reshape(B * K, -1).double()).clamp(-1, 1)
+    assert float((dpred.double() - want_g).abs().max()) < 1e-4
+    # deterministic (fixed-order reduction)
+    loss2, _, _ = ops.simdr_heads_loss(hm, split, torch.cat([bx, by]), tx, ty, w)
+    assert torch.equal(loss, loss2)
+
+
+def test_split_bf16_is_a_17_bit_split():
+    x = torch.randn(4096, device=DEV) * torch.logspace(-6, 6, 4096, device=DEV)
+    hi, lo = ops.split_bf16(x)
+    rec = hi.float() + lo.float()
+    assert float(((rec - x).abs() / x.abs().clamp_min(1e-30)).max()) <= 2.0 ** -16
+    assert torch.equal(hi, x.to(torch.bfloat16))
+
+
+def test_simdr_loss_module_fused_matches_unfused_and_backward():
+    """The drop-in SimDRLoss (reference parameters) — fused forward/backward against the reference's structure
+    (nn.Linear heads + KLDiscretLoss) in float64 autograd."""
+    from litehandnet_b200 import loss as LS
+    from oracle.ref_loader import _AttrDict
+    cfg = _AttrDict(DATASET=dict(image_size=[256, 256], heatmap_size=[64, 64]), PIPELINE=dict(simdr_split_ratio=2))
+    B, K = 6, 21
+    hm, wx, bx, wy, by, tx, ty, w = _heads_case(B, K, 4096, 512, 512, seed=77)
+    crit = LS.SimDRLoss(cfg).to(DEV)
+    with torch.no_grad():
+        crit.x_shared_decoder.weight.copy_(wx); crit.x_shared_decoder.bias.copy_(bx)
+        crit.y_shared_decoder.weight.copy_(wy); crit.y_shared_decoder.bias.copy_(by)
+    hm_f = hm.clone().requires_grad_(True)
+    loss = crit(hm_f, tx, ty, w)
+    (loss * 3.0).backward()
+    # float64 autograd through the literal module structure
+    hm_d = hm.double().clone().requires_grad_(True)
+    wxd, bxd, wyd, byd = [t.double().clone().requires_grad_(True) for t in (wx, bx, wy, by)]
+    px = hm_d.flatten(2) @ wxd.t() + bxd
+    py = hm_d.flatten(2) @ wyd.t() + byd
+    sl1 = torch.nn.SmoothL1Loss(reduction="mean")
+    ref = 0
+    for k in range(K):
+        ref = ref + (sl1(px[:, k], tx[:, k].double()) * w[:, k].squeeze().double()).mean()
+        ref = ref + (sl1(py[:, k], ty[:, k].double()) * w[:, k].squeeze().double()).mean()
+    ref = ref / K
+    (ref * 3.0).backward()
+    np.testing.assert_allclose(float(loss.item()), float(ref.item()), rtol=1e-5)
+
+    def close(a, b, what):
+        scale = float(b.abs().max())
+        assert float((a.double() - b).abs().max()) <= 2e-5 * scale + 1e-12, what
+
+    close(hm_f.grad, hm_d.grad, "d heatmap")
+    close(crit.x_shared_decoder.weight.grad, wxd.grad, "d Wx")
+    close(crit.y_shared_decoder.weight.grad, wyd.grad, "d Wy")
+    close(crit.x_shared_decoder.bias.grad, bxd.grad, "d bx")
+    close(crit.y_shared_decoder.bias.grad, byd.grad, "d by")
+    # the un-fused route (cuBLAS heads + lhn_simdr_smoothl1) gives the same loss
+    crit.fused = False
+    np.testing.assert_allclose(float(crit(hm, tx, ty, w).item()), float(ref.item()), rtol=1e-5)
+    # weights changed in place -> the cached bf16 split is rebuilt
+    crit.fused = True
+    with torch.no_grad():
+        crit.x_shared_decoder.weight.mul_(0.5)
+    l2 = crit(hm, tx, ty, w)
+    ref2, _ = _heads_reference(hm, wx * 0.5, bx, wy, by, tx, ty, w)
+    np.testing.assert_allclose(float(l2.item()), float(ref2.item()), rtol=1e-5)
+
+
+@pytest.mark.parametrize("bn", ["64", "128"])
+def test_simdr_heads_tile_straddles_the_xy_boundary(bn, monkeypatch):
+    """Lx = 448 = 3.5 tiles of 128 columns: one tile holds x columns and y columns (per-column target select)."""
+    monkeypatch.setenv("LHN_HEADS_BN", bn)
+    B, K, HW, Lx, Ly = 40, 16, 3136, 448, 448
+    hm, wx, bx, wy, by, tx, ty, w = _heads_case(B, K, HW, Lx, Ly, seed=91)
+    ref_loss, _ = _heads_reference(hm, wx, bx, wy, by, tx, ty, w)
+    loss, _, _ = ops.simdr_heads_loss(hm, ops.split_bf16(torch.cat([wx, wy]).contiguous()), torch.cat([bx, by]), tx, ty, w)
+    np.testing.assert_allclose(float(loss.item()), float(ref_loss.item()), rtol=1e-5)
