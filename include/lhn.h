@@ -79,8 +79,11 @@ typedef void* lhn_stream_t; /* cudaStream_t */
 #define LHN_FLAG_OVERLAP_PREVIOUS 1 /* This launch touches no buffer (inputs, outputs, workspace) that the previous
                                        launch on the same stream writes: it may begin while that launch is still
                                        draining (programmatic dependent launch), which hides the ~10 us launch gap
-                                       of back-to-back steps over rotating buffers.  Stream order is unchanged for
-                                       everything launched afterwards. */
+                                       of back-to-back steps over rotating buffers.  It is still ordered after
+                                       every EARLIER launch: an overlapped launch lets its own successor in only
+                                       after its predecessor has completed, so a launch never runs beside the one
+                                       two back and two rotating buffer sets are enough.  Stream order is unchanged
+                                       for everything launched afterwards. */
 
 #define LHN_FLAG_ACCUMULATE_LOSS 2  /* lhn_fused_render_loss_decode adds the finalised loss into loss[0] instead of
                                        overwriting it: the epoch sum of train_one_epoch's loss_dict['sum'] += v
@@ -93,6 +96,29 @@ typedef void* lhn_stream_t; /* cudaStream_t */
 
 #define LHN_MAX_TAPS 31
 #define LHN_MAX_STACKS 8
+
+/* ---- cross-GPU exchange inside the kernel (NVLink / NVSwitch peer memory) ----------------------------------------
+ * The path's only cross-rank data are a few hundred counters or four loss sums per step.  A
+ * persistent kernel that owns every SM leaves no room for a concurrent NCCL kernel, so the per-step all-reduce is
+ * done by the kernel itself: the last CTA of the grid stores this rank's block into every peer's MAILBOX (plain
+ * stores to peer-mapped memory, then a release flag), waits for the peers' flags in its own mailbox and adds the
+ * blocks in rank order — integers bit-exact, doubles in one fixed order, identical on every rank.
+ * Each rank owns one mailbox of LHN_XCH_MAILBOX_BYTES, zeroed once, mapped into every peer (symmetric memory or
+ * cudaIpc).  `seq` is the step number (1, 2, 3, ... — the same on every rank for the same step; slots rotate with it,
+ * LHN_XCH_SLOTS deep, which the launch ordering of LHN_FLAG_OVERLAP_PREVIOUS makes sufficient).  A peer that does not
+ * arrive within timeout_ms sets *status = 1 and the kernel finishes with the local block only. */
+#define LHN_XCH_MAX_RANKS 8
+#define LHN_XCH_SLOTS 4
+#define LHN_XCH_PAYLOAD_BYTES 8192
+#define LHN_XCH_CTRL_BYTES 4096   /* flags u32 [slots][ranks], then the launch ticket */
+#define LHN_XCH_MAILBOX_BYTES (LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + LHN_XCH_CTRL_BYTES)
+typedef struct {
+  void* mailbox[LHN_XCH_MAX_RANKS]; /* mailbox of rank r as mapped into THIS process; mailbox[rank] is the local one */
+  int32_t world, rank;
+  uint32_t seq;                     /* step number >= 1 */
+  uint32_t timeout_ms;              /* 0 = 2000 */
+  int32_t* status;                  /* device int32 (local), or NULL */
+} lhn_exchange;
 
 /* Decode parameters. */
 typedef struct {
@@ -198,6 +224,22 @@ LHN_API int lhn_fused_render_loss_decode(const void* hm, const void* hm_flip,
                                          void* workspace, int64_t workspace_bytes, double* sums,
                                          int sum_reduction, float loss_scale, float* loss,
                                          lhn_stream_t stream);
+
+/* The same with the loss sums all-reduced over the ranks INSIDE the kernel (lhn_exchange, above): `sums` and `loss`
+ * then hold the batch-GLOBAL (S_pos, S_neg, N_pos, numel) and the loss a single process would compute on the
+ * concatenated batch (global N_pos, loss/heatmapLoss.py:253-258) — one launch per step, no NCCL call. */
+LHN_API int lhn_fused_render_loss_decode_xch(const void* hm, const void* hm_flip,
+                                         const int32_t* flip_index, int dtype, int64_t B, int K, int H,
+                                         int W, int64_t stride_b, int64_t stride_c,
+                                         int64_t flip_stride_b, int64_t flip_stride_c,
+                                         const float* center, const float* scale,
+                                         const lhn_decode_params* dp, float* out_hm, float* out_kpts,
+                                         int32_t* out_idx, const lhn_render_params* rp,
+                                         const float* joints, int joints_stride, const float* vis,
+                                         int vis_stride, float* out_weight, double* partials,
+                                         void* workspace, int64_t workspace_bytes, double* sums,
+                                         int sum_reduction, float loss_scale, float* loss,
+                                         const lhn_exchange* xch, lhn_stream_t stream);
 
 /* ---- loss against an explicit target tensor (the un-fused drop-in) ----------------------------
  * DistanceLoss.forward(output, target, target_weight) / JointsDistanceLoss.forward
@@ -367,6 +409,19 @@ LHN_API int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, 
                                    const uint8_t* mask, const float* bbox_wh, float pck_thr,
                                    float auc_nor, int auc_steps, int64_t* counters,
                                    lhn_stream_t stream);
+
+/* The same with the per-step counter block all-reduced over the ranks INSIDE the kernel: `counters` is this rank's
+ * per-step block (zero at entry; the kernel leaves it zero), `totals` int64 [(auc_steps+5)*K] receives
+ * += sum over ranks of the step's blocks — after the launch every rank holds the same running totals, equal bit for
+ * bit to a single-process evaluation (datasets/base_dataset.py:193-261 on the gathered results). */
+LHN_API int lhn_decode_heatmap_pck_xch(const void* hm, int dtype, int64_t B, int K, int H, int W,
+                                   int64_t stride_b, int64_t stride_c, const float* center,
+                                   const float* scale, const lhn_decode_params* dp, float* out_hm,
+                                   float* out_kpts, int32_t* out_idx, const float* gt,
+                                   const uint8_t* mask, const float* bbox_wh, float pck_thr,
+                                   float auc_nor, int auc_steps, int64_t* counters,
+                                   int64_t* totals, const lhn_exchange* xch,
+                                          lhn_stream_t stream);
 
 /* evaluate_pck (evaluation.py:10-59): argmax (A1) on pred and gt heatmap batches [B,K,H,W],
  * * image_size/[W,H], distance / max(bbox[:,0,2:]), per-image hits/(2*sum w)*2 in f32.
