@@ -165,6 +165,7 @@ class Workload:
         self.args, self.rank, self.world, self.dev = args, rank, world, dev
         self.collective = "none"
         self.nccl_bytes_per_step = 0
+        self.nvlink_bytes_per_step = 0
 
     # -- hooks -------------------------------------------------------------------------------------------
     def step(self, i):
@@ -229,19 +230,28 @@ class FusedWorkload(Workload):
         self.sets = [make_set_2d(B, K, H, W, 1000 * rank + 10 * r + (0 if cfg_id == 2 else 50000), dev, self.image_size,
                                  sigma=float(self.sigma), flip=self.flip) for r in range(self.R_in)]
         self.global_loss = world > 1 and args.global_loss
+        self.xch = None
+        if self.global_loss and args.collective == "nvlink":
+            from litehandnet_b200.dist import PeerExchange
+            self.xch = PeerExchange(dev)
         self.epoch_loss = torch.zeros(1, dtype=torch.float32, device=dev) if (world > 1 and not self.global_loss) else None
         overlap = self.R >= 2 and not args.no_overlap
         self.overlap = overlap
         self.bound = []
         for r in range(self.R):
             s = self.sets[r % self.R_in]
+            nccl_global = self.global_loss and self.xch is None
             self.bound.append(fused.BoundFusedStep(self.step_cfg, s[0], s[2], s[3], s[4], s[5], hm_flip=s[1],
-                                                   finalize=not self.global_loss, overlap_previous=overlap,
-                                                   spare_sms=(args.spare_sms if self.global_loss else 0),
-                                                   accumulate_into=self.epoch_loss))
+                                                   finalize=not nccl_global, overlap_previous=overlap,
+                                                   spare_sms=(args.spare_sms if nccl_global else 0),
+                                                   accumulate_into=self.epoch_loss, exchange=self.xch))
         self.pending = []
         if world > 1:
-            if self.global_loss:
+            if self.xch is not None:
+                self.collective = ("batch-global loss: the 4 f64 loss sums are all-gathered EVERY step INSIDE the kernel through "
+                                   f"peer-mapped mailboxes over NVLink ({self.xch.how}) and added in rank order; no NCCL call, one launch per step")
+                self.nvlink_bytes_per_step = self.xch.bytes_per_step(32)
+            elif self.global_loss:
                 self.collective = "ncclAllReduce of the 4 f64 loss sums EVERY step (batch-global N_pos), lhn_loss_finalize after it"
                 self.nccl_bytes_per_step = 32
                 self.launches_per_step = 2
@@ -267,7 +277,7 @@ class FusedWorkload(Workload):
         import torch.distributed as dist
         b = self.bound[i % self.R]
         b.launch()
-        if self.global_loss:
+        if self.global_loss and self.xch is None:
             self.flush()
             self.pending.append((dist.all_reduce(b.sums, async_op=True), b))
 
@@ -331,7 +341,11 @@ class FusedWorkload(Workload):
             loss_rel = abs(float(self.local_epoch.item()) - want) / abs(want)
             note = "epoch loss sum of this rank over the timed steps vs the sum of the per-step reference losses"
         elif self.global_loss:
-            note = "loss not compared (global-N_pos loss spans all ranks); sums checked in tests/test_gpu_bench_path.py"
+            note = ("loss not compared here (the global-N_pos loss spans all ranks' inputs); tests/test_gpu_exchange.py checks it "
+                    "against the oracle on the concatenated batch")
+            if self.xch is not None and int(self.xch.status.item()) != 0:
+                idx_equal = False
+                note = "EXCHANGE TIMEOUT: a peer's block did not arrive"
         else:
             for r in range(self.R):
                 lr = abs(float(self.bound[r].loss.item()) - ref_losses[r % self.R_in]) / abs(ref_losses[r % self.R_in])
@@ -399,6 +413,10 @@ class DecodeWorkload(Workload):
         self.overlap = overlap
         self.bound = []
         self.T = 20
+        self.xch = None
+        if self.metrics and world > 1 and args.collective == "nvlink":
+            from litehandnet_b200.dist import PeerExchange
+            self.xch = PeerExchange(dev)
         if self.metrics:
             self.total = torch.zeros((self.T + 5) * K, dtype=torch.int64, device=dev)          # running global counters
             # per-step counter blocks (one per rotating set), all-reduced every step at N > 1
@@ -408,9 +426,16 @@ class DecodeWorkload(Workload):
             if self.metrics:
                 m = dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=self.step_cnt[r] if world > 1 else self.total,
                          pck_thr=0.2, auc_nor=30.0, auc_steps=self.T)
+                if self.xch is not None:
+                    m.update(exchange=self.xch, totals=self.total)
             self.bound.append(fused.BoundDecodeStep(s[0], s[1], s[2], L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE,
                                                     overlap_previous=overlap, metrics=m))
-        if self.metrics and world > 1:
+        if self.xch is not None:
+            self.collective = ("the per-step PCK/AUC/EPE counter block is all-gathered EVERY eval step INSIDE the kernel through "
+                               f"peer-mapped mailboxes over NVLink ({self.xch.how}) and added in rank order into the running totals; "
+                               "no NCCL call, one launch per step (datasets/base_dataset.py:193-261, spawn_dist.py:68-80)")
+            self.nvlink_bytes_per_step = self.xch.bytes_per_step((self.T + 5) * K * 8)
+        elif self.metrics and world > 1:
             self.aux = torch.cuda.Stream(device=dev)
             self.done = [torch.cuda.Event() for _ in range(self.R)]
             self.freed = [torch.cuda.Event() for _ in range(self.R)]
@@ -447,7 +472,7 @@ class DecodeWorkload(Workload):
         import torch.distributed as dist
         r = i % self.R
         b = self.bound[r]
-        if self.metrics and self.world > 1:
+        if self.metrics and self.world > 1 and self.xch is None:
             comp = torch.cuda.current_stream(self.dev)
             if self.used[r]:
                 comp.wait_event(self.freed[r])            # the block was folded into the totals and zeroed
@@ -465,7 +490,7 @@ class DecodeWorkload(Workload):
 
     def end_of_epoch(self):
         import torch
-        if self.metrics and self.world > 1:
+        if self.metrics and self.world > 1 and self.xch is None:
             torch.cuda.current_stream(self.dev).wait_stream(self.aux)
 
     def begin_epoch(self):
@@ -523,6 +548,8 @@ class DecodeWorkload(Workload):
             ok = ok and bool(cnt_equal)
             mono = self.monolithic_counters(steps)
             out["counters_equal_monolithic"] = bool(torch.equal(mono, self.total))
+            if self.xch is not None:
+                out["exchange_timeouts"] = int(self.xch.status.item())
             ok = ok and out["counters_equal_monolithic"]
             from litehandnet_b200 import ops
             v = ops.metrics_finalize(self.total, self.K, self.T)[:3].cpu().numpy()
@@ -940,6 +967,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         cfg["parallelism"] = f"batch-shard x{world}; {wl.collective}" if world > 1 else "single GPU"
         if world > 1:
             cfg["nccl_bytes_per_step"] = wl.nccl_bytes_per_step
+            cfg["nvlink_bytes_per_step_per_rank"] = wl.nvlink_bytes_per_step
         cfg["launch"] = "eager C-ABI launches, one kernel per step" + (
             "; LHN_FLAG_OVERLAP_PREVIOUS (programmatic dependent launch over rotating buffer sets)" if wl.overlap else "")
         if loss_val is not None:
@@ -1008,6 +1036,9 @@ def main():
     ap.add_argument("--global-loss", action="store_true",
                     help="N > 1, configs 2/5: balanced loss with batch-global N_pos (an all-reduce of the f64 sums every step) "
                          "instead of the reference's per-rank loss")
+    ap.add_argument("--collective", default="nvlink", choices=["nvlink", "nccl"],
+                    help="N > 1: how a PER-STEP exchange (config 4 counters, --global-loss sums) is done: inside the kernel over "
+                         "peer-mapped NVLink mailboxes (default) or as an NCCL all-reduce beside the kernel")
     ap.add_argument("--spare-sms", type=int, default=4,
                     help="N > 1 with --global-loss: SMs the persistent kernel leaves free for the NCCL all-reduce")
     ap.add_argument("--clock-interval-ms", type=float, default=0.0, help="NVML sampling period (0 = automatic)")

@@ -22,6 +22,8 @@ LOSS_NONE, LOSS_DISTANCE, LOSS_DISTANCE_BALANCE, LOSS_JOINTS_MSE = 0, 1, 2, 3
 FLAG_OVERLAP_PREVIOUS = 1
 FLAG_ACCUMULATE_LOSS = 2
 MAX_TAPS, MAX_STACKS = 31, 8
+XCH_MAX_RANKS, XCH_SLOTS, XCH_PAYLOAD_BYTES, XCH_CTRL_BYTES = 8, 4, 8192, 4096
+XCH_MAILBOX_BYTES = XCH_SLOTS * XCH_MAX_RANKS * XCH_PAYLOAD_BYTES + XCH_CTRL_BYTES
 REGION_SH, REGION_RP, REGION_CS = 0, 1, 2
 MAX_CANDIDATES = 32
 
@@ -35,6 +37,7 @@ EXPORTS = [
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_decode_simdr_flags", "lhn_simdr_loss_workspace_bytes",
     "lhn_simdr_smoothl1", "lhn_split_bf16", "lhn_simdr_heads_workspace_bytes", "lhn_simdr_heads_loss", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
+    "lhn_fused_render_loss_decode_xch", "lhn_decode_heatmap_pck_xch",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
     "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate", "lhn_region_bbox_decode", "lhn_heatmap_nms",
     "lhn_vector_nms", "lhn_refine_points", "lhn_decode_heatmap_roi", "lhn_box_nms", "lhn_render_region_wh", "lhn_dark_refine_points",
@@ -51,6 +54,11 @@ class RenderParams(C.Structure):
     _fields_ = [("loss_mode", C.c_int32), ("unbiased", C.c_int32), ("num_stacks", C.c_int32),
                 ("reserved", C.c_int32), ("image_w", C.c_float), ("image_h", C.c_float),
                 ("pos_value", C.c_float), ("sigma", C.c_float * MAX_STACKS)]
+
+
+class Exchange(C.Structure):
+    _fields_ = [("mailbox", C.c_void_p * XCH_MAX_RANKS), ("world", C.c_int32), ("rank", C.c_int32),
+                ("seq", C.c_uint32), ("timeout_ms", C.c_uint32), ("status", C.c_void_p)]
 
 
 class RegionParams(C.Structure):
@@ -82,6 +90,13 @@ def _declare(lib):
     lib.lhn_fused_render_loss_decode.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, i64, i64, i64, i64, vp, vp,
                                                  C.POINTER(DecodeParams), vp, vp, vp, C.POINTER(RenderParams),
                                                  vp, i32, vp, i32, vp, vp, vp, i64, vp, i32, f32, vp, vp]
+    lib.lhn_fused_render_loss_decode_xch.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, i64, i64, i64, i64, vp, vp,
+                                                     C.POINTER(DecodeParams), vp, vp, vp, C.POINTER(RenderParams),
+                                                     vp, i32, vp, i32, vp, vp, vp, i64, vp, i32, f32, vp,
+                                                     C.POINTER(Exchange), vp]
+    lib.lhn_decode_heatmap_pck_xch.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp,
+                                               C.POINTER(DecodeParams), vp, vp, vp, vp, vp, vp, f32, f32,
+                                               i32, vp, vp, C.POINTER(Exchange), vp]
     lib.lhn_loss_backward.argtypes = [vp, vp, vp, i32, i64, i64, i32, f32, vp, i32, f32, vp, vp, vp]
     lib.lhn_render_loss_backward.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, C.POINTER(RenderParams),
                                              vp, i32, vp, i32, vp, i32, f32, vp, vp, vp]

@@ -498,6 +498,19 @@ static int fill_decode(HmArgs& a, const lhn_decode_params* dp) {
   return LHN_OK;
 }
 
+static int fill_exchange(HmArgs& a, const lhn_exchange* x) {
+  if (!x) return LHN_OK;
+  if (x->world < 1 || x->world > LHN_XCH_MAX_RANKS || x->rank < 0 || x->rank >= x->world || x->seq == 0) return LHN_EINVAL;
+  for (int r = 0; r < x->world; ++r) {
+    if (!x->mailbox[r]) return LHN_EINVAL;
+    if ((uintptr_t)x->mailbox[r] % 16) return LHN_EALIGN;
+    a.xch_mail[r] = static_cast<unsigned char*>(x->mailbox[r]);
+  }
+  a.xch_world = x->world; a.xch_rank = x->rank; a.xch_seq = x->seq; a.xch_timeout_ms = x->timeout_ms;
+  a.xch_status = x->status;
+  return LHN_OK;
+}
+
 }  // namespace lhn
 
 using namespace lhn;
@@ -524,7 +537,7 @@ static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_
                                int joints_stride, const float* vis, int vis_stride,
                                float* out_weight, double* partials, bool fused, void* workspace,
                                int64_t workspace_bytes, double* sums, int sum_reduction,
-                               float loss_scale, float* loss, lhn_stream_t stream);
+                               float loss_scale, float* loss, lhn_stream_t stream, const lhn_exchange* xch = nullptr);
 
 extern "C" int lhn_fused_render_loss_decode(const void* hm, const void* hm_flip,
                                             const int32_t* flip_index, int dtype, int64_t B, int K,
@@ -544,6 +557,27 @@ extern "C" int lhn_fused_render_loss_decode(const void* hm, const void* hm_flip,
                              flip_stride_b, flip_stride_c, center, scale, dp, out_hm, out_kpts, out_idx,
                              rp, joints, joints_stride, vis, vis_stride, out_weight, partials, true,
                              workspace, workspace_bytes, sums, sum_reduction, loss_scale, loss, stream);
+}
+
+extern "C" int lhn_fused_render_loss_decode_xch(const void* hm, const void* hm_flip,
+                                                const int32_t* flip_index, int dtype, int64_t B, int K,
+                                                int H, int W, int64_t stride_b, int64_t stride_c,
+                                                int64_t flip_stride_b, int64_t flip_stride_c,
+                                                const float* center, const float* scale,
+                                                const lhn_decode_params* dp, float* out_hm,
+                                                float* out_kpts, int32_t* out_idx,
+                                                const lhn_render_params* rp, const float* joints,
+                                                int joints_stride, const float* vis, int vis_stride,
+                                                float* out_weight, double* partials, void* workspace,
+                                                int64_t workspace_bytes, double* sums, int sum_reduction,
+                                                float loss_scale, float* loss, const lhn_exchange* xch,
+                                                lhn_stream_t stream) {
+  if (!rp || rp->loss_mode == LHN_LOSS_NONE || !workspace || !xch) return LHN_EINVAL;
+  if ((uintptr_t)workspace % 16) return LHN_EALIGN;
+  return decode_heatmap_impl(hm, hm_flip, flip_index, dtype, B, K, H, W, stride_b, stride_c,
+                             flip_stride_b, flip_stride_c, center, scale, dp, out_hm, out_kpts, out_idx,
+                             rp, joints, joints_stride, vis, vis_stride, out_weight, partials, true,
+                             workspace, workspace_bytes, sums, sum_reduction, loss_scale, loss, stream, xch);
 }
 
 extern "C" int lhn_decode_heatmap(const void* hm, const void* hm_flip, const int32_t* flip_index,
@@ -569,7 +603,7 @@ static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_
                                int joints_stride, const float* vis, int vis_stride,
                                float* out_weight, double* partials, bool fused, void* workspace,
                                int64_t workspace_bytes, double* sums, int sum_reduction,
-                               float loss_scale, float* loss, lhn_stream_t stream) {
+                               float loss_scale, float* loss, lhn_stream_t stream, const lhn_exchange* xch) {
   if (B < 0 || K <= 0 || H <= 0 || W <= 0) return LHN_EINVAL;
   if (B == 0) return LHN_OK;
   if (!hm) return LHN_EINVAL;
@@ -614,8 +648,11 @@ static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_
   int used_team_kernel = 0;
   double* fallback_partials = partials ? partials : reinterpret_cast<double*>(ws + kWsHeader + ws_team_bytes());
   a.fallback_partials = fallback_partials;
+  rc = fill_exchange(a, xch);
+  if (rc) return rc;
   rc = run_heatmap(a, dtype, (cudaStream_t)stream, &used_team_kernel);
   if (rc || used_team_kernel) return rc;
+  if (xch && xch->world > 1) return LHN_EINVAL;      // the in-kernel exchange lives in the team kernel only
   // CTA-per-plane fallback wrote per-plane partials: reduce + finalise as separate launches
   double* tmp_sums = sums ? sums : reinterpret_cast<double*>(ws + kWsHeader);
   rc = lhn_loss_reduce(fallback_partials, a.n_planes, tmp_sums, 0, stream);
@@ -624,6 +661,14 @@ static int decode_heatmap_impl(const void* hm, const void* hm_flip, const int32_
   return rc;
 }
 
+static int decode_heatmap_pck_impl(const void* hm, int dtype, int64_t B, int K, int H, int W,
+                                   int64_t stride_b, int64_t stride_c, const float* center,
+                                   const float* scale, const lhn_decode_params* dp, float* out_hm,
+                                   float* out_kpts, int32_t* out_idx, const float* gt,
+                                   const uint8_t* mask, const float* bbox_wh, float pck_thr,
+                                   float auc_nor, int auc_steps, int64_t* counters, int64_t* totals,
+                                   const lhn_exchange* xch, lhn_stream_t stream);
+
 extern "C" int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, int H, int W,
                                       int64_t stride_b, int64_t stride_c, const float* center,
                                       const float* scale, const lhn_decode_params* dp, float* out_hm,
@@ -631,6 +676,30 @@ extern "C" int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int 
                                       const uint8_t* mask, const float* bbox_wh, float pck_thr,
                                       float auc_nor, int auc_steps, int64_t* counters,
                                       lhn_stream_t stream) {
+  return decode_heatmap_pck_impl(hm, dtype, B, K, H, W, stride_b, stride_c, center, scale, dp, out_hm, out_kpts, out_idx,
+                                 gt, mask, bbox_wh, pck_thr, auc_nor, auc_steps, counters, nullptr, nullptr, stream);
+}
+
+extern "C" int lhn_decode_heatmap_pck_xch(const void* hm, int dtype, int64_t B, int K, int H, int W,
+                                          int64_t stride_b, int64_t stride_c, const float* center,
+                                          const float* scale, const lhn_decode_params* dp, float* out_hm,
+                                          float* out_kpts, int32_t* out_idx, const float* gt,
+                                          const uint8_t* mask, const float* bbox_wh, float pck_thr,
+                                          float auc_nor, int auc_steps, int64_t* counters, int64_t* totals,
+                                          const lhn_exchange* xch, lhn_stream_t stream) {
+  if (!totals || !xch) return LHN_EINVAL;
+  if ((int64_t)(auc_steps + 5) * K * 8 > LHN_XCH_PAYLOAD_BYTES) return LHN_EINVAL;
+  return decode_heatmap_pck_impl(hm, dtype, B, K, H, W, stride_b, stride_c, center, scale, dp, out_hm, out_kpts, out_idx,
+                                 gt, mask, bbox_wh, pck_thr, auc_nor, auc_steps, counters, totals, xch, stream);
+}
+
+static int decode_heatmap_pck_impl(const void* hm, int dtype, int64_t B, int K, int H, int W,
+                                   int64_t stride_b, int64_t stride_c, const float* center,
+                                   const float* scale, const lhn_decode_params* dp, float* out_hm,
+                                   float* out_kpts, int32_t* out_idx, const float* gt,
+                                   const uint8_t* mask, const float* bbox_wh, float pck_thr,
+                                   float auc_nor, int auc_steps, int64_t* counters, int64_t* totals,
+                                   const lhn_exchange* xch, lhn_stream_t stream) {
   if (B < 0 || K <= 0 || H <= 0 || W <= 0 || auc_steps < 0 || !(auc_nor > 0.f)) return LHN_EINVAL;
   if (B == 0) return LHN_OK;
   if (!hm || !gt || !mask || !bbox_wh || !counters) return LHN_EINVAL;
@@ -648,5 +717,12 @@ extern "C" int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int 
   for (int t = 0; t < auc_steps; ++t) a.auc_thr[t] = (float)(1.0 * t / auc_steps);
   if (a.n_planes == 0) return LHN_OK;
   if (a.n_planes > 0x7fffffffLL) return LHN_EINVAL;
-  return run_heatmap(a, dtype, (cudaStream_t)stream);
+  if (!xch) return run_heatmap(a, dtype, (cudaStream_t)stream);
+  rc = fill_exchange(a, xch);
+  if (rc) return rc;
+  a.xch_totals = reinterpret_cast<long long*>(totals);
+  int used_team_kernel = 0;
+  rc = run_heatmap(a, dtype, (cudaStream_t)stream, &used_team_kernel);
+  if (rc) return rc;
+  return used_team_kernel ? LHN_OK : LHN_EINVAL;   // the in-kernel exchange lives in the team kernel only
 }

@@ -73,6 +73,12 @@ struct HmArgs {
   int overlap_previous;            // LHN_FLAG_OVERLAP_PREVIOUS: launch with programmatic stream serialization
   int feat_pow2;                   // feat_x, feat_y are powers of two: joint / feat == joint * inv_feat exactly
   double inv_feat_x, inv_feat_y;
+  // in-kernel cross-GPU exchange (lhn_exchange; team kernel only): mailboxes of all ranks as mapped here
+  unsigned char* xch_mail[LHN_XCH_MAX_RANKS];
+  int xch_world, xch_rank;         // xch_world == 0: no exchange
+  unsigned int xch_seq, xch_timeout_ms;
+  int* xch_status;
+  long long* xch_totals;           // fused metrics: running totals that receive += sum over ranks of the step's block
 };
 
 // ---- shared-memory layout --------------------------------------------------------------------

@@ -130,6 +130,56 @@ __device__ __forceinline__ float elem_f32(const T* p, int i) { return Elem<T>::t
 // quads per row of the DARK tile: the (ksize+4)-wide window starts 0..3 columns into its first quad
 __host__ __device__ constexpr int tile_quads(int td) { return (td + 6) >> 2; }
 
+// ---- in-kernel all-gather over peer-mapped mailboxes (lhn_exchange, include/lhn.h) -----------------------------------
+// One warp (the grid's last epilogue warp).  `local` holds n 64-bit words (n * 8 <= LHN_XCH_PAYLOAD_BYTES).  On return
+// every peer's block of this step is readable at xch_slot(a, r) (volatile loads: the data arrived over NVLink).
+// Returns false after a timeout (*status = 1): the caller then continues with the local block only.
+__device__ __forceinline__ unsigned char* xch_slot(const HmArgs& a, int mailbox_rank, int src_rank) {
+  const unsigned slot = a.xch_seq & (LHN_XCH_SLOTS - 1);
+  return a.xch_mail[mailbox_rank] + ((size_t)slot * LHN_XCH_MAX_RANKS + src_rank) * LHN_XCH_PAYLOAD_BYTES;
+}
+__device__ __forceinline__ unsigned int* xch_flag(const HmArgs& a, int mailbox_rank, int src_rank) {
+  const unsigned slot = a.xch_seq & (LHN_XCH_SLOTS - 1);
+  return reinterpret_cast<unsigned int*>(a.xch_mail[mailbox_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES) +
+         slot * LHN_XCH_MAX_RANKS + src_rank;
+}
+__device__ __forceinline__ unsigned int* xch_ticket(const HmArgs& a) {   // launch ticket of the fused-metrics variant
+  return reinterpret_cast<unsigned int*>(a.xch_mail[a.xch_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + 1024);
+}
+static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const unsigned long long* local, int n, int lane) {
+  const int world = a.xch_world, me = a.xch_rank;
+  // 1. this rank's block into every peer's mailbox (plain stores over NVLink), then a release flag per peer
+  for (int r = 0; r < world; ++r) {
+    if (r == me) continue;
+    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(xch_slot(a, r, me));
+    for (int e = lane; e < n; e += 32) dst[e] = __ldcg(local + e);
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < world && lane != me)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(a, lane, me)), "r"(a.xch_seq) : "memory");
+  // 2. the peers' flags in my mailbox
+  bool ok = true;
+  if (lane < world && lane != me) {
+    const unsigned int* f = xch_flag(a, me, lane);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long limit = (unsigned long long)(a.xch_timeout_ms ? a.xch_timeout_ms : 2000u) * 1000000ull;
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v == a.xch_seq) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > limit) { ok = false; break; }
+      __nanosleep(200);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system();
+  if (!ok && lane == 0 && a.xch_status) *a.xch_status = 1;
+  return ok;
+}
+
 // WC:  compile-time square plane size (64 or 56: 89 of the reference's 108 configs) with a compile-time team
 //      size (TWC warps = TWC-1 sweepers + 1 epilogue), so the sweep is a fully unrolled 128-bit loop with a
 //      loop-invariant column quad per thread and immediate address offsets; 0 = run-time H, W and team size.
@@ -714,6 +764,30 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             if (run) atomicAdd(gcnt + (int64_t)row * Ki + k, run);
           }
         }
+        if (a.xch_world > 0) {
+          // in-kernel all-reduce of this step's block (lhn_decode_heatmap_pck_xch): the grid's last CTA sends the
+          // block to every peer, waits for theirs and adds them in rank order into the running totals
+          asm volatile("griddepcontrol.wait;" ::: "memory");    // the ticket is shared with the previous launch
+          __threadfence();
+          __syncwarp();
+          unsigned int tk = 0;
+          if (lane == 0) tk = atomicAdd(xch_ticket(a), 1u);
+          tk = __shfl_sync(0xffffffffu, tk, 0);
+          if (tk == gridDim.x - 1) {
+            __threadfence();
+            const bool ok = a.xch_world > 1 ? xch_publish_and_wait(a, gcnt, n_cnt, lane) : true;
+            for (int e = lane; e < n_cnt; e += 32) {
+              long long sum = 0;
+              for (int r = 0; r < a.xch_world; ++r) {
+                if (r == a.xch_rank) sum += (long long)__ldcg(gcnt + e);
+                else if (ok) sum += (long long)reinterpret_cast<volatile unsigned long long*>(xch_slot(a, a.xch_rank, r))[e];
+              }
+              a.xch_totals[e] += sum;
+              gcnt[e] = 0ull;                                   // the per-step block is left zero for its next use
+            }
+            if (lane == 0) *xch_ticket(a) = 0u;
+          }
+        }
       }
     }
 #ifdef LHN_TRACE
@@ -777,6 +851,26 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           for (int u = 0; u < 5; ++u) { v0 += x[u].x; v1 += x[u].y; v2 += y[u].x; v3 += y[u].y; }
         }
         v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+        if (a.xch_world > 1) {
+          // batch-global loss (lhn_fused_render_loss_decode_xch): all-gather the four sums of every rank through the
+          // peer mailboxes and add them in rank order — the same doubles in the same order on every rank
+          unsigned long long* mine = reinterpret_cast<unsigned long long*>(xch_slot(a, a.xch_rank, a.xch_rank));
+          if (lane == 0) {
+            mine[0] = (unsigned long long)__double_as_longlong(v0); mine[1] = (unsigned long long)__double_as_longlong(v1);
+            mine[2] = (unsigned long long)__double_as_longlong(v2); mine[3] = (unsigned long long)__double_as_longlong(v3);
+          }
+          __syncwarp();
+          const bool ok = xch_publish_and_wait(a, mine, 4, lane);
+          if (ok) {
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+            for (int r = 0; r < a.xch_world; ++r) {
+              const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(xch_slot(a, a.xch_rank, r));
+              g0 += __longlong_as_double((long long)src[0]); g1 += __longlong_as_double((long long)src[1]);
+              g2 += __longlong_as_double((long long)src[2]); g3 += __longlong_as_double((long long)src[3]);
+            }
+            v0 = g0; v1 = g1; v2 = g2; v3 = g3;
+          }
+        }
         if (lane == 0) {
           if (a.sums_out) { a.sums_out[0] = v0; a.sums_out[1] = v1; a.sums_out[2] = v2; a.sums_out[3] = v3; }
           if (a.loss_out) {

@@ -55,3 +55,104 @@ def all_reduce_counters(counters):
     if _active():
         dist.all_reduce(counters, op=dist.ReduceOp.SUM)
     return counters
+
+
+class PeerExchange:
+    """Mailboxes of the in-kernel exchange (include/lhn.h lhn_exchange): every rank owns LHN_XCH_MAILBOX_BYTES of
+    zeroed device memory that is mapped into every peer of the node — torch symmetric memory (CUDA VMM handles
+    exchanged over the process group's store), or cudaIpc handles as the fallback.  The kernels of
+    lhn_fused_render_loss_decode_xch / lhn_decode_heatmap_pck_xch store their step's block straight into the peers'
+    mailboxes over NVLink and add what arrives, so the per-step all-reduce of SURVEY §8e needs no NCCL call and no SM
+    left free for one.  `next_seq()` numbers the steps; every rank must issue the same sequence of exchanging launches.
+    """
+
+    def __init__(self, device, group=None):
+        from . import _lib as L
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group) if _active() else 1
+        self.rank = dist.get_rank(group) if _active() else 0
+        if self.world > L.XCH_MAX_RANKS:
+            raise L.LhnError(f"in-kernel exchange supports up to {L.XCH_MAX_RANKS} ranks of one node")
+        self.seq = 0
+        self.how = "local"
+        self._keep = []
+        if self.world == 1:
+            self.mailbox = torch.zeros(L.XCH_MAILBOX_BYTES, dtype=torch.uint8, device=self.device)
+            self.ptrs = [self.mailbox.data_ptr()]
+        else:
+            try:
+                self.ptrs = self._symmetric(L.XCH_MAILBOX_BYTES, group)
+                self.how = "torch symmetric memory (CUDA VMM, peer-mapped over NVLink)"
+            except Exception as e:                                   # pragma: no cover - depends on the driver stack
+                self._symm_error = f"{type(e).__name__}: {e}"
+                self.ptrs = self._ipc(L.XCH_MAILBOX_BYTES, group)
+                self.how = "cudaIpc memory handles (peer-mapped over NVLink)"
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _symmetric(self, nbytes, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        g = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(g.group_name)
+        except Exception:
+            pass
+        self.mailbox = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.mailbox.zero_()
+        torch.cuda.synchronize(self.device)
+        hdl = symm_mem.rendezvous(self.mailbox, g)
+        self._keep.append(hdl)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.mailbox.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory handle layout")
+        return ptrs
+
+    def _ipc(self, nbytes, group):
+        self.mailbox = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        torch.cuda.synchronize(self.device)
+        handle = self.mailbox.untyped_storage()._share_cuda_()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self.mailbox.data_ptr())
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(*h)
+            t = torch.empty(0, dtype=torch.uint8, device=st.device).set_(st)
+            self._keep.append(t)
+            ptrs.append(t.data_ptr())
+        return ptrs
+
+    @classmethod
+    def local_group(cls, n, device):
+        """n mailboxes on ONE device wired to each other (protocol tests: n 'ranks' on n streams of a single GPU)."""
+        from . import _lib as L
+        boxes = [torch.zeros(L.XCH_MAILBOX_BYTES, dtype=torch.uint8, device=device) for _ in range(n)]
+        out = []
+        for r in range(n):
+            x = cls.__new__(cls)
+            x.device, x.world, x.rank, x.seq, x.how = torch.device(device), n, r, 0, "local test group"
+            x.mailbox, x.ptrs, x._keep = boxes[r], [b.data_ptr() for b in boxes], boxes
+            x.status = torch.zeros(1, dtype=torch.int32, device=device)
+            out.append(x)
+        return out
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
+    def struct(self, timeout_ms=2000):
+        """A fresh lhn_exchange for one bound launcher (its seq is set right before every launch)."""
+        from . import _lib as L
+        x = L.Exchange()
+        for r, p in enumerate(self.ptrs):
+            x.mailbox[r] = p
+        x.world, x.rank, x.seq, x.timeout_ms = self.world, self.rank, 0, int(timeout_ms)
+        x.status = self.status.data_ptr()
+        return x
+
+    def bytes_per_step(self, payload_bytes):
+        """NVLink bytes this rank sends per exchanging launch: the block + a 4-byte flag to each peer."""
+        return (self.world - 1) * (int(payload_bytes) + 4)

@@ -244,12 +244,16 @@ class BoundFusedStep:
     launch-bound at ~0.1 ms of GPU work per step)."""
 
     def __init__(self, step, hm, joints_3d, joints_3d_visible, center, scale, hm_flip=None,
-                 finalize=True, overlap_previous=False, spare_sms=0, accumulate_into=None, outputs=None):
+                 finalize=True, overlap_previous=False, spare_sms=0, accumulate_into=None, outputs=None,
+                 exchange=None):
         """overlap_previous: this step shares no buffer with the step launched just before it on the stream
         (rotating input/output sets), so its kernel may start while that one drains (LHN_FLAG_OVERLAP_PREVIOUS);
         it is still ordered after every EARLIER launch, so two rotating sets are enough.
         accumulate_into: f32 [1] device tensor that receives ``+= loss`` of every step (the epoch sum that
         train_one_epoch keeps in loss_dict['sum'], left on the device; LHN_FLAG_ACCUMULATE_LOSS).
+        exchange: a dist.PeerExchange — the four loss sums are all-reduced over the ranks INSIDE the kernel (peer-mapped
+        mailboxes over NVLink, lhn_fused_render_loss_decode_xch): `sums` / `loss` are then the batch-global values a
+        single process would compute on the concatenated batch, still one launch per step and no NCCL call.
         outputs: optional dict of caller-owned contiguous output tensors (hm_preds / preds f32 [B,K,3], idx int32
         [B,K], weight f32 [B,K], sums f64 [4], loss f32 [1]; larger leading sizes are fine) — e.g. the other
         output set of a rotation whose steps have different batch sizes."""
@@ -315,6 +319,10 @@ class BoundFusedStep:
             L.ptr(self.idx), C.byref(self.rp), L.ptr(joints), joints.shape[2], L.ptr(vis), vis.shape[2],
             L.ptr(self.weight), None, L.ptr(self.workspace), self.workspace.numel(), L.ptr(self.sums), 0,
             float(step.loss_weight), L.ptr(self.loss) if finalize else None)
+        self.exchange = exchange
+        if exchange is not None:
+            self.xch = exchange.struct()
+            self._xch_args = self._fused_args + (C.byref(self.xch),)
         self._decode_args = (
             L.ptr(hm), L.ptr(hm_flip), L.ptr(fi), L.dtype_code(hm), B, Cc, H, W, sb, sc, fb, fc,
             L.ptr(center), L.ptr(scale), C.byref(self.dp), L.ptr(self.hm_preds), L.ptr(self.preds),
@@ -326,6 +334,10 @@ class BoundFusedStep:
         self.launches_per_step = 1 if finalize else 2     # N > 1: + finalize after the all-reduce
 
     def launch_kernel(self, stream):
+        if self.exchange is not None:
+            self.xch.seq = self.exchange.next_seq()
+            L.check(self._lib.lhn_fused_render_loss_decode_xch(*self._xch_args, stream), "lhn_fused_render_loss_decode_xch")
+            return
         L.check(self._lib.lhn_fused_render_loss_decode(*self._fused_args, stream), "lhn_fused_render_loss_decode")
 
     def launch_kernel_partials(self, stream):
@@ -432,7 +444,9 @@ class BoundDecodeStep:
                  hm_flip=None, flip_pairs=(), kernel=11, scale_xy=(1.0, 1.0), overlap_previous=False, metrics=None,
                  outputs=None):
         """metrics: None or dict(gt [B,K,2] f32, mask [B,K] bool/u8, bbox_wh [B,2] f32, counters int64
-        [(auc_steps+5)*K], pck_thr=0.2, auc_nor=30.0, auc_steps=20)."""
+        [(auc_steps+5)*K], pck_thr=0.2, auc_nor=30.0, auc_steps=20[, exchange=dist.PeerExchange, totals=int64 like
+        counters]).  With `exchange`, `counters` is the rank's per-step block (zero before and after every launch) and
+        `totals` receives += the block summed over all ranks inside the kernel (lhn_decode_heatmap_pck_xch)."""
         import ctypes as C
         lib = L.lib()
         self._lib = lib
@@ -488,12 +502,24 @@ class BoundDecodeStep:
                           L.ptr(self.hm_preds), L.ptr(self.preds), L.ptr(self.idx), L.ptr(gt), L.ptr(mask), L.ptr(wh),
                           float(metrics.get("pck_thr", 0.2)), float(metrics.get("auc_nor", 30.0)), steps,
                           L.ptr(self.counters))
+            self.exchange = metrics.get("exchange")
+            if self.exchange is not None:
+                totals = metrics["totals"]
+                if totals.dtype != torch.int64 or totals.numel() != self.counters.numel() or not totals.is_contiguous() \
+                        or totals.device != dev:
+                    raise L.LhnError("totals must be a contiguous int64 tensor like counters")
+                self._keep.append(totals)
+                self.xch = self.exchange.struct()
+                self._fn, self._name = lib.lhn_decode_heatmap_pck_xch, "lhn_decode_heatmap_pck_xch"
+                self._args = self._args + (L.ptr(totals), C.byref(self.xch))
         self.graph = None
 
     def stream(self):
         return L.stream(self.dev)
 
     def launch_kernel(self, stream):
+        if getattr(self, "exchange", None) is not None:
+            self.xch.seq = self.exchange.next_seq()
         L.check(self._fn(*self._args, stream), self._name)
 
     def launch(self):

@@ -1,0 +1,122 @@
+"""GPU: the in-kernel cross-rank exchange (include/lhn.h lhn_exchange; litehandnet_b200.dist.PeerExchange).
+
+Single GPU: n 'ranks' = n streams of one device whose mailboxes point at each other — the protocol (slots, flags,
+sequence numbers, launch overlap) is the same as across GPUs, only the stores do not cross NVLink.
+Two or more GPUs: tests/mp_exchange_worker.py under torchrun (symmetric memory / cudaIpc mapping, real NVLink stores).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+from litehandnet_b200 import _lib as L
+from litehandnet_b200 import fused, metrics as M, synth
+from litehandnet_b200.dist import PeerExchange
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def pck_set(B, K, seed):
+    hm, cen = synth.blob_heatmaps(B, K, 64, 64, seed=seed, device=DEV, zero_frac=0.02)
+    c, s = synth.bbox_center_scale(B, seed=seed + 1, device=DEV)
+    gt, mask, wh = synth.pck_inputs(cen, seed=seed + 2, device=DEV)
+    return hm, c, s, gt, mask, wh
+
+
+@pytest.mark.parametrize("world,B", [(2, 256), (3, 40), (1, 64)])
+def test_counter_exchange_between_ranks_on_one_gpu(world, B):
+    K, T, R, steps = 16, 20, 2, 14
+    xs = PeerExchange.local_group(world, DEV)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    sets = [[pck_set(B, K, 100 * r + 10 * i) for i in range(R)] for r in range(world)]
+    totals = [torch.zeros((T + 5) * K, dtype=torch.int64, device=DEV) for _ in range(world)]
+    blocks = [[torch.zeros((T + 5) * K, dtype=torch.int64, device=DEV) for _ in range(R)] for _ in range(world)]
+    bound = [[fused.BoundDecodeStep(s[0], s[1], s[2], L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE, overlap_previous=True,
+                                    metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=blocks[r][i], auc_steps=T,
+                                                 exchange=xs[r], totals=totals[r]))
+              for i, s in enumerate(sets[r])] for r in range(world)]
+    torch.cuda.synchronize()
+    for step in range(steps):
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                bound[r][step % R].launch()
+    torch.cuda.synchronize()
+    assert all(int(x.status.item()) == 0 for x in xs), "a rank timed out waiting for its peers"
+    # what a single process accumulates over the same steps
+    per_set = []
+    for i in range(R):
+        acc = M.MetricAccumulator(K, device=DEV)
+        for r in range(world):
+            s = sets[r][i]
+            acc.update_from_heatmaps(s[0], s[1], s[2], s[3], s[4], s[5], post_process="default")
+        per_set.append(acc.counters)
+    mono = sum(per_set[step % R] for step in range(steps))
+    for r in range(world):
+        assert torch.equal(totals[r], mono), f"rank {r}: totals differ from the monolithic counters"
+        assert all(int(b.abs().sum().item()) == 0 for b in blocks[r]), "per-step blocks must be left zero"
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_loss_sum_exchange_gives_the_global_batch_loss(world):
+    """lhn_fused_render_loss_decode_xch: every rank ends with the loss of the CONCATENATED batch (global N_pos)."""
+    K, B, steps = 21, 96, 6
+    xs = PeerExchange.local_group(world, DEV)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    cfg = fused.FusedHeatmapStep((256, 256), sigma=2, post_process="unbiased", kernel=11)
+
+    def mk(seed):
+        hm, cen = synth.blob_heatmaps(B, K, 64, 64, seed=seed, device=DEV)
+        hf = synth.flipped_blob_heatmaps(cen, 64, 64, seed=seed + 1, device=DEV)
+        j, v = synth.hand_joints(B, K, seed=seed + 2, device=DEV)
+        c, s = synth.bbox_center_scale(B, seed=seed + 3, device=DEV)
+        return hm, hf, j, v, c, s
+
+    sets = [[mk(1000 * r + 10 * i) for i in range(2)] for r in range(world)]
+    bound = [[fused.BoundFusedStep(cfg, s[0], s[2], s[3], s[4], s[5], hm_flip=s[1], overlap_previous=True, exchange=xs[r])
+              for s in sets[r]] for r in range(world)]
+    torch.cuda.synchronize()
+    for step in range(steps):
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                bound[r][step % 2].launch()
+    torch.cuda.synchronize()
+    assert all(int(x.status.item()) == 0 for x in xs)
+    for i in range(2):
+        cat = [torch.cat([sets[r][i][k] for r in range(world)]).cpu().numpy() for k in range(6)]
+        with np.errstate(all="ignore"):
+            ref = O.fused_render_loss_decode(cat[0], cat[1], cat[2], cat[3], cat[4], cat[5], image_size=(256, 256), sigma=2)
+        for r in range(world):
+            b = bound[r][i]
+            np.testing.assert_allclose(float(b.loss.item()), float(ref["loss"]), rtol=1e-5)
+            assert torch.equal(b.sums, bound[0][i].sums), "every rank must hold the same global sums, bit for bit"
+            assert np.array_equal(b.idx.cpu().numpy(), ref["idx"][r * B:(r + 1) * B])
+
+
+def test_exchange_rejects_bad_arguments():
+    x = PeerExchange.local_group(1, DEV)[0]
+    st = x.struct()
+    st.seq = 0                                           # step numbers start at 1
+    s = pck_set(8, 16, 5)
+    cnt = torch.zeros(25 * 16, dtype=torch.int64, device=DEV)
+    b = fused.BoundDecodeStep(s[0], s[1], s[2], metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=cnt, exchange=x,
+                                                             totals=torch.zeros_like(cnt)))
+    b.exchange = None                                    # keep seq = 0
+    with pytest.raises(L.LhnError):
+        b.launch()
+
+
+@pytest.mark.parametrize("nproc", [2])
+def test_exchange_across_gpus_under_torchrun(nproc):
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(ROOT, "tests", "mp_exchange_worker.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "exchange ok" in r.stdout
