@@ -94,6 +94,7 @@ typedef void* lhn_stream_t; /* cudaStream_t */
                                        the 32-byte all-reduce of the previous step's loss sums — could not start
                                        before it ends.  The kernel is HBM-bound: 4 of 148 SMs cost < 1 %. */
 
+#define LHN_LOSS_MAX_TENSORS 8
 #define LHN_MAX_TAPS 31
 #define LHN_MAX_STACKS 8
 
@@ -339,6 +340,22 @@ LHN_API int64_t lhn_simdr_loss_workspace_bytes(int64_t B, int K);
 LHN_API int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const void* tgt_x,
                                const void* tgt_y, const float* weight, int dtype, int64_t B, int K,
                                int Lx, int Ly, void* workspace, int64_t workspace_bytes, float* loss,
+                               lhn_stream_t stream);
+
+/* DistanceLoss / JointsDistanceLoss against explicit target tensors in ONE launch, for n_tensors <= LHN_LOSS_MAX_TENSORS
+ * (output, target, weight) triples at once (loss/heatmapLoss.py:195-265; SRHandNetLoss._forward_only_heatmap,
+ * loss/loss.py:59-66: loss = sum_i loss_weights[i] * L2(outputs[i], targets[i], w[i])).
+ * outputs[i] / targets[i]: n_planes[i] contiguous planes of plane_elems[i] elements, all of `dtype`; weights[i] f32
+ * [n_planes[i]].  The arrays of pointers / sizes are HOST arrays.  sums (optional) f64 [n_tensors, 4] receives each
+ * tensor's (S_pos, S_neg, N_pos, numel) for the backward; per_tensor_loss (optional) f32 [n_tensors]; loss f32 [1]
+ * = scale * sum_i loss_weights[i] * loss_i (added to loss[0] when accumulate != 0).  workspace: zeroed once,
+ * lhn_loss_mse_workspace_bytes() bytes, 16-byte aligned; the kernel leaves it ready for the next launch. */
+LHN_API int64_t lhn_loss_mse_workspace_bytes(void);
+LHN_API int lhn_loss_mse_multi(int n_tensors, const void* const* outputs, const void* const* targets,
+                               const float* const* weights, const int64_t* n_planes, const int64_t* plane_elems,
+                               const float* loss_weights, int dtype, int loss_mode, float pos_value,
+                               int sum_reduction, float scale, void* workspace, int64_t workspace_bytes,
+                               double* sums, float* per_tensor_loss, float* loss, int accumulate,
                                lhn_stream_t stream);
 
 /* ---- SimDRLoss with its two nn.Linear heads fused (centernet_simdr_loss.py:42-69) -------------------------------

@@ -22,6 +22,7 @@ LOSS_NONE, LOSS_DISTANCE, LOSS_DISTANCE_BALANCE, LOSS_JOINTS_MSE = 0, 1, 2, 3
 FLAG_OVERLAP_PREVIOUS = 1
 FLAG_ACCUMULATE_LOSS = 2
 MAX_TAPS, MAX_STACKS = 31, 8
+LOSS_MAX_TENSORS = 8
 XCH_MAX_RANKS, XCH_SLOTS, XCH_PAYLOAD_BYTES, XCH_CTRL_BYTES = 8, 4, 8192, 4096
 XCH_MAILBOX_BYTES = XCH_SLOTS * XCH_MAX_RANKS * XCH_PAYLOAD_BYTES + XCH_CTRL_BYTES
 REGION_SH, REGION_RP, REGION_CS = 0, 1, 2
@@ -33,7 +34,7 @@ ERRORS = {-1: "LHN_EINVAL (bad shape / null pointer / bad enum)", -2: "LHN_EDTYP
 
 EXPORTS = [
     "lhn_version", "lhn_last_cuda_error", "lhn_gaussian_taps", "lhn_decode_heatmap",
-    "lhn_decode_heatmap_pck", "lhn_loss_partials", "lhn_loss_reduce", "lhn_loss_finalize",
+    "lhn_decode_heatmap_pck", "lhn_loss_partials", "lhn_loss_reduce", "lhn_loss_finalize", "lhn_loss_mse_workspace_bytes", "lhn_loss_mse_multi",
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_decode_simdr_flags", "lhn_simdr_loss_workspace_bytes",
     "lhn_simdr_smoothl1", "lhn_split_bf16", "lhn_simdr_heads_workspace_bytes", "lhn_simdr_heads_loss", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
@@ -110,6 +111,10 @@ def _declare(lib):
                                            i32, vp, vp]
     lib.lhn_loss_partials.argtypes = [vp, vp, vp, i32, i64, i64, i32, f32, vp, vp]
     lib.lhn_loss_reduce.argtypes = [vp, i64, vp, i32, vp]
+    lib.lhn_loss_mse_workspace_bytes.argtypes = []
+    lib.lhn_loss_mse_workspace_bytes.restype = i64
+    lib.lhn_loss_mse_multi.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64),
+                                       C.POINTER(f32), i32, i32, f32, i32, f32, vp, i64, vp, vp, vp, i32, vp]
     lib.lhn_loss_finalize.argtypes = [vp, i32, i32, f32, vp, i32, vp]
     lib.lhn_render_targets.argtypes = [vp, i32, vp, i32, i64, i32, i32, i32, C.POINTER(RenderParams),
                                        vp, vp, vp]

@@ -119,8 +119,9 @@ struct TeamHeader {
   float side[8][12];
 };
 constexpr int kSideAhead = 4;
-// overlapped launches: team 0's epilogue warp lets the successor grid in after this many of its planes (see the kernel)
-constexpr int kTriggerPlane = 2;
+// Overlapped launches: team 0's epilogue warp lets the successor grid in half-way through its planes (see the kernel).
+// Any point well before the CTA's end costs nothing (the successor cannot get an SM earlier); half-way leaves the
+// predecessor — whose completion may hang on a peer's block in the exchanging variants — the longest slack.
 // SD_MASK: the aligned 32-bit word that holds the plane's fused-metrics mask byte (cp.async moves >= 4 bytes)
 enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_MASK, SD_N };
 
@@ -143,8 +144,10 @@ __device__ __forceinline__ unsigned int* xch_flag(const HmArgs& a, int mailbox_r
   return reinterpret_cast<unsigned int*>(a.xch_mail[mailbox_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES) +
          slot * LHN_XCH_MAX_RANKS + src_rank;
 }
-__device__ __forceinline__ unsigned int* xch_ticket(const HmArgs& a) {   // launch ticket of the fused-metrics variant
-  return reinterpret_cast<unsigned int*>(a.xch_mail[a.xch_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + 1024);
+// launch ticket of the fused-metrics variant: one per slot, so consecutive (overlapping) launches never share one
+__device__ __forceinline__ unsigned int* xch_ticket(const HmArgs& a) {
+  return reinterpret_cast<unsigned int*>(a.xch_mail[a.xch_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + 1024) +
+         (a.xch_seq & (LHN_XCH_SLOTS - 1));
 }
 static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const unsigned long long* local, int n, int lane) {
   const int world = a.xch_world, me = a.xch_rank;
@@ -383,6 +386,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     if (lane == 0) mbar_arrive(&th->empty[1]);
 
     int n_it = 0;
+    // planes of this team: p, p + total_teams, ... < n_planes; the successor grid is let in after plane kTrig of team 0
+    const int kTrig = (int)(((n_planes - 1u - p) / total_teams + 1u) >> 1);
     for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
       const int buf = n_it & 1;
       mbar_wait(&th->full[buf], (uint32_t)(n_it >> 1) & 1u);
@@ -723,12 +728,12 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       TRE(12);
       __syncwarp();
       if (lane == 0) mbar_arrive(&th->empty[buf]);   // release: record/tile buffer free, tables of n+2 ready
-      if (a.overlap_previous && team == 0 && n_it == kTriggerPlane) {
+      if (a.overlap_previous && team == 0 && n_it == kTrig) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;");
       }
     }
-    if (a.overlap_previous && team == 0 && n_it <= kTriggerPlane) {   // fewer planes than that: trigger at the end
+    if (a.overlap_previous && team == 0 && n_it <= kTrig) {   // a single plane: trigger at the end
       asm volatile("griddepcontrol.wait;" ::: "memory");
       asm volatile("griddepcontrol.launch_dependents;");
     }
@@ -767,7 +772,6 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         if (a.xch_world > 0) {
           // in-kernel all-reduce of this step's block (lhn_decode_heatmap_pck_xch): the grid's last CTA sends the
           // block to every peer, waits for theirs and adds them in rank order into the running totals
-          asm volatile("griddepcontrol.wait;" ::: "memory");    // the ticket is shared with the previous launch
           __threadfence();
           __syncwarp();
           unsigned int tk = 0;
@@ -776,6 +780,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           if (tk == gridDim.x - 1) {
             __threadfence();
             const bool ok = a.xch_world > 1 ? xch_publish_and_wait(a, gcnt, n_cnt, lane) : true;
+            // the running totals are shared with the previous launch, whose own update may still be waiting for a
+            // peer: only this one warp of the grid waits for it
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             for (int e = lane; e < n_cnt; e += 32) {
               long long sum = 0;
               for (int r = 0; r < a.xch_world; ++r) {

@@ -24,15 +24,16 @@ def _as_cuda(t, device):
 
 
 class _HeatmapLossFn(torch.autograd.Function):
-    """forward: per-plane sums -> fixed-order reduce -> finalise; backward: lhn_loss_backward."""
+    """forward: ONE launch (lhn_loss_mse_multi: streaming sums, fixed-order two-level reduction, finalisation);
+    backward: lhn_loss_backward."""
 
     @staticmethod
     def forward(ctx, output, target, weight, mode, value, reduction):
-        partials = ops.loss_partials(output.detach(), target, weight, mode, value)
-        sums = ops.loss_reduce(partials)
+        loss, sums, _ = ops.loss_mse_multi([output], [target], [weight], mode, value, reduction)
+        sums = sums[0]
         ctx.save_for_backward(output.detach(), target, weight, sums)
         ctx.cfg = (mode, value, reduction)
-        return ops.loss_finalize(sums, mode, reduction)[0]
+        return loss[0]
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -40,6 +41,32 @@ class _HeatmapLossFn(torch.autograd.Function):
         mode, value, reduction = ctx.cfg
         g = ops.loss_backward(output, target, weight, mode, sums, value, reduction, 1.0, grad_out)
         return g, None, None, None, None, None
+
+
+class _MultiHeatmapLossFn(torch.autograd.Function):
+    """sum_i loss_weight[i] * DistanceLoss(outputs[i], targets[i], w[i]) in ONE launch (SRHandNetLoss's four scales,
+    loss/loss.py:59-66); backward: one lhn_loss_backward per tensor, scaled by its loss weight."""
+
+    @staticmethod
+    def forward(ctx, mode, value, reduction, loss_weights, n, *tensors):
+        outputs, targets, weights = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
+        loss, sums, _ = ops.loss_mse_multi(list(outputs), list(targets), list(weights), mode, value, reduction, loss_weights)
+        ctx.save_for_backward(*[o.detach() for o in outputs], *targets, *weights, sums)
+        ctx.cfg = (mode, value, reduction, [float(x) for x in loss_weights], n)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mode, value, reduction, lw, n = ctx.cfg
+        saved = ctx.saved_tensors
+        outputs, targets, weights, sums = saved[:n], saved[n:2 * n], saved[2 * n:3 * n], saved[3 * n]
+        grads = []
+        for i in range(n):
+            if ctx.needs_input_grad[5 + i]:
+                grads.append(ops.loss_backward(outputs[i], targets[i], weights[i], mode, sums[i], value, reduction, lw[i], grad_out))
+            else:
+                grads.append(None)
+        return (None, None, None, None, None, *grads, *([None] * (2 * n)))
 
 
 class _FusedHeatmapLossFn(torch.autograd.Function):
@@ -302,11 +329,15 @@ class SRHandNetLoss(nn.Module):
 
     def _forward_only_heatmap(self, outputs, targets, target_weight):
         device = outputs[-1].device
-        loss = 0
-        for i in range(self.num_out):
-            w = target_weight[i] if isinstance(target_weight, (list, tuple)) else target_weight
-            loss = loss + self.loss_weight[i] * self.mse_loss(outputs[i], _as_cuda(targets[i], device),
-                                                              _as_cuda(w, device))
+        ws = [_as_cuda(target_weight[i] if isinstance(target_weight, (list, tuple)) else target_weight, device)
+              for i in range(self.num_out)]
+        tg = [_as_cuda(targets[i], device) for i in range(self.num_out)]
+        outs = [outputs[i] for i in range(self.num_out)]
+        for o in outs:
+            L.require_cuda(o, "output")
+        # the four scales in ONE launch (it used to be 4 x 3)
+        loss = _MultiHeatmapLossFn.apply(self.mse_loss._mode, self.mse_loss.value, self.mse_loss.reduction,
+                                         [float(x) for x in self.loss_weight], self.num_out, *outs, *tg, *ws)
         return loss, dict(kpt_loss=loss.item())
 
 

@@ -350,6 +350,57 @@ def loss_partials(output, target, weight, loss_mode, pos_value=0.5):
     return partials
 
 
+_LOSS_WS = {}
+
+
+def _loss_workspace(device):
+    """Zeroed once per (device, stream); lhn_loss_mse_multi leaves its ticket at zero."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _LOSS_WS.get(key)
+    if ws is None:
+        ws = _LOSS_WS[key] = torch.zeros(int(L.lib().lhn_loss_mse_workspace_bytes()), dtype=torch.uint8, device=device)
+    return ws
+
+
+@_on_device
+def loss_mse_multi(outputs, targets, weights, loss_mode, pos_value=0.5, reduction="mean", loss_weights=None, scale=1.0):
+    """lhn_loss_mse_multi: DistanceLoss / JointsDistanceLoss of up to 8 (output, target, weight) triples in ONE launch.
+    Returns (loss f32[1] = scale * sum_i loss_weights[i] * loss_i, sums f64 [n,4], per_tensor f32 [n])."""
+    n = len(outputs)
+    if n < 1 or n > L.LOSS_MAX_TENSORS or len(targets) != n or len(weights) != n:
+        raise L.LhnError(f"loss_mse_multi takes 1..{L.LOSS_MAX_TENSORS} (output, target, weight) triples")
+    dt = outputs[0].dtype
+    keep, po, pt, pw, npl, hw = [], [], [], [], [], []
+    for o, t, w in zip(outputs, targets, weights):
+        L.require_cuda(o, "output")
+        L.require_cuda(t, "target")
+        if t.shape != o.shape:
+            raise L.LhnError("output and target shapes differ")
+        if o.dtype != dt:
+            raise L.LhnError("all outputs must share one dtype")
+        o = o.detach().contiguous()
+        t = t.detach().to(dt).contiguous()
+        H, W = o.shape[-2:]
+        P = o.numel() // (H * W)
+        w = _f32c(w.detach(), "target_weight").reshape(-1)
+        if w.numel() != P:
+            raise L.LhnError(f"target_weight has {w.numel()} entries for {P} planes")
+        keep += [o, t, w]
+        po.append(o.data_ptr()); pt.append(t.data_ptr()); pw.append(w.data_ptr()); npl.append(P); hw.append(H * W)
+    dev = outputs[0].device
+    lw = [1.0] * n if loss_weights is None else [float(x) for x in loss_weights]
+    sums = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    per = torch.empty(n, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = _loss_workspace(dev)
+    VP, I64, F32 = C.c_void_p * n, C.c_int64 * n, C.c_float * n
+    rc = L.lib().lhn_loss_mse_multi(n, VP(*po), VP(*pt), VP(*pw), I64(*npl), I64(*hw), F32(*lw), L.dtype_code(keep[0]),
+                                    int(loss_mode), float(pos_value), int(reduction == "sum"), float(scale), L.ptr(ws),
+                                    ws.numel(), L.ptr(sums), L.ptr(per), L.ptr(loss), 0, L.stream())
+    L.check(rc, "lhn_loss_mse_multi")
+    return loss, sums, per
+
+
 def _grad_out_ptr(grad_out, device):
     if grad_out is None:
         return None, None

@@ -164,3 +164,49 @@ def test_simdr_heads_tile_straddles_the_xy_boundary(bn, monkeypatch):
     ref_loss, _ = _heads_reference(hm, wx, bx, wy, by, tx, ty, w)
     loss, _, _ = ops.simdr_heads_loss(hm, ops.split_bf16(torch.cat([wx, wy]).contiguous()), torch.cat([bx, by]), tx, ty, w)
     np.testing.assert_allclose(float(loss.item()), float(ref_loss.item()), rtol=1e-5)
+
+
+# ---- the un-fused criterion in ONE launch, several tensors at once (lhn_loss_mse_multi) ----------------------
+@pytest.mark.parametrize("mode", [L.LOSS_DISTANCE_BALANCE, L.LOSS_DISTANCE, L.LOSS_JOINTS_MSE])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_loss_mse_multi_matches_three_launch_path_and_oracle(mode, dtype):
+    shapes = [(6, 21, 16, 16), (6, 21, 16, 16), (6, 21, 32, 32), (6, 21, 64, 64)]       # SRHandNet's four scales
+    g = torch.Generator(device=DEV).manual_seed(3)
+    outs, tgts, ws = [], [], []
+    for i, (B, K, H, W) in enumerate(shapes):
+        j, v = synth.hand_joints(B, K, (256, 256), seed=20 + i, device=DEV)
+        t, tw = ops.render_targets(j, v, (256, 256), (W, H), 2.0 if H > 16 else 1.0, True)
+        o = (t + torch.randn(t.shape, generator=g, device=DEV) * 0.1).to(dtype)
+        outs.append(o); tgts.append(t.to(dtype)); ws.append(tw)
+    lw = [0.3, 0.3, 0.5, 1.0]
+    loss, sums, per = ops.loss_mse_multi(outs, tgts, ws, mode, 0.5, "mean", lw)
+    want_total = 0.0
+    for i in range(4):
+        partials = ops.loss_partials(outs[i], tgts[i], ws[i], mode, 0.5)
+        s3 = ops.loss_reduce(partials)
+        l3 = ops.loss_finalize(s3, mode, "mean")
+        np.testing.assert_allclose(sums[i].cpu().numpy(), s3.cpu().numpy(), rtol=1e-12)
+        np.testing.assert_allclose(float(per[i].item()), float(l3.item()), rtol=1e-6)
+        o64, t64, w64 = outs[i].float().cpu().numpy(), tgts[i].float().cpu().numpy(), ws[i].cpu().numpy()
+        if mode == L.LOSS_JOINTS_MSE:
+            ref = O.joints_distance_loss_mse(o64, t64, w64)
+        else:
+            ref = O.distance_loss_l2(o64, t64, w64, balance=(mode == L.LOSS_DISTANCE_BALANCE))
+        np.testing.assert_allclose(float(per[i].item()), float(ref), rtol=1e-5)
+        want_total += lw[i] * float(ref)
+    np.testing.assert_allclose(float(loss.item()), want_total, rtol=1e-5)
+    loss2, _, _ = ops.loss_mse_multi(outs, tgts, ws, mode, 0.5, "mean", lw)
+    assert torch.equal(loss, loss2), "fixed-order reduction: bitwise reproducible"
+
+
+def test_loss_mse_multi_single_large_tensor_and_sum_reduction():
+    B, K = 300, 21
+    j, v = synth.hand_joints(B, K, (256, 256), seed=31, device=DEV)
+    t, tw = ops.render_targets(j, v, (256, 256), (64, 64), 2.0, True)
+    o = t + torch.randn(t.shape, generator=torch.Generator(device=DEV).manual_seed(4), device=DEV) * 0.05
+    for red in ("mean", "sum"):
+        loss, sums, _ = ops.loss_mse_multi([o], [t], [tw], L.LOSS_DISTANCE_BALANCE, 0.5, red)
+        ref = O.distance_loss_l2(o.cpu().numpy(), t.cpu().numpy(), tw.cpu().numpy(), balance=True, reduction=red)
+        np.testing.assert_allclose(float(loss.item()), float(ref), rtol=1e-5)
+    with pytest.raises(L.LhnError):
+        ops.loss_mse_multi([o] * 9, [t] * 9, [tw] * 9, L.LOSS_DISTANCE)
