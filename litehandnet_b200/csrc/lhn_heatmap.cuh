@@ -79,6 +79,7 @@ struct HmArgs {
   unsigned int xch_seq, xch_timeout_ms;
   int* xch_status;
   long long* xch_totals;           // fused metrics: running totals that receive += sum over ranks of the step's block
+  int trigger_halfway;             // overlapped launch: let the successor grid in half-way (else after the third plane)
 };
 
 // ---- shared-memory layout --------------------------------------------------------------------

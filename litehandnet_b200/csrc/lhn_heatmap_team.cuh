@@ -119,9 +119,8 @@ struct TeamHeader {
   float side[8][12];
 };
 constexpr int kSideAhead = 4;
-// Overlapped launches: team 0's epilogue warp lets the successor grid in half-way through its planes (see the kernel).
-// Any point well before the CTA's end costs nothing (the successor cannot get an SM earlier); half-way leaves the
-// predecessor — whose completion may hang on a peer's block in the exchanging variants — the longest slack.
+// Overlapped launches: team 0's epilogue warp lets the successor grid in after its third plane, or half-way through
+// its planes in the exchanging variants (a.trigger_halfway; see the kernel).
 // SD_MASK: the aligned 32-bit word that holds the plane's fused-metrics mask byte (cp.async moves >= 4 bytes)
 enum { SD_JX = 0, SD_JY, SD_VIS, SD_CX, SD_CY, SD_SX, SD_SY, SD_GX, SD_GY, SD_BW, SD_BH, SD_MASK, SD_N };
 
@@ -149,8 +148,22 @@ __device__ __forceinline__ unsigned int* xch_ticket(const HmArgs& a) {
   return reinterpret_cast<unsigned int*>(a.xch_mail[a.xch_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + 1024) +
          (a.xch_seq & (LHN_XCH_SLOTS - 1));
 }
+// in-kernel timing of the exchange (globaltimer ns), kept per slot in the local control page: [seq, t_enter,
+// t_published, t_peers_arrived] — read by profiles/probes/xch_timing.py; four 64-bit stores per launch by one lane
+__device__ __forceinline__ unsigned long long* xch_stamps(const HmArgs& a) {
+  return reinterpret_cast<unsigned long long*>(a.xch_mail[a.xch_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + 2048) +
+         8 * (a.xch_seq & (LHN_XCH_SLOTS - 1));
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const unsigned long long* local, int n, int lane) {
   const int world = a.xch_world, me = a.xch_rank;
+  unsigned long long* stamps = xch_stamps(a);
+  if (lane == 0) { stamps[0] = a.xch_seq; stamps[1] = gtimer(); }
   // 1. this rank's block into every peer's mailbox (plain stores over NVLink), then a release flag per peer
   for (int r = 0; r < world; ++r) {
     if (r == me) continue;
@@ -161,6 +174,7 @@ static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const 
   __syncwarp();
   if (lane < world && lane != me)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(a, lane, me)), "r"(a.xch_seq) : "memory");
+  if (lane == 0) stamps[2] = gtimer();
   // 2. the peers' flags in my mailbox
   bool ok = true;
   if (lane < world && lane != me) {
@@ -179,6 +193,7 @@ static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const 
   }
   ok = __all_sync(0xffffffffu, ok);
   __threadfence_system();
+  if (lane == 0) stamps[3] = gtimer();
   if (!ok && lane == 0 && a.xch_status) *a.xch_status = 1;
   return ok;
 }
@@ -387,7 +402,10 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
 
     int n_it = 0;
     // planes of this team: p, p + total_teams, ... < n_planes; the successor grid is let in after plane kTrig of team 0
-    const int kTrig = (int)(((n_planes - 1u - p) / total_teams + 1u) >> 1);
+    // plane 2 for plain launches (measured best: the earlier the successor grid is staged the better); half-way
+    // for exchanging launches, whose predecessor's completion hangs on a peer's block and needs the slack
+    const int n_mine = (int)((n_planes - 1u - p) / total_teams + 1u);
+    const int kTrig = a.trigger_halfway ? (n_mine >> 1) : (n_mine > 2 ? 2 : n_mine - 1);
     for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
       const int buf = n_it & 1;
       mbar_wait(&th->full[buf], (uint32_t)(n_it >> 1) & 1u);
@@ -1295,7 +1313,14 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   // need MANY epilogue warps: stages of <= 16 KB run up to 12 teams of 2 warps (1 sweeper + 1 epilogue), larger
   // ones 6 teams of 4 warps (3 sweepers + 1 epilogue) or 3 / 2 teams of 8 warps.  Spare shared memory then
   // multiplies the stages per team (2 or 4): the next planes of a team are already in flight while it sweeps.
-  const size_t budget = 227 * 1024;
+  size_t budget = 227 * 1024;
+  {
+    // Experimental (profiles/r02_two_launch_interleave.txt): an OVERLAPPED launch may take only half of each SM's
+    // shared memory, so that the successor launch becomes co-resident half-way through (the trigger point) and the
+    // two launches' fill / drain bubbles interleave instead of coinciding.  LHN_CTAS_PER_SM=2 selects it.
+    const char* cps = getenv("LHN_CTAS_PER_SM");
+    if (cps && cps[0] == '2' && a.overlap_previous) budget = 113 * 1024;
+  }
   const size_t aux_al = align_up(aux, 128);
   const size_t per_team = a.stage_bytes + aux_al;
   int nteams, tw;
@@ -1317,6 +1342,10 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
     // headline shape; pointless (and a visible delay) when a team only has a few planes
     const char* sg = getenv("LHN_STAGGER_NS");
     a.stagger_ns = sg ? atoi(sg) : ((a.n_planes >= (int64_t)8 * nteams * sm_count()) ? 600 : 0);
+  }
+  {
+    const char* tg = getenv("LHN_TRIGGER");               // "half" / "early": override the trigger point (experiments)
+    a.trigger_halfway = tg ? (tg[0] == 'h') : (a.xch_world > 1);
   }
   a.sweeper_tables = (nstg >= 2 && tw >= 4) ? 1 : 0;
   a.team_warps = tw;
