@@ -160,15 +160,39 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
-static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const unsigned long long* local, int n, int lane) {
+// `stage`: 16-byte aligned shared memory of at least (n + 1) words, or nullptr for blocks of <= 32 words.  With a
+// stage the block goes out as ONE bulk copy (TMA, shared -> peer global) per peer, all peers in flight together; a
+// loop of per-word loads and remote stores measured 7-13 us for 3.2 KB (profiles/r02_xch_timing.txt: each iteration
+// paid an L2 round trip in front of its store).
+static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const unsigned long long* local, int n, int lane,
+                                                         unsigned long long* stage) {
   const int world = a.xch_world, me = a.xch_rank;
   unsigned long long* stamps = xch_stamps(a);
   if (lane == 0) { stamps[0] = a.xch_seq; stamps[1] = gtimer(); }
-  // 1. this rank's block into every peer's mailbox (plain stores over NVLink), then a release flag per peer
-  for (int r = 0; r < world; ++r) {
-    if (r == me) continue;
-    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(xch_slot(a, r, me));
-    for (int e = lane; e < n; e += 32) dst[e] = __ldcg(local + e);
+  // 1. this rank's block into every peer's mailbox, then a release flag per peer
+  if (stage) {
+    const int n2 = (n + 1) & ~1;                             // bulk copies move multiples of 16 bytes
+    for (int e0 = lane; e0 < n2; e0 += 128) {                // four independent loads per lane in flight
+      unsigned long long v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; v[u] = e < n ? __ldcg(local + e) : 0ull; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; if (e < n2) stage[e] = v[u]; }
+    }
+    __syncwarp();
+    fence_proxy_async();                                     // generic-proxy writes of the stage -> async proxy
+    if (lane < world && lane != me) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xch_slot(a, lane, me)),
+                   "r"(smem_u32(stage)), "r"((unsigned)(n2 * 8)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    const unsigned long long v = lane < n ? __ldcg(local + lane) : 0ull;
+    for (int r = 0; r < world; ++r) {
+      if (r == me || lane >= n) continue;
+      reinterpret_cast<volatile unsigned long long*>(xch_slot(a, r, me))[lane] = v;
+    }
   }
   __threadfence_system();
   __syncwarp();
@@ -179,16 +203,14 @@ static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const 
   bool ok = true;
   if (lane < world && lane != me) {
     const unsigned int* f = xch_flag(a, me, lane);
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long t0 = gtimer();
     const unsigned long long limit = (unsigned long long)(a.xch_timeout_ms ? a.xch_timeout_ms : 2000u) * 1000000ull;
     for (;;) {
       unsigned int v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if (v == a.xch_seq) break;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > limit) { ok = false; break; }
-      __nanosleep(200);
+      if (gtimer() - t0 > limit) { ok = false; break; }
+      __nanosleep(100);
     }
   }
   ok = __all_sync(0xffffffffu, ok);
@@ -387,18 +409,27 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       cp_async_commit();
       pq += total_teams; advance(qb, qc);
     }
-    cp_async_wait<kSideAhead - 2>();               // the first two planes' side inputs have landed
-    __syncwarp();
-    if (!a.sweeper_tables) prologue(pc, 0, 0, lane, 32);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&th->empty[0]);
-    if (!a.sweeper_tables && p + total_teams < n_planes) {
-      uint32_t nb = pb, nc = pc;
-      advance(nb, nc);
-      prologue(nc, 1, 1, lane, 32);
+    if (!LOSS) {
+      // decode only: the sweepers need nothing from the side inputs (the epilogue does, for the back-transform), so
+      // both record buffers are handed over at once — on a one-wave launch (BASELINE config 1: 64 samples) the
+      // side-input round trip (~1.5 us cold) would otherwise sit in front of the first sweep
+      if (lane == 0) { mbar_arrive(&th->empty[0]); mbar_arrive(&th->empty[1]); }
+      cp_async_wait<kSideAhead - 2>();
+      __syncwarp();
+    } else {
+      cp_async_wait<kSideAhead - 2>();               // the first two planes' side inputs have landed
+      __syncwarp();
+      if (!a.sweeper_tables) prologue(pc, 0, 0, lane, 32);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&th->empty[0]);
+      if (!a.sweeper_tables && p + total_teams < n_planes) {
+        uint32_t nb = pb, nc = pc;
+        advance(nb, nc);
+        prologue(nc, 1, 1, lane, 32);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&th->empty[1]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&th->empty[1]);
 
     int n_it = 0;
     // planes of this team: p, p + total_teams, ... < n_planes; the successor grid is let in after plane kTrig of team 0
@@ -797,7 +828,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           tk = __shfl_sync(0xffffffffu, tk, 0);
           if (tk == gridDim.x - 1) {
             __threadfence();
-            const bool ok = a.xch_world > 1 ? xch_publish_and_wait(a, gcnt, n_cnt, lane) : true;
+            // the CTA's own counters are flushed: their shared memory stages the outgoing block
+            const bool ok = a.xch_world > 1 ? xch_publish_and_wait(a, gcnt, n_cnt, lane, cta_cnt) : true;
             // the running totals are shared with the previous launch, whose own update may still be waiting for a
             // peer: only this one warp of the grid waits for it
             asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -885,7 +917,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             mine[2] = (unsigned long long)__double_as_longlong(v2); mine[3] = (unsigned long long)__double_as_longlong(v3);
           }
           __syncwarp();
-          const bool ok = xch_publish_and_wait(a, mine, 4, lane);
+          const bool ok = xch_publish_and_wait(a, mine, 4, lane, nullptr);
           if (ok) {
             double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
             for (int r = 0; r < a.xch_world; ++r) {

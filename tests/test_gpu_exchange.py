@@ -21,6 +21,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+# Several 'ranks' on ONE GPU are kernels that wait on one another on different streams: nothing guarantees that the
+# hardware runs them at the same time (B200_PROFILING.md warns about exactly this).  The kernels bound the wait with a
+# timeout, so the worst case is a failed test, not a hang — still, these cases only run on request
+# (LHN_TEST_XCH_SHARED_GPU=1; green in every run of this round, profiles/r02_tests_2gpu.log).  The default suite keeps
+# the single-rank case (no wait) and, with two or more GPUs, the torchrun test over real peer mappings.
+SHARED_GPU = os.environ.get("LHN_TEST_XCH_SHARED_GPU") == "1"
+
+
+def need_shared(world):
+    if world > 1 and not SHARED_GPU:
+        pytest.skip("several ranks on one GPU: set LHN_TEST_XCH_SHARED_GPU=1")
+
 
 def pck_set(B, K, seed):
     hm, cen = synth.blob_heatmaps(B, K, 64, 64, seed=seed, device=DEV, zero_frac=0.02)
@@ -31,6 +43,7 @@ def pck_set(B, K, seed):
 
 @pytest.mark.parametrize("world,B", [(2, 256), (3, 40), (1, 64)])
 def test_counter_exchange_between_ranks_on_one_gpu(world, B):
+    need_shared(world)
     K, T, R, steps = 16, 20, 2, 14
     xs = PeerExchange.local_group(world, DEV)
     streams = [torch.cuda.Stream() for _ in range(world)]
@@ -65,6 +78,7 @@ def test_counter_exchange_between_ranks_on_one_gpu(world, B):
 @pytest.mark.parametrize("world", [2, 4])
 def test_loss_sum_exchange_gives_the_global_batch_loss(world):
     """lhn_fused_render_loss_decode_xch: every rank ends with the loss of the CONCATENATED batch (global N_pos)."""
+    need_shared(world)
     K, B, steps = 21, 96, 6
     xs = PeerExchange.local_group(world, DEV)
     streams = [torch.cuda.Stream() for _ in range(world)]
