@@ -427,13 +427,15 @@ class DecodeWorkload(Workload):
                 m = dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=self.step_cnt[r] if world > 1 else self.total,
                          pck_thr=0.2, auc_nor=30.0, auc_steps=self.T)
                 if self.xch is not None:
-                    m.update(exchange=self.xch, totals=self.total)
+                    m = dict(gt=s[3], mask=s[4], bbox_wh=s[5], pck_thr=0.2, auc_nor=30.0, auc_steps=self.T,
+                             exchange=self.xch, totals=self.total)
             self.bound.append(fused.BoundDecodeStep(s[0], s[1], s[2], L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE,
                                                     overlap_previous=overlap, metrics=m))
         if self.xch is not None:
-            self.collective = ("the per-step PCK/AUC/EPE counter block is all-gathered EVERY eval step INSIDE the kernel through "
-                               f"peer-mapped mailboxes over NVLink ({self.xch.how}) and added in rank order into the running totals; "
-                               "no NCCL call, one launch per step (datasets/base_dataset.py:193-261, spawn_dist.py:68-80)")
+            self.collective = ("the per-step PCK/AUC/EPE counter block is all-gathered EVERY eval step INSIDE the kernel (one "
+                               "launch behind: the next step's first-finishing CTA sends it) through peer-mapped mailboxes over "
+                               f"NVLink ({self.xch.how}) and added in rank order into the running totals; no NCCL call, one launch "
+                               "per step + one flush per epoch (datasets/base_dataset.py:193-261, spawn_dist.py:68-80)")
             self.nvlink_bytes_per_step = self.xch.bytes_per_step((self.T + 5) * K * 8)
         elif self.metrics and world > 1:
             self.aux = torch.cuda.Stream(device=dev)
@@ -492,6 +494,8 @@ class DecodeWorkload(Workload):
         import torch
         if self.metrics and self.world > 1 and self.xch is None:
             torch.cuda.current_stream(self.dev).wait_stream(self.aux)
+        if self.xch is not None:
+            self.xch.flush()                    # the in-kernel exchange runs one launch behind: complete the last step
 
     def begin_epoch(self):
         if self.metrics:

@@ -119,6 +119,10 @@ typedef struct {
   uint32_t seq;                     /* step number >= 1 */
   uint32_t timeout_ms;              /* 0 = 2000 */
   int32_t* status;                  /* device int32 (local), or NULL */
+  void* prev_block;                 /* lhn_decode_heatmap_pck_xch: the per-step block of the PREVIOUS exchanging launch
+                                       (exchanged by this launch), or NULL for the first launch of a sequence */
+  uint32_t prev_seq;                /* ... and that launch's step number */
+  uint32_t reserved;
 } lhn_exchange;
 
 /* Decode parameters. */
@@ -427,10 +431,14 @@ LHN_API int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, 
                                    float auc_nor, int auc_steps, int64_t* counters,
                                    lhn_stream_t stream);
 
-/* The same with the per-step counter block all-reduced over the ranks INSIDE the kernel: `counters` is this rank's
- * per-step block (zero at entry; the kernel leaves it zero), `totals` int64 [(auc_steps+5)*K] receives
- * += sum over ranks of the step's blocks — after the launch every rank holds the same running totals, equal bit for
- * bit to a single-process evaluation (datasets/base_dataset.py:193-261 on the gathered results). */
+/* The same with the per-step counter block all-reduced over the ranks INSIDE the kernel, ONE LAUNCH BEHIND: `counters`
+ * is this rank's block for THIS step (zero at entry; rotate at least LHN_XCH_SLOTS blocks), xch->prev_block the block
+ * of the previous exchanging launch: the first CTA of this grid to finish sends that block to every peer, waits for
+ * theirs and adds them in rank order into `totals` int64 [(auc_steps+5)*K] (then zeroes it).  lhn_exchange_flush
+ * does the same for the last block of a sequence (xch->seq = that step's number); after it every rank holds the same
+ * running totals, equal bit for bit to a single-process evaluation (datasets/base_dataset.py:193-261 on the gathered
+ * results).  Why one launch behind: whoever exchanges holds its SM for the NVLink round trip; the first CTA to
+ * finish has the slack of the grid's finish-time spread, the last one has none. */
 LHN_API int lhn_decode_heatmap_pck_xch(const void* hm, int dtype, int64_t B, int K, int H, int W,
                                    int64_t stride_b, int64_t stride_c, const float* center,
                                    const float* scale, const lhn_decode_params* dp, float* out_hm,
@@ -439,6 +447,7 @@ LHN_API int lhn_decode_heatmap_pck_xch(const void* hm, int dtype, int64_t B, int
                                    float auc_nor, int auc_steps, int64_t* counters,
                                    int64_t* totals, const lhn_exchange* xch,
                                           lhn_stream_t stream);
+LHN_API int lhn_exchange_flush(const lhn_exchange* xch, int64_t* block, int n, int64_t* totals, lhn_stream_t stream);
 
 /* evaluate_pck (evaluation.py:10-59): argmax (A1) on pred and gt heatmap batches [B,K,H,W],
  * * image_size/[W,H], distance / max(bbox[:,0,2:]), per-image hits/(2*sum w)*2 in f32.

@@ -38,7 +38,7 @@ EXPORTS = [
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_decode_simdr_flags", "lhn_simdr_loss_workspace_bytes",
     "lhn_simdr_smoothl1", "lhn_split_bf16", "lhn_simdr_heads_workspace_bytes", "lhn_simdr_heads_loss", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
-    "lhn_fused_render_loss_decode_xch", "lhn_decode_heatmap_pck_xch",
+    "lhn_fused_render_loss_decode_xch", "lhn_decode_heatmap_pck_xch", "lhn_exchange_flush",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
     "lhn_simdr_smoothl1_backward", "lhn_mpii_pckh_accumulate", "lhn_region_bbox_decode", "lhn_heatmap_nms",
     "lhn_vector_nms", "lhn_refine_points", "lhn_decode_heatmap_roi", "lhn_box_nms", "lhn_render_region_wh", "lhn_dark_refine_points",
@@ -59,7 +59,8 @@ class RenderParams(C.Structure):
 
 class Exchange(C.Structure):
     _fields_ = [("mailbox", C.c_void_p * XCH_MAX_RANKS), ("world", C.c_int32), ("rank", C.c_int32),
-                ("seq", C.c_uint32), ("timeout_ms", C.c_uint32), ("status", C.c_void_p)]
+                ("seq", C.c_uint32), ("timeout_ms", C.c_uint32), ("status", C.c_void_p), ("prev_block", C.c_void_p),
+                ("prev_seq", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class RegionParams(C.Structure):
@@ -98,6 +99,7 @@ def _declare(lib):
     lib.lhn_decode_heatmap_pck_xch.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp,
                                                C.POINTER(DecodeParams), vp, vp, vp, vp, vp, vp, f32, f32,
                                                i32, vp, vp, C.POINTER(Exchange), vp]
+    lib.lhn_exchange_flush.argtypes = [C.POINTER(Exchange), vp, i32, vp, vp]
     lib.lhn_loss_backward.argtypes = [vp, vp, vp, i32, i64, i64, i32, f32, vp, i32, f32, vp, vp, vp]
     lib.lhn_render_loss_backward.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, C.POINTER(RenderParams),
                                              vp, i32, vp, i32, vp, i32, f32, vp, vp, vp]
@@ -164,6 +166,29 @@ def lib():
         _declare(handle)
         _lib = handle
     return _lib
+
+
+_ext = False
+
+
+def ext():
+    """The torch-extension shim (csrc/ext/lhn_torch_ext.cpp, built in-tree by litehandnet_b200.build) or None when it
+    is absent or LHN_NO_EXT=1.  It is a faster route to the SAME library (a few microseconds of host time per call
+    instead of 20-30 through ctypes); the kernels and their results are identical."""
+    global _ext
+    if _ext is False:
+        _ext = None
+        if os.environ.get("LHN_NO_EXT") != "1":
+            import glob
+            import importlib.util
+            cands = glob.glob(os.path.join(_HERE, "lib", "lhn_torch_ext*.so"))
+            if cands:
+                lib()                                            # liblhn.so first (the shim links against it)
+                spec = importlib.util.spec_from_file_location("lhn_torch_ext", cands[0])
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _ext = mod
+    return _ext
 
 
 def check(rc, what):

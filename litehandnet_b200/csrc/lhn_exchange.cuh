@@ -1,0 +1,117 @@
+// In-kernel all-gather over peer-mapped mailboxes (lhn_exchange, include/lhn.h): device-side protocol, shared by the
+// persistent heatmap kernel (lhn_heatmap_team.cuh) and the flush kernel (lhn_exchange.cu).
+//
+// Mailbox of one rank (LHN_XCH_MAILBOX_BYTES, zeroed once, mapped into every peer):
+//   [slot 0..3][source rank 0..7] payload of LHN_XCH_PAYLOAD_BYTES      slot = step number & 3
+//   control page: flags u32 [slot][source rank] (the step number once the payload has landed),
+//                 +1024 launch tickets u32 [slot], +2048 timing stamps u64 [slot][8]
+// A step's block travels as ONE bulk copy (TMA, shared -> peer global) per peer, all peers in flight together, then a
+// system-scope release of one flag per peer; the receiver polls its own (local) flags with acquire loads.
+#pragma once
+#include "lhn_common.cuh"
+
+namespace lhn {
+
+struct XchCtx {
+  unsigned char* mail[LHN_XCH_MAX_RANKS];   // mailbox of rank r as mapped into this process
+  int world, rank;                          // world == 0: no exchange
+  unsigned int timeout_ms;
+  int* status;
+};
+
+__device__ __forceinline__ unsigned char* xch_ctrl(const XchCtx& x, int mailbox_rank) {
+  return x.mail[mailbox_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES;
+}
+__device__ __forceinline__ unsigned char* xch_slot(const XchCtx& x, unsigned seq, int mailbox_rank, int src_rank) {
+  return x.mail[mailbox_rank] + ((size_t)(seq & (LHN_XCH_SLOTS - 1)) * LHN_XCH_MAX_RANKS + src_rank) * LHN_XCH_PAYLOAD_BYTES;
+}
+__device__ __forceinline__ unsigned int* xch_flag(const XchCtx& x, unsigned seq, int mailbox_rank, int src_rank) {
+  return reinterpret_cast<unsigned int*>(xch_ctrl(x, mailbox_rank)) + (seq & (LHN_XCH_SLOTS - 1)) * LHN_XCH_MAX_RANKS + src_rank;
+}
+// launch ticket: one per slot, so consecutive (overlapping) launches never share one
+__device__ __forceinline__ unsigned int* xch_ticket(const XchCtx& x, unsigned seq) {
+  return reinterpret_cast<unsigned int*>(xch_ctrl(x, x.rank) + 1024) + (seq & (LHN_XCH_SLOTS - 1));
+}
+// timing stamps (globaltimer ns) of the exchange of step `seq`: [seq, t_enter, t_published, t_peers_arrived]
+__device__ __forceinline__ unsigned long long* xch_stamps(const XchCtx& x, unsigned seq) {
+  return reinterpret_cast<unsigned long long*>(xch_ctrl(x, x.rank) + 2048) + 8 * (seq & (LHN_XCH_SLOTS - 1));
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One warp.  `local`: n 64-bit words in global memory (n * 8 <= LHN_XCH_PAYLOAD_BYTES).  `stage`: 16-byte aligned
+// shared memory of n + 1 words, or nullptr for blocks of <= 32 words (plain stores).  On return every peer's block
+// of step `seq` is readable at xch_slot(x, seq, x.rank, r) with volatile loads.  false = a peer timed out.
+static __device__ __noinline__ bool xch_publish_and_wait(const XchCtx& x, unsigned seq, const unsigned long long* local, int n,
+                                                         int lane, unsigned long long* stage) {
+  const int world = x.world, me = x.rank;
+  unsigned long long* stamps = xch_stamps(x, seq);
+  if (lane == 0) { stamps[0] = seq; stamps[1] = gtimer(); }
+  if (stage) {
+    const int n2 = (n + 1) & ~1;                             // bulk copies move multiples of 16 bytes
+    for (int e0 = lane; e0 < n2; e0 += 128) {                // four independent loads per lane in flight
+      unsigned long long v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; v[u] = e < n ? __ldcg(local + e) : 0ull; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; if (e < n2) stage[e] = v[u]; }
+    }
+    __syncwarp();
+    fence_proxy_async();                                     // generic-proxy writes of the stage -> async proxy
+    if (lane < world && lane != me) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xch_slot(x, seq, lane, me)),
+                   "r"(smem_u32(stage)), "r"((unsigned)(n2 * 8)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    const unsigned long long v = lane < n ? __ldcg(local + lane) : 0ull;
+    for (int r = 0; r < world; ++r) {
+      if (r == me || lane >= n) continue;
+      reinterpret_cast<volatile unsigned long long*>(xch_slot(x, seq, r, me))[lane] = v;
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < world && lane != me)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(x, seq, lane, me)), "r"(seq) : "memory");
+  if (lane == 0) stamps[2] = gtimer();
+  bool ok = true;
+  if (lane < world && lane != me) {
+    const unsigned int* f = xch_flag(x, seq, me, lane);
+    const unsigned long long t0 = gtimer();
+    const unsigned long long limit = (unsigned long long)(x.timeout_ms ? x.timeout_ms : 2000u) * 1000000ull;
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v == seq) break;
+      if (gtimer() - t0 > limit) { ok = false; break; }
+      __nanosleep(100);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system();
+  if (lane == 0) stamps[3] = gtimer();
+  if (!ok && lane == 0 && x.status) *x.status = 1;
+  return ok;
+}
+
+// totals[e] += sum over ranks (rank order) of step `seq`'s block; the local block is left zero.  One warp.
+static __device__ __noinline__ void xch_allreduce_block_i64(const XchCtx& x, unsigned seq, unsigned long long* block, int n,
+                                                            long long* totals, int lane, unsigned long long* stage) {
+  const bool ok = x.world > 1 ? xch_publish_and_wait(x, seq, block, n, lane, stage) : true;
+  for (int e = lane; e < n; e += 32) {
+    long long sum = 0;
+    for (int r = 0; r < x.world; ++r) {
+      if (r == x.rank) sum += (long long)__ldcg(block + e);
+      else if (ok) sum += (long long)reinterpret_cast<volatile unsigned long long*>(xch_slot(x, seq, x.rank, r))[e];
+    }
+    totals[e] += sum;
+    block[e] = 0ull;
+  }
+}
+
+}  // namespace lhn

@@ -504,10 +504,13 @@ static int fill_exchange(HmArgs& a, const lhn_exchange* x) {
   for (int r = 0; r < x->world; ++r) {
     if (!x->mailbox[r]) return LHN_EINVAL;
     if ((uintptr_t)x->mailbox[r] % 16) return LHN_EALIGN;
-    a.xch_mail[r] = static_cast<unsigned char*>(x->mailbox[r]);
+    a.xch.mail[r] = static_cast<unsigned char*>(x->mailbox[r]);
   }
-  a.xch_world = x->world; a.xch_rank = x->rank; a.xch_seq = x->seq; a.xch_timeout_ms = x->timeout_ms;
-  a.xch_status = x->status;
+  a.xch.world = x->world; a.xch.rank = x->rank; a.xch.timeout_ms = x->timeout_ms; a.xch.status = x->status;
+  a.xch_seq = x->seq;
+  a.xch_prev_block = static_cast<unsigned long long*>(x->prev_block);
+  a.xch_prev_seq = x->prev_seq;
+  if (x->prev_block && x->prev_seq == 0) return LHN_EINVAL;
   return LHN_OK;
 }
 

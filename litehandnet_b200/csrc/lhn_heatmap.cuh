@@ -6,6 +6,7 @@
 #include <type_traits>
 
 #include "lhn_common.cuh"
+#include "lhn_exchange.cuh"
 
 namespace lhn {
 
@@ -73,12 +74,12 @@ struct HmArgs {
   int overlap_previous;            // LHN_FLAG_OVERLAP_PREVIOUS: launch with programmatic stream serialization
   int feat_pow2;                   // feat_x, feat_y are powers of two: joint / feat == joint * inv_feat exactly
   double inv_feat_x, inv_feat_y;
-  // in-kernel cross-GPU exchange (lhn_exchange; team kernel only): mailboxes of all ranks as mapped here
-  unsigned char* xch_mail[LHN_XCH_MAX_RANKS];
-  int xch_world, xch_rank;         // xch_world == 0: no exchange
-  unsigned int xch_seq, xch_timeout_ms;
-  int* xch_status;
-  long long* xch_totals;           // fused metrics: running totals that receive += sum over ranks of the step's block
+  // in-kernel cross-GPU exchange (lhn_exchange; team kernel only)
+  XchCtx xch;                      // xch.world == 0: no exchange
+  unsigned int xch_seq;            // this launch's step number
+  long long* xch_totals;           // fused metrics: running totals that receive += sum over ranks of a step's block
+  unsigned long long* xch_prev_block;   // fused metrics: the PREVIOUS launch's per-step block (exchanged by this launch)
+  unsigned int xch_prev_seq;            // ... and its step number
   int trigger_halfway;             // overlapped launch: let the successor grid in half-way (else after the third plane)
 };
 

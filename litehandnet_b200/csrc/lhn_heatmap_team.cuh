@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "lhn_heatmap.cuh"
+#include "lhn_exchange.cuh"
 
 namespace lhn {
 
@@ -129,96 +130,6 @@ __device__ __forceinline__ float elem_f32(const T* p, int i) { return Elem<T>::t
 
 // quads per row of the DARK tile: the (ksize+4)-wide window starts 0..3 columns into its first quad
 __host__ __device__ constexpr int tile_quads(int td) { return (td + 6) >> 2; }
-
-// ---- in-kernel all-gather over peer-mapped mailboxes (lhn_exchange, include/lhn.h) -----------------------------------
-// One warp (the grid's last epilogue warp).  `local` holds n 64-bit words (n * 8 <= LHN_XCH_PAYLOAD_BYTES).  On return
-// every peer's block of this step is readable at xch_slot(a, r) (volatile loads: the data arrived over NVLink).
-// Returns false after a timeout (*status = 1): the caller then continues with the local block only.
-__device__ __forceinline__ unsigned char* xch_slot(const HmArgs& a, int mailbox_rank, int src_rank) {
-  const unsigned slot = a.xch_seq & (LHN_XCH_SLOTS - 1);
-  return a.xch_mail[mailbox_rank] + ((size_t)slot * LHN_XCH_MAX_RANKS + src_rank) * LHN_XCH_PAYLOAD_BYTES;
-}
-__device__ __forceinline__ unsigned int* xch_flag(const HmArgs& a, int mailbox_rank, int src_rank) {
-  const unsigned slot = a.xch_seq & (LHN_XCH_SLOTS - 1);
-  return reinterpret_cast<unsigned int*>(a.xch_mail[mailbox_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES) +
-         slot * LHN_XCH_MAX_RANKS + src_rank;
-}
-// launch ticket of the fused-metrics variant: one per slot, so consecutive (overlapping) launches never share one
-__device__ __forceinline__ unsigned int* xch_ticket(const HmArgs& a) {
-  return reinterpret_cast<unsigned int*>(a.xch_mail[a.xch_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + 1024) +
-         (a.xch_seq & (LHN_XCH_SLOTS - 1));
-}
-// in-kernel timing of the exchange (globaltimer ns), kept per slot in the local control page: [seq, t_enter,
-// t_published, t_peers_arrived] — read by profiles/probes/xch_timing.py; four 64-bit stores per launch by one lane
-__device__ __forceinline__ unsigned long long* xch_stamps(const HmArgs& a) {
-  return reinterpret_cast<unsigned long long*>(a.xch_mail[a.xch_rank] + (size_t)LHN_XCH_SLOTS * LHN_XCH_MAX_RANKS * LHN_XCH_PAYLOAD_BYTES + 2048) +
-         8 * (a.xch_seq & (LHN_XCH_SLOTS - 1));
-}
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// `stage`: 16-byte aligned shared memory of at least (n + 1) words, or nullptr for blocks of <= 32 words.  With a
-// stage the block goes out as ONE bulk copy (TMA, shared -> peer global) per peer, all peers in flight together; a
-// loop of per-word loads and remote stores measured 7-13 us for 3.2 KB (profiles/r02_xch_timing.txt: each iteration
-// paid an L2 round trip in front of its store).
-static __device__ __noinline__ bool xch_publish_and_wait(const HmArgs& a, const unsigned long long* local, int n, int lane,
-                                                         unsigned long long* stage) {
-  const int world = a.xch_world, me = a.xch_rank;
-  unsigned long long* stamps = xch_stamps(a);
-  if (lane == 0) { stamps[0] = a.xch_seq; stamps[1] = gtimer(); }
-  // 1. this rank's block into every peer's mailbox, then a release flag per peer
-  if (stage) {
-    const int n2 = (n + 1) & ~1;                             // bulk copies move multiples of 16 bytes
-    for (int e0 = lane; e0 < n2; e0 += 128) {                // four independent loads per lane in flight
-      unsigned long long v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; v[u] = e < n ? __ldcg(local + e) : 0ull; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; if (e < n2) stage[e] = v[u]; }
-    }
-    __syncwarp();
-    fence_proxy_async();                                     // generic-proxy writes of the stage -> async proxy
-    if (lane < world && lane != me) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xch_slot(a, lane, me)),
-                   "r"(smem_u32(stage)), "r"((unsigned)(n2 * 8)) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-  } else {
-    const unsigned long long v = lane < n ? __ldcg(local + lane) : 0ull;
-    for (int r = 0; r < world; ++r) {
-      if (r == me || lane >= n) continue;
-      reinterpret_cast<volatile unsigned long long*>(xch_slot(a, r, me))[lane] = v;
-    }
-  }
-  __threadfence_system();
-  __syncwarp();
-  if (lane < world && lane != me)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(a, lane, me)), "r"(a.xch_seq) : "memory");
-  if (lane == 0) stamps[2] = gtimer();
-  // 2. the peers' flags in my mailbox
-  bool ok = true;
-  if (lane < world && lane != me) {
-    const unsigned int* f = xch_flag(a, me, lane);
-    const unsigned long long t0 = gtimer();
-    const unsigned long long limit = (unsigned long long)(a.xch_timeout_ms ? a.xch_timeout_ms : 2000u) * 1000000ull;
-    for (;;) {
-      unsigned int v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v == a.xch_seq) break;
-      if (gtimer() - t0 > limit) { ok = false; break; }
-      __nanosleep(100);
-    }
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  __threadfence_system();
-  if (lane == 0) stamps[3] = gtimer();
-  if (!ok && lane == 0 && a.xch_status) *a.xch_status = 1;
-  return ok;
-}
 
 // WC:  compile-time square plane size (64 or 56: 89 of the reference's 108 configs) with a compile-time team
 //      size (TWC warps = TWC-1 sweepers + 1 epilogue), so the sweep is a fully unrolled 128-bit loop with a
@@ -818,32 +729,24 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             if (run) atomicAdd(gcnt + (int64_t)row * Ki + k, run);
           }
         }
-        if (a.xch_world > 0) {
-          // in-kernel all-reduce of this step's block (lhn_decode_heatmap_pck_xch): the grid's last CTA sends the
-          // block to every peer, waits for theirs and adds them in rank order into the running totals
+        if (a.xch.world > 0) {
+          // In-kernel all-reduce of the per-step block (lhn_decode_heatmap_pck_xch), ONE LAUNCH BEHIND: the first CTA of
+          // this grid to finish publishes the PREVIOUS launch's block to every peer, waits for theirs and adds them in
+          // rank order into the running totals.  The last CTA of the grid would be the natural place, but whoever does
+          // the exchange holds its SM for the ~10 us of the NVLink round trip, the successor grid's CTA on that SM then
+          // starts late and — the plane assignment being static — finishes last again: measured, the step went from
+          // 42 to 70 us (profiles/r02_xch_timing.txt).  The first CTA to finish runs ~13 us ahead of the last (the
+          // finish-time spread of the grid), so the round trip is absorbed where there is slack.
           __threadfence();
           __syncwarp();
           unsigned int tk = 0;
-          if (lane == 0) tk = atomicAdd(xch_ticket(a), 1u);
+          if (lane == 0) tk = atomicAdd(xch_ticket(a.xch, a.xch_seq), 1u);
           tk = __shfl_sync(0xffffffffu, tk, 0);
-          if (tk == gridDim.x - 1) {
-            __threadfence();
-            // the CTA's own counters are flushed: their shared memory stages the outgoing block
-            const bool ok = a.xch_world > 1 ? xch_publish_and_wait(a, gcnt, n_cnt, lane, cta_cnt) : true;
-            // the running totals are shared with the previous launch, whose own update may still be waiting for a
-            // peer: only this one warp of the grid waits for it
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            for (int e = lane; e < n_cnt; e += 32) {
-              long long sum = 0;
-              for (int r = 0; r < a.xch_world; ++r) {
-                if (r == a.xch_rank) sum += (long long)__ldcg(gcnt + e);
-                else if (ok) sum += (long long)reinterpret_cast<volatile unsigned long long*>(xch_slot(a, a.xch_rank, r))[e];
-              }
-              a.xch_totals[e] += sum;
-              gcnt[e] = 0ull;                                   // the per-step block is left zero for its next use
-            }
-            if (lane == 0) *xch_ticket(a) = 0u;
+          if (tk == 0 && a.xch_prev_block) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous launch is complete: its block is final
+            xch_allreduce_block_i64(a.xch, a.xch_prev_seq, a.xch_prev_block, n_cnt, a.xch_totals, lane, cta_cnt);
           }
+          if (tk == gridDim.x - 1 && lane == 0) *xch_ticket(a.xch, a.xch_seq) = 0u;
         }
       }
     }
@@ -908,20 +811,20 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           for (int u = 0; u < 5; ++u) { v0 += x[u].x; v1 += x[u].y; v2 += y[u].x; v3 += y[u].y; }
         }
         v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
-        if (a.xch_world > 1) {
+        if (a.xch.world > 1) {
           // batch-global loss (lhn_fused_render_loss_decode_xch): all-gather the four sums of every rank through the
           // peer mailboxes and add them in rank order — the same doubles in the same order on every rank
-          unsigned long long* mine = reinterpret_cast<unsigned long long*>(xch_slot(a, a.xch_rank, a.xch_rank));
+          unsigned long long* mine = reinterpret_cast<unsigned long long*>(xch_slot(a.xch, a.xch_seq, a.xch.rank, a.xch.rank));
           if (lane == 0) {
             mine[0] = (unsigned long long)__double_as_longlong(v0); mine[1] = (unsigned long long)__double_as_longlong(v1);
             mine[2] = (unsigned long long)__double_as_longlong(v2); mine[3] = (unsigned long long)__double_as_longlong(v3);
           }
           __syncwarp();
-          const bool ok = xch_publish_and_wait(a, mine, 4, lane, nullptr);
+          const bool ok = xch_publish_and_wait(a.xch, a.xch_seq, mine, 4, lane, nullptr);
           if (ok) {
             double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-            for (int r = 0; r < a.xch_world; ++r) {
-              const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(xch_slot(a, a.xch_rank, r));
+            for (int r = 0; r < a.xch.world; ++r) {
+              const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(xch_slot(a.xch, a.xch_seq, a.xch.rank, r));
               g0 += __longlong_as_double((long long)src[0]); g1 += __longlong_as_double((long long)src[1]);
               g2 += __longlong_as_double((long long)src[2]); g3 += __longlong_as_double((long long)src[3]);
             }
@@ -1377,7 +1280,7 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   }
   {
     const char* tg = getenv("LHN_TRIGGER");               // "half" / "early": override the trigger point (experiments)
-    a.trigger_halfway = tg ? (tg[0] == 'h') : (a.xch_world > 1);
+    a.trigger_halfway = tg ? (tg[0] == 'h') : (a.xch.world > 1);
   }
   a.sweeper_tables = (nstg >= 2 && tw >= 4) ? 1 : 0;
   a.team_warps = tw;

@@ -76,6 +76,7 @@ class PeerExchange:
         self.seq = 0
         self.how = "local"
         self._keep = []
+        self._blocks, self._pending = None, None
         if self.world == 1:
             self.mailbox = torch.zeros(L.XCH_MAILBOX_BYTES, dtype=torch.uint8, device=self.device)
             self.ptrs = [self.mailbox.data_ptr()]
@@ -134,6 +135,7 @@ class PeerExchange:
         for r in range(n):
             x = cls.__new__(cls)
             x.device, x.world, x.rank, x.seq, x.how = torch.device(device), n, r, 0, "local test group"
+            x._blocks, x._pending = None, None
             x.mailbox, x.ptrs, x._keep = boxes[r], [b.data_ptr() for b in boxes], boxes
             x.status = torch.zeros(1, dtype=torch.int32, device=device)
             out.append(x)
@@ -142,6 +144,40 @@ class PeerExchange:
     def next_seq(self):
         self.seq += 1
         return self.seq
+
+    # ---- per-step counter blocks of the one-launch-behind exchange (lhn_decode_heatmap_pck_xch) --------------------
+    def step_blocks(self, n):
+        """[LHN_XCH_SLOTS, n] int64 zeros: the launch of step s accumulates into row s % LHN_XCH_SLOTS; the NEXT
+        exchanging launch (or flush()) sends it to the peers, adds all ranks' rows into the totals and zeroes it."""
+        from . import _lib as L
+        if self._blocks is None or self._blocks.shape[1] != n:
+            if self._pending is not None:
+                raise L.LhnError("flush() the exchange before changing the block size")
+            self._blocks = torch.zeros((L.XCH_SLOTS, n), dtype=torch.int64, device=self.device)
+        return self._blocks
+
+    def begin_step(self, n, totals):
+        """-> (seq, this step's block ptr, previous step's block ptr or None, its seq); remembers what flush() must
+        finish."""
+        from . import _lib as L
+        blocks = self.step_blocks(n)
+        seq = self.next_seq()
+        prev, prev_seq = (self._pending[1], self._pending[0]) if self._pending is not None else (None, 0)
+        cur = blocks[seq % L.XCH_SLOTS].data_ptr()
+        self._pending = (seq, cur, n, totals)
+        return seq, cur, prev, prev_seq
+
+    def flush(self, timeout_ms=2000):
+        """Exchange the last step's block (lhn_exchange_flush) — after it `totals` is complete on every rank."""
+        from . import _lib as L
+        if self._pending is None:
+            return
+        seq, cur, n, totals = self._pending
+        x = self.struct(timeout_ms)
+        x.seq = seq
+        with L.on_device(self.device):
+            L.check(L.lib().lhn_exchange_flush(x, cur, n, L.ptr(totals), L.stream(self.device)), "lhn_exchange_flush")
+        self._pending = None
 
     def struct(self, timeout_ms=2000):
         """A fresh lhn_exchange for one bound launcher (its seq is set right before every launch)."""

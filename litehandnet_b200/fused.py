@@ -444,9 +444,10 @@ class BoundDecodeStep:
                  hm_flip=None, flip_pairs=(), kernel=11, scale_xy=(1.0, 1.0), overlap_previous=False, metrics=None,
                  outputs=None):
         """metrics: None or dict(gt [B,K,2] f32, mask [B,K] bool/u8, bbox_wh [B,2] f32, counters int64
-        [(auc_steps+5)*K], pck_thr=0.2, auc_nor=30.0, auc_steps=20[, exchange=dist.PeerExchange, totals=int64 like
-        counters]).  With `exchange`, `counters` is the rank's per-step block (zero before and after every launch) and
-        `totals` receives += the block summed over all ranks inside the kernel (lhn_decode_heatmap_pck_xch)."""
+        [(auc_steps+5)*K], pck_thr=0.2, auc_nor=30.0, auc_steps=20), or with the in-kernel cross-rank exchange
+        dict(gt, mask, bbox_wh, exchange=dist.PeerExchange, totals=int64 [(auc_steps+5)*K], ...): every launch accumulates
+        into one of the exchange's rotating per-step blocks and all-reduces the PREVIOUS launch's block into `totals`
+        inside the kernel (lhn_decode_heatmap_pck_xch); exchange.flush() completes the last step."""
         import ctypes as C
         lib = L.lib()
         self._lib = lib
@@ -492,26 +493,27 @@ class BoundDecodeStep:
             mask = ops._mask_u8(metrics["mask"])
             wh = ops._f32c(metrics["bbox_wh"], "bbox_wh")
             steps = int(metrics.get("auc_steps", 20))
-            self.counters = metrics["counters"]
+            self.exchange = metrics.get("exchange")
+            self.counters = metrics["counters"] if self.exchange is None else self.exchange.step_blocks((steps + 5) * Cc)[0]
             if self.counters.dtype != torch.int64 or self.counters.numel() != (steps + 5) * Cc or \
                     not self.counters.is_contiguous() or self.counters.device != dev:
                 raise L.LhnError("counters must be a contiguous int64 tensor of (auc_steps+5)*K entries on the heatmaps' device")
             self._keep += [gt, mask, wh, self.counters]
             self._fn, self._name = lib.lhn_decode_heatmap_pck, "lhn_decode_heatmap_pck"
-            self._args = (L.ptr(hm), L.dtype_code(hm), B, Cc, H, W, sb, sc, L.ptr(center), L.ptr(scale), C.byref(self.dp),
+            self._args = [L.ptr(hm), L.dtype_code(hm), B, Cc, H, W, sb, sc, L.ptr(center), L.ptr(scale), C.byref(self.dp),
                           L.ptr(self.hm_preds), L.ptr(self.preds), L.ptr(self.idx), L.ptr(gt), L.ptr(mask), L.ptr(wh),
                           float(metrics.get("pck_thr", 0.2)), float(metrics.get("auc_nor", 30.0)), steps,
-                          L.ptr(self.counters))
-            self.exchange = metrics.get("exchange")
+                          L.ptr(self.counters)]
             if self.exchange is not None:
                 totals = metrics["totals"]
                 if totals.dtype != torch.int64 or totals.numel() != self.counters.numel() or not totals.is_contiguous() \
                         or totals.device != dev:
-                    raise L.LhnError("totals must be a contiguous int64 tensor like counters")
+                    raise L.LhnError("totals must be a contiguous int64 tensor of (auc_steps+5)*K entries")
+                self.totals, self._n_cnt = totals, (steps + 5) * Cc
                 self._keep.append(totals)
                 self.xch = self.exchange.struct()
                 self._fn, self._name = lib.lhn_decode_heatmap_pck_xch, "lhn_decode_heatmap_pck_xch"
-                self._args = self._args + (L.ptr(totals), C.byref(self.xch))
+                self._args = self._args + [L.ptr(totals), C.byref(self.xch)]
         self.graph = None
 
     def stream(self):
@@ -519,7 +521,10 @@ class BoundDecodeStep:
 
     def launch_kernel(self, stream):
         if getattr(self, "exchange", None) is not None:
-            self.xch.seq = self.exchange.next_seq()
+            # this step's block, and the previous step's block for this launch to exchange
+            seq, cur, prev, prev_seq = self.exchange.begin_step(self._n_cnt, self.totals)
+            self.xch.seq, self.xch.prev_block, self.xch.prev_seq = seq, prev, prev_seq
+            self._args[20] = cur
         L.check(self._fn(*self._args, stream), self._name)
 
     def launch(self):

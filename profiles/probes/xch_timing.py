@@ -29,10 +29,9 @@ def main():
         gt, mask, wh = synth.pck_inputs(cen, seed=100 * rank + i + 2, device=dev)
         sets.append((hm, c, s, gt, mask, wh))
     totals = torch.zeros((T + 5) * K, dtype=torch.int64, device=dev)
-    blocks = [torch.zeros((T + 5) * K, dtype=torch.int64, device=dev) for _ in range(R)]
     bound = [fused.BoundDecodeStep(s[0], s[1], s[2], L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE, overlap_previous=True,
-                                   metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=blocks[i], auc_steps=T,
-                                                exchange=x, totals=totals)) for i, s in enumerate(sets)]
+                                   metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], auc_steps=T, exchange=x, totals=totals))
+             for i, s in enumerate(sets)]
     for step in range(10):
         bound[step % R].launch()
     torch.cuda.synchronize()

@@ -27,12 +27,12 @@ def main():
         gt, mask, wh = synth.pck_inputs(cen, seed=100 * rank + i + 2, device=dev)
         sets.append((hm, c, s, gt, mask, wh))
     totals = torch.zeros((T + 5) * K, dtype=torch.int64, device=dev)
-    blocks = [torch.zeros((T + 5) * K, dtype=torch.int64, device=dev) for _ in range(R)]
     bound = [fused.BoundDecodeStep(s[0], s[1], s[2], L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE, overlap_previous=True,
-                                   metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=blocks[i], auc_steps=T,
-                                                exchange=x, totals=totals)) for i, s in enumerate(sets)]
+                                   metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], auc_steps=T, exchange=x, totals=totals))
+             for i, s in enumerate(sets)]
     for step in range(steps):
         bound[step % R].launch()
+    x.flush()                                    # the exchange runs one launch behind
     torch.cuda.synchronize()
     assert int(x.status.item()) == 0, "timed out waiting for a peer"
     want = torch.zeros_like(totals)
@@ -54,11 +54,12 @@ def main():
     local_step.launch()
     sums = local_step.sums.clone()
     dist.all_reduce(sums)
-    xb = fused.BoundFusedStep(cfg, hm, j, v, c, s, hm_flip=hf, exchange=x)
+    x2 = PeerExchange(dev)                       # the loss sums exchange immediately (its own mailbox and step numbers)
+    xb = fused.BoundFusedStep(cfg, hm, j, v, c, s, hm_flip=hf, exchange=x2)
     for _ in range(3):
         xb.launch()
     torch.cuda.synchronize()
-    assert int(x.status.item()) == 0
+    assert int(x2.status.item()) == 0
     assert torch.allclose(xb.sums, sums, rtol=1e-12), (xb.sums, sums)
     gathered = [torch.zeros_like(xb.sums) for _ in range(world)]
     dist.all_gather(gathered, xb.sums)

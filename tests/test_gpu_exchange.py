@@ -49,16 +49,17 @@ def test_counter_exchange_between_ranks_on_one_gpu(world, B):
     streams = [torch.cuda.Stream() for _ in range(world)]
     sets = [[pck_set(B, K, 100 * r + 10 * i) for i in range(R)] for r in range(world)]
     totals = [torch.zeros((T + 5) * K, dtype=torch.int64, device=DEV) for _ in range(world)]
-    blocks = [[torch.zeros((T + 5) * K, dtype=torch.int64, device=DEV) for _ in range(R)] for _ in range(world)]
     bound = [[fused.BoundDecodeStep(s[0], s[1], s[2], L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE, overlap_previous=True,
-                                    metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=blocks[r][i], auc_steps=T,
-                                                 exchange=xs[r], totals=totals[r]))
+                                    metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], auc_steps=T, exchange=xs[r], totals=totals[r]))
               for i, s in enumerate(sets[r])] for r in range(world)]
     torch.cuda.synchronize()
     for step in range(steps):
         for r in range(world):
             with torch.cuda.stream(streams[r]):
                 bound[r][step % R].launch()
+    for r in range(world):                       # the exchange runs one launch behind: finish the last step
+        with torch.cuda.stream(streams[r]):
+            xs[r].flush()
     torch.cuda.synchronize()
     assert all(int(x.status.item()) == 0 for x in xs), "a rank timed out waiting for its peers"
     # what a single process accumulates over the same steps
@@ -72,7 +73,7 @@ def test_counter_exchange_between_ranks_on_one_gpu(world, B):
     mono = sum(per_set[step % R] for step in range(steps))
     for r in range(world):
         assert torch.equal(totals[r], mono), f"rank {r}: totals differ from the monolithic counters"
-        assert all(int(b.abs().sum().item()) == 0 for b in blocks[r]), "per-step blocks must be left zero"
+        assert int(xs[r].step_blocks((T + 5) * K).abs().sum().item()) == 0, "per-step blocks must be left zero"
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -118,11 +119,12 @@ def test_exchange_rejects_bad_arguments():
     st.seq = 0                                           # step numbers start at 1
     s = pck_set(8, 16, 5)
     cnt = torch.zeros(25 * 16, dtype=torch.int64, device=DEV)
-    b = fused.BoundDecodeStep(s[0], s[1], s[2], metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], counters=cnt, exchange=x,
-                                                             totals=torch.zeros_like(cnt)))
+    b = fused.BoundDecodeStep(s[0], s[1], s[2], metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], exchange=x, totals=cnt))
     b.exchange = None                                    # keep seq = 0
     with pytest.raises(L.LhnError):
         b.launch()
+    with pytest.raises(L.LhnError):                      # totals of the wrong size
+        fused.BoundDecodeStep(s[0], s[1], s[2], metrics=dict(gt=s[3], mask=s[4], bbox_wh=s[5], exchange=x, totals=cnt[:-1]))
 
 
 @pytest.mark.parametrize("nproc", [2])
