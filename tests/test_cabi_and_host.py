@@ -32,12 +32,40 @@ def test_library_exports_every_declared_symbol(lib_path):
     assert handle.lhn_version() == 100
 
 
+def test_torch_extension_shim_loads():
+    """The shim is built in-tree next to liblhn.so and exposes its two entry points (no compute without a GPU)."""
+    from litehandnet_b200 import _lib
+    e = _lib.ext()
+    assert e is not None and hasattr(e, "decode_heatmap") and hasattr(e, "decode_simdr")
+    assert os.path.dirname(e.__file__) == os.path.join(ROOT, "litehandnet_b200", "lib")
+
+
 def test_struct_layouts_match_header():
     from litehandnet_b200 import _lib
     # lhn_decode_params: 6 int32 + 2 float + 31 double ; lhn_render_params: 4 int32 + 3 float + 8 float
     assert ctypes.sizeof(_lib.DecodeParams) == 6 * 4 + 2 * 4 + 31 * 8
     assert ctypes.sizeof(_lib.RenderParams) == 4 * 4 + 3 * 4 + 8 * 4
     assert _lib.DecodeParams.taps.offset == 32 and _lib.RenderParams.sigma.offset == 28
+    # lhn_exchange: 8 pointers, world, rank, seq, timeout_ms, status*, prev_block*, prev_seq, reserved
+    assert ctypes.sizeof(_lib.Exchange) == 8 * 8 + 4 * 4 + 8 + 8 + 2 * 4
+    assert _lib.Exchange.status.offset == 80 and _lib.Exchange.prev_block.offset == 88 and _lib.Exchange.prev_seq.offset == 96
+    assert _lib.XCH_MAILBOX_BYTES == 4 * 8 * 8192 + 4096
+
+
+def test_exchange_argument_validation_without_gpu(lib_path):
+    from litehandnet_b200 import _lib
+    lib = _lib.lib()
+    x = _lib.Exchange()
+    x.world, x.rank, x.seq = 2, 0, 1
+    x.mailbox[0] = 4096                                 # mailbox[1] missing
+    assert lib.lhn_exchange_flush(ctypes.byref(x), ctypes.c_void_p(4096), 400, ctypes.c_void_p(4096), None) == -1
+    x.mailbox[1] = 8192
+    x.seq = 0                                           # step numbers start at 1
+    assert lib.lhn_exchange_flush(ctypes.byref(x), ctypes.c_void_p(4096), 400, ctypes.c_void_p(4096), None) == -1
+    x.seq = 1
+    assert lib.lhn_exchange_flush(ctypes.byref(x), ctypes.c_void_p(4096), 2000, ctypes.c_void_p(4096), None) == -1   # > payload
+    assert lib.lhn_simdr_heads_workspace_bytes(64, 21, 512, 512) == 16 * 64 * 21 * 16
+    assert lib.lhn_split_bf16(ctypes.c_void_p(16), 6, ctypes.c_void_p(16), ctypes.c_void_p(16), None) == -1       # n % 4
 
 
 def test_gaussian_taps_match_opencv(lib_path):

@@ -210,3 +210,29 @@ def test_loss_mse_multi_single_large_tensor_and_sum_reduction():
         np.testing.assert_allclose(float(loss.item()), float(ref), rtol=1e-5)
     with pytest.raises(L.LhnError):
         ops.loss_mse_multi([o] * 9, [t] * 9, [tw] * 9, L.LOSS_DISTANCE)
+
+
+# ---- the torch-extension shim: same library entry point, same results as the ctypes route ---------------------
+def test_torch_extension_route_equals_ctypes_route():
+    assert L.ext() is not None, "the extension shim must be built in-tree (litehandnet_b200.build)"
+    hm, cen = synth.blob_heatmaps(16, 21, 64, 64, seed=5, device=DEV, zero_frac=0.05, tie_frac=0.05)
+    hf = synth.flipped_blob_heatmaps(cen, 64, 64, seed=6, device=DEV)
+    c, s = synth.bbox_center_scale(16, seed=7, device=DEV)
+    for refine in (L.REFINE_SIGN, L.REFINE_DARK, L.REFINE_OFFSET_HALF):
+        for flip in (None, hf):
+            a = ops.decode_heatmap(hm, L.MASK_NEG1, refine, L.XFORM_CENTER_SCALE, c, s, hm_flip=flip)
+            b = ops._decode_heatmap_ctypes(hm, L.MASK_NEG1, refine, L.XFORM_CENTER_SCALE, c, s, hm_flip=flip)
+            for k in ("hm_kpts", "kpts", "idx"):
+                assert torch.equal(a[k], b[k]), (refine, k)
+    # channel slice (stride_c != H*W) and bf16 go through the shim as well
+    big = torch.cat([hm, hm.flip(1)], 1)
+    a = ops.decode_heatmap(big[:, :21], L.MASK_ZERO, L.REFINE_NONE)
+    b = ops._decode_heatmap_ctypes(hm, L.MASK_ZERO, L.REFINE_NONE)
+    assert torch.equal(a["kpts"], b["kpts"])
+    a = ops.decode_heatmap(hm.bfloat16(), L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE, c, s, want_idx=False)
+    b = ops._decode_heatmap_ctypes(hm.bfloat16(), L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE, c, s)
+    assert a["idx"] is None and torch.equal(a["kpts"], b["kpts"])
+    with pytest.raises(L.LhnError):
+        ops.decode_heatmap(hm.cpu(), L.MASK_NEG1, L.REFINE_SIGN)
+    with pytest.raises(L.LhnError):                       # f64 heatmaps: rejected by the shim, as an LhnError
+        ops.decode_heatmap(hm.double(), L.MASK_NEG1, L.REFINE_SIGN)
