@@ -119,10 +119,12 @@ typedef struct {
   uint32_t seq;                     /* step number >= 1 */
   uint32_t timeout_ms;              /* 0 = 2000 */
   int32_t* status;                  /* device int32 (local), or NULL */
-  void* prev_block;                 /* lhn_decode_heatmap_pck_xch: the per-step block of the PREVIOUS exchanging launch
-                                       (exchanged by this launch), or NULL for the first launch of a sequence */
+  /* lhn_decode_heatmap_pck_xch / lhn_exchange_flush only — the pipelined counter exchange: */
+  void* prev_block;                 /* per-step block of the PREVIOUS exchanging launch (this launch publishes it), or NULL */
   uint32_t prev_seq;                /* ... and that launch's step number */
-  uint32_t reserved;
+  uint32_t prev2_seq;               /* step number of the launch before that */
+  void* prev2_block;                /* ... and its block (published by the previous launch; this launch adds every
+                                       rank's copy into the totals and zeroes it), or NULL */
 } lhn_exchange;
 
 /* Decode parameters. */
@@ -431,14 +433,15 @@ LHN_API int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, 
                                    float auc_nor, int auc_steps, int64_t* counters,
                                    lhn_stream_t stream);
 
-/* The same with the per-step counter block all-reduced over the ranks INSIDE the kernel, ONE LAUNCH BEHIND: `counters`
- * is this rank's block for THIS step (zero at entry; rotate at least LHN_XCH_SLOTS blocks), xch->prev_block the block
- * of the previous exchanging launch: the first CTA of this grid to finish sends that block to every peer, waits for
- * theirs and adds them in rank order into `totals` int64 [(auc_steps+5)*K] (then zeroes it).  lhn_exchange_flush
- * does the same for the last block of a sequence (xch->seq = that step's number); after it every rank holds the same
- * running totals, equal bit for bit to a single-process evaluation (datasets/base_dataset.py:193-261 on the gathered
- * results).  Why one launch behind: whoever exchanges holds its SM for the NVLink round trip; the first CTA to
- * finish has the slack of the grid's finish-time spread, the last one has none. */
+/* The same with the per-step counter block all-reduced over the ranks INSIDE the kernel, pipelined over two launches:
+ * `counters` is this rank's block for THIS step (zero at entry; rotate LHN_XCH_SLOTS blocks).  The first CTA of this
+ * grid to finish (a) adds every rank's copy of xch->prev2_block's step (sent during the previous launch, so nothing
+ * is waited for) in rank order into `totals` int64 [(auc_steps+5)*K] and zeroes that block, (b) sends xch->prev_block
+ * — the previous launch's block — to every peer.  lhn_exchange_flush(xch, n, totals) completes the (up to two)
+ * steps still in flight when a sequence ends; after it every rank holds the same running totals, equal bit for bit to
+ * a single-process evaluation (datasets/base_dataset.py:193-261 on the gathered results).  Why pipelined: whoever
+ * exchanges holds its SM for the NVLink round trip; the first CTA to finish has the slack of the grid's finish-time
+ * spread for ~7 us of sends and local adds, the last CTA has none, and nobody has 10-20 us. */
 LHN_API int lhn_decode_heatmap_pck_xch(const void* hm, int dtype, int64_t B, int K, int H, int W,
                                    int64_t stride_b, int64_t stride_c, const float* center,
                                    const float* scale, const lhn_decode_params* dp, float* out_hm,
@@ -447,7 +450,7 @@ LHN_API int lhn_decode_heatmap_pck_xch(const void* hm, int dtype, int64_t B, int
                                    float auc_nor, int auc_steps, int64_t* counters,
                                    int64_t* totals, const lhn_exchange* xch,
                                           lhn_stream_t stream);
-LHN_API int lhn_exchange_flush(const lhn_exchange* xch, int64_t* block, int n, int64_t* totals, lhn_stream_t stream);
+LHN_API int lhn_exchange_flush(const lhn_exchange* xch, int n, int64_t* totals, lhn_stream_t stream);
 
 /* evaluate_pck (evaluation.py:10-59): argmax (A1) on pred and gt heatmap batches [B,K,H,W],
  * * image_size/[W,H], distance / max(bbox[:,0,2:]), per-image hits/(2*sum w)*2 in f32.

@@ -60,7 +60,7 @@ class RenderParams(C.Structure):
 class Exchange(C.Structure):
     _fields_ = [("mailbox", C.c_void_p * XCH_MAX_RANKS), ("world", C.c_int32), ("rank", C.c_int32),
                 ("seq", C.c_uint32), ("timeout_ms", C.c_uint32), ("status", C.c_void_p), ("prev_block", C.c_void_p),
-                ("prev_seq", C.c_uint32), ("reserved", C.c_uint32)]
+                ("prev_seq", C.c_uint32), ("prev2_seq", C.c_uint32), ("prev2_block", C.c_void_p)]
 
 
 class RegionParams(C.Structure):
@@ -99,7 +99,7 @@ def _declare(lib):
     lib.lhn_decode_heatmap_pck_xch.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, vp, vp,
                                                C.POINTER(DecodeParams), vp, vp, vp, vp, vp, vp, f32, f32,
                                                i32, vp, vp, C.POINTER(Exchange), vp]
-    lib.lhn_exchange_flush.argtypes = [C.POINTER(Exchange), vp, i32, vp, vp]
+    lib.lhn_exchange_flush.argtypes = [C.POINTER(Exchange), i32, vp, vp]
     lib.lhn_loss_backward.argtypes = [vp, vp, vp, i32, i64, i64, i32, f32, vp, i32, f32, vp, vp, vp]
     lib.lhn_render_loss_backward.argtypes = [vp, i32, i64, i32, i32, i32, i64, i64, C.POINTER(RenderParams),
                                              vp, i32, vp, i32, vp, i32, f32, vp, vp, vp]

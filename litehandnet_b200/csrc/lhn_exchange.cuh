@@ -43,10 +43,10 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 
 // One warp.  `local`: n 64-bit words in global memory (n * 8 <= LHN_XCH_PAYLOAD_BYTES).  `stage`: 16-byte aligned
-// shared memory of n + 1 words, or nullptr for blocks of <= 32 words (plain stores).  On return every peer's block
-// of step `seq` is readable at xch_slot(x, seq, x.rank, r) with volatile loads.  false = a peer timed out.
-static __device__ __noinline__ bool xch_publish_and_wait(const XchCtx& x, unsigned seq, const unsigned long long* local, int n,
-                                                         int lane, unsigned long long* stage) {
+// shared memory of n + 1 words, or nullptr for blocks of <= 32 words (plain stores).  Sends the block of step `seq`
+// to every peer's mailbox and releases the flags; does not wait for anybody.
+static __device__ __noinline__ void xch_publish(const XchCtx& x, unsigned seq, const unsigned long long* local, int n,
+                                                int lane, unsigned long long* stage) {
   const int world = x.world, me = x.rank;
   unsigned long long* stamps = xch_stamps(x, seq);
   if (lane == 0) { stamps[0] = seq; stamps[1] = gtimer(); }
@@ -79,6 +79,14 @@ static __device__ __noinline__ bool xch_publish_and_wait(const XchCtx& x, unsign
   if (lane < world && lane != me)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(x, seq, lane, me)), "r"(seq) : "memory");
   if (lane == 0) stamps[2] = gtimer();
+}
+
+// One warp: wait until every peer's block of step `seq` has landed in this rank's mailbox (readable with volatile loads
+// at xch_slot(x, seq, x.rank, r)).  false = a peer timed out (*status = 1).
+static __device__ __noinline__ bool xch_wait(const XchCtx& x, unsigned seq, int lane) {
+  const int world = x.world, me = x.rank;
+  unsigned long long* stamps = xch_stamps(x, seq);
+  if (lane == 0) stamps[4] = gtimer();
   bool ok = true;
   if (lane < world && lane != me) {
     const unsigned int* f = xch_flag(x, seq, me, lane);
@@ -99,10 +107,17 @@ static __device__ __noinline__ bool xch_publish_and_wait(const XchCtx& x, unsign
   return ok;
 }
 
-// totals[e] += sum over ranks (rank order) of step `seq`'s block; the local block is left zero.  One warp.
-static __device__ __noinline__ void xch_allreduce_block_i64(const XchCtx& x, unsigned seq, unsigned long long* block, int n,
-                                                            long long* totals, int lane, unsigned long long* stage) {
-  const bool ok = x.world > 1 ? xch_publish_and_wait(x, seq, block, n, lane, stage) : true;
+static __device__ __forceinline__ bool xch_publish_and_wait(const XchCtx& x, unsigned seq, const unsigned long long* local, int n,
+                                                            int lane, unsigned long long* stage) {
+  xch_publish(x, seq, local, n, lane, stage);
+  return xch_wait(x, seq, lane);
+}
+
+// totals[e] += sum over ranks (rank order) of step `seq`'s block, which this rank has published before; the local
+// block is left zero.  One warp.
+static __device__ __noinline__ void xch_consume_block_i64(const XchCtx& x, unsigned seq, unsigned long long* block, int n,
+                                                          long long* totals, int lane) {
+  const bool ok = x.world > 1 ? xch_wait(x, seq, lane) : true;
   for (int e = lane; e < n; e += 32) {
     long long sum = 0;
     for (int r = 0; r < x.world; ++r) {

@@ -510,7 +510,9 @@ static int fill_exchange(HmArgs& a, const lhn_exchange* x) {
   a.xch_seq = x->seq;
   a.xch_prev_block = static_cast<unsigned long long*>(x->prev_block);
   a.xch_prev_seq = x->prev_seq;
-  if (x->prev_block && x->prev_seq == 0) return LHN_EINVAL;
+  a.xch_prev2_block = static_cast<unsigned long long*>(x->prev2_block);
+  a.xch_prev2_seq = x->prev2_seq;
+  if ((x->prev_block && x->prev_seq == 0) || (x->prev2_block && x->prev2_seq == 0)) return LHN_EINVAL;
   return LHN_OK;
 }
 

@@ -80,6 +80,8 @@ struct HmArgs {
   long long* xch_totals;           // fused metrics: running totals that receive += sum over ranks of a step's block
   unsigned long long* xch_prev_block;   // fused metrics: the PREVIOUS launch's per-step block (exchanged by this launch)
   unsigned int xch_prev_seq;            // ... and its step number
+  unsigned long long* xch_prev2_block;  // the block of two launches back (published by the previous launch, consumed by this one)
+  unsigned int xch_prev2_seq;
   int trigger_halfway;             // overlapped launch: let the successor grid in half-way (else after the third plane)
 };
 

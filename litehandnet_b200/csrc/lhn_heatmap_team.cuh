@@ -730,21 +730,23 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           }
         }
         if (a.xch.world > 0) {
-          // In-kernel all-reduce of the per-step block (lhn_decode_heatmap_pck_xch), ONE LAUNCH BEHIND: the first CTA of
-          // this grid to finish publishes the PREVIOUS launch's block to every peer, waits for theirs and adds them in
-          // rank order into the running totals.  The last CTA of the grid would be the natural place, but whoever does
-          // the exchange holds its SM for the ~10 us of the NVLink round trip, the successor grid's CTA on that SM then
-          // starts late and — the plane assignment being static — finishes last again: measured, the step went from
-          // 42 to 70 us (profiles/r02_xch_timing.txt).  The first CTA to finish runs ~13 us ahead of the last (the
-          // finish-time spread of the grid), so the round trip is absorbed where there is slack.
+          // In-kernel all-reduce of the per-step blocks (lhn_decode_heatmap_pck_xch), pipelined over two launches: the
+          // first CTA of this grid to finish CONSUMES the block of two launches back (every rank sent it during the
+          // previous launch, so nothing is waited for: adds the ranks' blocks in rank order into the running totals)
+          // and PUBLISHES the previous launch's block to every peer.  The last CTA of the grid would be the natural
+          // place for an immediate exchange, but whoever exchanges holds its SM for the NVLink round trip, the successor
+          // grid's CTA on that SM then starts late and — the plane assignment being static — finishes last again:
+          // measured, the step went from 42 to 70 us (profiles/r02_xch_timing.txt).  The first CTA to finish runs
+          // ~13 us ahead of the last (the grid's finish-time spread): ~7 us of sends and local adds fit in that slack.
           __threadfence();
           __syncwarp();
           unsigned int tk = 0;
           if (lane == 0) tk = atomicAdd(xch_ticket(a.xch, a.xch_seq), 1u);
           tk = __shfl_sync(0xffffffffu, tk, 0);
-          if (tk == 0 && a.xch_prev_block) {
+          if (tk == 0 && (a.xch_prev_block || a.xch_prev2_block)) {
             asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous launch is complete: its block is final
-            xch_allreduce_block_i64(a.xch, a.xch_prev_seq, a.xch_prev_block, n_cnt, a.xch_totals, lane, cta_cnt);
+            if (a.xch_prev2_block) xch_consume_block_i64(a.xch, a.xch_prev2_seq, a.xch_prev2_block, n_cnt, a.xch_totals, lane);
+            if (a.xch_prev_block && a.xch.world > 1) xch_publish(a.xch, a.xch_prev_seq, a.xch_prev_block, n_cnt, lane, cta_cnt);
           }
           if (tk == gridDim.x - 1 && lane == 0) *xch_ticket(a.xch, a.xch_seq) = 0u;
         }

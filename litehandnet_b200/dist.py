@@ -151,32 +151,41 @@ class PeerExchange:
         exchanging launch (or flush()) sends it to the peers, adds all ranks' rows into the totals and zeroes it."""
         from . import _lib as L
         if self._blocks is None or self._blocks.shape[1] != n:
-            if self._pending is not None:
+            if self._pending:
                 raise L.LhnError("flush() the exchange before changing the block size")
             self._blocks = torch.zeros((L.XCH_SLOTS, n), dtype=torch.int64, device=self.device)
         return self._blocks
 
-    def begin_step(self, n, totals):
-        """-> (seq, this step's block ptr, previous step's block ptr or None, its seq); remembers what flush() must
-        finish."""
+    def begin_step(self, n, totals, x):
+        """Number a new exchanging launch and fill its lhn_exchange `x`: this step's sequence number, the previous
+        step's block (this launch publishes it) and the block of the step before (this launch adds it into the totals).
+        Returns this step's block pointer."""
         from . import _lib as L
         blocks = self.step_blocks(n)
         seq = self.next_seq()
-        prev, prev_seq = (self._pending[1], self._pending[0]) if self._pending is not None else (None, 0)
+        p = self._pending or []
+        x.seq = seq
+        x.prev_block, x.prev_seq = (p[-1][1], p[-1][0]) if len(p) >= 1 else (None, 0)
+        x.prev2_block, x.prev2_seq = (p[-2][1], p[-2][0]) if len(p) >= 2 else (None, 0)
         cur = blocks[seq % L.XCH_SLOTS].data_ptr()
-        self._pending = (seq, cur, n, totals)
-        return seq, cur, prev, prev_seq
+        self._pending = (p + [(seq, cur)])[-2:]
+        self._pending_meta = (n, totals)
+        return cur
 
     def flush(self, timeout_ms=2000):
-        """Exchange the last step's block (lhn_exchange_flush) — after it `totals` is complete on every rank."""
+        """Complete the (up to two) steps still in flight (lhn_exchange_flush) — after it `totals` holds every step of
+        every rank, on every rank."""
         from . import _lib as L
-        if self._pending is None:
+        if not self._pending:
             return
-        seq, cur, n, totals = self._pending
+        n, totals = self._pending_meta
+        p = self._pending
         x = self.struct(timeout_ms)
-        x.seq = seq
+        x.seq = p[-1][0]
+        x.prev_block, x.prev_seq = p[-1][1], p[-1][0]
+        x.prev2_block, x.prev2_seq = (p[-2][1], p[-2][0]) if len(p) >= 2 else (None, 0)
         with L.on_device(self.device):
-            L.check(L.lib().lhn_exchange_flush(x, cur, n, L.ptr(totals), L.stream(self.device)), "lhn_exchange_flush")
+            L.check(L.lib().lhn_exchange_flush(x, n, L.ptr(totals), L.stream(self.device)), "lhn_exchange_flush")
         self._pending = None
 
     def struct(self, timeout_ms=2000):

@@ -521,10 +521,8 @@ class BoundDecodeStep:
 
     def launch_kernel(self, stream):
         if getattr(self, "exchange", None) is not None:
-            # this step's block, and the previous step's block for this launch to exchange
-            seq, cur, prev, prev_seq = self.exchange.begin_step(self._n_cnt, self.totals)
-            self.xch.seq, self.xch.prev_block, self.xch.prev_seq = seq, prev, prev_seq
-            self._args[20] = cur
+            # this step's block; the two previous steps' blocks for this launch to publish / add up
+            self._args[20] = self.exchange.begin_step(self._n_cnt, self.totals, self.xch)
         L.check(self._fn(*self._args, stream), self._name)
 
     def launch(self):

@@ -63,12 +63,26 @@ def main():
         l0, l1 = float(unfused().item()), float(fused().item())
         t_un, t_tf32, t_fu = timed(unfused), timed(unfused_tf32), timed(fused)
         t_split = timed(lambda: ops.split_bf16(hm.reshape(B * K, HW)))
+
+        def graphed(fn):
+            """device time per call: the call captured once into a CUDA graph and replayed (no host work between kernels)"""
+            fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return timed(g.replay)
+
+        t_un_dev, t_fu_dev, t_split_dev = graphed(unfused), graphed(fused), graphed(lambda: ops.split_bf16(hm.reshape(B * K, HW)))
         M, N = B * K, Lx + Ly
         flops = 2.0 * M * N * HW
         print(json.dumps({
             "shape": f"B={B} K={K} HW={HW} N={N}", "loss_cublas_fp32": l0, "loss_fused": l1, "rel": abs(l0 - l1) / abs(l0),
             "us_cublas_fp32_plus_smoothl1": t_un, "us_cublas_tf32_plus_smoothl1": t_tf32, "us_fused_total": t_fu,
             "us_of_which_split_of_A": t_split, "speedup_vs_fp32": t_un / t_fu,
+            "device_us_cublas_fp32_plus_smoothl1": t_un_dev, "device_us_fused_total": t_fu_dev, "device_us_split_of_A": t_split_dev,
+            "device_speedup_vs_fp32": t_un_dev / t_fu_dev,
+            "device_frac_bf16_sustained": 3 * flops / ((t_fu_dev - t_split_dev) * 1e-6) / 1e12 / peak,
             "useful_tflops_fused": flops / (t_fu * 1e-6) / 1e12,
             "executed_tflops_fused_kernel": 3 * flops / ((t_fu - t_split) * 1e-6) / 1e12,
             "frac_bf16_sustained": 3 * flops / ((t_fu - t_split) * 1e-6) / 1e12 / peak,

@@ -1,6 +1,7 @@
 """In-kernel timing of the NVLink exchange (torchrun, one process per GPU): runs config-4-like steps with the per-step
 counter exchange and prints, per rank, the last launches' stamps kept in the mailbox control page:
-publish = t_published - t_enter (stores of the block to every peer + system fence), wait = t_peers_arrived - t_published.
+publish = t_published - t_enter (bulk copy of the block to every peer + system fence + flags), wait = the time the
+consumer (two launches later) spent polling for the peers' flags of that step.
     python -m torch.distributed.run --nproc-per-node 2 profiles/probes/xch_timing.py"""
 import os
 import sys
@@ -42,6 +43,7 @@ def main():
     for step in range(n):
         bound[step % R].launch()
     e1.record()
+    x.flush()
     torch.cuda.synchronize()
     ctrl = x.mailbox[L.XCH_SLOTS * L.XCH_MAX_RANKS * L.XCH_PAYLOAD_BYTES + 2048:][:4 * 8 * 8].view(torch.int64).cpu().view(4, 8)
     rows = sorted(ctrl.tolist(), key=lambda r: r[0])
@@ -49,7 +51,8 @@ def main():
     prev = None
     for r in rows:
         gap = "" if prev is None else f" since previous launch's arrival {(r[1] - prev) / 1e3:7.1f} us"
-        out.append(f"  seq {r[0]:4d}: publish {(r[2] - r[1]) / 1e3:6.1f} us, wait for peers {(r[3] - r[2]) / 1e3:7.1f} us{gap}")
+        out.append(f"  seq {r[0]:4d}: publish {(r[2] - r[1]) / 1e3:6.1f} us, consumer waited for peers {(r[3] - r[4]) / 1e3:7.1f} us, "
+                   f"publish -> consumed {(r[3] - r[2]) / 1e3:7.1f} us{gap}")
         prev = r[3]
     for rk in range(world):
         if rk == rank:

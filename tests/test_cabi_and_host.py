@@ -46,9 +46,10 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.DecodeParams) == 6 * 4 + 2 * 4 + 31 * 8
     assert ctypes.sizeof(_lib.RenderParams) == 4 * 4 + 3 * 4 + 8 * 4
     assert _lib.DecodeParams.taps.offset == 32 and _lib.RenderParams.sigma.offset == 28
-    # lhn_exchange: 8 pointers, world, rank, seq, timeout_ms, status*, prev_block*, prev_seq, reserved
-    assert ctypes.sizeof(_lib.Exchange) == 8 * 8 + 4 * 4 + 8 + 8 + 2 * 4
+    # lhn_exchange: 8 pointers, world, rank, seq, timeout_ms, status*, prev_block*, prev_seq, prev2_seq, prev2_block*
+    assert ctypes.sizeof(_lib.Exchange) == 8 * 8 + 4 * 4 + 8 + 8 + 2 * 4 + 8
     assert _lib.Exchange.status.offset == 80 and _lib.Exchange.prev_block.offset == 88 and _lib.Exchange.prev_seq.offset == 96
+    assert _lib.Exchange.prev2_block.offset == 104
     assert _lib.XCH_MAILBOX_BYTES == 4 * 8 * 8192 + 4096
 
 
@@ -58,12 +59,15 @@ def test_exchange_argument_validation_without_gpu(lib_path):
     x = _lib.Exchange()
     x.world, x.rank, x.seq = 2, 0, 1
     x.mailbox[0] = 4096                                 # mailbox[1] missing
-    assert lib.lhn_exchange_flush(ctypes.byref(x), ctypes.c_void_p(4096), 400, ctypes.c_void_p(4096), None) == -1
+    x.prev_block, x.prev_seq = 4096, 1
+    assert lib.lhn_exchange_flush(ctypes.byref(x), 400, ctypes.c_void_p(4096), None) == -1
     x.mailbox[1] = 8192
-    x.seq = 0                                           # step numbers start at 1
-    assert lib.lhn_exchange_flush(ctypes.byref(x), ctypes.c_void_p(4096), 400, ctypes.c_void_p(4096), None) == -1
-    x.seq = 1
-    assert lib.lhn_exchange_flush(ctypes.byref(x), ctypes.c_void_p(4096), 2000, ctypes.c_void_p(4096), None) == -1   # > payload
+    x.prev_seq = 0                                      # step numbers start at 1
+    assert lib.lhn_exchange_flush(ctypes.byref(x), 400, ctypes.c_void_p(4096), None) == -1
+    x.prev_seq = 1
+    assert lib.lhn_exchange_flush(ctypes.byref(x), 2000, ctypes.c_void_p(4096), None) == -1   # > payload
+    x.prev_block, x.prev_seq = None, 0                  # nothing pending: a no-op
+    assert lib.lhn_exchange_flush(ctypes.byref(x), 400, ctypes.c_void_p(4096), None) == 0
     assert lib.lhn_simdr_heads_workspace_bytes(64, 21, 512, 512) == 16 * 64 * 21 * 16
     assert lib.lhn_split_bf16(ctypes.c_void_p(16), 6, ctypes.c_void_p(16), ctypes.c_void_p(16), None) == -1       # n % 4
 
