@@ -9,12 +9,13 @@ int check_launch();
 
 __global__ void __launch_bounds__(32) xch_flush_kernel(const XchCtx x, unsigned seq2, unsigned long long* block2, unsigned seq,
                                                        unsigned long long* block, int n, long long* totals) {
-  extern __shared__ __align__(16) unsigned long long stage[];
+  extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x;
-  if (block2) xch_consume_block_i64(x, seq2, block2, n, totals, lane);        // published by the last launch
+  unsigned char* scratch = smem + (((size_t)n + 2) * 8 + 15) / 16 * 16;       // after the publish stage
+  if (block2) xch_consume_block_i64(x, seq2, block2, n, totals, lane, scratch);   // published by the last launch
   if (block) {
-    if (x.world > 1) xch_publish(x, seq, block, n, lane, stage);              // the last launch's own block
-    xch_consume_block_i64(x, seq, block, n, totals, lane);
+    if (x.world > 1) xch_publish(x, seq, block, n, lane, reinterpret_cast<unsigned long long*>(smem));   // the last launch's own block
+    xch_consume_block_i64(x, seq, block, n, totals, lane, scratch);
   }
 }
 
@@ -33,7 +34,12 @@ extern "C" int lhn_exchange_flush(const lhn_exchange* xch, int n, int64_t* total
     x.mail[r] = static_cast<unsigned char*>(xch->mailbox[r]);
   }
   x.world = xch->world; x.rank = xch->rank; x.timeout_ms = xch->timeout_ms; x.status = xch->status;
-  xch_flush_kernel<<<1, 32, (size_t)(n + 2) * 8, (cudaStream_t)stream>>>(
+  const size_t smem = (((size_t)n + 2) * 8 + 15) / 16 * 16 + xch_scratch_bytes(x.world, n);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(xch_flush_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return LHN_ECUDA;
+  }
+  xch_flush_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(
       x, xch->prev2_seq, static_cast<unsigned long long*>(xch->prev2_block), xch->prev_seq,
       static_cast<unsigned long long*>(xch->prev_block), n, reinterpret_cast<long long*>(totals));
   return check_launch();

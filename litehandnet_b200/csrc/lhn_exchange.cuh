@@ -52,12 +52,14 @@ static __device__ __noinline__ void xch_publish(const XchCtx& x, unsigned seq, c
   if (lane == 0) { stamps[0] = seq; stamps[1] = gtimer(); }
   if (stage) {
     const int n2 = (n + 1) & ~1;                             // bulk copies move multiples of 16 bytes
-    for (int e0 = lane; e0 < n2; e0 += 128) {                // four independent loads per lane in flight
-      unsigned long long v[4];
+    // sixteen independent loads per lane in flight: under the streaming kernels' traffic one L2 round trip costs
+    // 1-3 us, and a block of 400 words read four words at a time took 4-12 us (profiles/r02_xch_timing.txt)
+    for (int e0 = lane; e0 < n2; e0 += 32 * 16) {
+      unsigned long long v[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; v[u] = e < n ? __ldcg(local + e) : 0ull; }
+      for (int u = 0; u < 16; ++u) { const int e = e0 + 32 * u; v[u] = e < n ? __ldcg(local + e) : 0ull; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; if (e < n2) stage[e] = v[u]; }
+      for (int u = 0; u < 16; ++u) { const int e = e0 + 32 * u; if (e < n2) stage[e] = v[u]; }
     }
     __syncwarp();
     fence_proxy_async();                                     // generic-proxy writes of the stage -> async proxy
@@ -113,20 +115,49 @@ static __device__ __forceinline__ bool xch_publish_and_wait(const XchCtx& x, uns
   return xch_wait(x, seq, lane);
 }
 
-// totals[e] += sum over ranks (rank order) of step `seq`'s block, which this rank has published before; the local
-// block is left zero.  One warp.
+// totals[e] += sum over ranks of step `seq`'s block, which this rank has published before; the local block is left
+// zero.  One warp.  `scratch`: 16-byte aligned shared memory of xch_scratch_bytes(world, n) bytes.
+// Every source — the local block and each peer's copy in this rank's mailbox — comes in as ONE bulk copy (TMA, global ->
+// shared), all in flight together behind one mbarrier, and the running totals as one batch of register loads: a single
+// loaded-L2 round trip instead of one per word (under the streaming kernels' traffic a dependent load costs 1-3 us,
+// and whoever runs this holds an SM).
+__host__ __device__ inline size_t xch_scratch_bytes(int world, int n) { return 16 + (size_t)(world > 0 ? world : 1) * (((size_t)n + 1) & ~(size_t)1) * 8; }
+
 static __device__ __noinline__ void xch_consume_block_i64(const XchCtx& x, unsigned seq, unsigned long long* block, int n,
-                                                          long long* totals, int lane) {
+                                                          long long* totals, int lane, unsigned char* scratch) {
   const bool ok = x.world > 1 ? xch_wait(x, seq, lane) : true;
-  for (int e = lane; e < n; e += 32) {
-    long long sum = 0;
-    for (int r = 0; r < x.world; ++r) {
-      if (r == x.rank) sum += (long long)__ldcg(block + e);
-      else if (ok) sum += (long long)reinterpret_cast<volatile unsigned long long*>(xch_slot(x, seq, x.rank, r))[e];
-    }
-    totals[e] += sum;
-    block[e] = 0ull;
+  const int n2 = (n + 1) & ~1;
+  const uint32_t bytes = (uint32_t)n2 * 8u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(scratch);
+  unsigned long long* data = reinterpret_cast<unsigned long long*>(scratch + 16);
+  const int nsrc = ok ? x.world : 1;                          // source 0: the local block; then the peers in rank order
+  if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncwarp();
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)nsrc * bytes);
+  __syncwarp();
+  if (lane < nsrc) {
+    const void* src = block;
+    if (lane > 0) { const int r = lane - 1 < x.rank ? lane - 1 : lane; src = xch_slot(x, seq, x.rank, r); }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(data + (size_t)lane * n2)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
   }
+  for (int e0 = lane; e0 < n; e0 += 32 * 16) {
+    long long tot[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const int e = e0 + 32 * u; tot[u] = e < n ? __ldcg(totals + e) : 0ll; }
+    if (e0 == lane) mbar_wait(bar, 0u);                       // the bulk copies land while the totals are in flight
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = e0 + 32 * u;
+      if (e < n) {
+        long long sum = 0;
+        for (int sidx = 0; sidx < nsrc; ++sidx) sum += (long long)data[(size_t)sidx * n2 + e];
+        totals[e] = tot[u] + sum;
+        block[e] = 0ull;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 }  // namespace lhn

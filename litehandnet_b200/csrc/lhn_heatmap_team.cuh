@@ -745,7 +745,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
           tk = __shfl_sync(0xffffffffu, tk, 0);
           if (tk == 0 && (a.xch_prev_block || a.xch_prev2_block)) {
             asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous launch is complete: its block is final
-            if (a.xch_prev2_block) xch_consume_block_i64(a.xch, a.xch_prev2_seq, a.xch_prev2_block, n_cnt, a.xch_totals, lane);
+            // every team of this CTA has finished: the stages' shared memory is free scratch for the gather
+            if (a.xch_prev2_block) xch_consume_block_i64(a.xch, a.xch_prev2_seq, a.xch_prev2_block, n_cnt, a.xch_totals, lane, smem_raw);
             if (a.xch_prev_block && a.xch.world > 1) xch_publish(a.xch, a.xch_prev_seq, a.xch_prev_block, n_cnt, lane, cta_cnt);
           }
           if (tk == gridDim.x - 1 && lane == 0) *xch_ticket(a.xch, a.xch_seq) = 0u;
@@ -1308,6 +1309,8 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
     while (nteams > 2 && (size_t)nteams * a.warp_smem + cnt_bytes > budget) --nteams;
     smem = (size_t)nteams * a.warp_smem + cnt_bytes;
     if (smem > budget) return 1;
+    // the in-kernel exchange gathers every rank's block in the CTA's (by then idle) shared memory
+    if (a.xch.world > 0 && smem < xch_scratch_bytes(a.xch.world, (a.auc_steps + 5) * a.K)) return LHN_EINVAL;
   }
   switch (dtype) {
     case LHN_F32: return dispatch_team<float>(a, flip, loss, wc, nteams, smem, st);

@@ -145,30 +145,42 @@ class PeerExchange:
         self.seq += 1
         return self.seq
 
-    # ---- per-step counter blocks of the one-launch-behind exchange (lhn_decode_heatmap_pck_xch) --------------------
+    # ---- per-step counter blocks of the pipelined exchange (lhn_decode_heatmap_pck_xch) ---------------------------
     def step_blocks(self, n):
-        """[LHN_XCH_SLOTS, n] int64 zeros: the launch of step s accumulates into row s % LHN_XCH_SLOTS; the NEXT
-        exchanging launch (or flush()) sends it to the peers, adds all ranks' rows into the totals and zeroes it."""
+        """[LHN_XCH_SLOTS, n] int64 zeros: the launch of step s accumulates into row s % LHN_XCH_SLOTS; the next
+        exchanging launch sends it to the peers, the one after adds all ranks' rows into the totals and zeroes it
+        (flush() does both for what is still in flight)."""
         from . import _lib as L
-        if self._blocks is None or self._blocks.shape[1] != n:
+        if self._blocks is None or self._blk_n != n:
             if self._pending:
                 raise L.LhnError("flush() the exchange before changing the block size")
-            self._blocks = torch.zeros((L.XCH_SLOTS, n), dtype=torch.int64, device=self.device)
+            # rows padded to an even word count: the kernel moves them with 16-byte-granular bulk copies
+            self._blocks = torch.zeros((L.XCH_SLOTS, (n + 1) & ~1), dtype=torch.int64, device=self.device)
+            self._blk_ptrs = [self._blocks[i].data_ptr() for i in range(L.XCH_SLOTS)]
+            self._blk_n = n
         return self._blocks
 
     def begin_step(self, n, totals, x):
         """Number a new exchanging launch and fill its lhn_exchange `x`: this step's sequence number, the previous
         step's block (this launch publishes it) and the block of the step before (this launch adds it into the totals).
-        Returns this step's block pointer."""
-        from . import _lib as L
-        blocks = self.step_blocks(n)
-        seq = self.next_seq()
-        p = self._pending or []
+        Returns this step's block pointer.  (Runs once per launch on the host: kept to a few attribute stores.)"""
+        if self._blocks is None or self._blk_n != n:
+            self.step_blocks(n)
+        seq = self.seq = self.seq + 1
+        cur = self._blk_ptrs[seq & 3]
+        p = self._pending
         x.seq = seq
-        x.prev_block, x.prev_seq = (p[-1][1], p[-1][0]) if len(p) >= 1 else (None, 0)
-        x.prev2_block, x.prev2_seq = (p[-2][1], p[-2][0]) if len(p) >= 2 else (None, 0)
-        cur = blocks[seq % L.XCH_SLOTS].data_ptr()
-        self._pending = (p + [(seq, cur)])[-2:]
+        if p:
+            x.prev_block, x.prev_seq = p[-1][1], p[-1][0]
+            if len(p) > 1:
+                x.prev2_block, x.prev2_seq = p[0][1], p[0][0]
+                self._pending = [p[1], (seq, cur)]
+            else:
+                x.prev2_block, x.prev2_seq = None, 0
+                self._pending = [p[0], (seq, cur)]
+        else:
+            x.prev_block, x.prev_seq, x.prev2_block, x.prev2_seq = None, 0, None, 0
+            self._pending = [(seq, cur)]
         self._pending_meta = (n, totals)
         return cur
 

@@ -494,7 +494,8 @@ class BoundDecodeStep:
             wh = ops._f32c(metrics["bbox_wh"], "bbox_wh")
             steps = int(metrics.get("auc_steps", 20))
             self.exchange = metrics.get("exchange")
-            self.counters = metrics["counters"] if self.exchange is None else self.exchange.step_blocks((steps + 5) * Cc)[0]
+            self.counters = metrics["counters"] if self.exchange is None else \
+                self.exchange.step_blocks((steps + 5) * Cc)[0][:(steps + 5) * Cc]
             if self.counters.dtype != torch.int64 or self.counters.numel() != (steps + 5) * Cc or \
                     not self.counters.is_contiguous() or self.counters.device != dev:
                 raise L.LhnError("counters must be a contiguous int64 tensor of (auc_steps+5)*K entries on the heatmaps' device")

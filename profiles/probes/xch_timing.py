@@ -39,15 +39,18 @@ def main():
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 60
+    import time
     e0.record()
+    th = time.perf_counter()
     for step in range(n):
         bound[step % R].launch()
+    host_us = (time.perf_counter() - th) / n * 1e6
     e1.record()
     x.flush()
     torch.cuda.synchronize()
     ctrl = x.mailbox[L.XCH_SLOTS * L.XCH_MAX_RANKS * L.XCH_PAYLOAD_BYTES + 2048:][:4 * 8 * 8].view(torch.int64).cpu().view(4, 8)
     rows = sorted(ctrl.tolist(), key=lambda r: r[0])
-    out = [f"rank {rank}: {e0.elapsed_time(e1) / n * 1e3:.1f} us per step over {n} steps ({x.how})"]
+    out = [f"rank {rank}: {e0.elapsed_time(e1) / n * 1e3:.1f} us per step over {n} steps, host time per launch {host_us:.1f} us ({x.how})"]
     prev = None
     for r in rows:
         gap = "" if prev is None else f" since previous launch's arrival {(r[1] - prev) / 1e3:7.1f} us"
