@@ -63,23 +63,28 @@ static __device__ __noinline__ void xch_publish(const XchCtx& x, unsigned seq, c
     }
     __syncwarp();
     fence_proxy_async();                                     // generic-proxy writes of the stage -> async proxy
+    // lane r owns peer r: its bulk copy, the wait for that copy's completion and the flag — the release store of the
+    // SAME thread orders the flag behind the completed copy, so no warp-wide system fence is needed on this path
     if (lane < world && lane != me) {
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xch_slot(x, seq, lane, me)),
                    "r"(smem_u32(stage)), "r"((unsigned)(n2 * 8)) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(x, seq, lane, me)), "r"(seq) : "memory");
     }
+    __syncwarp();
   } else {
     const unsigned long long v = lane < n ? __ldcg(local + lane) : 0ull;
     for (int r = 0; r < world; ++r) {
       if (r == me || lane >= n) continue;
       reinterpret_cast<volatile unsigned long long*>(xch_slot(x, seq, r, me))[lane] = v;
     }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < world && lane != me)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(x, seq, lane, me)), "r"(seq) : "memory");
   }
-  __threadfence_system();
-  __syncwarp();
-  if (lane < world && lane != me)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xch_flag(x, seq, lane, me)), "r"(seq) : "memory");
   if (lane == 0) stamps[2] = gtimer();
 }
 
