@@ -290,6 +290,12 @@ class TopdownHeatmapLoss(nn.Module):
             target_weight = meta['target_weight'].to(device)
             hl = self.heatmap_loss(output, target, target_weight)
         else:
+            # the in-kernel render multiplies no per-joint weights into target_weight (generateTarget.py:156-157);
+            # every hand dataset forces them off (freihand_dataset.py:62) — refuse rather than silently ignore
+            ann = meta.get('ann_info', {}) if hasattr(meta, 'get') else {}
+            if meta.get('use_different_joint_weights', False) or (hasattr(ann, 'get') and ann.get('use_different_joint_weights', False)):
+                raise NotImplementedError("use_different_joint_weights: render the targets with TopDownGenerateTarget "
+                                          "and pass meta['target'] / meta['target_weight'] instead of the fused entry")
             hl, target_weight = self.heatmap_loss.forward_fused(
                 output, meta['joints_3d'], meta['joints_3d_visible'], self._image_size, self._sigma,
                 self._unbiased)
