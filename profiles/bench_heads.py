@@ -33,7 +33,10 @@ def main():
     except Exception:
         peak = 1387.3
     torch.backends.cuda.matmul.allow_tf32 = False           # torch's default: the reference's nn.Linear runs in fp32
-    for B, K, HW, Lx, Ly in ((64, 21, 4096, 512, 512), (32, 21, 4096, 512, 512), (256, 21, 4096, 512, 512), (64, 21, 3136, 448, 448)):
+    shapes = ((64, 21, 4096, 512, 512), (32, 21, 4096, 512, 512), (256, 21, 4096, 512, 512), (64, 21, 3136, 448, 448))
+    if "--only" in sys.argv:
+        shapes = (shapes[int(sys.argv[sys.argv.index("--only") + 1])],)
+    for B, K, HW, Lx, Ly in shapes:
         side = int(round(HW ** 0.5))
         hm, _ = synth.blob_heatmaps(B, K, side, side, seed=1, device=dev)
         lin_x = torch.nn.Linear(HW, Lx).to(dev)
