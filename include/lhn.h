@@ -378,6 +378,13 @@ LHN_API int lhn_loss_mse_multi(int n_tensors, const void* const* outputs, const 
  *   backward;  pred (optional) f32 [B*K, Lx+Ly] = the predictions (inference).  All pointers 16-byte aligned. */
 LHN_API int lhn_split_bf16(const float* x, int64_t n, void* hi, void* lo, lhn_stream_t stream);
 LHN_API int64_t lhn_simdr_heads_workspace_bytes(int64_t B, int K, int Lx, int Ly);
+/* lhn_simdr_heads_loss straight from the f32 heatmaps [B,K,H*W]: the bf16 split of the heatmaps goes into the workspace
+ * (lhn_simdr_heads_f32_workspace_bytes bytes, 256-byte aligned) as a first streaming launch — one call per step. */
+LHN_API int64_t lhn_simdr_heads_f32_workspace_bytes(int64_t B, int K, int Kd, int Lx, int Ly);
+LHN_API int lhn_simdr_heads_loss_f32(const float* heatmap, const void* w_hi, const void* w_lo, const float* bias,
+                                     const float* target_x, const float* target_y, const float* weight, int64_t B,
+                                     int K, int Kd, int Lx, int Ly, void* workspace, int64_t workspace_bytes,
+                                     float* loss, float* dpred, float* pred, lhn_stream_t stream);
 LHN_API int lhn_simdr_heads_loss(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                                  const float* bias, const float* target_x, const float* target_y,
                                  const float* weight, int64_t B, int K, int Kd, int Lx, int Ly, void* workspace,

@@ -36,7 +36,8 @@ EXPORTS = [
     "lhn_version", "lhn_last_cuda_error", "lhn_gaussian_taps", "lhn_decode_heatmap",
     "lhn_decode_heatmap_pck", "lhn_loss_partials", "lhn_loss_reduce", "lhn_loss_finalize", "lhn_loss_mse_workspace_bytes", "lhn_loss_mse_multi",
     "lhn_render_targets", "lhn_render_simdr", "lhn_decode_simdr", "lhn_decode_simdr_flags", "lhn_simdr_loss_workspace_bytes",
-    "lhn_simdr_smoothl1", "lhn_split_bf16", "lhn_simdr_heads_workspace_bytes", "lhn_simdr_heads_loss", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
+    "lhn_simdr_smoothl1", "lhn_split_bf16", "lhn_simdr_heads_workspace_bytes", "lhn_simdr_heads_loss",
+    "lhn_simdr_heads_f32_workspace_bytes", "lhn_simdr_heads_loss_f32", "lhn_pck_accumulate", "lhn_metrics_finalize", "lhn_evaluate_pck_workspace_bytes",
     "lhn_evaluate_pck", "lhn_flip_back", "lhn_fused_workspace_bytes", "lhn_fused_render_loss_decode",
     "lhn_fused_render_loss_decode_xch", "lhn_decode_heatmap_pck_xch", "lhn_exchange_flush",
     "lhn_loss_backward", "lhn_render_loss_backward", "lhn_simdr_backward_workspace_bytes",
@@ -132,6 +133,9 @@ def _declare(lib):
     lib.lhn_split_bf16.argtypes = [vp, i64, vp, vp, vp]
     lib.lhn_simdr_heads_workspace_bytes.argtypes = [i64, i32, i32, i32]
     lib.lhn_simdr_heads_workspace_bytes.restype = i64
+    lib.lhn_simdr_heads_f32_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
+    lib.lhn_simdr_heads_f32_workspace_bytes.restype = i64
+    lib.lhn_simdr_heads_loss_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.lhn_simdr_heads_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.lhn_evaluate_pck_workspace_bytes.argtypes = [i64, i32]
     lib.lhn_evaluate_pck_workspace_bytes.restype = i64

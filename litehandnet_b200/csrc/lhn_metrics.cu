@@ -27,7 +27,13 @@ __device__ __forceinline__ double ld_as_f64(const void* p, int dtype, int64_t i)
   return dtype == LHN_F64 ? reinterpret_cast<const double*>(p)[i] : (double)reinterpret_cast<const float*>(p)[i];
 }
 
-// block-local counters in shared memory, flushed once per block
+// The grid stride is a multiple of K, so a thread meets ONE joint for its whole loop and counts in registers
+// (valid, the fixed-point distance sum, one hit counter per threshold); block-local shared-memory counters take one
+// 32-bit add per thread and counter at the end (counts per block stay far below 2^32; the distance sum is 64-bit), and
+// the block flushes once into the global int64 counters.  Round 1 did three or more 64-bit shared atomics — compare-
+// and-swap loops — per element on K hot addresses plus a 64-bit division: 16 % of the HBM peak.
+constexpr int kPckRegThr = 24;     // thresholds counted in registers (AUC uses 20); beyond that: the shared-atomic path
+
 __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_constant__ PckArgs a) {
   extern __shared__ unsigned long long sc[];   // (T+2)*K
   const int K = a.K, T = a.T;
@@ -35,33 +41,58 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
   for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sc[i] = 0ull;
   __syncthreads();
   const int64_t total = a.N * K;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = e / K;
-    const int k = (int)(e - n * K);
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (nthreads + K - 1) / K * K;                 // a multiple of K: k is loop-invariant
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (int)(e0 % K);
+  unsigned int valid = 0, hits[kPckRegThr];
+  unsigned long long dsum = 0ull;
+#pragma unroll
+  for (int t = 0; t < kPckRegThr; ++t) hits[t] = 0u;
+  const bool reg_thr = T <= kPckRegThr;
+  for (int64_t e = e0; e < total; e += stride) {
     if (!a.mask[e]) continue;
+    const int64_t n = e / K;
     double nx = a.norm_const, ny = a.norm_const;
     if (a.normalize) { nx = ld_as_f64(a.normalize, a.norm_dtype, 2 * n); ny = ld_as_f64(a.normalize, a.norm_dtype, 2 * n + 1); }
     if (nx == 0.0 || ny == 0.0) continue;              // _mask[normalize==0 rows] = False
     if (nx < 0.0) nx = 1e6;                            // normalize[normalize<=0] = 1e6
     if (ny < 0.0) ny = 1e6;
-    const double px = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride);
-    const double py = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride + 1);
-    const double gx = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride);
-    const double gy = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride + 1);
     float d;
     if (a.all_f32) {
-      const float qx = __fdiv_rn(__fsub_rn((float)px, (float)gx), (float)nx);
-      const float qy = __fdiv_rn(__fsub_rn((float)py, (float)gy), (float)ny);
+      const float* pp = reinterpret_cast<const float*>(a.pred) + e * a.pred_stride;
+      const float* gp = reinterpret_cast<const float*>(a.gt) + e * a.gt_stride;
+      const float qx = __fdiv_rn(__fsub_rn(pp[0], gp[0]), (float)nx);
+      const float qy = __fdiv_rn(__fsub_rn(pp[1], gp[1]), (float)ny);
       d = __fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)));
     } else {
+      const double px = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride);
+      const double py = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride + 1);
+      const double gx = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride);
+      const double gy = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride + 1);
       const double qx = __ddiv_rn(__dsub_rn(px, gx), nx), qy = __ddiv_rn(__dsub_rn(py, gy), ny);
       d = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
     }
-    atomicAdd(&sc[T * K + k], 1ull);
-    if (d == d) atomicAdd(&sc[(T + 1) * K + k], (unsigned long long)llrint((double)d * 1048576.0));
-    for (int t = 0; t < T; ++t)
-      if (d < a.thr[t]) atomicAdd(&sc[t * K + k], 1ull);
+    ++valid;
+    if (d == d) dsum += (unsigned long long)llrint((double)d * 1048576.0);
+    if (reg_thr) {
+#pragma unroll
+      for (int t = 0; t < kPckRegThr; ++t)
+        if (t < T && d < a.thr[t]) ++hits[t];
+    } else {
+      for (int t = 0; t < T; ++t)
+        if (d < a.thr[t]) atomicAdd(reinterpret_cast<unsigned int*>(&sc[t * K + k]), 1u);
+    }
+  }
+  // per-thread registers -> block counters (low words: native 32-bit shared atomics)
+  if (valid) {
+    atomicAdd(reinterpret_cast<unsigned int*>(&sc[T * K + k]), valid);
+    atomicAdd(&sc[(T + 1) * K + k], dsum);
+    if (reg_thr) {
+#pragma unroll
+      for (int t = 0; t < kPckRegThr; ++t)
+        if (t < T && hits[t]) atomicAdd(reinterpret_cast<unsigned int*>(&sc[t * K + k]), hits[t]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ncnt; i += blockDim.x)

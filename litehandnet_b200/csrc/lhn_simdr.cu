@@ -352,8 +352,10 @@ __global__ void __launch_bounds__(1024) simdr_loss_finalize_kernel(const double*
   double acc = 0.0;
   for (int j = warp; j < K; j += nwarps) {
     double sx = 0, sy = 0, sw = 0;
-    for (int64_t b = lane; b < B; b += 32) {
-      sx += per_bk[2 * (b * K + j)]; sy += per_bk[2 * (b * K + j) + 1]; sw += (double)weight[b * K + j];
+#pragma unroll 8
+    for (int64_t b = lane; b < B; b += 32) {                  // independent loads: eight iterations in flight
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(per_bk + 2 * (b * K + j)));
+      sx += v.x; sy += v.y; sw += (double)__ldg(weight + b * K + j);
     }
     sx = warp_sum(sx); sy = warp_sum(sy); sw = warp_sum(sw);
     acc += (sx / ((double)B * Lx) + sy / ((double)B * Ly)) * (sw / (double)B);
@@ -462,7 +464,7 @@ extern "C" int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const vo
       Lx <= 0 || Ly <= 0)
     return LHN_EINVAL;
   if (workspace_bytes < lhn_simdr_loss_workspace_bytes(B, K)) return LHN_EWORKSPACE;
-  if ((uintptr_t)workspace % 8) return LHN_EALIGN;
+  if ((uintptr_t)workspace % 16) return LHN_EALIGN;
   const int64_t n = B * K;
   const int threads = 256;
   int64_t need = (n * 32 + threads - 1) / threads, cap = (int64_t)num_sms() * 8;

@@ -359,6 +359,39 @@ extern "C" int64_t lhn_simdr_heads_workspace_bytes(int64_t B, int K, int Lx, int
   return (int64_t)((Lx + Ly + 63) / 64) * B * K * 2 * (int64_t)sizeof(double);     // the narrowest N tile is 64 columns
 }
 
+// The same from the f32 heatmaps: splits them into the workspace first (one more streaming launch, no host round trip).
+// workspace: lhn_simdr_heads_f32_workspace_bytes(B, K, Kd, Lx, Ly) = partial sums + 2 x bf16 [B*K, Kd].
+extern "C" int64_t lhn_simdr_heads_f32_workspace_bytes(int64_t B, int K, int Kd, int Lx, int Ly) {
+  const int64_t p = lhn_simdr_heads_workspace_bytes(B, K, Lx, Ly);
+  if (p < 0 || Kd <= 0) return LHN_EINVAL;
+  return (p + 255) / 256 * 256 + 2 * B * K * (int64_t)Kd * 2;
+}
+
+extern "C" int lhn_simdr_heads_loss(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                                    const float* bias, const float* target_x, const float* target_y,
+                                    const float* weight, int64_t B, int K, int Kd, int Lx, int Ly, void* workspace,
+                                    int64_t workspace_bytes, float* loss, float* dpred, float* pred,
+                                    lhn_stream_t stream);
+
+extern "C" int lhn_simdr_heads_loss_f32(const float* heatmap, const void* w_hi, const void* w_lo, const float* bias,
+                                        const float* target_x, const float* target_y, const float* weight, int64_t B,
+                                        int K, int Kd, int Lx, int Ly, void* workspace, int64_t workspace_bytes,
+                                        float* loss, float* dpred, float* pred, lhn_stream_t stream) {
+  if (!heatmap || !workspace || B <= 0 || K <= 0 || Kd <= 0 || (Kd & 3)) return LHN_EINVAL;
+  const int64_t need = lhn_simdr_heads_f32_workspace_bytes(B, K, Kd, Lx, Ly);
+  if (need < 0) return LHN_EINVAL;
+  if (workspace_bytes < need) return LHN_EWORKSPACE;
+  if ((uintptr_t)workspace % 256 || (uintptr_t)heatmap % 16) return LHN_EALIGN;
+  const int64_t p = (lhn_simdr_heads_workspace_bytes(B, K, Lx, Ly) + 255) / 256 * 256;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  void* a_hi = ws + p;
+  void* a_lo = ws + p + B * K * (int64_t)Kd * 2;
+  int rc = lhn_split_bf16(heatmap, B * K * (int64_t)Kd, a_hi, a_lo, stream);
+  if (rc) return rc;
+  return lhn_simdr_heads_loss(a_hi, a_lo, w_hi, w_lo, bias, target_x, target_y, weight, B, K, Kd, Lx, Ly, workspace, p, loss,
+                              dpred, pred, stream);
+}
+
 extern "C" int lhn_simdr_heads_loss(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                                     const float* bias, const float* target_x, const float* target_y,
                                     const float* weight, int64_t B, int K, int Kd, int Lx, int Ly, void* workspace,

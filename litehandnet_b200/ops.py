@@ -627,18 +627,21 @@ def simdr_heads_loss(heatmap, w_split, bias, tgt_x, tgt_y, weight, want_dpred=Fa
     Lx, Ly = tgt_x.shape[-1], tgt_y.shape[-1]
     if Lx + Ly != N or w_hi.shape[1] != Kd or tgt_x.shape[:2] != (B, K) or tgt_y.shape[:2] != (B, K):
         raise L.LhnError("simdr_heads_loss: shapes of the heads, the heatmap and the targets do not agree")
-    a_hi, a_lo = split_bf16(heatmap.reshape(B * K, Kd))
+    hm = heatmap.detach()
+    if hm.dtype != torch.float32 or not hm.is_contiguous():
+        hm = hm.to(torch.float32).contiguous()
     bias = _f32c(bias, "bias")
     weight = _f32c(weight, "target_weight").reshape(B, K)
     dev = heatmap.device
-    nbytes = int(L.lib().lhn_simdr_heads_workspace_bytes(B, K, Lx, Ly))
+    # one C call: the bf16 split of the heatmaps goes into the workspace, then the GEMM + loss kernel and its finalise
+    nbytes = int(L.lib().lhn_simdr_heads_f32_workspace_bytes(B, K, Kd, Lx, Ly))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     dpred = torch.empty((B * K, N), dtype=torch.float32, device=dev) if want_dpred else None
     pred = torch.empty((B * K, N), dtype=torch.float32, device=dev) if want_pred else None
-    L.check(L.lib().lhn_simdr_heads_loss(L.ptr(a_hi), L.ptr(a_lo), L.ptr(w_hi), L.ptr(w_lo), L.ptr(bias), L.ptr(tgt_x),
-                                         L.ptr(tgt_y), L.ptr(weight), B, K, Kd, Lx, Ly, L.ptr(ws), nbytes, L.ptr(loss),
-                                         L.ptr(dpred), L.ptr(pred), L.stream()), "lhn_simdr_heads_loss")
+    L.check(L.lib().lhn_simdr_heads_loss_f32(L.ptr(hm), L.ptr(w_hi), L.ptr(w_lo), L.ptr(bias), L.ptr(tgt_x), L.ptr(tgt_y),
+                                             L.ptr(weight), B, K, Kd, Lx, Ly, L.ptr(ws), nbytes, L.ptr(loss), L.ptr(dpred),
+                                             L.ptr(pred), L.stream()), "lhn_simdr_heads_loss_f32")
     return loss, dpred, pred
 
 
