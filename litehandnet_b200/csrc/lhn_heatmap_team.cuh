@@ -1199,6 +1199,23 @@ static int dispatch_variant(HmArgs& a, int wc, int nteams, size_t smem, cudaStre
       if (ks11) return launch_one<T, 128, 8, FLIP, LOSS, 11>(a, nteams, smem, st);
       return launch_one<T, 128, 8, FLIP, LOSS, 0>(a, nteams, smem, st);
     }
+    // the lower scales of SRHandNet's output pyramid ([16,16,32,64], generateTarget.py:383-386): 1 / 4 KB planes,
+    // 12 teams of 2 warps with up to 4 stages each
+    if (wc == 32 && a.team_warps == 2) {
+      if (ks11) return launch_one<T, 32, 2, FLIP, LOSS, 11>(a, nteams, smem, st);
+      return launch_one<T, 32, 2, FLIP, LOSS, 0>(a, nteams, smem, st);
+    }
+    if (wc == 16 && a.team_warps == 2) {
+      if (ks11) return launch_one<T, 16, 2, FLIP, LOSS, 11>(a, nteams, smem, st);
+      return launch_one<T, 16, 2, FLIP, LOSS, 0>(a, nteams, smem, st);
+    }
+  }
+  // 128x128 in bf16 / f16: 32 KB planes -> 6 teams of 4 warps without a flip plane, 3 teams of 8 warps with one
+  if constexpr (sizeof(T) == 2) {
+    if (wc == 128 && a.team_warps == (FLIP ? 8 : 4)) {
+      if (ks11) return launch_one<T, 128, (FLIP ? 8 : 4), FLIP, LOSS, 11>(a, nteams, smem, st);
+      return launch_one<T, 128, (FLIP ? 8 : 4), FLIP, LOSS, 0>(a, nteams, smem, st);
+    }
   }
   if (wc == 64 && a.team_warps == TWF) {
     if (ks11) return launch_one<T, 64, TWF, FLIP, LOSS, 11>(a, nteams, smem, st);
@@ -1302,7 +1319,7 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
     a.pos_radius[i] = (a.pos_value > 0.f && a.pos_value < 1.f && sg > 0)
                           ? (float)(sg * sqrt(-2.0 * log((double)a.pos_value)) * 1.001 + 0.01) : 0.f;
   }
-  const int wc = (a.W == 64 && a.H == 64) ? 64 : ((a.W == 56 && a.H == 56) ? 56 : ((a.W == 128 && a.H == 128) ? 128 : 0));
+  const int wc = (a.W != a.H) ? 0 : ((a.W == 64 || a.W == 56 || a.W == 128 || a.W == 32 || a.W == 16) ? a.W : 0);
   size_t smem = (size_t)nteams * a.warp_smem;
   if (a.counters) {
     // CTA-shared metric counters after the teams' regions; drop a team if they do not fit

@@ -236,3 +236,36 @@ def test_torch_extension_route_equals_ctypes_route():
         ops.decode_heatmap(hm.cpu(), L.MASK_NEG1, L.REFINE_SIGN)
     with pytest.raises(L.LhnError):                       # f64 heatmaps: rejected by the shim, as an LhnError
         ops.decode_heatmap(hm.double(), L.MASK_NEG1, L.REFINE_SIGN)
+
+
+# ---- low-precision inputs at the sizes that are measured ---------------------------------
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,HW,flip,sigma", [(1024, 64, True, 2), (1024, 56, False, 2), (96, 128, False, 4)])
+def test_low_precision_fused_at_measured_sizes(dt, B, HW, flip, sigma):
+    """bf16 / f16 network outputs through the one-launch fused step (render + balanced loss + [flip] + DARK) at the
+    batch sizes of the roofline rows: oracle = the reference pipeline on the upcast f32 tensors, all samples."""
+    from conftest import assert_coords_close, xform_magnitude
+    from oracle import cpu_path
+    from litehandnet_b200 import fused
+    K = 21
+    img = (4 * HW, 4 * HW)
+    hm, cen = synth.blob_heatmaps(B, K, HW, HW, seed=61, device=DEV, sigma=float(sigma), zero_frac=0.01)
+    hm = hm.to(dt)
+    hf = synth.flipped_blob_heatmaps(cen, HW, HW, seed=62, device=DEV, sigma=float(sigma)).to(dt) if flip else None
+    j, v = synth.hand_joints(B, K, img, seed=63, device=DEV)
+    c, s = synth.bbox_center_scale(B, seed=64, device=DEV)
+    out = fused.fused_render_loss_decode(hm, j, v, c, s, hm_flip=hf, image_size=img, sigma=sigma)
+    runner = cpu_path.FusedCpuRunner(hm.float().cpu().numpy(), None if hf is None else hf.float().cpu().numpy(),
+                                     j.cpu().numpy(), v.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy(),
+                                     image_size=img, sigma=sigma, kernel=11)
+    try:
+        with np.errstate(all="ignore"):
+            preds, loss, _ = runner.run()
+        ridx = runner.last_idx
+    finally:
+        runner.close()
+    assert np.array_equal(out["idx"].cpu().numpy(), ridx), "argmax (first index on the many bf16/f16 ties)"
+    got = out["preds"].cpu().numpy()
+    assert_coords_close(got[..., :2], preds[..., :2], what=f"{dt} {HW}x{HW}", mag=xform_magnitude(c.cpu().numpy(), s.cpu().numpy()))
+    assert np.array_equal(got[..., 2], preds[..., 2], equal_nan=True)
+    np.testing.assert_allclose(float(out["loss"].item()), float(loss), rtol=1e-5)
