@@ -50,9 +50,11 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
 #pragma unroll
   for (int t = 0; t < kPckRegThr; ++t) hits[t] = 0u;
   const bool reg_thr = T <= kPckRegThr;
-  for (int64_t e = e0; e < total; e += stride) {
+  const int64_t n_step = stride / K;
+  int64_t n = e0 / K;                                  // the sample index advances by stride / K: no division in the loop
+#pragma unroll 4
+  for (int64_t e = e0; e < total; e += stride, n += n_step) {
     if (!a.mask[e]) continue;
-    const int64_t n = e / K;
     double nx = a.norm_const, ny = a.norm_const;
     if (a.normalize) { nx = ld_as_f64(a.normalize, a.norm_dtype, 2 * n); ny = ld_as_f64(a.normalize, a.norm_dtype, 2 * n + 1); }
     if (nx == 0.0 || ny == 0.0) continue;              // _mask[normalize==0 rows] = False
@@ -209,7 +211,7 @@ extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_str
   a.all_f32 = pred_dtype == LHN_F32 && gt_dtype == LHN_F32 && normalize && norm_dtype == LHN_F32;
   a.counters = reinterpret_cast<unsigned long long*>(counters);
   const int threads = 256;
-  int64_t need = (N * K + threads - 1) / threads, cap = (int64_t)num_sms() * 4;
+  int64_t need = (N * K + threads - 1) / threads, cap = (int64_t)num_sms() * 8;
   int blocks = (int)(need < cap ? need : cap);
   size_t smem = (size_t)(T + 2) * K * sizeof(unsigned long long);
   if (smem > 48 * 1024) return LHN_EINVAL;

@@ -335,9 +335,34 @@ __global__ void __launch_bounds__(256) simdr_sl1_kernel(const T* __restrict__ ox
   const int lane = threadIdx.x & 31;
   const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = ((Lx | Ly) & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(ox) | reinterpret_cast<uintptr_t>(oy) | reinterpret_cast<uintptr_t>(tx) |
+                     reinterpret_cast<uintptr_t>(ty)) % (4 * sizeof(T)) == 0);
   for (int64_t bk = wg; bk < n_bk; bk += nw) {
-    const double sx = warp_sl1_sum<T>(ox + bk * Lx, tx + bk * Lx, Lx, lane);
-    const double sy = warp_sl1_sum<T>(oy + bk * Ly, ty + bk * Ly, Ly, lane);
+    double sx, sy;
+    if (vec) {
+      // both vectors of the pair in ONE loop: all sixteen 128-bit loads of a 512-bin pair are in flight together
+      const T* px = ox + bk * Lx; const T* qx = tx + bk * Lx;
+      const T* py = oy + bk * Ly; const T* qy = ty + bk * Ly;
+      const int nqx = Lx >> 2, nqy = Ly >> 2, nq = nqx > nqy ? nqx : nqy;
+      float ax = 0.f, bx = 0.f, ay = 0.f, by = 0.f;
+#pragma unroll 4
+      for (int q = lane; q < nq; q += 32) {
+        if (q < nqx) {
+          const float4 a = ldg_stream4<T>(px + 4 * q), g = ldg_stream4<T>(qx + 4 * q);
+          ax += smooth_l1(a.x - g.x); bx += smooth_l1(a.y - g.y); ax += smooth_l1(a.z - g.z); bx += smooth_l1(a.w - g.w);
+        }
+        if (q < nqy) {
+          const float4 a = ldg_stream4<T>(py + 4 * q), g = ldg_stream4<T>(qy + 4 * q);
+          ay += smooth_l1(a.x - g.x); by += smooth_l1(a.y - g.y); ay += smooth_l1(a.z - g.z); by += smooth_l1(a.w - g.w);
+        }
+      }
+      sx = warp_sum((double)ax + (double)bx);
+      sy = warp_sum((double)ay + (double)by);
+    } else {
+      sx = warp_sl1_sum<T>(ox + bk * Lx, tx + bk * Lx, Lx, lane);
+      sy = warp_sl1_sum<T>(oy + bk * Ly, ty + bk * Ly, Ly, lane);
+    }
     if (lane == 0) { per_bk[2 * bk] = sx; per_bk[2 * bk + 1] = sy; }
   }
 }

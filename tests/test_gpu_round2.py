@@ -269,3 +269,44 @@ def test_low_precision_fused_at_measured_sizes(dt, B, HW, flip, sigma):
     assert_coords_close(got[..., :2], preds[..., :2], what=f"{dt} {HW}x{HW}", mag=xform_magnitude(c.cpu().numpy(), s.cpu().numpy()))
     assert np.array_equal(got[..., 2], preds[..., 2], equal_nan=True)
     np.testing.assert_allclose(float(out["loss"].item()), float(loss), rtol=1e-5)
+
+
+# ---- compile-time instantiations added in round 2: 32x32 / 16x16 f32, 128x128 bf16 / f16 (+ flip) ---------------
+@pytest.mark.parametrize("HW,dt,flip,sigma,B", [(32, torch.float32, False, 1.5, 300), (16, torch.float32, False, 1.0, 700),
+                                                (128, torch.bfloat16, True, 4, 24), (128, torch.float16, True, 4, 24),
+                                                (32, torch.float32, True, 1.5, 50)])
+def test_fused_step_on_the_new_compile_time_shapes(HW, dt, flip, sigma, B):
+    from conftest import assert_coords_close, xform_magnitude
+    from oracle import cpu_path
+    from litehandnet_b200 import fused
+    K = 21
+    img = (4 * HW, 4 * HW)
+    hm, cen = synth.blob_heatmaps(B, K, HW, HW, seed=71, device=DEV, sigma=float(sigma), margin=min(4.0, HW / 8), zero_frac=0.02,
+                                  tie_frac=0.02)
+    hm = hm.to(dt)
+    hf = synth.flipped_blob_heatmaps(cen, HW, HW, seed=72, device=DEV, sigma=float(sigma)).to(dt) if flip else None
+    j, v = synth.hand_joints(B, K, img, seed=73, device=DEV)
+    c, s = synth.bbox_center_scale(B, seed=74, device=DEV)
+    out = fused.fused_render_loss_decode(hm, j, v, c, s, hm_flip=hf, image_size=img, sigma=sigma)
+    runner = cpu_path.FusedCpuRunner(hm.float().cpu().numpy(), None if hf is None else hf.float().cpu().numpy(),
+                                     j.cpu().numpy(), v.cpu().numpy(), c.cpu().numpy(), s.cpu().numpy(),
+                                     image_size=img, sigma=sigma, kernel=11)
+    try:
+        with np.errstate(all="ignore"):
+            preds, loss, _ = runner.run()
+        ridx = runner.last_idx
+    finally:
+        runner.close()
+    assert np.array_equal(out["idx"].cpu().numpy(), ridx)
+    got = out["preds"].cpu().numpy()
+    assert_coords_close(got[..., :2], preds[..., :2], what=f"{dt} {HW}x{HW} flip={flip}",
+                        mag=xform_magnitude(c.cpu().numpy(), s.cpu().numpy()))
+    assert np.array_equal(got[..., 2], preds[..., 2], equal_nan=True)
+    np.testing.assert_allclose(float(out["loss"].item()), float(loss), rtol=1e-5)
+    # decode only ('default' refinement) on the same shapes
+    r = ops.decode_heatmap(hm, L.MASK_NEG1, L.REFINE_SIGN, L.XFORM_CENTER_SCALE, c, s, hm_flip=hf)
+    avg = hm.float().cpu().numpy() if hf is None else O.flip_average(hm.float().cpu().numpy(), hf.float().cpu().numpy(), ())
+    with np.errstate(all="ignore"):
+        _, p, mv = O.keypoints_from_heatmaps(avg, c.cpu().numpy(), s.cpu().numpy(), "default", 11)
+    assert np.array_equal(r["idx"].cpu().numpy(), avg.reshape(B, K, -1).argmax(-1))
+    assert_coords_close(r["kpts"].cpu().numpy()[..., :2], p, what="decode default", mag=xform_magnitude(c.cpu().numpy(), s.cpu().numpy()))
