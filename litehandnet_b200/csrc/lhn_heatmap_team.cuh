@@ -1319,7 +1319,11 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
     a.pos_radius[i] = (a.pos_value > 0.f && a.pos_value < 1.f && sg > 0)
                           ? (float)(sg * sqrt(-2.0 * log((double)a.pos_value)) * 1.001 + 0.01) : 0.f;
   }
-  const int wc = (a.W != a.H) ? 0 : ((a.W == 64 || a.W == 56 || a.W == 128 || a.W == 32 || a.W == 16) ? a.W : 0);
+  int wc = (a.W != a.H) ? 0 : ((a.W == 64 || a.W == 56 || a.W == 128 || a.W == 32 || a.W == 16) ? a.W : 0);
+  {
+    const char* nf = getenv("LHN_NO_FAST");              // tests: run the run-time-size instantiation on every shape
+    if (nf && nf[0] == '1') wc = 0;
+  }
   size_t smem = (size_t)nteams * a.warp_smem;
   if (a.counters) {
     // CTA-shared metric counters after the teams' regions; drop a team if they do not fit

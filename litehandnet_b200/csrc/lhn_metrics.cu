@@ -52,29 +52,32 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
   const bool reg_thr = T <= kPckRegThr;
   const int64_t n_step = stride / K;
   int64_t n = e0 / K;                                  // the sample index advances by stride / K: no division in the loop
-#pragma unroll 4
+#pragma unroll 2
   for (int64_t e = e0; e < total; e += stride, n += n_step) {
-    if (!a.mask[e]) continue;
+    // every load of the element is issued before anything is decided: mask -> branch -> normalize -> branch -> pred / gt
+    // was three dependent round trips per iteration (~2 us under load), which is what bounded this kernel
+    const bool m = a.mask[e] != 0;
     double nx = a.norm_const, ny = a.norm_const;
     if (a.normalize) { nx = ld_as_f64(a.normalize, a.norm_dtype, 2 * n); ny = ld_as_f64(a.normalize, a.norm_dtype, 2 * n + 1); }
-    if (nx == 0.0 || ny == 0.0) continue;              // _mask[normalize==0 rows] = False
-    if (nx < 0.0) nx = 1e6;                            // normalize[normalize<=0] = 1e6
-    if (ny < 0.0) ny = 1e6;
     float d;
     if (a.all_f32) {
       const float* pp = reinterpret_cast<const float*>(a.pred) + e * a.pred_stride;
       const float* gp = reinterpret_cast<const float*>(a.gt) + e * a.gt_stride;
-      const float qx = __fdiv_rn(__fsub_rn(pp[0], gp[0]), (float)nx);
-      const float qy = __fdiv_rn(__fsub_rn(pp[1], gp[1]), (float)ny);
+      const float p0 = pp[0], p1 = pp[1], g0 = gp[0], g1 = gp[1];
+      const float fx = nx < 0.0 ? 1e6f : (float)nx, fy = ny < 0.0 ? 1e6f : (float)ny;   // normalize[normalize<=0] = 1e6
+      const float qx = __fdiv_rn(__fsub_rn(p0, g0), fx);
+      const float qy = __fdiv_rn(__fsub_rn(p1, g1), fy);
       d = __fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)));
     } else {
       const double px = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride);
       const double py = ld_as_f64(a.pred, a.pred_dtype, e * a.pred_stride + 1);
       const double gx = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride);
       const double gy = ld_as_f64(a.gt, a.gt_dtype, e * a.gt_stride + 1);
-      const double qx = __ddiv_rn(__dsub_rn(px, gx), nx), qy = __ddiv_rn(__dsub_rn(py, gy), ny);
+      const double dx = nx < 0.0 ? 1e6 : nx, dy = ny < 0.0 ? 1e6 : ny;
+      const double qx = __ddiv_rn(__dsub_rn(px, gx), dx), qy = __ddiv_rn(__dsub_rn(py, gy), dy);
       d = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
     }
+    if (!m || nx == 0.0 || ny == 0.0) continue;        // masked joint / _mask[normalize == 0 rows] = False
     ++valid;
     if (d == d) dsum += (unsigned long long)llrint((double)d * 1048576.0);
     if (reg_thr) {
