@@ -321,3 +321,21 @@ def test_fused_step_on_the_new_compile_time_shapes(HW, dt, flip, sigma, B, monke
         _, p, mv = O.keypoints_from_heatmaps(avg, c.cpu().numpy(), s.cpu().numpy(), "default", 11)
     assert np.array_equal(r["idx"].cpu().numpy(), avg.reshape(B, K, -1).argmax(-1))
     assert_coords_close(r["kpts"].cpu().numpy()[..., :2], p, what="decode default", mag=xform_magnitude(c.cpu().numpy(), s.cpu().numpy()))
+
+
+def test_fused_criterion_refuses_joint_weights():
+    """the in-kernel render applies no per-joint weights (generateTarget.py:156-157) — refuse, do not ignore."""
+    from litehandnet_b200 import loss as LS
+    from oracle.ref_loader import _AttrDict
+    cfg = _AttrDict(DATASET=dict(image_size=[256, 256], heatmap_size=[64, 64], num_joints=21),
+                    PIPELINE=dict(unbiased_encoding=True, kernel=(11, 11), use_udp=False, simdr_split_ratio=0, sigma=2),
+                    MODEL=dict(name="litehandnet"), LOSS=dict(type="TopdownHeatmapLoss", loss_weight=[1.0, 1.0], auto_weight=False))
+    crit = LS.get_loss(cfg)
+    hm, _ = synth.blob_heatmaps(2, 21, 64, 64, seed=1, device=DEV)
+    j, v = synth.hand_joints(2, 21, seed=2, device=DEV)
+    loss, d = crit(hm, dict(joints_3d=j, joints_3d_visible=v))
+    assert np.isfinite(d["heatmap"])
+    with pytest.raises(NotImplementedError):
+        crit(hm, dict(joints_3d=j, joints_3d_visible=v, use_different_joint_weights=True))
+    with pytest.raises(NotImplementedError):
+        crit(hm, dict(joints_3d=j, joints_3d_visible=v, ann_info=dict(use_different_joint_weights=True)))
