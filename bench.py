@@ -69,52 +69,69 @@ def recorded_traffic(cfg_id, batch):
     return None
 
 
-class ClockSampler:
-    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
-
-    def __init__(self, index, interval_s=0.0005):
-        self.interval_s = interval_s
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thread = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
-
-    def _run(self):
-        nv = self.nv
+def _clock_proc(index, interval_s, active, stop, out):
+    """Sampler PROCESS (no GIL shared with the launch loop, which starves a sampler thread down to one sample per
+    timed region): SM clock + throttle reasons through NVML while `active` is set, until `stop`."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
                  "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                  "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                  "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        samples, reasons = [], set()
+        out.put("ready")
+        while not stop.is_set():
+            if active.is_set():
+                samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for n, bit in names.items():
                     if r & bit:
-                        self.reasons.add(n)
-            except Exception:
-                pass
-            time.sleep(self.interval_s)
+                        reasons.add(n)
+            time.sleep(interval_s)
+        out.put((samples, sorted(reasons), max_mhz))
+    except Exception as e:                                   # no NVML: report nothing rather than die
+        out.put("ready")
+        out.put(([], [f"sampler error: {type(e).__name__}"], None))
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled by a separate process while the timed region runs."""
+
+    def __init__(self, index, interval_s=0.0005):
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        self.active, self._stop, self.q = ctx.Event(), ctx.Event(), ctx.Queue()
+        self.p = ctx.Process(target=_clock_proc, args=(index, interval_s, self.active, self._stop, self.q), daemon=True)
+        self.ok = True
 
     def start(self):
-        if self.nv is not None:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
+        """Start the process and wait until NVML is initialised in it (before the barrier: nvmlInit takes
+        milliseconds); sampling itself begins with begin()."""
+        try:
+            self.p.start()
+            self.q.get(timeout=20)
+        except Exception:
+            self.ok = False
+
+    def begin(self):
+        self.active.set()
 
     def stop(self):
-        if self._thread is not None:
-            self._stop.set()
-            self._thread.join()
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+        self.active.clear()
+        self._stop.set()
+        samples, reasons, max_mhz = [], [], None
+        if self.ok:
+            try:
+                samples, reasons, max_mhz = self.q.get(timeout=10)
+                self.p.join(timeout=5)
+            except Exception:
+                pass
+        s = sorted(samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": max_mhz, "reasons": reasons, "samples": len(s),
+                "how": "NVML from a sampler process during the timed region"}
 
 
 def physical_gpu_index(local_rank):
@@ -909,7 +926,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     fence()
     wl.begin_epoch()
     fence()
-    sampler.samples.clear()
+    sampler.begin()
     e0.record()
     for i in range(args.steps):
         wl.step(i)

@@ -97,7 +97,7 @@ __device__ __forceinline__ float smooth_l1_f(float d) {
 
 template <int BN>
 struct HeadsTile {
-  static constexpr int kStages = BN <= 64 ? 4 : 3;
+  static constexpr int kStages = BN <= 80 ? 4 : 3;
   static constexpr uint32_t kABytes = kHeadsBM * kHeadsBK * 2;   // 16 KB
   static constexpr uint32_t kWBytes = BN * kHeadsBK * 2;
   static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kWBytes;
@@ -204,6 +204,7 @@ simdr_heads_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const int col = n0 + c0 + i;                        // a group of 4 never straddles Lx (Lx % 4 == 0)
+          if (c0 + i >= BN || col >= a.N) continue;           // BN = 80: the third chunk is half used; ragged last N tile
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col));
           const bool isx = col < a.Lx;
           const float4 t4 = isx ? __ldg(reinterpret_cast<const float4*>(txr + col))
@@ -313,17 +314,23 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t c
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// N tile: 128 columns unless 64 gives a fuller last wave (BASELINE shapes: M = 1344, N = 1024 -> 88 CTAs at 128)
+// N tile (64, 80 or 128 columns): the one with the shortest makespan = waves x tile width.  The reference's training
+// shape (M = 64 x 21 = 1344 rows, N = 1024) gives 88 tiles of 128 columns on 148 SMs, but 143 tiles of 80 (12 full
+// + one of 64 valid columns per row block): one wave either way, 0.625 of the work per CTA.
 static int pick_bn(int64_t M, int N) {
   const char* env = getenv("LHN_HEADS_BN");
-  if (env && (atoi(env) == 64 || atoi(env) == 128) && N % atoi(env) == 0) return atoi(env);
-  if (N % 128 != 0) return 64;
+  if (env && (atoi(env) == 64 || atoi(env) == 80 || atoi(env) == 128)) return atoi(env);
   const int64_t mt = (M + kHeadsBM - 1) / kHeadsBM, sms = num_sms();
-  const int64_t c128 = mt * (N / 128), c64 = mt * (N / 64);
-  // time ~ waves x tile work (a 64-wide tile is half the MMA work but re-reads A): prefer 128 unless it leaves
-  // more than half of the SMs idle and 64 still fits in one wave
-  if (c128 * 2 <= sms && c64 <= sms) return 64;
-  return 128;
+  int best = 128;
+  int64_t best_cost = -1;
+  const int cands[3] = {128, 80, 64};
+  for (int c = 0; c < 3; ++c) {
+    const int bn = cands[c];
+    const int64_t tiles = mt * ((N + bn - 1) / bn);
+    const int64_t cost = ((tiles + sms - 1) / sms) * bn;
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 template <int BN>
@@ -333,7 +340,7 @@ static int launch_heads(const CUtensorMap& ahi, const CUtensorMap& alo, const CU
   const size_t smem = HeadsTile<BN>::kSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_last_error(e); return LHN_ECUDA; }
-  dim3 grid((unsigned)(a.N / BN), (unsigned)((a.M + kHeadsBM - 1) / kHeadsBM));
+  dim3 grid((unsigned)((a.N + BN - 1) / BN), (unsigned)((a.M + kHeadsBM - 1) / kHeadsBM));
   kern<<<grid, 256, smem, st>>>(ahi, alo, whi, wlo, a);
   return check_launch();
 }
@@ -418,8 +425,9 @@ extern "C" int lhn_simdr_heads_loss(const void* a_hi, const void* a_lo, const vo
   a.bias = bias; a.tx = target_x; a.ty = target_y; a.partial = (double*)workspace; a.dpred = dpred; a.pred = pred;
   a.M = (int)M; a.N = N; a.Kd = Kd; a.Lx = Lx; a.Ly = Ly;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = bn == 128 ? launch_heads<128>(ahi, alo, whi, wlo, a, st) : launch_heads<64>(ahi, alo, whi, wlo, a, st);
+  int rc = bn == 128 ? launch_heads<128>(ahi, alo, whi, wlo, a, st)
+                     : (bn == 80 ? launch_heads<80>(ahi, alo, whi, wlo, a, st) : launch_heads<64>(ahi, alo, whi, wlo, a, st));
   if (rc) return rc;
-  simdr_heads_finalize_kernel<<<1, 1024, 0, st>>>((const double*)workspace, N / bn, weight, B, K, Lx, Ly, loss);
+  simdr_heads_finalize_kernel<<<1, 1024, 0, st>>>((const double*)workspace, (N + bn - 1) / bn, weight, B, K, Lx, Ly, loss);
   return check_launch();
 }

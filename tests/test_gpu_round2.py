@@ -155,15 +155,20 @@ def test_simdr_loss_module_fused_matches_unfused_and_backward():
     np.testing.assert_allclose(float(l2.item()), float(ref2.item()), rtol=1e-5)
 
 
-@pytest.mark.parametrize("bn", ["64", "128"])
+@pytest.mark.parametrize("bn", ["64", "80", "128"])
 def test_simdr_heads_tile_straddles_the_xy_boundary(bn, monkeypatch):
-    """Lx = 448 = 3.5 tiles of 128 columns: one tile holds x columns and y columns (per-column target select)."""
+    """Lx = 448 = 3.5 tiles of 128 columns (5.6 of 80: the last N tile is ragged too): one tile holds x columns and y
+    columns (per-column target select)."""
     monkeypatch.setenv("LHN_HEADS_BN", bn)
     B, K, HW, Lx, Ly = 40, 16, 3136, 448, 448
     hm, wx, bx, wy, by, tx, ty, w = _heads_case(B, K, HW, Lx, Ly, seed=91)
     ref_loss, _ = _heads_reference(hm, wx, bx, wy, by, tx, ty, w)
-    loss, _, _ = ops.simdr_heads_loss(hm, ops.split_bf16(torch.cat([wx, wy]).contiguous()), torch.cat([bx, by]), tx, ty, w)
+    loss, dpred, pred = ops.simdr_heads_loss(hm, ops.split_bf16(torch.cat([wx, wy]).contiguous()), torch.cat([bx, by]), tx, ty, w,
+                                             want_dpred=True, want_pred=True)
     np.testing.assert_allclose(float(loss.item()), float(ref_loss.item()), rtol=1e-5)
+    _, ref_pred = _heads_reference(hm, wx, bx, wy, by, tx, ty, w)
+    mag = (hm.flatten(2).double().abs() @ torch.cat([wx, wy]).double().abs().t()).reshape(B * K, -1)
+    assert float(((pred.double() - ref_pred.reshape(B * K, -1)).abs() / mag).max()) < 2e-5      # every column of every tile
 
 
 # ---- the un-fused criterion in ONE launch, several tensors at once (lhn_loss_mse_multi) ----------------------
