@@ -314,23 +314,17 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t c
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// N tile (64, 80 or 128 columns): the one with the shortest makespan = waves x tile width.  The reference's training
-// shape (M = 64 x 21 = 1344 rows, N = 1024) gives 88 tiles of 128 columns on 148 SMs, but 143 tiles of 80 (12 full
-// + one of 64 valid columns per row block): one wave either way, 0.625 of the work per CTA.
+// N tile: 128 columns unless that leaves more than half of the SMs idle and 64 still fits in one wave.  An 80-column
+// tile (LHN_HEADS_BN=80) fills 143 of 148 SMs at the reference's training shape (M = 1344, N = 1024) where 128 fills
+// 88 — and is NOT faster (54.2 against 53.3 us, 212 against 176 us at M = 5376, profiles/r02_simdr_heads_bn80.txt): the
+// kernel is bound by L2 -> shared-memory traffic, and narrower tiles re-read the A operand more often.
 static int pick_bn(int64_t M, int N) {
   const char* env = getenv("LHN_HEADS_BN");
   if (env && (atoi(env) == 64 || atoi(env) == 80 || atoi(env) == 128)) return atoi(env);
   const int64_t mt = (M + kHeadsBM - 1) / kHeadsBM, sms = num_sms();
-  int best = 128;
-  int64_t best_cost = -1;
-  const int cands[3] = {128, 80, 64};
-  for (int c = 0; c < 3; ++c) {
-    const int bn = cands[c];
-    const int64_t tiles = mt * ((N + bn - 1) / bn);
-    const int64_t cost = ((tiles + sms - 1) / sms) * bn;
-    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
-  }
-  return best;
+  const int64_t c128 = mt * ((N + 127) / 128), c64 = mt * ((N + 63) / 64);
+  if (c128 * 2 <= sms && c64 <= sms) return 64;
+  return 128;
 }
 
 template <int BN>
