@@ -244,7 +244,8 @@ decode_simdr_ring_kernel(const T* __restrict__ xv, const T* __restrict__ yv, int
   }
   __syncthreads();
   const uint64_t pol = policy_evict_first();
-  const SimdrDiv dv = simdr_div(k, Lx, Ly);
+  SimdrDiv dv{};                                             // only lane 0 stores: only lane 0 pays for the reciprocals
+  if (lane == 0) dv = simdr_div(k, Lx, Ly);
   const int64_t total = (int64_t)gridDim.x * nwarps;
   const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;   // warp-major: the leftover pairs spread over all SMs
   auto issue = [&](int s, int64_t pair) {
@@ -367,29 +368,49 @@ __global__ void __launch_bounds__(256) simdr_sl1_kernel(const T* __restrict__ ox
   }
 }
 
-// one block: joint j handled by warp j%nwarps in fixed batch order -> deterministic
+// One block.  The first T = (1024 / K) * K threads walk the [B*K] rows with a stride of T — a multiple of K, so a thread
+// meets ONE joint and its loads are coalesced (a warp per joint walking b with a stride of K rows touched 32 sectors per
+// load) — then the threads of a joint are added in thread order, the joints in joint order: a fixed summation order.
 __global__ void __launch_bounds__(1024) simdr_loss_finalize_kernel(const double* __restrict__ per_bk,
                                                                    const float* __restrict__ weight,
                                                                    int64_t B, int K, int Lx, int Ly,
                                                                    float* __restrict__ loss) {
-  __shared__ double red[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  double acc = 0.0;
-  for (int j = warp; j < K; j += nwarps) {
-    double sx = 0, sy = 0, sw = 0;
-#pragma unroll 8
-    for (int64_t b = lane; b < B; b += 32) {                  // independent loads: eight iterations in flight
-      const double2 v = __ldcg(reinterpret_cast<const double2*>(per_bk + 2 * (b * K + j)));
-      sx += v.x; sy += v.y; sw += (double)__ldg(weight + b * K + j);
+  __shared__ double s_x[1024], s_y[1024], s_w[1024];
+  __shared__ double term[1024];
+  const int tid = threadIdx.x;
+  const int T = K <= (int)blockDim.x ? ((int)blockDim.x / K) * K : 0;
+  if (T == 0) {                                               // more joints than threads: the plain loop
+    if (tid == 0) {
+      double t = 0.0;
+      for (int jj = 0; jj < K; ++jj) {
+        double sx = 0, sy = 0, sw = 0;
+        for (int64_t b = 0; b < B; ++b) { sx += per_bk[2 * (b * K + jj)]; sy += per_bk[2 * (b * K + jj) + 1]; sw += (double)weight[b * K + jj]; }
+        t += (sx / ((double)B * Lx) + sy / ((double)B * Ly)) * (sw / (double)B);
+      }
+      loss[0] = (float)(t / (double)K);
     }
-    sx = warp_sum(sx); sy = warp_sum(sy); sw = warp_sum(sw);
-    acc += (sx / ((double)B * Lx) + sy / ((double)B * Ly)) * (sw / (double)B);
+    return;
   }
-  if (lane == 0) red[warp] = acc;
+  double sx = 0, sy = 0, sw = 0;
+  if (tid < T) {
+    const int64_t n = B * K;
+#pragma unroll 8
+    for (int64_t i = tid; i < n; i += T) {                    // i % K == tid % K
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(per_bk + 2 * i));
+      sx += v.x; sy += v.y; sw += (double)__ldg(weight + i);
+    }
+  }
+  s_x[tid] = sx; s_y[tid] = sy; s_w[tid] = sw;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid < K) {
+    double ax = 0, ay = 0, aw = 0;
+    for (int t = tid; t < T; t += K) { ax += s_x[t]; ay += s_y[t]; aw += s_w[t]; }
+    term[tid] = (ax / ((double)B * Lx) + ay / ((double)B * Ly)) * (aw / (double)B);
+  }
+  __syncthreads();
+  if (tid == 0) {
     double t = 0.0;
-    for (int i = 0; i < nwarps; ++i) t += red[i];
+    for (int jj = 0; jj < K; ++jj) t += term[jj];
     loss[0] = (float)(t / (double)K);
   }
 }
