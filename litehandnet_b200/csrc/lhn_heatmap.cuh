@@ -82,7 +82,8 @@ struct HmArgs {
   unsigned int xch_prev_seq;            // ... and its step number
   unsigned long long* xch_prev2_block;  // the block of two launches back (published by the previous launch, consumed by this one)
   unsigned int xch_prev2_seq;
-  int trigger_halfway;             // overlapped launch: let the successor grid in half-way (else after the third plane)
+  int trigger_halfway;             // overlapped launch: let the successor grid in half-way (else after plane `trigger_plane`)
+  int trigger_plane;               // default 2 (the third plane)
 };
 
 // ---- shared-memory layout --------------------------------------------------------------------

@@ -348,7 +348,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
     // for exchanging launches (measured at N = 8 on one box: 0.0515 ms per step half-way against 0.0540 early for the
     // counter exchange — the predecessor's completion includes its exchange and needs the slack)
     const int n_mine = (int)((n_planes - 1u - p) / total_teams + 1u);
-    const int kTrig = a.trigger_halfway ? (n_mine >> 1) : (n_mine > 2 ? 2 : n_mine - 1);
+    const int kTrig = a.trigger_halfway ? (n_mine >> 1) : (n_mine > a.trigger_plane ? a.trigger_plane : n_mine - 1);
     for (; p < n_planes; p += total_teams, ++n_it, advance(pb, pc)) {
       const int buf = n_it & 1;
       mbar_wait(&th->full[buf], (uint32_t)(n_it >> 1) & 1u);
@@ -1300,8 +1300,9 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
     a.stagger_ns = sg ? atoi(sg) : ((a.n_planes >= (int64_t)8 * nteams * sm_count()) ? 600 : 0);
   }
   {
-    const char* tg = getenv("LHN_TRIGGER");               // "half" / "early": override the trigger point (experiments)
+    const char* tg = getenv("LHN_TRIGGER");               // "half" / "early" / "p<n>": override the trigger point (experiments)
     a.trigger_halfway = tg ? (tg[0] == 'h') : (a.xch.world > 1);
+    a.trigger_plane = (tg && tg[0] == 'p' && tg[1] >= '0' && tg[1] <= '9') ? (tg[1] - '0') : 2;
   }
   a.sweeper_tables = (nstg >= 2 && tw >= 4) ? 1 : 0;
   a.team_warps = tw;
