@@ -20,6 +20,7 @@ struct PckArgs {
   int64_t N; int K, T;
   float thr[kMaxThr];
   int all_f32;
+  int sorted_thr;             // thr[] is non-decreasing (host-checked): histogram counting
   unsigned long long* counters;
 };
 
@@ -27,35 +28,32 @@ __device__ __forceinline__ double ld_as_f64(const void* p, int dtype, int64_t i)
   return dtype == LHN_F64 ? reinterpret_cast<const double*>(p)[i] : (double)reinterpret_cast<const float*>(p)[i];
 }
 
-// The grid stride is a multiple of K, so a thread meets ONE joint for its whole loop and counts in registers
-// (valid, the fixed-point distance sum, one hit counter per threshold); block-local shared-memory counters take one
-// 32-bit add per thread and counter at the end (counts per block stay far below 2^32; the distance sum is 64-bit), and
-// the block flushes once into the global int64 counters.  Round 1 did three or more 64-bit shared atomics — compare-
-// and-swap loops — per element on K hot addresses plus a 64-bit division: 16 % of the HBM peak.
-constexpr int kPckRegThr = 24;     // thresholds counted in registers (AUC uses 20); beyond that: the shared-atomic path
-
+// The grid stride is a multiple of K, so a thread meets ONE joint for its whole loop: `valid` and the fixed-point
+// distance sum live in registers and the sample index advances without a division.  Thresholds in ascending order
+// (every caller: one PCK threshold, or keypoint_auc's i / num_step) are counted as a HISTOGRAM of "thresholds passed" —
+// one native 32-bit shared-memory add per element — and turned into per-threshold hit counts when the block flushes;
+// unsorted thresholds take one add per passed threshold.  Every load of an element is issued before anything is
+// decided, four elements per thread in flight.  Round 1: three or more 64-bit shared atomics (compare-and-swap loops)
+// per element behind three DEPENDENT loads and a 64-bit division — 16 % of the HBM peak.
 __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_constant__ PckArgs a) {
-  extern __shared__ unsigned long long sc[];   // (T+2)*K
+  extern __shared__ unsigned long long sc[];   // [(T+2)*K] u64 block counters, then [(T+1)*K] u32 histogram
   const int K = a.K, T = a.T;
   const int ncnt = (T + 2) * K;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(sc + ncnt);
   for (int i = threadIdx.x; i < ncnt; i += blockDim.x) sc[i] = 0ull;
+  for (int i = threadIdx.x; i < (T + 1) * K; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
   const int64_t total = a.N * K;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t stride = (nthreads + K - 1) / K * K;                 // a multiple of K: k is loop-invariant
   const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = (int)(e0 % K);
-  unsigned int valid = 0, hits[kPckRegThr];
-  unsigned long long dsum = 0ull;
-#pragma unroll
-  for (int t = 0; t < kPckRegThr; ++t) hits[t] = 0u;
-  const bool reg_thr = T <= kPckRegThr;
   const int64_t n_step = stride / K;
-  int64_t n = e0 / K;                                  // the sample index advances by stride / K: no division in the loop
-#pragma unroll 2
+  int64_t n = e0 / K;
+  unsigned int valid = 0;
+  unsigned long long dsum = 0ull;
+#pragma unroll 4
   for (int64_t e = e0; e < total; e += stride, n += n_step) {
-    // every load of the element is issued before anything is decided: mask -> branch -> normalize -> branch -> pred / gt
-    // was three dependent round trips per iteration (~2 us under load), which is what bounded this kernel
     const bool m = a.mask[e] != 0;
     double nx = a.norm_const, ny = a.norm_const;
     if (a.normalize) { nx = ld_as_f64(a.normalize, a.norm_dtype, 2 * n); ny = ld_as_f64(a.normalize, a.norm_dtype, 2 * n + 1); }
@@ -80,26 +78,28 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
     if (!m || nx == 0.0 || ny == 0.0) continue;        // masked joint / _mask[normalize == 0 rows] = False
     ++valid;
     if (d == d) dsum += (unsigned long long)llrint((double)d * 1048576.0);
-    if (reg_thr) {
-#pragma unroll
-      for (int t = 0; t < kPckRegThr; ++t)
-        if (t < T && d < a.thr[t]) ++hits[t];
+    if (a.sorted_thr) {
+      int nh = 0;                                      // ascending thresholds: passed ones form a suffix
+      for (int t = 0; t < T; ++t) nh += (d < a.thr[t]) ? 1 : 0;
+      if (nh) atomicAdd(&hist[nh * K + k], 1u);
     } else {
       for (int t = 0; t < T; ++t)
         if (d < a.thr[t]) atomicAdd(reinterpret_cast<unsigned int*>(&sc[t * K + k]), 1u);
     }
   }
-  // per-thread registers -> block counters (low words: native 32-bit shared atomics)
   if (valid) {
-    atomicAdd(reinterpret_cast<unsigned int*>(&sc[T * K + k]), valid);
+    atomicAdd(reinterpret_cast<unsigned int*>(&sc[T * K + k]), valid);      // low word: per-block counts stay < 2^32
     atomicAdd(&sc[(T + 1) * K + k], dsum);
-    if (reg_thr) {
-#pragma unroll
-      for (int t = 0; t < kPckRegThr; ++t)
-        if (t < T && hits[t]) atomicAdd(reinterpret_cast<unsigned int*>(&sc[t * K + k]), hits[t]);
-    }
   }
   __syncthreads();
+  if (a.sorted_thr) {
+    // hits[t] = elements that passed at least T - t thresholds: a running sum down the histogram, one joint per thread
+    for (int kk = threadIdx.x; kk < K; kk += blockDim.x) {
+      unsigned long long run = 0ull;
+      for (int nh = T; nh >= 1; --nh) { run += hist[nh * K + kk]; sc[(T - nh) * K + kk] = run; }
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < ncnt; i += blockDim.x)
     if (sc[i]) atomicAdd(a.counters + i, sc[i]);
 }
@@ -209,14 +209,15 @@ extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_str
   a.gt = gt; a.gt_dtype = gt_dtype; a.gt_stride = gt_stride;
   a.mask = mask; a.normalize = normalize; a.norm_dtype = norm_dtype; a.norm_const = norm_const;
   a.N = N; a.K = K; a.T = T;
-  for (int i = 0; i < T; ++i) a.thr[i] = thr[i];
+  a.sorted_thr = 1;
+  for (int i = 0; i < T; ++i) { a.thr[i] = thr[i]; if (i > 0 && !(thr[i] >= thr[i - 1])) a.sorted_thr = 0; }
   // numpy promotion: f32 only if every array operand is f32 (a python-float constant is f64)
   a.all_f32 = pred_dtype == LHN_F32 && gt_dtype == LHN_F32 && normalize && norm_dtype == LHN_F32;
   a.counters = reinterpret_cast<unsigned long long*>(counters);
   const int threads = 256;
   int64_t need = (N * K + threads - 1) / threads, cap = (int64_t)num_sms() * 8;
   int blocks = (int)(need < cap ? need : cap);
-  size_t smem = (size_t)(T + 2) * K * sizeof(unsigned long long);
+  size_t smem = (size_t)(T + 2) * K * sizeof(unsigned long long) + (size_t)(T + 1) * K * sizeof(unsigned int);
   if (smem > 48 * 1024) return LHN_EINVAL;
   pck_accumulate_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
   return check_launch();
