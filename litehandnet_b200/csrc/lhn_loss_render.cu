@@ -191,26 +191,88 @@ __global__ void __launch_bounds__(128) render_targets_kernel(const __grid_consta
 }
 
 // ---- SimDR target (generate_simder.py:9-31): f32 arithmetic throughout ---------------------------
-__global__ void __launch_bounds__(128) render_simdr_kernel(const float* __restrict__ joints, int js,
+// One (sample, joint) per CTA; a thread writes four neighbouring positions with one 16-byte store (VEC) — the vectors are
+// the only traffic.  exp runs in f64 on the f32 argument (rounded once, = the correctly rounded f32 exp numpy's result is
+// compared against) but only where the result is not exactly 0: exp(a) < 2^-150 — half the smallest f32 denormal — for
+// a < -104, so everything farther than ~14.4 sigma from the joint is a plain zero store (9 positions in 10 at sigma 2,
+// 512 bins); without the cut the kernel sat on the FP64 pipe at 21 % of the HBM peak.
+__device__ __forceinline__ float simdr_bin(int pos, float mu, float den) {
+  const float d = __fsub_rn((float)pos, mu);
+  const float arg = __fdiv_rn(-__fmul_rn(d, d), den);
+  if (arg < -104.f) return 0.f;
+  return (float)exp((double)arg);                                    // f32 argument, exp rounded once
+}
+
+// VEC: one (sample, joint) per WARP and a grid-stride loop over them; the next pair's joint is loaded while this one is
+// written.  The warp first evaluates the window of bins that can be non-zero (|pos - mu| <= sqrt(104 * 2 sigma^2) + 1,
+// 64 bins at sigma 2) ONE bin per lane into shared memory, then streams the vectors out as 16-byte stores that pick
+// from the window or write the fill value.  Evaluating inside the store loop had each lane walk four divergent f64
+// exps in turn — 8x the FP64 issue slots, and FP64 (64 lanes per SM) was what the kernel waited on.
+constexpr int kSimdrWindowMax = 256;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) render_simdr_kernel(const float* __restrict__ joints, int js,
                                                            const float* __restrict__ vis, int vs,
                                                            int64_t n_bk, int Lx, int Ly, float kf,
                                                            float sigma, float* __restrict__ sx,
                                                            float* __restrict__ sy) {
-  const int64_t bk = blockIdx.x;
-  if (bk >= n_bk) return;
-  const bool on = vis[bk * vs] > 0.f;
-  const float mux = __fmul_rn(joints[bk * js], kf), muy = __fmul_rn(joints[bk * js + 1], kf);
   const float den = 2.f * sigma * sigma;
-  float* dx = sx + bk * Lx; float* dy = sy + bk * Ly;
-  for (int i = threadIdx.x; i < Lx + Ly; i += blockDim.x) {
-    const bool isx = i < Lx;
-    const int pos = isx ? i : i - Lx;
-    float v = 0.f;
-    if (on) {
-      const float d = __fsub_rn((float)pos, isx ? mux : muy);
-      v = (float)exp((double)__fdiv_rn(-__fmul_rn(d, d), den));   // f32 argument, exp rounded once
+  if (VEC) {
+    __shared__ float win_all[8][kSimdrWindowMax];
+    const int lane = threadIdx.x & 31;
+    float* win = win_all[threadIdx.x >> 5];
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t bk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bk >= n_bk) return;
+    const float reach = sqrtf(104.f * den) + 1.f;
+    const int nw = 2 * (int)ceilf(reach) + 2;                       // host: nw <= kSimdrWindowMax on this path
+    float jx = joints[bk * js], jy = joints[bk * js + 1], vv = vis[bk * vs];
+    for (; bk < n_bk; bk += nwarps) {
+      const bool on = vv > 0.f;
+      const float mus[2] = {__fmul_rn(jx, kf), __fmul_rn(jy, kf)};
+      const int64_t nb = bk + nwarps;
+      if (nb < n_bk) { jx = joints[nb * js]; jy = joints[nb * js + 1]; vv = vis[nb * vs]; }
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        const float mu = mus[ax];
+        const int L = ax ? Ly : Lx;
+        float* dst = ax ? sy + bk * Ly : sx + bk * Lx;
+        // a NaN joint makes every bin NaN (exp(NaN)); an infinite or far-away one makes every bin 0
+        const float fill = (on && mu != mu) ? mu : 0.f;
+        const bool near = on && fabsf(mu) < 1e9f;
+        const int p0 = near ? (int)floorf(mu - reach) : 0;
+        const unsigned span = near ? (unsigned)nw : 0u;
+        if (near)
+          for (int w = lane; w < nw; w += 32) {
+            const int pos = p0 + w;
+            if (pos >= 0 && pos < L) win[w] = simdr_bin(pos, mu, den);
+          }
+        __syncwarp();
+        for (int q = lane; q < (L >> 2); q += 32) {
+          const int pos = 4 * q;
+          const unsigned w = (unsigned)(pos - p0);
+          float4 v;
+          v.x = w < span ? win[w] : fill;
+          v.y = w + 1u < span ? win[w + 1u] : fill;
+          v.z = w + 2u < span ? win[w + 2u] : fill;
+          v.w = w + 3u < span ? win[w + 3u] : fill;
+          __stcs(reinterpret_cast<float4*>(dst + pos), v);
+        }
+        __syncwarp();
+      }
     }
-    if (isx) dx[pos] = v; else dy[pos] = v;
+  } else {
+    const int64_t bk = blockIdx.x;
+    if (bk >= n_bk) return;
+    const bool on = vis[bk * vs] > 0.f;
+    const float mux = __fmul_rn(joints[bk * js], kf), muy = __fmul_rn(joints[bk * js + 1], kf);
+    float* dx = sx + bk * Lx; float* dy = sy + bk * Ly;
+    for (int i = threadIdx.x; i < Lx + Ly; i += blockDim.x) {
+      const bool isx = i < Lx;
+      const int pos = isx ? i : i - Lx;
+      const float v = on ? simdr_bin(pos, isx ? mux : muy, den) : 0.f;
+      if (isx) dx[pos] = v; else dy[pos] = v;
+    }
   }
 }
 
@@ -321,7 +383,12 @@ extern "C" int lhn_render_simdr(const float* joints, int joints_stride, const fl
   const int64_t n = B * K;
   if (n == 0) return LHN_OK;
   if (n > 0x7fffffffLL) return LHN_EINVAL;
-  render_simdr_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(joints, joints_stride, vis, vis_stride,
+  const bool vec = Lx % 4 == 0 && Ly % 4 == 0 && ((uintptr_t)simdr_x % 16) == 0 && ((uintptr_t)simdr_y % 16) == 0 &&
+                   2 * (int)ceilf(sqrtf(104.f * 2.f * sigma * sigma) + 1.f) + 2 <= kSimdrWindowMax;
+  const int64_t want = (n + 7) / 8, cap = (int64_t)num_sms() * 8;
+  if (vec) render_simdr_kernel<true><<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(joints, joints_stride, vis, vis_stride,
+      n, Lx, Ly, split_ratio, sigma, simdr_x, simdr_y);
+  else render_simdr_kernel<false><<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(joints, joints_stride, vis, vis_stride,
       n, Lx, Ly, split_ratio, sigma, simdr_x, simdr_y);
   return check_launch();
 }

@@ -2,6 +2,7 @@
 // The arithmetic of _calc_distances is reproduced in the dtype numpy would promote to (f64 unless
 // every input is f32), rounded to f32 and compared with the f32 threshold, so hit counts are
 // bit-exact; counters are int64 and order-independent, hence identical for any sharding.
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "lhn_common.cuh"
@@ -35,6 +36,9 @@ __device__ __forceinline__ double ld_as_f64(const void* p, int dtype, int64_t i)
 // unsorted thresholds take one add per passed threshold.  Every load of an element is issued before anything is
 // decided, four elements per thread in flight.  Round 1: three or more 64-bit shared atomics (compare-and-swap loops)
 // per element behind three DEPENDENT loads and a 64-bit division — 16 % of the HBM peak.
+// FAST: every array is f32 with (x, y) pairs 8-byte aligned — the shape every caller on the hot path has (decoded f32
+// points against f32 ground truth, f32 or constant normaliser): 64-bit loads, no dtype switches, f32 arithmetic.
+template <bool FAST, int U>
 __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_constant__ PckArgs a) {
   extern __shared__ unsigned long long sc[];   // [(T+2)*K] u64 block counters, then [(T+1)*K] u32 histogram
   const int K = a.K, T = a.T;
@@ -52,12 +56,56 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
   int64_t n = e0 / K;
   unsigned int valid = 0;
   unsigned long long dsum = 0ull;
+  unsigned int hit1 = 0;                               // T == 1 (PCK at one threshold): the count stays in a register
+  const float thr0 = T > 0 ? a.thr[0] : 0.f;
+  auto consume = [&](float d) {
+    ++valid;
+    if (d == d) dsum += (unsigned long long)__float2ll_rn(d * 1048576.f);   // a power of two: exact in f32 as in f64
+    if (T == 1) {
+      hit1 += (d < thr0) ? 1u : 0u;
+    } else if (a.sorted_thr) {
+      int nh = 0;                                      // ascending thresholds: passed ones form a suffix
+      for (int t = 0; t < T; ++t) nh += (d < a.thr[t]) ? 1 : 0;
+      if (nh) atomicAdd(&hist[nh * K + k], 1u);
+    } else {
+      for (int t = 0; t < T; ++t)
+        if (d < a.thr[t]) atomicAdd(reinterpret_cast<unsigned int*>(&sc[t * K + k]), 1u);
+    }
+  };
+  if (FAST) {
+    // four elements' loads (28 B each) are issued before any arithmetic: the shared atomics and the early-outs of
+    // consume() would otherwise pin every load behind the previous element's decision
+    const float2* P = reinterpret_cast<const float2*>(a.pred);
+    const float2* G = reinterpret_cast<const float2*>(a.gt);
+    const float2* Z = reinterpret_cast<const float2*>(a.normalize);
+    const float nc = (float)a.norm_const;
+    for (int64_t e = e0; e < total; e += U * stride, n += U * n_step) {
+      float2 p[U], g[U], z[U];
+      unsigned char m[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t eu = e + u * stride;
+        m[u] = 0; p[u] = g[u] = make_float2(0.f, 0.f); z[u] = make_float2(nc, nc);
+        if (eu < total) {
+          m[u] = a.mask[eu]; p[u] = __ldg(P + eu); g[u] = __ldg(G + eu);
+          if (Z) z[u] = __ldg(Z + n + u * n_step);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!m[u] || z[u].x == 0.f || z[u].y == 0.f) continue;   // masked joint / _mask[normalize == 0 rows] = False
+        const float fx = z[u].x < 0.f ? 1e6f : z[u].x, fy = z[u].y < 0.f ? 1e6f : z[u].y;   // normalize[normalize<=0] = 1e6
+        const float qx = __fdiv_rn(__fsub_rn(p[u].x, g[u].x), fx), qy = __fdiv_rn(__fsub_rn(p[u].y, g[u].y), fy);
+        consume(__fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy))));
+      }
+    }
+  } else {
 #pragma unroll 4
   for (int64_t e = e0; e < total; e += stride, n += n_step) {
     const bool m = a.mask[e] != 0;
+    float d;
     double nx = a.norm_const, ny = a.norm_const;
     if (a.normalize) { nx = ld_as_f64(a.normalize, a.norm_dtype, 2 * n); ny = ld_as_f64(a.normalize, a.norm_dtype, 2 * n + 1); }
-    float d;
     if (a.all_f32) {
       const float* pp = reinterpret_cast<const float*>(a.pred) + e * a.pred_stride;
       const float* gp = reinterpret_cast<const float*>(a.gt) + e * a.gt_stride;
@@ -76,23 +124,16 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
       d = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)));
     }
     if (!m || nx == 0.0 || ny == 0.0) continue;        // masked joint / _mask[normalize == 0 rows] = False
-    ++valid;
-    if (d == d) dsum += (unsigned long long)llrint((double)d * 1048576.0);
-    if (a.sorted_thr) {
-      int nh = 0;                                      // ascending thresholds: passed ones form a suffix
-      for (int t = 0; t < T; ++t) nh += (d < a.thr[t]) ? 1 : 0;
-      if (nh) atomicAdd(&hist[nh * K + k], 1u);
-    } else {
-      for (int t = 0; t < T; ++t)
-        if (d < a.thr[t]) atomicAdd(reinterpret_cast<unsigned int*>(&sc[t * K + k]), 1u);
-    }
+    consume(d);
   }
+  }
+  if (T == 1 && hit1) atomicAdd(reinterpret_cast<unsigned int*>(&sc[k]), hit1);
   if (valid) {
     atomicAdd(reinterpret_cast<unsigned int*>(&sc[T * K + k]), valid);      // low word: per-block counts stay < 2^32
     atomicAdd(&sc[(T + 1) * K + k], dsum);
   }
   __syncthreads();
-  if (a.sorted_thr) {
+  if (a.sorted_thr && T > 1) {
     // hits[t] = elements that passed at least T - t thresholds: a running sum down the histogram, one joint per thread
     for (int kk = threadIdx.x; kk < K; kk += blockDim.x) {
       unsigned long long run = 0ull;
@@ -219,7 +260,14 @@ extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_str
   int blocks = (int)(need < cap ? need : cap);
   size_t smem = (size_t)(T + 2) * K * sizeof(unsigned long long) + (size_t)(T + 1) * K * sizeof(unsigned int);
   if (smem > 48 * 1024) return LHN_EINVAL;
-  pck_accumulate_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  auto al8 = [](const void* p) { return ((uintptr_t)p % 8) == 0; };
+  // the f32 fast path needs a normaliser that is f32 (numpy then computes in f32) or absent with all-f32 points: with a
+  // python-float constant numpy promotes to f64, so a constant normaliser keeps the general path
+  const bool fast = a.all_f32 && pred_stride == 2 && gt_stride == 2 && al8(pred) && al8(gt) && al8(normalize);
+  static const int u8 = [] { const char* e = getenv("LHN_PCK_U"); return e && atoi(e) == 8; }();
+  if (fast && u8) pck_accumulate_kernel<true, 8><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  else if (fast) pck_accumulate_kernel<true, 4><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  else pck_accumulate_kernel<false, 4><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
   return check_launch();
 }
 

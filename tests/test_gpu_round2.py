@@ -344,3 +344,27 @@ def test_fused_criterion_refuses_joint_weights():
         crit(hm, dict(joints_3d=j, joints_3d_visible=v, use_different_joint_weights=True))
     with pytest.raises(NotImplementedError):
         crit(hm, dict(joints_3d=j, joints_3d_visible=v, ann_info=dict(use_different_joint_weights=True)))
+
+
+@pytest.mark.parametrize("sigma,isz,k", [(2, (256, 256), 2), (3, (256, 192), 2), (10, (256, 256), 2), (2, (255, 253), 1)])
+def test_render_simdr_window_edges(sigma, isz, k):
+    """generate_simder.py:9-31 with the joints a data pipeline can hand over: on a bin, between bins, at and beyond the
+    borders, far outside, infinite, NaN, invisible.  sigma 2/3 take the windowed path (lhn_loss_render.cu), sigma 10 the
+    window is wider than the kernel's buffer and (255, 253) is not 16-byte tileable: both take the plain path."""
+    rng = np.random.default_rng(7)
+    B, K = 6, 21
+    j = np.zeros((B, K, 3), np.float32)
+    j[..., 0] = rng.uniform(-40, isz[0] + 40, (B, K))
+    j[..., 1] = rng.uniform(-40, isz[1] + 40, (B, K))
+    j[0, 0, :2] = (0.0, isz[1] - 1); j[0, 1, :2] = (isz[0] - 0.5, 0.25); j[0, 2, :2] = (-14.4 * sigma / k, isz[1] + 14.4 * sigma / k)
+    j[0, 3, :2] = (-1e12, 1e12); j[0, 4, :2] = (np.inf, -np.inf); j[0, 5, :2] = (np.nan, 10.0); j[0, 6, :2] = (17.0, np.nan)
+    j[0, 7, :2] = (3e9, 64.0)
+    v = (rng.uniform(size=(B, K, 1)) < 0.8).astype(np.float32)
+    v[0, :8] = 1
+    with np.errstate(all="ignore"):
+        want_x, want_y = O.render_simdr_batch(j, v, isz, k, sigma)
+    sx, sy = ops.render_simdr(torch.from_numpy(j).to(DEV), torch.from_numpy(v).to(DEV), isz, k, sigma)
+    nump = lambda t: t.cpu().numpy()
+    np.testing.assert_allclose(nump(sx), want_x, rtol=1e-5, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(nump(sy), want_y, rtol=1e-5, atol=1e-7, equal_nan=True)
+    assert np.array_equal(nump(sx) == 0, want_x == 0) or np.abs(nump(sx) - want_x).max() < 1e-37   # the cut is exact up to denormals
