@@ -78,6 +78,30 @@ template <> __device__ __forceinline__ float4 ldg_stream4<__half>(const __half* 
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// eight 16-bit elements with ONE 128-bit streaming load (a lane's 64-bit loads keep half the bytes in flight)
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+template <typename T> __device__ __forceinline__ void ldg_stream8(const T* p, float4& lo, float4& hi);
+template <> __device__ __forceinline__ void ldg_stream8<__nv_bfloat16>(const __nv_bfloat16* p, float4& lo, float4& hi) {
+  const uint4 r = ldg_stream_u4(reinterpret_cast<const uint4*>(p));
+  lo.x = __uint_as_float(r.x << 16); lo.y = __uint_as_float(r.x & 0xffff0000u);
+  lo.z = __uint_as_float(r.y << 16); lo.w = __uint_as_float(r.y & 0xffff0000u);
+  hi.x = __uint_as_float(r.z << 16); hi.y = __uint_as_float(r.z & 0xffff0000u);
+  hi.z = __uint_as_float(r.w << 16); hi.w = __uint_as_float(r.w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void ldg_stream8<__half>(const __half* p, float4& lo, float4& hi) {
+  uint4 r = ldg_stream_u4(reinterpret_cast<const uint4*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x)), b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+  const float2 c = __half22float2(*reinterpret_cast<__half2*>(&r.z)), d = __half22float2(*reinterpret_cast<__half2*>(&r.w));
+  lo = make_float4(a.x, a.y, b.x, b.y); hi = make_float4(c.x, c.y, d.x, d.y);
+}
+template <> __device__ __forceinline__ void ldg_stream8<float>(const float* p, float4& lo, float4& hi) {
+  lo = ldg_stream_f4(reinterpret_cast<const float4*>(p)); hi = ldg_stream_f4(reinterpret_cast<const float4*>(p) + 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // argmax with torch/numpy semantics: first maximal index; NaN is maximal; -0 == +0
 // ---------------------------------------------------------------------------------------------

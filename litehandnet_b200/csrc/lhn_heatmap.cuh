@@ -84,6 +84,7 @@ struct HmArgs {
   unsigned int xch_prev2_seq;
   int trigger_halfway;             // overlapped launch: let the successor grid in half-way (else after plane `trigger_plane`)
   int trigger_plane;               // default 2 (the third plane)
+  int xch_courier;                 // 1: the grid's last CTA carries no planes and runs the exchange (set by the launcher)
 };
 
 // ---- shared-memory layout --------------------------------------------------------------------

@@ -148,6 +148,24 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   const int team = warp / TW, wt = warp - team * TW; // team in CTA, warp in team
   const int nteams = (blockDim.x >> 5) / TW;
   const int bar_id = 1 + team;                       // named barrier of this team's sweepers
+  // Courier CTA of the exchanging launches (a.xch_courier: the grid's last CTA, on the one SM the host left without a
+  // plane-carrying CTA).  It owns no planes: once the previous launch has completed it adds the block of two launches
+  // back (all ranks' copies are in the mailbox by then) into the totals and sends the previous launch's block to the
+  // peers.  On a plane-carrying CTA the same ~7 us held that CTA's SM, the successor grid's CTA there started late and,
+  // the plane assignment being static, finished last: the delay was paid on every step (0.79 efficiency at 8 GPUs).
+  const uint32_t wctas = gridDim.x - (uint32_t)a.xch_courier;      // plane-carrying CTAs
+  if (a.xch_courier && blockIdx.x == wctas) {
+    asm volatile("griddepcontrol.launch_dependents;");             // the plane-carrying CTAs pace the successor grid
+    if (warp == 0 && (a.xch_prev_block || a.xch_prev2_block)) {
+      const int n_blk = (a.auc_steps + 5) * a.K;
+      asm volatile("griddepcontrol.wait;" ::: "memory");           // the previous launch is complete: its block is final
+      if (a.xch_prev2_block) xch_consume_block_i64(a.xch, a.xch_prev2_seq, a.xch_prev2_block, n_blk, a.xch_totals, lane, smem_raw);
+      __syncwarp();
+      if (a.xch_prev_block && a.xch.world > 1)
+        xch_publish(a.xch, a.xch_prev_seq, a.xch_prev_block, n_blk, lane, reinterpret_cast<unsigned long long*>(smem_raw));
+    }
+    return;
+  }
   // Roles rotate over the warps of a team so that the epilogue warps of the CTA's teams are spread over
   // the four SM sub-partitions (warp w issues on SMSP w % 4): role 0 = epilogue, roles 1..TW-1 = sweepers.
   const int ew = (TW >= 4 ? team : (team >> 1)) % TW;
@@ -171,9 +189,9 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
   float* hout = reinterpret_cast<float*>(hbuf + (size_t)TD * 5);
   int* fidx = reinterpret_cast<int*>(hout + 32);     // this team's copy of flip_index[K]
 
-  const uint32_t total_teams = gridDim.x * nteams;
+  const uint32_t total_teams = wctas * nteams;
   // team-major numbering: the n_planes % total_teams leftover planes spread over all SMs instead of the first few
-  const uint32_t gteam = team * gridDim.x + blockIdx.x;
+  const uint32_t gteam = team * wctas + blockIdx.x;
   const uint32_t n_planes = (uint32_t)a.n_planes;
   const uint32_t plane_bytes = (uint32_t)HW * sizeof(T);
   const uint32_t C = (uint32_t)a.C, K = (uint32_t)a.K;
@@ -705,7 +723,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       unsigned int last = 0;
       if (lane == 0) {
         unsigned int active = 0;
-        for (int t = 0; t < nteams; ++t) active += ((uint64_t)t * gridDim.x + blockIdx.x < n_planes) ? 1u : 0u;
+        for (int t = 0; t < nteams; ++t) active += ((uint64_t)t * wctas + blockIdx.x < n_planes) ? 1u : 0u;
         __threadfence_block();
         last = (atomicAdd(cta_done, 1u) == active - 1u) ? 1u : 0u;
       }
@@ -730,8 +748,8 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             if (run) atomicAdd(gcnt + (int64_t)row * Ki + k, run);
           }
         }
-        if (a.xch.world > 0) {
-          // In-kernel all-reduce of the per-step blocks (lhn_decode_heatmap_pck_xch), pipelined over two launches: the
+        if (a.xch.world > 0 && !a.xch_courier) {
+          // (Without a courier CTA — LHN_XCH_COURIER=0.)  In-kernel all-reduce of the per-step blocks (lhn_decode_heatmap_pck_xch), pipelined over two launches: the
           // first CTA of this grid to finish CONSUMES the block of two launches back (every rank sent it during the
           // previous launch, so nothing is waited for: adds the ranks' blocks in rank order into the running totals)
           // and PUBLISHES the previous launch's block to every peer.  The last CTA of the grid would be the natural
@@ -750,7 +768,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
             if (a.xch_prev2_block) xch_consume_block_i64(a.xch, a.xch_prev2_seq, a.xch_prev2_block, n_cnt, a.xch_totals, lane, smem_raw);
             if (a.xch_prev_block && a.xch.world > 1) xch_publish(a.xch, a.xch_prev_seq, a.xch_prev_block, n_cnt, lane, cta_cnt);
           }
-          if (tk == gridDim.x - 1 && lane == 0) *xch_ticket(a.xch, a.xch_seq) = 0u;
+          if (tk == wctas - 1 && lane == 0) *xch_ticket(a.xch, a.xch_seq) = 0u;
         }
       }
     }
@@ -775,7 +793,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
       if (lane == 0) {
         th->tsum[0] = acc_sp; th->tsum[1] = acc_sn; th->tsum[2] = acc_np; th->tsum[3] = acc_ne;
         unsigned int cta_teams = 0;
-        for (int t = 0; t < nteams; ++t) cta_teams += ((uint64_t)t * gridDim.x + blockIdx.x < n_planes) ? 1u : 0u;
+        for (int t = 0; t < nteams; ++t) cta_teams += ((uint64_t)t * wctas + blockIdx.x < n_planes) ? 1u : 0u;
         __threadfence_block();
         last = (atomicAdd(&th0->cta_done, 1u) == cta_teams - 1u) ? 1u : 0u;
       }
@@ -785,7 +803,7 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         __threadfence_block();
         double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
         for (int t = 0; t < nteams; ++t) {
-          if ((uint64_t)t * gridDim.x + blockIdx.x >= n_planes) break;
+          if ((uint64_t)t * wctas + blockIdx.x >= n_planes) break;
           const TeamHeader* tt = reinterpret_cast<const TeamHeader*>(reinterpret_cast<const unsigned char*>(th0) +
                                                                      (size_t)t * a.warp_smem);
           c0 += tt->tsum[0]; c1 += tt->tsum[1]; c2 += tt->tsum[2]; c3 += tt->tsum[3];
@@ -797,16 +815,16 @@ heatmap_team_kernel(const __grid_constant__ HmArgs a) {
         ticket = atomicAdd(a.ticket, 1u);
       }
       ticket = __shfl_sync(0xffffffffu, ticket, 0);
-      if (ticket == gridDim.x - 1) {                            // every CTA of the grid owns at least one plane
+      if (ticket == wctas - 1) {                            // every CTA of the grid owns at least one plane
         __threadfence();
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        for (uint32_t t0 = lane; t0 < gridDim.x; t0 += 160) {   // five rows per lane in flight: 148 SMs in one trip
+        for (uint32_t t0 = lane; t0 < wctas; t0 += 160) {   // five rows per lane in flight: 148 SMs in one trip
           double2 x[5], y[5];
 #pragma unroll
           for (int u = 0; u < 5; ++u) {
             const uint32_t t = t0 + 32u * u;
             x[u] = y[u] = make_double2(0.0, 0.0);               // rows past the end add +0.0
-            if (t < gridDim.x) {
+            if (t < wctas) {
               x[u] = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t));
               y[u] = __ldcg(reinterpret_cast<const double2*>(a.team_sums + 4 * (size_t)t) + 1);
             }
@@ -1171,7 +1189,9 @@ static int launch_one(HmArgs& a, int nteams, size_t smem, cudaStream_t st) {
   // one CTA per SM; small problems still spread over as many SMs as they have planes (team-major numbering)
   int sms = sm_count() - a.spare_sms;
   if (sms < 1) sms = 1;
-  int64_t ctas = a.n_planes < sms ? a.n_planes : sms;
+  if (a.xch_courier && sms < 2) a.xch_courier = 0;
+  if (a.xch_courier) --sms;                                   // one SM carries the courier CTA instead of planes
+  int64_t ctas = (a.n_planes < sms ? a.n_planes : sms) + a.xch_courier;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3((unsigned)(nteams * a.team_warps * 32));
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -1301,7 +1321,14 @@ int launch_heatmap_warp_kernel(HmArgs& a, int dtype, cudaStream_t st) {
   }
   {
     const char* tg = getenv("LHN_TRIGGER");               // "half" / "early" / "p<n>": override the trigger point (experiments)
-    a.trigger_halfway = tg ? (tg[0] == 'h') : (a.xch.world > 1);
+    if (a.xch.world > 0 && !loss && a.counters) {
+      const char* cr = getenv("LHN_XCH_COURIER");             // "0": the first plane-carrying CTA to finish exchanges
+      a.xch_courier = (cr && cr[0] == '0') ? 0 : 1;
+    }
+    // half-way only where a plane-carrying CTA exchanges (the batch-global loss; counters without a courier CTA): there
+    // the predecessor's completion includes its exchange and needs the slack.  With the courier the early trigger is
+    // best again (measured at 2 GPUs: 42.3 us per step early, 44.3 half-way; profiles/r02_courier.txt)
+    a.trigger_halfway = tg ? (tg[0] == 'h') : (a.xch.world > 1 && !a.xch_courier);
     a.trigger_plane = (tg && tg[0] == 'p' && tg[1] >= '0' && tg[1] <= '9') ? (tg[1] - '0') : 2;
   }
   a.sweeper_tables = (nstg >= 2 && tw >= 4) ? 1 : 0;

@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(256) simdr_sl1_kernel(const T* __restrict__ ox
                                                         const T* __restrict__ tx, const T* __restrict__ ty,
                                                         int64_t n_bk, int Lx, int Ly,
                                                         double* __restrict__ per_bk /* [n_bk,2] */) {
+  asm volatile("griddepcontrol.launch_dependents;");          // the finalize cluster queues up behind this grid
   const int lane = threadIdx.x & 31;
   const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -366,6 +367,45 @@ __global__ void __launch_bounds__(256) simdr_sl1_kernel(const T* __restrict__ ox
     }
     if (lane == 0) { per_bk[2 * bk] = sx; per_bk[2 * bk + 1] = sy; }
   }
+}
+
+// The same scan when the grid's warp count is a multiple of K (the host sizes it so): every row a warp meets belongs
+// to ONE joint, so the lanes keep f64 running sums over the warp's rows and are added once, after the loop — no
+// shuffle tree between rows (two f64 trees per 4 KB row were a quarter of the warp's instructions and held the next
+// row's loads back) and K-fold fewer entries for the finalize.  Entry of warp w: (sum_x, sum_y, sum_weight).
+template <typename T>
+__global__ void __launch_bounds__(256) simdr_sl1_joint_kernel(const T* __restrict__ ox, const T* __restrict__ oy,
+                                                              const T* __restrict__ tx, const T* __restrict__ ty,
+                                                              const float* __restrict__ weight,
+                                                              int64_t n_bk, int Lx, int Ly,
+                                                              double* __restrict__ part /* [warps,3] */) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int lane = threadIdx.x & 31;
+  const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nqx = Lx >> 2, nqy = Ly >> 2, nq = nqx > nqy ? nqx : nqy;
+  double accx = 0.0, accy = 0.0, accw = 0.0;
+  for (int64_t bk = wg; bk < n_bk; bk += nw) {
+    const T* px = ox + bk * Lx; const T* qx = tx + bk * Lx;
+    const T* py = oy + bk * Ly; const T* qy = ty + bk * Ly;
+    float ax = 0.f, bx = 0.f, ay = 0.f, by = 0.f;
+#pragma unroll 4
+    for (int q = lane; q < nq; q += 32) {
+      if (q < nqx) {
+        const float4 a = ldg_stream4<T>(px + 4 * q), g = ldg_stream4<T>(qx + 4 * q);
+        ax += smooth_l1(a.x - g.x); bx += smooth_l1(a.y - g.y); ax += smooth_l1(a.z - g.z); bx += smooth_l1(a.w - g.w);
+      }
+      if (q < nqy) {
+        const float4 a = ldg_stream4<T>(py + 4 * q), g = ldg_stream4<T>(qy + 4 * q);
+        ay += smooth_l1(a.x - g.x); by += smooth_l1(a.y - g.y); ay += smooth_l1(a.z - g.z); by += smooth_l1(a.w - g.w);
+      }
+    }
+    accx += (double)ax + (double)bx;
+    accy += (double)ay + (double)by;
+    accw += (double)__ldg(weight + bk);                      // warp-uniform
+  }
+  accx = warp_sum(accx); accy = warp_sum(accy);
+  if (lane == 0) { part[3 * wg] = accx; part[3 * wg + 1] = accy; part[3 * wg + 2] = accw; }
 }
 
 // One block.  The first T = (1024 / K) * K threads walk the [B*K] rows with a stride of T — a multiple of K, so a thread
@@ -412,6 +452,77 @@ __global__ void __launch_bounds__(1024) simdr_loss_finalize_kernel(const double*
     double t = 0.0;
     for (int jj = 0; jj < K; ++jj) t += term[jj];
     loss[0] = (float)(t / (double)K);
+  }
+}
+
+// The same sum on a cluster of 8 CTAs (one launch of 8 SMs instead of one: the single block spent ~6 us walking the
+// [B*K] rows in 43 dependent rounds).  CTA r takes the rows r*T + tid + i*8T — 8T a multiple of K, so a thread still
+// meets ONE joint — adds its threads per joint in thread order, and CTA 0 adds the eight per-joint partials in rank
+// order through distributed shared memory: a fixed summation order again (a different one from the single block's;
+// both agree with the f64 oracle to ~1e-15).  Launched with programmatic stream serialization: it is resident-ready
+// when the last rows are written.
+constexpr int kFinClusterMaxK = 128;
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(1024)
+simdr_loss_finalize_cluster_kernel(const double* __restrict__ per_bk, const float* __restrict__ weight,
+                                   int64_t n, int64_t B, int K, int Lx, int Ly, float* __restrict__ loss) {
+  // weight != nullptr: n = B*K rows of (sx, sy) + weight[row];  weight == nullptr: n per-warp entries of (sx, sy, sw)
+  // written by simdr_sl1_joint_kernel.  Either way entry i belongs to joint i % K.
+  __shared__ double s_x[1024], s_y[1024], s_w[1024];
+  __shared__ double part[3][kFinClusterMaxK];
+  __shared__ double term[kFinClusterMaxK];
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int tid = threadIdx.x;
+  const int T = ((int)blockDim.x / K) * K;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  double sx = 0, sy = 0, sw = 0;
+  if (tid < T) {
+    if (weight) {
+#pragma unroll 8
+      for (int64_t i = (int64_t)rank * T + tid; i < n; i += 8 * (int64_t)T) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(per_bk + 2 * i));
+        sx += v.x; sy += v.y; sw += (double)__ldg(weight + i);
+      }
+    } else {
+#pragma unroll 4
+      for (int64_t i = (int64_t)rank * T + tid; i < n; i += 8 * (int64_t)T) {
+        const double* e = per_bk + 3 * i;
+        sx += __ldcg(e); sy += __ldcg(e + 1); sw += __ldcg(e + 2);
+      }
+    }
+  }
+  s_x[tid] = sx; s_y[tid] = sy; s_w[tid] = sw;
+  __syncthreads();
+  if (tid < K) {
+    double ax = 0, ay = 0, aw = 0;
+    for (int t = tid; t < T; t += K) { ax += s_x[t]; ay += s_y[t]; aw += s_w[t]; }
+    part[0][tid] = ax; part[1][tid] = ay; part[2][tid] = aw;
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0 && tid < K) {
+    double ax = 0, ay = 0, aw = 0;
+    const unsigned base = (unsigned)__cvta_generic_to_shared(&part[0][0]);
+    for (unsigned r = 0; r < 8; ++r) {
+      double v[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        unsigned remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(base + (unsigned)((c * kFinClusterMaxK + tid) * 8)), "r"(r));
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v[c]) : "r"(remote) : "memory");
+      }
+      ax += v[0]; ay += v[1]; aw += v[2];
+    }
+    term[tid] = (ax / ((double)B * Lx) + ay / ((double)B * Ly)) * (aw / (double)B);
+  }
+  // no CTA may exit while CTA 0 still reads its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0) {
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int jj = 0; jj < K; ++jj) t += term[jj];
+      loss[0] = (float)(t / (double)K);
+    }
   }
 }
 
@@ -517,6 +628,64 @@ extern "C" int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const vo
   int blocks = (int)(need < cap ? need : cap);
   cudaStream_t st = (cudaStream_t)stream;
   double* per_bk = (double*)workspace;
+  static const int mode = [] { const char* e = getenv("LHN_SIMDR_LOSS_PATH"); return e ? atoi(e) : 0; }();   // 1: rows + one block, 2: rows + cluster
+  const size_t es = dtype == LHN_F32 ? 4 : 2;
+  const bool vec = ((Lx | Ly) & 3) == 0 && (((uintptr_t)out_x | (uintptr_t)out_y | (uintptr_t)tgt_x | (uintptr_t)tgt_y) % (4 * es)) == 0;
+  auto finalize_cluster = [&](const float* w, int64_t entries) -> int {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(8); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, simdr_loss_finalize_cluster_kernel, (const double*)per_bk, w, entries, B, K, Lx, Ly, loss);
+    if (e != cudaSuccess) { cudaGetLastError(); return LHN_ECUDA; }
+    return LHN_OK;
+  };
+  if (need > cap && vec && K <= kFinClusterMaxK && mode == 0) {
+    // warps: a multiple of K (one joint per warp) and of 8 (whole CTAs), with rows / warps just under an integer so
+    // every warp walks the same number of rows (43008 rows: 8736 warps x 4.92 rows instead of 9472 x 4.54)
+    auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
+    const int64_t unit = 8 * (int64_t)K / gcd(8, K);
+    // ... and no more CTAs than are resident at once (6 per SM at 40 registers): a second, thin wave of CTAs would
+    // walk its rows with a fraction of the loads in flight
+    static int resident[3] = {0, 0, 0};
+    const int di = dtype == LHN_F32 ? 0 : dtype == LHN_BF16 ? 1 : 2;
+    if (!resident[di]) {
+      int nb = 0;
+      cudaError_t e = di == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, simdr_sl1_joint_kernel<float>, threads, 0)
+                    : di == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, simdr_sl1_joint_kernel<__nv_bfloat16>, threads, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, simdr_sl1_joint_kernel<__half>, threads, 0);
+      if (e != cudaSuccess) { cudaGetLastError(); nb = 0; }
+      resident[di] = nb > 0 ? nb : 4;
+    }
+    if (const char* e = getenv("LHN_SIMDR_LOSS_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 8) resident[di] = v; }
+    cap = (int64_t)num_sms() * resident[di];
+    const int64_t rounds = (n + cap * 8 - 1) / (cap * 8);
+    int64_t warps = (n + rounds - 1) / rounds;
+    warps = (warps + unit - 1) / unit * unit;
+    if (warps * 3 * (int64_t)sizeof(double) <= workspace_bytes && warps / 8 <= 2 * cap) {
+      const int jb = (int)(warps / 8);
+      switch (dtype) {
+        case LHN_F32:
+          simdr_sl1_joint_kernel<float><<<jb, threads, 0, st>>>((const float*)out_x, (const float*)out_y,
+              (const float*)tgt_x, (const float*)tgt_y, weight, n, Lx, Ly, per_bk);
+          break;
+        case LHN_BF16:
+          simdr_sl1_joint_kernel<__nv_bfloat16><<<jb, threads, 0, st>>>((const __nv_bfloat16*)out_x,
+              (const __nv_bfloat16*)out_y, (const __nv_bfloat16*)tgt_x, (const __nv_bfloat16*)tgt_y, weight, n, Lx, Ly, per_bk);
+          break;
+        case LHN_F16:
+          simdr_sl1_joint_kernel<__half><<<jb, threads, 0, st>>>((const __half*)out_x, (const __half*)out_y,
+              (const __half*)tgt_x, (const __half*)tgt_y, weight, n, Lx, Ly, per_bk);
+          break;
+        default: return LHN_EDTYPE;
+      }
+      int rc = check_launch();
+      if (rc) return rc;
+      return finalize_cluster(nullptr, warps);
+    }
+  }
   switch (dtype) {
     case LHN_F32:
       simdr_sl1_kernel<float><<<blocks, threads, 0, st>>>((const float*)out_x, (const float*)out_y,
@@ -534,6 +703,7 @@ extern "C" int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const vo
   }
   int rc = check_launch();
   if (rc) return rc;
+  if (K <= kFinClusterMaxK && n >= 8192 && mode != 1) return finalize_cluster(weight, n);
   simdr_loss_finalize_kernel<<<1, 1024, 0, st>>>(per_bk, weight, B, K, Lx, Ly, loss);
   return check_launch();
 }
