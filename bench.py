@@ -450,7 +450,7 @@ class DecodeWorkload(Workload):
                                                     overlap_previous=overlap, metrics=m))
         if self.xch is not None:
             self.collective = ("the per-step PCK/AUC/EPE counter block is all-gathered EVERY eval step INSIDE the kernel (one "
-                               "launch behind: the next step's first-finishing CTA sends it) through peer-mapped mailboxes over "
+                               "launch behind: the next launch's courier CTA — an extra CTA on one SM without planes — sends it) through peer-mapped mailboxes over "
                                f"NVLink ({self.xch.how}) and added in rank order into the running totals; no NCCL call, one launch "
                                "per step + one flush per epoch (datasets/base_dataset.py:193-261, spawn_dist.py:68-80)")
             self.nvlink_bytes_per_step = self.xch.bytes_per_step((self.T + 5) * K * 8)

@@ -441,14 +441,16 @@ LHN_API int lhn_decode_heatmap_pck(const void* hm, int dtype, int64_t B, int K, 
                                    lhn_stream_t stream);
 
 /* The same with the per-step counter block all-reduced over the ranks INSIDE the kernel, pipelined over two launches:
- * `counters` is this rank's block for THIS step (zero at entry; rotate LHN_XCH_SLOTS blocks).  The first CTA of this
- * grid to finish (a) adds every rank's copy of xch->prev2_block's step (sent during the previous launch, so nothing
- * is waited for) in rank order into `totals` int64 [(auc_steps+5)*K] and zeroes that block, (b) sends xch->prev_block
- * — the previous launch's block — to every peer.  lhn_exchange_flush(xch, n, totals) completes the (up to two)
- * steps still in flight when a sequence ends; after it every rank holds the same running totals, equal bit for bit to
- * a single-process evaluation (datasets/base_dataset.py:193-261 on the gathered results).  Why pipelined: whoever
- * exchanges holds its SM for the NVLink round trip; the first CTA to finish has the slack of the grid's finish-time
- * spread for ~7 us of sends and local adds, the last CTA has none, and nobody has 10-20 us. */
+ * `counters` is this rank's block for THIS step (zero at entry; rotate LHN_XCH_SLOTS blocks).  The launch carries one
+ * extra CTA — the courier, on one SM that gets no planes — which, once the previous launch has completed, (a) adds
+ * every rank's copy of xch->prev2_block's step (sent during the previous launch, so nothing is waited for) in rank
+ * order into `totals` int64 [(auc_steps+5)*K] and zeroes that block, (b) sends xch->prev_block — the previous launch's
+ * block — to every peer.  lhn_exchange_flush(xch, n, totals) completes the (up to two) steps still in flight when a
+ * sequence ends; after it every rank holds the same running totals, equal bit for bit to a single-process evaluation
+ * (datasets/base_dataset.py:193-261 on the gathered results).  Why a courier and why pipelined: whoever exchanges
+ * holds its SM for the NVLink round trip, and a plane-carrying CTA that does so delays its SM's CTA of the next launch
+ * on every step (LHN_XCH_COURIER=0 in the environment selects that older variant, where the first
+ * plane-carrying CTA to finish exchanges). */
 LHN_API int lhn_decode_heatmap_pck_xch(const void* hm, int dtype, int64_t B, int K, int H, int W,
                                    int64_t stride_b, int64_t stride_c, const float* center,
                                    const float* scale, const lhn_decode_params* dp, float* out_hm,
