@@ -250,12 +250,15 @@ __global__ void __launch_bounds__(256) render_simdr_kernel(const float* __restri
         __syncwarp();
         for (int q = lane; q < (L >> 2); q += 32) {
           const int pos = 4 * q;
-          const unsigned w = (unsigned)(pos - p0);
-          float4 v;
-          v.x = w < span ? win[w] : fill;
-          v.y = w + 1u < span ? win[w + 1u] : fill;
-          v.z = w + 2u < span ? win[w + 2u] : fill;
-          v.w = w + 3u < span ? win[w + 3u] : fill;
+          const int d = pos - p0;
+          float4 v = make_float4(fill, fill, fill, fill);
+          if (d > -4 && d < (int)span) {                 // 7 quads in 8 lie wholly outside the window: just the store
+            const unsigned w = (unsigned)d;
+            v.x = w < span ? win[w] : fill;
+            v.y = w + 1u < span ? win[w + 1u] : fill;
+            v.z = w + 2u < span ? win[w + 2u] : fill;
+            v.w = w + 3u < span ? win[w + 3u] : fill;
+          }
           __stcs(reinterpret_cast<float4*>(dst + pos), v);
         }
         __syncwarp();

@@ -368,3 +368,27 @@ def test_render_simdr_window_edges(sigma, isz, k):
     np.testing.assert_allclose(nump(sx), want_x, rtol=1e-5, atol=1e-7, equal_nan=True)
     np.testing.assert_allclose(nump(sy), want_y, rtol=1e-5, atol=1e-7, equal_nan=True)
     assert np.all(nump(sx)[want_x > 1e-30] > 0) and np.all(nump(sy)[want_y > 1e-30] > 0)   # the cut removes only what rounds to 0
+
+
+@pytest.mark.parametrize("B,K,Lx,Ly,dt", [(1024, 21, 64, 48, torch.float32), (700, 17, 128, 128, torch.float32),
+                                          (1024, 16, 64, 64, torch.bfloat16), (96, 21, 512, 512, torch.float32),
+                                          (420, 21, 64, 64, torch.float32)])
+def test_simdr_smoothl1_large_batches_take_the_joint_per_warp_path(B, K, Lx, Ly, dt):
+    """KLDiscretLoss (loss/simdrLoss.py) at sizes where lhn_simdr_smoothl1 runs one joint per warp with per-lane f64
+    sums and the cluster finalise (B*K rows > the resident warps; (96, 21) stays on the row-per-warp path with the
+    one-block finalise, (420, 21) on the row-per-warp path with the cluster finalise):
+    against the NumPy oracle on the same values, weights with zeros and non-unit values."""
+    g = torch.Generator(device=DEV).manual_seed(B + K)
+    ox = torch.randn(B, K, Lx, generator=g, device=DEV) * 0.7
+    oy = torch.randn(B, K, Ly, generator=g, device=DEV) * 0.7
+    tx = torch.rand(B, K, Lx, generator=g, device=DEV)
+    ty = torch.rand(B, K, Ly, generator=g, device=DEV)
+    ox[0, 0, :5] = 3.0; oy[1, 2, -3:] = -2.5                      # |d| > 1: the linear branch
+    w = (torch.rand(B, K, 1, generator=g, device=DEV) < 0.8).float() * (0.5 + torch.rand(B, K, 1, generator=g, device=DEV))
+    ox, oy, tx, ty = (t.to(dt) for t in (ox, oy, tx, ty))
+    got = float(ops.simdr_smoothl1(ox, oy, tx, ty, w).item())
+    f = lambda t: t.float().cpu().numpy()
+    want = float(O.kl_discret_loss(f(ox), f(oy), f(tx), f(ty), f(w)))
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+    # run-to-run: the summation order is fixed
+    assert float(ops.simdr_smoothl1(ox, oy, tx, ty, w).item()) == got
