@@ -219,9 +219,7 @@ extern "C" int lhn_loss_mse_multi(int n_tensors, const void* const* outputs, con
                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, loss_multi_kernel<__half>, kLossThreads, 0);
     if (e != cudaSuccess) { cudaGetLastError(); nb = 0; }
     resident[di] = nb > 0 ? (nb < 8 ? nb : 8) : 4;
-    if (const char* v = getenv("LHN_LOSS_CTAS")) { const int c = atoi(v); if (c >= 1 && c <= 8) resident[di] = c; }
   }
-  static const bool balance = [] { const char* e = getenv("LHN_LOSS_BALANCE"); return !(e && e[0] == '0'); }();
   const int64_t grid_max = (int64_t)num_sms() * resident[di];
   // pass 1: CTAs in proportion to each tensor's elements, at least one, at most one per kLossWarps planes; pass 2: what
   // the capped (small) tensors left over goes to the others, so a small problem still gets a warp per plane
@@ -244,7 +242,7 @@ extern "C" int lhn_loss_mse_multi(int n_tensors, const void* const* outputs, con
     a.t[i].loss_weight = loss_weights ? loss_weights[i] : 1.f;
     a.t[i].cta_begin = cta;
     int64_t want = wants[i];
-    if (balance) {
+    {
       // planes / warps just under an integer: every warp walks the same number of planes
       const int64_t rounds = (n_planes[i] + want * kLossWarps - 1) / (want * kLossWarps);
       const int64_t warps = (n_planes[i] + rounds - 1) / rounds;

@@ -38,7 +38,7 @@ __device__ __forceinline__ double ld_as_f64(const void* p, int dtype, int64_t i)
 // per element behind three DEPENDENT loads and a 64-bit division — 16 % of the HBM peak.
 // FAST: every array is f32 with (x, y) pairs 8-byte aligned — the shape every caller on the hot path has (decoded f32
 // points against f32 ground truth, f32 or constant normaliser): 64-bit loads, no dtype switches, f32 arithmetic.
-template <bool FAST, int U, bool PIPE>
+template <bool FAST, int U>
 __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_constant__ PckArgs a) {
   extern __shared__ unsigned long long sc[];   // [(T+2)*K] u64 block counters, then [(T+1)*K] u32 histogram
   const int K = a.K, T = a.T;
@@ -79,34 +79,24 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
     const float2* G = reinterpret_cast<const float2*>(a.gt);
     const float2* Z = reinterpret_cast<const float2*>(a.normalize);
     const float nc = (float)a.norm_const;
-    float2 p[U], g[U], z[U], p2[U], g2[U], z2[U];
-    unsigned char m[U], m2[U];
-    auto load = [&](float2* lp, float2* lg, float2* lz, unsigned char* lm, int64_t e, int64_t nn) {
+    for (int64_t e = e0; e < total; e += U * stride, n += U * n_step) {
+      float2 p[U], g[U], z[U];
+      unsigned char m[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t eu = e + u * stride;
-        lm[u] = 0; lp[u] = lg[u] = make_float2(0.f, 0.f); lz[u] = make_float2(nc, nc);
+        m[u] = 0; p[u] = g[u] = make_float2(0.f, 0.f); z[u] = make_float2(nc, nc);
         if (eu < total) {
-          lm[u] = a.mask[eu]; lp[u] = __ldg(P + eu); lg[u] = __ldg(G + eu);
-          if (Z) lz[u] = __ldg(Z + nn + u * n_step);
+          m[u] = a.mask[eu]; p[u] = __ldg(P + eu); g[u] = __ldg(G + eu);
+          if (Z) z[u] = __ldg(Z + n + u * n_step);
         }
       }
-    };
-    if (PIPE) load(p, g, z, m, e0, n);
-    for (int64_t e = e0; e < total; e += U * stride, n += U * n_step) {
-      // PIPE: the next batch's loads go out before this batch's arithmetic, so a thread always has one in flight
-      if (PIPE) load(p2, g2, z2, m2, e + U * stride, n + U * n_step);
-      else load(p, g, z, m, e, n);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (!m[u] || z[u].x == 0.f || z[u].y == 0.f) continue;   // masked joint / _mask[normalize == 0 rows] = False
         const float fx = z[u].x < 0.f ? 1e6f : z[u].x, fy = z[u].y < 0.f ? 1e6f : z[u].y;   // normalize[normalize<=0] = 1e6
         const float qx = __fdiv_rn(__fsub_rn(p[u].x, g[u].x), fx), qy = __fdiv_rn(__fsub_rn(p[u].y, g[u].y), fy);
         consume(__fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy))));
-      }
-      if (PIPE) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) { p[u] = p2[u]; g[u] = g2[u]; z[u] = z2[u]; m[u] = m2[u]; }
       }
     }
   } else {
@@ -266,8 +256,7 @@ extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_str
   a.all_f32 = pred_dtype == LHN_F32 && gt_dtype == LHN_F32 && normalize && norm_dtype == LHN_F32;
   a.counters = reinterpret_cast<unsigned long long*>(counters);
   const int threads = 256;
-  static const int ctas_per_sm = [] { const char* e = getenv("LHN_PCK_CTAS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 8; }();
-  int64_t need = (N * K + threads - 1) / threads, cap = (int64_t)num_sms() * ctas_per_sm;
+  int64_t need = (N * K + threads - 1) / threads, cap = (int64_t)num_sms() * 8;
   int blocks = (int)(need < cap ? need : cap);
   size_t smem = (size_t)(T + 2) * K * sizeof(unsigned long long) + (size_t)(T + 1) * K * sizeof(unsigned int);
   if (smem > 48 * 1024) return LHN_EINVAL;
@@ -275,11 +264,10 @@ extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_str
   // the f32 fast path needs a normaliser that is f32 (numpy then computes in f32) or absent with all-f32 points: with a
   // python-float constant numpy promotes to f64, so a constant normaliser keeps the general path
   const bool fast = a.all_f32 && pred_stride == 2 && gt_stride == 2 && al8(pred) && al8(gt) && al8(normalize);
-  static const int variant = [] { const char* e = getenv("LHN_PCK_VARIANT"); return e ? atoi(e) : 0; }();
-  if (fast && variant == 1) pck_accumulate_kernel<true, 4, true><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
-  else if (fast && variant == 2) pck_accumulate_kernel<true, 2, true><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
-  else if (fast) pck_accumulate_kernel<true, 4, false><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
-  else pck_accumulate_kernel<false, 4, false><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  // (measured and not kept: eight elements per batch, 76 us against 67; a software-pipelined batch of four or of two,
+  // 66.6 / 68.0 us; four resident CTAs per SM instead of a grid of eight, 66.9 us — profiles/r02_kernels.txt history)
+  if (fast) pck_accumulate_kernel<true, 4><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  else pck_accumulate_kernel<false, 4><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
   return check_launch();
 }
 

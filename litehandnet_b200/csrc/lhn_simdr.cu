@@ -659,7 +659,6 @@ extern "C" int lhn_simdr_smoothl1(const void* out_x, const void* out_y, const vo
       if (e != cudaSuccess) { cudaGetLastError(); nb = 0; }
       resident[di] = nb > 0 ? nb : 4;
     }
-    if (const char* e = getenv("LHN_SIMDR_LOSS_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 8) resident[di] = v; }
     cap = (int64_t)num_sms() * resident[di];
     const int64_t rounds = (n + cap * 8 - 1) / (cap * 8);
     int64_t warps = (n + rounds - 1) / rounds;
