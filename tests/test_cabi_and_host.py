@@ -238,3 +238,39 @@ def test_decode_params_cache_is_keyed_on_every_field(lib_path):
     assert d is not a and (d.scale_x, d.scale_y, d.transform) == (4.0, 2.0, L.XFORM_SCALE)
     e = ops._decode_params(L.MASK_ZERO, L.REFINE_SIGN, L.XFORM_NONE, use_udp=True)
     assert e.use_udp == 1 and e.mask_mode == L.MASK_ZERO and e.blur_ksize == 0
+
+
+def test_exchange_step_bookkeeping_on_cpu():
+    """dist.PeerExchange.begin_step is the host half of the pipelined counter exchange (include/lhn.h
+    lhn_decode_heatmap_pck_xch): launch s accumulates into block s % LHN_XCH_SLOTS, publishes the block of launch s-1 and
+    adds the block of launch s-2 into the totals.  Checked here without a GPU on a CPU-resident instance."""
+    import torch
+    from litehandnet_b200 import _lib as L
+    from litehandnet_b200.dist import PeerExchange
+    x = PeerExchange.local_group(1, "cpu")[0]
+    n = 25 * 16                                     # odd word counts are padded to an even row
+    blocks = x.step_blocks(n + 1)
+    assert blocks.shape == (L.XCH_SLOTS, n + 2) and blocks.dtype == torch.int64
+    blocks = x.step_blocks(n)
+    ptrs = [blocks[i].data_ptr() for i in range(L.XCH_SLOTS)]
+    totals = torch.zeros(n, dtype=torch.int64)
+    s = x.struct()
+    assert s.world == 1 and s.rank == 0 and s.mailbox[0] == x.mailbox.data_ptr() and s.status == x.status.data_ptr()
+    seen = []
+    for step in range(1, 8):
+        cur = x.begin_step(n, totals, s)
+        assert s.seq == step and cur == ptrs[step % L.XCH_SLOTS]
+        prev = (s.prev_seq, s.prev_block)
+        prev2 = (s.prev2_seq, s.prev2_block)
+        assert prev == ((step - 1, ptrs[(step - 1) % L.XCH_SLOTS]) if step > 1 else (0, None))
+        assert prev2 == ((step - 2, ptrs[(step - 2) % L.XCH_SLOTS]) if step > 2 else (0, None))
+        # a block is only reused after it was consumed (zeroed): LHN_XCH_SLOTS steps later, two after its consumption
+        assert cur not in (s.prev_block, s.prev2_block)
+        seen.append(cur)
+    assert len(set(seen[:L.XCH_SLOTS])) == L.XCH_SLOTS
+    assert [p[0] for p in x._pending] == [6, 7]     # what flush() completes: publish 7, consume 6 and 7
+    with pytest.raises(L.LhnError):
+        x.step_blocks(n + 8)                        # steps in flight: the block size cannot change before flush()
+    assert x.bytes_per_step(n * 8) == 0             # one rank: nothing crosses NVLink
+    y = PeerExchange.local_group(8, "cpu")[3]
+    assert y.bytes_per_step(n * 8) == 7 * (n * 8 + 4)
