@@ -75,30 +75,33 @@ __global__ void __launch_bounds__(256) pck_accumulate_kernel(const __grid_consta
   if (FAST) {
     // four elements' loads (28 B each) are issued before any arithmetic: the shared atomics and the early-outs of
     // consume() would otherwise pin every load behind the previous element's decision
-    const float2* P = reinterpret_cast<const float2*>(a.pred);
-    const float2* G = reinterpret_cast<const float2*>(a.gt);
-    const float2* Z = reinterpret_cast<const float2*>(a.normalize);
-    const float nc = (float)a.norm_const;
-    for (int64_t e = e0; e < total; e += U * stride, n += U * n_step) {
+    // Running pointers, and a main loop over FULL batches without per-element bounds checks (then a plain tail): the
+    // kernel is issue-bound — two IEEE divisions and a square root per 25-byte element — so the 64-bit index
+    // arithmetic and predicates of a guarded batch (a quarter of the instructions) were worth removing.
+    auto elem = [&](const float2 p, const float2 g, const float2 z, const unsigned char m) {
+      if (!m || z.x == 0.f || z.y == 0.f) return;             // masked joint / _mask[normalize == 0 rows] = False
+      const float fx = z.x < 0.f ? 1e6f : z.x, fy = z.y < 0.f ? 1e6f : z.y;      // normalize[normalize<=0] = 1e6
+      const float qx = __fdiv_rn(__fsub_rn(p.x, g.x), fx), qy = __fdiv_rn(__fsub_rn(p.y, g.y), fy);
+      consume(__fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy))));
+    };
+    const float2* pp = reinterpret_cast<const float2*>(a.pred) + e0;
+    const float2* gp = reinterpret_cast<const float2*>(a.gt) + e0;
+    const float2* zp = reinterpret_cast<const float2*>(a.normalize) + n;    // the launcher takes this path only with a normaliser
+    const unsigned char* mp = a.mask + e0;
+    int64_t e = e0;
+    for (; e + (U - 1) * stride < total; e += U * stride) {
       float2 p[U], g[U], z[U];
       unsigned char m[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t eu = e + u * stride;
-        m[u] = 0; p[u] = g[u] = make_float2(0.f, 0.f); z[u] = make_float2(nc, nc);
-        if (eu < total) {
-          m[u] = a.mask[eu]; p[u] = __ldg(P + eu); g[u] = __ldg(G + eu);
-          if (Z) z[u] = __ldg(Z + n + u * n_step);
-        }
+        m[u] = mp[u * stride]; p[u] = __ldg(pp + u * stride); g[u] = __ldg(gp + u * stride); z[u] = __ldg(zp + u * n_step);
       }
+      pp += U * stride; gp += U * stride; mp += U * stride; zp += U * n_step;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!m[u] || z[u].x == 0.f || z[u].y == 0.f) continue;   // masked joint / _mask[normalize == 0 rows] = False
-        const float fx = z[u].x < 0.f ? 1e6f : z[u].x, fy = z[u].y < 0.f ? 1e6f : z[u].y;   // normalize[normalize<=0] = 1e6
-        const float qx = __fdiv_rn(__fsub_rn(p[u].x, g[u].x), fx), qy = __fdiv_rn(__fsub_rn(p[u].y, g[u].y), fy);
-        consume(__fsqrt_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy))));
-      }
+      for (int u = 0; u < U; ++u) elem(p[u], g[u], z[u], m[u]);
     }
+    for (; e < total; e += stride, pp += stride, gp += stride, mp += stride, zp += n_step)
+      elem(__ldg(pp), __ldg(gp), __ldg(zp), *mp);
   } else {
 #pragma unroll 4
   for (int64_t e = e0; e < total; e += stride, n += n_step) {
@@ -263,7 +266,7 @@ extern "C" int lhn_pck_accumulate(const void* pred, int pred_dtype, int pred_str
   auto al8 = [](const void* p) { return ((uintptr_t)p % 8) == 0; };
   // the f32 fast path needs a normaliser that is f32 (numpy then computes in f32) or absent with all-f32 points: with a
   // python-float constant numpy promotes to f64, so a constant normaliser keeps the general path
-  const bool fast = a.all_f32 && pred_stride == 2 && gt_stride == 2 && al8(pred) && al8(gt) && al8(normalize);
+  const bool fast = a.all_f32 && normalize && pred_stride == 2 && gt_stride == 2 && al8(pred) && al8(gt) && al8(normalize);
   // (measured and not kept: eight elements per batch, 76 us against 67; a software-pipelined batch of four or of two,
   // 66.6 / 68.0 us; four resident CTAs per SM instead of a grid of eight, 66.9 us — profiles/r02_kernels.txt history)
   if (fast) pck_accumulate_kernel<true, 4><<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
